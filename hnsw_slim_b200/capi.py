@@ -1,0 +1,254 @@
+"""ctypes binding of include/hnswslim_b200.h (libhnswslim_b200.so).
+
+This is the only way Python (tests, bench.py) reaches the engine: every call goes through
+the same C ABI a C++ host links against.  There is no fallback: if the shared library is
+missing, or no CUDA device is present, calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import build as _build
+
+HS_KIND_SLIM, HS_KIND_SLIMQ = 0, 1
+HS_METRIC_L2, HS_METRIC_IP = 0, 1
+
+EXPORTS = [
+    "hs_load", "hs_load_memory", "hs_free", "hs_set_ef", "hs_get_info", "hs_search_batch",
+    "hs_search_batch_counts", "hs_search_batch_device", "hs_stats", "hs_reset_stats", "hs_bruteforce_knn",
+    "hs_bruteforce_knn_device", "hs_topk_merge_device", "hs_recall", "hs_last_error", "hs_abi_version",
+    "hs_debug_flatten", "hs_debug_free", "hs_debug_info", "hs_debug_row", "hs_debug_node",
+]
+
+
+class HsError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"hnswslim_b200 error {code}: {msg}")
+        self.code = code
+
+
+class IndexInfo(C.Structure):
+    _fields_ = [("n", C.c_uint64), ("dim", C.c_uint64), ("dim_padded", C.c_uint64), ("M", C.c_uint64),
+                ("maxM", C.c_uint64), ("maxM0", C.c_uint64), ("ef_construction", C.c_uint64),
+                ("maxlevel", C.c_int32), ("threshold_level", C.c_int32), ("enterpoint", C.c_uint32),
+                ("has_deleted", C.c_int32), ("kind", C.c_int32), ("metric", C.c_int32),
+                ("deg0_stride", C.c_uint32), ("max_deg0", C.c_uint32), ("upper_stride", C.c_uint32),
+                ("n_upper", C.c_uint32), ("sum_deg0", C.c_uint64), ("device_bytes", C.c_uint64),
+                ("ef", C.c_uint64), ("padded_dim_q", C.c_uint64), ("num_cluster", C.c_uint64)]
+
+    def as_dict(self) -> dict:
+        return {f: getattr(self, f) for f, _ in self._fields_}
+
+
+_lib = None
+
+
+def lib_path() -> str:
+    return _build.LIB
+
+
+def lib():
+    """The loaded shared library (raises if it was not built — no fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_build.LIB):
+            raise FileNotFoundError(
+                f"{_build.LIB} is missing: run `python -m hnsw_slim_b200.build` (nvcc, sm_100a). "
+                "hnsw_slim_b200 has no CPU / PyTorch fallback.")
+        L = C.CDLL(_build.LIB)
+        vp, sz, i32 = C.c_void_p, C.c_size_t, C.c_int
+        L.hs_last_error.restype = C.c_char_p
+        L.hs_abi_version.restype = i32
+        L.hs_load.argtypes = [C.c_char_p, i32, i32, sz, vp, sz, i32, C.POINTER(vp)]
+        L.hs_load_memory.argtypes = [vp, sz, i32, i32, sz, vp, sz, i32, C.POINTER(vp)]
+        L.hs_free.argtypes = [vp]
+        L.hs_free.restype = None
+        L.hs_set_ef.argtypes = [vp, sz]
+        L.hs_get_info.argtypes = [vp, C.POINTER(IndexInfo)]
+        L.hs_search_batch.argtypes = [vp, vp, sz, sz, vp, vp]
+        L.hs_search_batch_counts.argtypes = [vp, vp, sz, sz, vp, vp, vp]
+        L.hs_search_batch_device.argtypes = [vp, vp, sz, sz, vp, vp, vp]
+        L.hs_stats.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+        L.hs_reset_stats.argtypes = [vp]
+        L.hs_bruteforce_knn.argtypes = [vp, sz, sz, vp, sz, sz, i32, i32, vp, vp]
+        L.hs_bruteforce_knn_device.argtypes = [vp, sz, sz, vp, sz, sz, i32, vp, vp, vp]
+        L.hs_topk_merge_device.argtypes = [vp, vp, sz, sz, sz, vp, vp, vp]
+        L.hs_recall.argtypes = [vp, sz, sz, vp, sz, vp, sz, vp, sz, i32, i32, C.POINTER(C.c_double)]
+        L.hs_debug_flatten.argtypes = [C.c_char_p, i32, sz, C.POINTER(vp)]
+        L.hs_debug_free.argtypes = [vp]
+        L.hs_debug_free.restype = None
+        L.hs_debug_info.argtypes = [vp, C.POINTER(IndexInfo)]
+        L.hs_debug_row.argtypes = [vp, C.c_uint32, i32, vp, i32]
+        L.hs_debug_node.argtypes = [vp, C.c_uint32, C.POINTER(i32), C.POINTER(C.c_uint32), vp]
+        for name in EXPORTS:
+            if name not in ("hs_last_error", "hs_free", "hs_debug_free"):
+                getattr(L, name).restype = i32
+        _lib = L
+    return _lib
+
+
+def _check(rc: int) -> None:
+    if rc != 0:
+        raise HsError(rc, lib().hs_last_error().decode(errors="replace"))
+
+
+def _f32(a) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+class Index:
+    """An HBM-resident HNSW-Slim index (hs_index*)."""
+
+    def __init__(self, graph_path: str, dim: int, *, kind: int = HS_KIND_SLIM, metric: int = HS_METRIC_L2,
+                 raw_base: np.ndarray | None = None, device: int = 0):
+        self._h = C.c_void_p()
+        raw = _f32(raw_base) if raw_base is not None else None
+        _check(lib().hs_load(graph_path.encode(), kind, metric, dim,
+                             raw.ctypes.data if raw is not None else None,
+                             raw.shape[0] if raw is not None else 0, device, C.byref(self._h)))
+        self.dim = dim
+
+    @classmethod
+    def from_bytes(cls, image: bytes, dim: int, *, kind: int = HS_KIND_SLIM, metric: int = HS_METRIC_L2,
+                   device: int = 0) -> "Index":
+        self = cls.__new__(cls)
+        self._h = C.c_void_p()
+        buf = np.frombuffer(image, dtype=np.uint8)
+        _check(lib().hs_load_memory(buf.ctypes.data, buf.size, kind, metric, dim, None, 0, device,
+                                    C.byref(self._h)))
+        self.dim = dim
+        return self
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            lib().hs_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def handle(self):
+        return self._h
+
+    def info(self) -> dict:
+        s = IndexInfo()
+        _check(lib().hs_get_info(self._h, C.byref(s)))
+        return s.as_dict()
+
+    def set_ef(self, ef: int) -> None:
+        _check(lib().hs_set_ef(self._h, ef))
+
+    def search(self, queries, k: int, *, want_dists: bool = True, counts: bool = False):
+        """Host buffers in/out (hs_search_batch).  -> labels[nq,k], dists[nq,k] (, counts[nq,2])."""
+        q = _f32(queries)
+        assert q.ndim == 2 and q.shape[1] == self.dim
+        nq = q.shape[0]
+        lab = np.empty((nq, k), dtype=np.uint32)
+        dist = np.empty((nq, k), dtype=np.float32) if want_dists else None
+        if counts:
+            cnt = np.zeros((nq, 2), dtype=np.uint32)
+            _check(lib().hs_search_batch_counts(self._h, q.ctypes.data, nq, k, lab.ctypes.data,
+                                                dist.ctypes.data if want_dists else None, cnt.ctypes.data))
+            return lab, dist, cnt
+        _check(lib().hs_search_batch(self._h, q.ctypes.data, nq, k, lab.ctypes.data,
+                                     dist.ctypes.data if want_dists else None))
+        return lab, dist
+
+    def search_ptr(self, q_ptr: int, nq: int, k: int, lab_ptr: int, dist_ptr: int | None) -> None:
+        """hs_search_batch on raw HOST pointers (e.g. pinned torch tensors)."""
+        _check(lib().hs_search_batch(self._h, q_ptr, nq, k, lab_ptr, dist_ptr))
+
+    def search_device(self, d_queries: int, nq: int, k: int, d_labels: int, d_dists: int | None,
+                      stream: int = 0) -> None:
+        """Device pointers, asynchronous on `stream` (hs_search_batch_device)."""
+        _check(lib().hs_search_batch_device(self._h, d_queries, nq, k, d_labels, d_dists, stream))
+
+    def stats(self) -> dict:
+        a, b, c = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)
+        _check(lib().hs_stats(self._h, C.byref(a), C.byref(b), C.byref(c)))
+        return {"n_dist": a.value, "n_hops": b.value, "n_rerank": c.value}
+
+    def reset_stats(self) -> None:
+        _check(lib().hs_reset_stats(self._h))
+
+
+class HostGraph:
+    """Host-side flattened .graph (hs_debug_flatten) — loader inspection, no GPU needed."""
+
+    def __init__(self, graph_path: str, dim: int, kind: int = HS_KIND_SLIM):
+        self._h = C.c_void_p()
+        _check(lib().hs_debug_flatten(graph_path.encode(), kind, dim, C.byref(self._h)))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().hs_debug_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def info(self) -> dict:
+        s = IndexInfo()
+        _check(lib().hs_debug_info(self._h, C.byref(s)))
+        return s.as_dict()
+
+    def row(self, node: int, level: int) -> np.ndarray:
+        """Valid ids of the node's level-`level` row (padding stripped; checks it is a suffix)."""
+        out = np.full(1024, 0xFFFFFFFF, dtype=np.uint32)
+        stride = lib().hs_debug_row(self._h, node, level, out.ctypes.data, 1024)
+        if stride < 0:
+            _check(stride)
+        r = out[:stride]
+        valid = r != 0xFFFFFFFF
+        cnt = int(valid.sum())
+        assert valid[:cnt].all(), "padding must follow the valid ids"
+        return r[:cnt].copy()
+
+    def node(self, i: int):
+        lvl, lab = C.c_int(0), C.c_uint32(0)
+        info = self.info()
+        vec = np.zeros(info["dim_padded"], dtype=np.float32)
+        _check(lib().hs_debug_node(self._h, i, C.byref(lvl), C.byref(lab), vec.ctypes.data))
+        return lvl.value, lab.value, vec
+
+
+def bruteforce_knn(base, queries, k: int, *, metric: int = HS_METRIC_L2, device: int = 0):
+    """Exact kNN, nearest first (hs_bruteforce_knn).  -> labels[nq,k], dists[nq,k]."""
+    b, q = _f32(base), _f32(queries)
+    lab = np.empty((q.shape[0], k), dtype=np.uint32)
+    dist = np.empty((q.shape[0], k), dtype=np.float32)
+    _check(lib().hs_bruteforce_knn(b.ctypes.data, b.shape[0], b.shape[1], q.ctypes.data, q.shape[0], k, metric,
+                                   device, lab.ctypes.data, dist.ctypes.data))
+    return lab, dist
+
+
+def bruteforce_knn_device(d_base: int, n: int, dim: int, d_queries: int, nq: int, k: int, d_labels: int,
+                          d_dists: int | None, *, metric: int = HS_METRIC_L2, stream: int = 0) -> None:
+    _check(lib().hs_bruteforce_knn_device(d_base, n, dim, d_queries, nq, k, metric, d_labels, d_dists, stream))
+
+
+def topk_merge_device(d_labels_in: int, d_dists_in: int, n_parts: int, nq: int, k: int, d_labels_out: int,
+                      d_dists_out: int | None, stream: int = 0) -> None:
+    _check(lib().hs_topk_merge_device(d_labels_in, d_dists_in, n_parts, nq, k, d_labels_out, d_dists_out, stream))
+
+
+def recall(base, queries, knn, gt, K: int | None = None, *, metric: int = HS_METRIC_L2, device: int = 0) -> float:
+    """SolveStrategy::recall on the device (hs_recall)."""
+    b, q = _f32(base), _f32(queries)
+    knn = np.ascontiguousarray(knn, dtype=np.uint32)
+    gt = np.ascontiguousarray(gt, dtype=np.uint32)
+    K = K or knn.shape[1]
+    out = C.c_double(0)
+    _check(lib().hs_recall(b.ctypes.data, b.shape[0], b.shape[1], q.ctypes.data, q.shape[0], knn.ctypes.data, K,
+                           gt.ctypes.data, gt.shape[1], metric, device, C.byref(out)))
+    return out.value

@@ -1,0 +1,298 @@
+// Host side of hs_load: parse the reference's .graph image and flatten it.
+//
+// File format (written by HierarchicalNSWSlim::saveIndex, slim.h:717-751; read by
+// loadIndex, slim.h:753-815), no padding between fields:
+//   size_t cur_element_count, size_data_per_element, label_offset, offsetTotalNeighbor,
+//          offsetData, offsetNeighbor; int maxlevel, threshold_level; uint32 enterpoint;
+//   size_t maxM, maxM0, M, ef_construction; bool has_deleted;
+//   [hnsw_slimq only: RaBitQ metadata, centroids, rotator — slimq.h:1184-1203]
+//   cur_element_count records of size_data_per_element bytes:
+//       [int32 level @0][uint32 total_nbr @4][uint64 label @8][stale pointer @16][payload @24]
+//   per node: uint32 blobSize, then blobSize bytes iff blobSize != 0 && total_nbr != 0:
+//       [uint16 offsets[level]][uint32 ids[total_nbr]]           (slim.h:1096-1106)
+//   level-l slice of a node = ids[(l ? offsets[l-1] : 0) .. (l == level ? total : offsets[l]))
+//
+// Flattened form (DESIGN.md "HBM layout"): fixed-stride, 128-byte-aligned rows so one
+// hop costs one dependent load instead of the reference's record -> blob pointer chase.
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <cstring>
+#include <numeric>
+
+#include "hs_internal.h"
+
+namespace hs {
+
+namespace {
+
+struct Reader {
+  const uint8_t *p;
+  size_t size, pos = 0;
+  bool ok = true;
+  template <typename T> T get() {
+    T v{};
+    if (pos + sizeof(T) > size) {
+      ok = false;
+      return v;
+    }
+    std::memcpy(&v, p + pos, sizeof(T));
+    pos += sizeof(T);
+    return v;
+  }
+  const uint8_t *take(size_t nbytes) {
+    if (pos + nbytes > size || pos + nbytes < pos) {
+      ok = false;
+      return nullptr;
+    }
+    const uint8_t *r = p + pos;
+    pos += nbytes;
+    return r;
+  }
+};
+
+inline uint32_t round_up(uint32_t v, uint32_t m) { return (v + m - 1) / m * m; }
+
+}  // namespace
+
+int read_file(const char *path, std::vector<uint8_t> *out) {
+  int fd = ::open(path, O_RDONLY);
+  if (fd < 0) {
+    set_error(std::string("Cannot open file ") + path);   // slim.h:757-758
+    return HS_ERR_IO;
+  }
+  struct stat st;
+  if (fstat(fd, &st) != 0) {
+    ::close(fd);
+    set_error(std::string("Cannot stat file ") + path);
+    return HS_ERR_IO;
+  }
+  out->resize((size_t)st.st_size);
+  size_t got = 0;
+  while (got < out->size()) {
+    ssize_t r = ::read(fd, out->data() + got, std::min<size_t>(out->size() - got, 1u << 30));
+    if (r <= 0) break;
+    got += (size_t)r;
+  }
+  ::close(fd);
+  if (got != out->size()) {
+    set_error(std::string("short read on ") + path);
+    return HS_ERR_IO;
+  }
+  return HS_OK;
+}
+
+int parse_graph(const uint8_t *bytes, size_t size, int kind, size_t dim, HostGraph *g) {
+  Reader r{bytes, size};
+  g->kind = kind;
+  g->dim = dim;
+  g->n = r.get<uint64_t>();
+  g->size_data_per_element = r.get<uint64_t>();
+  g->label_offset = r.get<uint64_t>();
+  g->offset_total = r.get<uint64_t>();
+  g->offset_data = r.get<uint64_t>();
+  g->offset_nbr = r.get<uint64_t>();
+  g->maxlevel = r.get<int32_t>();
+  g->threshold_level = r.get<int32_t>();
+  g->enterpoint = r.get<uint32_t>();
+  g->maxM = r.get<uint64_t>();
+  g->maxM0 = r.get<uint64_t>();
+  g->M = r.get<uint64_t>();
+  g->ef_construction = r.get<uint64_t>();
+  g->has_deleted = r.get<uint8_t>() != 0;
+  if (!r.ok) {
+    set_error("truncated .graph header");
+    return HS_ERR_IO;
+  }
+  if (g->offset_total != 4 || g->label_offset != 8 || g->offset_nbr != 16 || g->offset_data != 24) {
+    set_error("unexpected record offsets in .graph header (not a HNSW-Slim index?)");
+    return HS_ERR_IO;
+  }
+  if (g->n >= (1ull << 31)) {
+    set_error("index has >= 2^31 nodes");
+    return HS_ERR_UNSUPPORTED;
+  }
+  if (g->n > 0 && (g->maxlevel < 0 || g->maxlevel >= kMaxLevels || g->enterpoint >= g->n)) {
+    set_error("bad maxlevel / enterpoint in .graph header");
+    return HS_ERR_IO;
+  }
+
+  size_t payload_off = 24;
+  if (kind == HS_KIND_SLIM) {
+    if (g->size_data_per_element != 24 + 4 * dim) {
+      set_error("size_data_per_element " + std::to_string(g->size_data_per_element) +
+                " does not match dim " + std::to_string(dim) + " (expected 24 + 4*dim)");
+      return HS_ERR_IO;
+    }
+  } else if (kind == HS_KIND_SLIMQ) {
+    // slimq.h:1184-1203
+    g->num_cluster = r.get<uint64_t>();
+    uint64_t qdim = r.get<uint64_t>();
+    g->padded_dim_q = r.get<uint64_t>();
+    uint64_t off_cluster = r.get<uint64_t>(), off_bin = r.get<uint64_t>(), off_ex = r.get<uint64_t>();
+    uint64_t size_bin = r.get<uint64_t>(), size_ex = r.get<uint64_t>();
+    g->ex_bits = r.get<uint64_t>();
+    g->metric_type_q = r.get<uint8_t>();
+    (void)off_ex;
+    (void)size_ex;
+    if (!r.ok || qdim != dim || g->padded_dim_q % 64 != 0 || g->padded_dim_q < dim ||
+        off_cluster != 24 || off_bin != 28 || size_bin != g->padded_dim_q / 8 + 12) {
+      set_error("inconsistent RaBitQ metadata in hnsw_slimq .graph header");
+      return HS_ERR_IO;
+    }
+    const uint8_t *c = r.take(g->num_cluster * g->padded_dim_q * sizeof(float));
+    const uint8_t *f = r.take(4 * g->padded_dim_q / 8);   // FhtKacRotator::save, rotator.hpp:263-275
+    if (!r.ok) {
+      set_error("truncated centroids / rotator in hnsw_slimq .graph");
+      return HS_ERR_IO;
+    }
+    g->centroids.resize(g->num_cluster * g->padded_dim_q);
+    std::memcpy(g->centroids.data(), c, g->centroids.size() * sizeof(float));
+    g->rotator_flip.assign(f, f + 4 * g->padded_dim_q / 8);
+  } else {
+    set_error("unknown index kind");
+    return HS_ERR_ARG;
+  }
+
+  const size_t n = g->n, rec = g->size_data_per_element;
+  const uint8_t *elements = r.take(n * rec);
+  if (!r.ok) {
+    set_error("truncated element records in .graph");
+    return HS_ERR_IO;
+  }
+
+  g->dim_padded = (dim + kRowAlignFloats - 1) / kRowAlignFloats * kRowAlignFloats;
+  g->labels.resize(n);
+  g->levels.resize(n);
+  g->deleted.assign(n, 0);
+  std::vector<uint32_t> total(n);
+  if (kind == HS_KIND_SLIM) g->vec.assign(n * g->dim_padded, 0.f);
+  if (kind == HS_KIND_SLIMQ) {
+    const size_t words = g->padded_dim_q / 64;
+    g->cluster_id.resize(n);
+    g->bin_code.resize(n * words);
+    g->f_add.resize(n);
+    g->f_rescale.resize(n);
+    g->f_error.resize(n);
+  }
+  for (size_t i = 0; i < n; ++i) {
+    const uint8_t *e = elements + i * rec;
+    int32_t lvl;
+    uint64_t label;
+    std::memcpy(&lvl, e, 4);
+    std::memcpy(&total[i], e + 4, 4);
+    std::memcpy(&label, e + 8, 8);
+    if (lvl < 0 || lvl > g->maxlevel) {
+      set_error("node level out of range in .graph");
+      return HS_ERR_IO;
+    }
+    g->levels[i] = (int8_t)lvl;
+    g->labels[i] = (uint32_t)label;     // slim.h:2129 result[i] = (tableint) label
+    g->deleted[i] = e[6] & 1;           // slim.h:1776-1781
+    if (kind == HS_KIND_SLIM) {
+      std::memcpy(&g->vec[i * g->dim_padded], e + payload_off, 4 * dim);
+    } else {
+      // [uint32 cluster @24][bin @28: uint64 code[pd/64], float f_add, f_rescale, f_error]
+      const size_t words = g->padded_dim_q / 64;
+      std::memcpy(&g->cluster_id[i], e + 24, 4);
+      std::memcpy(&g->bin_code[i * words], e + 28, 8 * words);
+      std::memcpy(&g->f_add[i], e + 28 + 8 * words, 4);
+      std::memcpy(&g->f_rescale[i], e + 28 + 8 * words + 4, 4);
+      std::memcpy(&g->f_error[i], e + 28 + 8 * words + 8, 4);
+    }
+  }
+
+  // ---- pass 1 over the blobs: degrees ----
+  struct BlobRef {
+    const uint8_t *p;
+    uint32_t size;
+  };
+  std::vector<BlobRef> blobs(n, BlobRef{nullptr, 0});
+  uint32_t max_deg0 = 0, max_deg_up = 0;
+  uint64_t sum_deg0 = 0;
+  for (size_t i = 0; i < n; ++i) {
+    uint32_t bsz = r.get<uint32_t>();
+    if (!r.ok) {
+      set_error("truncated neighbour blobs in .graph");
+      return HS_ERR_IO;
+    }
+    if (bsz == 0 || total[i] == 0) continue;          // slim.h:741-748 / :796-808
+    const uint8_t *b = r.take(bsz);
+    const int lvl = g->levels[i];
+    if (!r.ok || bsz != 2u * lvl + 4u * total[i]) {
+      set_error("neighbour blob size mismatch in .graph (node " + std::to_string(i) + ")");
+      return HS_ERR_IO;
+    }
+    blobs[i] = BlobRef{b, bsz};
+    const uint16_t *offs = reinterpret_cast<const uint16_t *>(b);
+    uint32_t prev = 0;
+    for (int l = 0; l <= lvl; ++l) {
+      uint32_t end = (l == lvl) ? total[i] : offs[l];
+      if (end < prev || end > total[i]) {
+        set_error("corrupt level offsets in .graph (node " + std::to_string(i) + ")");
+        return HS_ERR_IO;
+      }
+      uint32_t deg = end - prev;
+      if (l == 0) {
+        max_deg0 = std::max(max_deg0, deg);
+        sum_deg0 += deg;
+      } else {
+        max_deg_up = std::max(max_deg_up, deg);
+      }
+      prev = end;
+    }
+  }
+  g->max_deg0 = max_deg0;
+  g->max_deg_upper = max_deg_up;
+  g->sum_deg0 = sum_deg0;
+  g->deg0_stride = std::max<uint32_t>(32, round_up(max_deg0, 32));
+  g->upper_stride = std::max<uint32_t>(8, round_up(max_deg_up, 8));
+
+  // ---- upper-level slots: nodes sorted by level descending, so the rows of level l are
+  //      the dense slot prefix [0, level_count[l]) ----
+  g->level_count.assign(g->maxlevel + 2, 0);
+  std::vector<uint32_t> upper_nodes;
+  for (size_t i = 0; i < n; ++i) {
+    for (int l = 0; l <= g->levels[i]; ++l) g->level_count[l]++;
+    if (g->levels[i] > 0) upper_nodes.push_back((uint32_t)i);
+  }
+  std::stable_sort(upper_nodes.begin(), upper_nodes.end(),
+                   [&](uint32_t a, uint32_t b) { return g->levels[a] > g->levels[b]; });
+  g->n_upper = (uint32_t)upper_nodes.size();
+  g->upper_slot.assign(n, -1);
+  for (uint32_t s = 0; s < upper_nodes.size(); ++s) g->upper_slot[upper_nodes[s]] = (int32_t)s;
+
+  // ---- pass 2: fill the fixed-stride rows ----
+  g->adj0.assign(n * (size_t)g->deg0_stride, kInvalid);
+  g->upper_adj.assign(g->maxlevel + 1, {});
+  for (int l = 1; l <= g->maxlevel; ++l)
+    g->upper_adj[l].assign((size_t)g->level_count[l] * g->upper_stride, kInvalid);
+  for (size_t i = 0; i < n; ++i) {
+    if (!blobs[i].p) continue;
+    const int lvl = g->levels[i];
+    const uint16_t *offs = reinterpret_cast<const uint16_t *>(blobs[i].p);
+    const uint8_t *ids = blobs[i].p + 2 * (size_t)lvl;
+    uint32_t prev = 0;
+    for (int l = 0; l <= lvl; ++l) {
+      uint32_t end = (l == lvl) ? total[i] : offs[l];
+      uint32_t *dst = (l == 0) ? &g->adj0[i * (size_t)g->deg0_stride]
+                               : &g->upper_adj[l][(size_t)g->upper_slot[i] * g->upper_stride];
+      for (uint32_t j = prev; j < end; ++j) {
+        uint32_t id;
+        std::memcpy(&id, ids + 4 * (size_t)j, 4);
+        if (id >= n) {
+          set_error("neighbour id out of range in .graph (node " + std::to_string(i) + ")");
+          return HS_ERR_IO;
+        }
+        dst[j - prev] = id;
+      }
+      prev = end;
+    }
+  }
+  return HS_OK;
+}
+
+}  // namespace hs

@@ -1,0 +1,558 @@
+// C ABI of libhnswslim_b200.so (include/hnswslim_b200.h): index lifetime, batched search.
+#include <cuda_runtime.h>
+
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <string>
+
+#include "bruteforce.cuh"
+#include "hs_internal.h"
+#include "traverse_fp32.cuh"
+
+namespace hs {
+static thread_local std::string g_error;
+void set_error(const std::string &msg) { g_error = msg; }
+}  // namespace hs
+
+using namespace hs;
+
+#define HS_CUDA(call)                                                                 \
+  do {                                                                                \
+    cudaError_t e__ = (call);                                                         \
+    if (e__ != cudaSuccess) {                                                         \
+      set_error(std::string(#call) + ": " + cudaGetErrorString(e__));                 \
+      return HS_ERR_CUDA;                                                             \
+    }                                                                                 \
+  } while (0)
+
+struct hs_index {
+  hs_index_info info{};
+  int device = 0;
+  int sm_count = 148;
+  // HBM-resident index
+  float *d_vec = nullptr;
+  uint32_t *d_adj0 = nullptr;
+  int32_t *d_upper_slot = nullptr;
+  uint32_t *d_upper_adj[kMaxLevels] = {};
+  uint32_t *d_labels = nullptr;
+  uint8_t *d_deleted = nullptr;
+  // per-call scratch
+  unsigned int *d_work = nullptr;
+  unsigned long long *d_stats = nullptr;   // [0] n_dist [1] n_hops [2] n_rerank
+  // staging for the host-buffer entry points
+  cudaStream_t stream = nullptr;
+  float *d_q = nullptr;
+  uint32_t *d_lab = nullptr;
+  float *d_dist = nullptr;
+  uint32_t *d_perq = nullptr;
+  size_t cap_q = 0, cap_out = 0, cap_perq = 0;
+  int hash_bits_override = 0;
+  std::mutex mu;
+};
+
+namespace {
+
+template <typename T>
+int upload(T **dst, const T *src, size_t count, size_t *bytes_total) {
+  *dst = nullptr;
+  if (count == 0) return HS_OK;
+  cudaError_t e = cudaMalloc(reinterpret_cast<void **>(dst), count * sizeof(T));
+  if (e != cudaSuccess) {
+    set_error(std::string("cudaMalloc(") + std::to_string(count * sizeof(T)) + "): " + cudaGetErrorString(e));
+    return e == cudaErrorMemoryAllocation ? HS_ERR_NOMEM : HS_ERR_CUDA;
+  }
+  e = cudaMemcpy(*dst, src, count * sizeof(T), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) {
+    set_error(std::string("cudaMemcpy H2D: ") + cudaGetErrorString(e));
+    return HS_ERR_CUDA;
+  }
+  *bytes_total += count * sizeof(T);
+  return HS_OK;
+}
+
+int select_device(int device) {
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) {
+    set_error(std::string("no CUDA device available (") + cudaGetErrorString(e) +
+              "); hnswslim_b200 has no CPU fallback");
+    return HS_ERR_CUDA;
+  }
+  if (device < 0 || device >= count) {
+    set_error("device ordinal out of range");
+    return HS_ERR_ARG;
+  }
+  HS_CUDA(cudaSetDevice(device));
+  return HS_OK;
+}
+
+int build_index(const HostGraph &g, int metric, int device, hs_index **out) {
+  int rc = select_device(device);
+  if (rc != HS_OK) return rc;
+  std::unique_ptr<hs_index> ix(new hs_index);
+  ix->device = device;
+  cudaDeviceProp prop;
+  HS_CUDA(cudaGetDeviceProperties(&prop, device));
+  ix->sm_count = prop.multiProcessorCount;
+  if (const char *hb = std::getenv("HS_HASH_BITS")) ix->hash_bits_override = std::atoi(hb);
+
+  size_t bytes = 0;
+  auto fail = [&](int code) {
+    hs_free(ix.release());
+    return code;
+  };
+  if ((rc = upload(&ix->d_vec, g.vec.data(), g.vec.size(), &bytes)) != HS_OK) return fail(rc);
+  if ((rc = upload(&ix->d_adj0, g.adj0.data(), g.adj0.size(), &bytes)) != HS_OK) return fail(rc);
+  if ((rc = upload(&ix->d_upper_slot, g.upper_slot.data(), g.upper_slot.size(), &bytes)) != HS_OK) return fail(rc);
+  if ((rc = upload(&ix->d_labels, g.labels.data(), g.labels.size(), &bytes)) != HS_OK) return fail(rc);
+  if ((rc = upload(&ix->d_deleted, g.deleted.data(), g.deleted.size(), &bytes)) != HS_OK) return fail(rc);
+  for (int l = 1; l <= g.maxlevel && l < kMaxLevels; ++l)
+    if ((rc = upload(&ix->d_upper_adj[l], g.upper_adj[l].data(), g.upper_adj[l].size(), &bytes)) != HS_OK)
+      return fail(rc);
+  if (cudaMalloc(&ix->d_work, sizeof(unsigned int)) != cudaSuccess ||
+      cudaMalloc(&ix->d_stats, 4 * sizeof(unsigned long long)) != cudaSuccess ||
+      cudaMemset(ix->d_stats, 0, 4 * sizeof(unsigned long long)) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    set_error(std::string("scratch allocation: ") + cudaGetErrorString(cudaGetLastError()));
+    return fail(HS_ERR_CUDA);
+  }
+
+  hs_index_info &I = ix->info;
+  I.n = g.n;
+  I.dim = g.dim;
+  I.dim_padded = g.dim_padded;
+  I.M = g.M;
+  I.maxM = g.maxM;
+  I.maxM0 = g.maxM0;
+  I.ef_construction = g.ef_construction;
+  I.maxlevel = g.maxlevel;
+  I.threshold_level = g.threshold_level;
+  I.enterpoint = g.enterpoint;
+  I.has_deleted = g.has_deleted ? 1 : 0;
+  I.kind = g.kind;
+  I.metric = metric;
+  I.deg0_stride = g.deg0_stride;
+  I.max_deg0 = g.max_deg0;
+  I.upper_stride = g.upper_stride;
+  I.n_upper = g.n_upper;
+  I.sum_deg0 = g.sum_deg0;
+  I.device_bytes = bytes;
+  I.ef = 10;   // ef_ = 10 after loadIndex (slim.h:794)
+  I.padded_dim_q = g.padded_dim_q;
+  I.num_cluster = g.num_cluster;
+  *out = ix.release();
+  return HS_OK;
+}
+
+int load_common(const uint8_t *bytes, size_t size, int kind, int metric, size_t dim, const float *raw_base,
+                size_t n_raw, int device, hs_index **out) {
+  if (!out || !bytes) {
+    set_error("null argument");
+    return HS_ERR_ARG;
+  }
+  *out = nullptr;
+  if (metric != HS_METRIC_L2 && metric != HS_METRIC_IP) {
+    set_error("unknown metric");
+    return HS_ERR_ARG;
+  }
+  if (dim == 0) {
+    set_error("dim must be > 0");
+    return HS_ERR_ARG;
+  }
+  if (kind == HS_KIND_SLIMQ) {
+    (void)raw_base;
+    (void)n_raw;
+    set_error("hnsw_slimq engine not built yet");
+    return HS_ERR_UNSUPPORTED;
+  }
+  HostGraph g;
+  int rc = parse_graph(bytes, size, kind, dim, &g);
+  if (rc != HS_OK) return rc;
+  if (g.threshold_level > 0) {
+    set_error("threshold_level > 0 (layered beam, slim.h:222-316) not supported yet");
+    return HS_ERR_UNSUPPORTED;
+  }
+  if (g.has_deleted) {
+    set_error("indices with deleted elements (slim.h:2119-2122) not supported yet");
+    return HS_ERR_UNSUPPORTED;
+  }
+  return build_index(g, metric, device, out);
+}
+
+int ensure(void **p, size_t *cap, size_t need) {
+  if (need <= *cap) return HS_OK;
+  if (*p) cudaFree(*p);
+  *p = nullptr;
+  *cap = 0;
+  cudaError_t e = cudaMalloc(p, need);
+  if (e != cudaSuccess) {
+    set_error(std::string("cudaMalloc scratch: ") + cudaGetErrorString(e));
+    return HS_ERR_NOMEM;
+  }
+  *cap = need;
+  return HS_OK;
+}
+
+int search_device(hs_index *ix, const float *d_queries, size_t nq, size_t k, uint32_t *d_labels,
+                  float *d_dists, uint32_t *d_perq, cudaStream_t stream) {
+  if (!ix || (!d_queries && nq) || (!d_labels && nq) || k == 0) {
+    set_error("null argument / k == 0");
+    return HS_ERR_ARG;
+  }
+  if (nq == 0 || ix->info.n == 0) return HS_OK;    // slim.h:2031-2032
+  if (nq > 0x7fffffffu || k > 4096) {
+    set_error("nq or k too large");
+    return HS_ERR_ARG;
+  }
+  TraverseParams p{};
+  p.vec = reinterpret_cast<const float4 *>(ix->d_vec);
+  p.adj0 = ix->d_adj0;
+  p.upper_slot = ix->d_upper_slot;
+  for (int l = 0; l < kMaxLevels; ++l) p.upper_adj[l] = ix->d_upper_adj[l];
+  p.labels = ix->d_labels;
+  p.deleted = ix->d_deleted;
+  p.n = (uint32_t)ix->info.n;
+  p.row_chunks = (uint32_t)(ix->info.dim_padded / 4);
+  p.deg0_stride = ix->info.deg0_stride;
+  p.upper_stride = ix->info.upper_stride;
+  p.enterpoint = ix->info.enterpoint;
+  p.maxlevel = ix->info.maxlevel;
+  p.threshold_level = ix->info.threshold_level;
+  p.has_deleted = ix->info.has_deleted;
+  p.queries = d_queries;
+  p.nq = (uint32_t)nq;
+  p.dim = (uint32_t)ix->info.dim;
+  p.k = (uint32_t)k;
+  p.ef = (uint32_t)std::max<size_t>(ix->info.ef, k);   // slim.h:2080
+  p.out_labels = d_labels;
+  p.out_dists = d_dists;
+  p.work_counter = ix->d_work;
+  p.stats = ix->d_stats;
+  p.per_query = d_perq;
+  TraverseLaunch l{};
+  int rc = plan_traverse(p, ix->info.metric, ix->hash_bits_override, ix->sm_count, (int)nq, &l);
+  if (rc != HS_OK) return rc;
+  HS_CUDA(cudaMemsetAsync(ix->d_work, 0, sizeof(unsigned int), stream));
+  return launch_traverse(p, ix->info.metric, l, stream);
+}
+
+int search_host(hs_index *ix, const float *queries, size_t nq, size_t k, uint32_t *labels_out,
+                float *dists_out, uint32_t *perq_out) {
+  if (!ix || (!queries && nq) || (!labels_out && nq)) {
+    set_error("null argument");
+    return HS_ERR_ARG;
+  }
+  if (nq == 0 || ix->info.n == 0) return HS_OK;
+  std::lock_guard<std::mutex> lock(ix->mu);
+  HS_CUDA(cudaSetDevice(ix->device));
+  const size_t dim = ix->info.dim;
+  int rc;
+  if ((rc = ensure((void **)&ix->d_q, &ix->cap_q, nq * dim * sizeof(float))) != HS_OK) return rc;
+  size_t cap_lab = ix->cap_out, cap_dist = ix->cap_out;
+  if ((rc = ensure((void **)&ix->d_lab, &cap_lab, nq * k * 4)) != HS_OK) return rc;
+  if ((rc = ensure((void **)&ix->d_dist, &cap_dist, nq * k * 4)) != HS_OK) return rc;
+  ix->cap_out = std::min(cap_lab, cap_dist);
+  if (perq_out && (rc = ensure((void **)&ix->d_perq, &ix->cap_perq, nq * 8)) != HS_OK) return rc;
+  HS_CUDA(cudaMemcpyAsync(ix->d_q, queries, nq * dim * sizeof(float), cudaMemcpyHostToDevice, ix->stream));
+  rc = search_device(ix, ix->d_q, nq, k, ix->d_lab, ix->d_dist, perq_out ? ix->d_perq : nullptr, ix->stream);
+  if (rc != HS_OK) return rc;
+  HS_CUDA(cudaMemcpyAsync(labels_out, ix->d_lab, nq * k * 4, cudaMemcpyDeviceToHost, ix->stream));
+  if (dists_out)
+    HS_CUDA(cudaMemcpyAsync(dists_out, ix->d_dist, nq * k * 4, cudaMemcpyDeviceToHost, ix->stream));
+  if (perq_out) HS_CUDA(cudaMemcpyAsync(perq_out, ix->d_perq, nq * 8, cudaMemcpyDeviceToHost, ix->stream));
+  HS_CUDA(cudaStreamSynchronize(ix->stream));
+  return HS_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *hs_last_error(void) { return g_error.c_str(); }
+int hs_abi_version(void) { return HS_ABI_VERSION; }
+
+int hs_load_memory(const void *graph_bytes, size_t graph_size, int kind, int metric, size_t dim,
+                   const float *raw_base, size_t n_raw, int device, hs_index **out) {
+  return load_common(static_cast<const uint8_t *>(graph_bytes), graph_size, kind, metric, dim, raw_base,
+                     n_raw, device, out);
+}
+
+int hs_load(const char *graph_path, int kind, int metric, size_t dim, const float *raw_base, size_t n_raw,
+            int device, hs_index **out) {
+  if (!graph_path || !out) {
+    set_error("null argument");
+    return HS_ERR_ARG;
+  }
+  *out = nullptr;
+  std::vector<uint8_t> bytes;
+  int rc = read_file(graph_path, &bytes);
+  if (rc != HS_OK) return rc;
+  return load_common(bytes.data(), bytes.size(), kind, metric, dim, raw_base, n_raw, device, out);
+}
+
+void hs_free(hs_index *ix) {
+  if (!ix) return;
+  cudaSetDevice(ix->device);
+  cudaFree(ix->d_vec);
+  cudaFree(ix->d_adj0);
+  cudaFree(ix->d_upper_slot);
+  for (auto *p : ix->d_upper_adj) cudaFree(p);
+  cudaFree(ix->d_labels);
+  cudaFree(ix->d_deleted);
+  cudaFree(ix->d_work);
+  cudaFree(ix->d_stats);
+  cudaFree(ix->d_q);
+  cudaFree(ix->d_lab);
+  cudaFree(ix->d_dist);
+  cudaFree(ix->d_perq);
+  if (ix->stream) cudaStreamDestroy(ix->stream);
+  delete ix;
+}
+
+int hs_set_ef(hs_index *ix, size_t ef) {
+  if (!ix || ef == 0 || ef > 4096) {
+    set_error("hs_set_ef: ef must be in [1, 4096]");
+    return HS_ERR_ARG;
+  }
+  ix->info.ef = ef;
+  return HS_OK;
+}
+
+int hs_get_info(const hs_index *ix, hs_index_info *out) {
+  if (!ix || !out) {
+    set_error("null argument");
+    return HS_ERR_ARG;
+  }
+  *out = ix->info;
+  return HS_OK;
+}
+
+int hs_search_batch(hs_index *ix, const float *queries, size_t nq, size_t k, uint32_t *labels_out,
+                    float *dists_out) {
+  return search_host(ix, queries, nq, k, labels_out, dists_out, nullptr);
+}
+
+int hs_search_batch_counts(hs_index *ix, const float *queries, size_t nq, size_t k, uint32_t *labels_out,
+                           float *dists_out, uint32_t *per_query_counts) {
+  return search_host(ix, queries, nq, k, labels_out, dists_out, per_query_counts);
+}
+
+int hs_search_batch_device(hs_index *ix, const float *d_queries, size_t nq, size_t k, uint32_t *d_labels,
+                           float *d_dists, void *stream) {
+  return search_device(ix, d_queries, nq, k, d_labels, d_dists, nullptr, static_cast<cudaStream_t>(stream));
+}
+
+int hs_bruteforce_knn_device(const float *d_base, size_t n, size_t dim, const float *d_queries, size_t nq,
+                             size_t k, int metric, uint32_t *d_labels, float *d_dists, void *stream) {
+  if ((!d_base && n) || (!d_queries && nq) || (!d_labels && nq)) {
+    set_error("null argument");
+    return HS_ERR_ARG;
+  }
+  if (k > n) {
+    set_error("bruteforce: k > n (bruteforce.h:107 asserts k <= cur_element_count)");
+    return HS_ERR_ARG;
+  }
+  return bruteforce_device(d_base, n, dim, d_queries, nq, k, metric, d_labels, d_dists,
+                           static_cast<cudaStream_t>(stream));
+}
+
+int hs_bruteforce_knn(const float *base, size_t n, size_t dim, const float *queries, size_t nq, size_t k,
+                      int metric, int device, uint32_t *labels_out, float *dists_out) {
+  if ((!base && n) || (!queries && nq) || (!labels_out && nq)) {
+    set_error("null argument");
+    return HS_ERR_ARG;
+  }
+  int rc = select_device(device);
+  if (rc != HS_OK) return rc;
+  if (nq == 0 || n == 0) return HS_OK;
+  float *d_base = nullptr, *d_q = nullptr, *d_dist = nullptr;
+  uint32_t *d_lab = nullptr;
+  size_t bytes = 0;
+  auto cleanup = [&]() {
+    cudaFree(d_base);
+    cudaFree(d_q);
+    cudaFree(d_dist);
+    cudaFree(d_lab);
+  };
+  if ((rc = upload(&d_base, base, n * dim, &bytes)) != HS_OK || (rc = upload(&d_q, queries, nq * dim, &bytes)) != HS_OK) {
+    cleanup();
+    return rc;
+  }
+  if (cudaMalloc(&d_lab, nq * k * 4) != cudaSuccess || cudaMalloc(&d_dist, nq * k * 4) != cudaSuccess) {
+    set_error("cudaMalloc (bruteforce outputs) failed");
+    cleanup();
+    return HS_ERR_NOMEM;
+  }
+  rc = hs_bruteforce_knn_device(d_base, n, dim, d_q, nq, k, metric, d_lab, d_dist, nullptr);
+  if (rc == HS_OK) {
+    cudaError_t e = cudaMemcpy(labels_out, d_lab, nq * k * 4, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && dists_out) e = cudaMemcpy(dists_out, d_dist, nq * k * 4, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) {
+      set_error(std::string("bruteforce: ") + cudaGetErrorString(e));
+      rc = HS_ERR_CUDA;
+    }
+  }
+  cleanup();
+  return rc;
+}
+
+int hs_topk_merge_device(const uint32_t *d_labels_in, const float *d_dists_in, size_t n_parts, size_t nq,
+                         size_t k, uint32_t *d_labels_out, float *d_dists_out, void *stream) {
+  if (!d_labels_in || !d_dists_in || !d_labels_out) {
+    set_error("null argument");
+    return HS_ERR_ARG;
+  }
+  return topk_merge_device(d_labels_in, d_dists_in, n_parts, nq, k, d_labels_out, d_dists_out,
+                           static_cast<cudaStream_t>(stream));
+}
+
+int hs_recall(const float *base, size_t n, size_t dim, const float *queries, size_t nq, const uint32_t *knn,
+              size_t K, const uint32_t *gt, size_t gt_k, int metric, int device, double *recall_out) {
+  if (!base || !queries || !knn || !gt || !recall_out || nq == 0 || K == 0) {
+    set_error("null argument");
+    return HS_ERR_ARG;
+  }
+  int rc = select_device(device);
+  if (rc != HS_OK) return rc;
+  float *d_base = nullptr, *d_q = nullptr;
+  uint32_t *d_knn = nullptr, *d_gt = nullptr;
+  unsigned long long *d_hits = nullptr;
+  size_t bytes = 0;
+  auto cleanup = [&]() {
+    cudaFree(d_base);
+    cudaFree(d_q);
+    cudaFree(d_knn);
+    cudaFree(d_gt);
+    cudaFree(d_hits);
+  };
+  if ((rc = upload(&d_base, base, n * dim, &bytes)) != HS_OK || (rc = upload(&d_q, queries, nq * dim, &bytes)) != HS_OK ||
+      (rc = upload(&d_knn, knn, nq * K, &bytes)) != HS_OK || (rc = upload(&d_gt, gt, nq * gt_k, &bytes)) != HS_OK) {
+    cleanup();
+    return rc;
+  }
+  if (cudaMalloc(&d_hits, 8) != cudaSuccess) {
+    set_error("cudaMalloc failed");
+    cleanup();
+    return HS_ERR_NOMEM;
+  }
+  rc = recall_device(d_base, n, dim, d_q, nq, d_knn, K, d_gt, gt_k, metric, d_hits, nullptr);
+  if (rc == HS_OK) {
+    unsigned long long hits = 0;
+    if (cudaMemcpy(&hits, d_hits, 8, cudaMemcpyDeviceToHost) != cudaSuccess) {
+      set_error("recall: cudaMemcpy failed");
+      rc = HS_ERR_CUDA;
+    } else {
+      *recall_out = (double)hits / ((double)nq * (double)K);    // solve_strategy.h:101
+    }
+  }
+  cleanup();
+  return rc;
+}
+
+// ---- host-only inspection of the flattened graph (used by the CPU test-suite; no CUDA) ----
+struct hs_host_graph {
+  HostGraph g;
+};
+
+int hs_debug_flatten(const char *graph_path, int kind, size_t dim, hs_host_graph **out) {
+  if (!graph_path || !out) {
+    set_error("null argument");
+    return HS_ERR_ARG;
+  }
+  *out = nullptr;
+  std::vector<uint8_t> bytes;
+  int rc = read_file(graph_path, &bytes);
+  if (rc != HS_OK) return rc;
+  std::unique_ptr<hs_host_graph> h(new hs_host_graph);
+  rc = parse_graph(bytes.data(), bytes.size(), kind, dim, &h->g);
+  if (rc != HS_OK) return rc;
+  *out = h.release();
+  return HS_OK;
+}
+
+void hs_debug_free(hs_host_graph *h) { delete h; }
+
+int hs_debug_info(const hs_host_graph *h, hs_index_info *I) {
+  if (!h || !I) return HS_ERR_ARG;
+  const HostGraph &g = h->g;
+  std::memset(I, 0, sizeof *I);
+  I->n = g.n;
+  I->dim = g.dim;
+  I->dim_padded = g.dim_padded;
+  I->M = g.M;
+  I->maxM = g.maxM;
+  I->maxM0 = g.maxM0;
+  I->ef_construction = g.ef_construction;
+  I->maxlevel = g.maxlevel;
+  I->threshold_level = g.threshold_level;
+  I->enterpoint = g.enterpoint;
+  I->has_deleted = g.has_deleted;
+  I->kind = g.kind;
+  I->deg0_stride = g.deg0_stride;
+  I->max_deg0 = g.max_deg0;
+  I->upper_stride = g.upper_stride;
+  I->n_upper = g.n_upper;
+  I->sum_deg0 = g.sum_deg0;
+  I->padded_dim_q = g.padded_dim_q;
+  I->num_cluster = g.num_cluster;
+  return HS_OK;
+}
+
+// level-`level` row of `node` as stored for the device (kInvalid-padded); returns the row
+// stride, 0 if the node has no row at that level, negative on error.
+int hs_debug_row(const hs_host_graph *h, uint32_t node, int level, uint32_t *out, int cap) {
+  if (!h || !out || node >= h->g.n || level < 0) return HS_ERR_ARG;
+  const HostGraph &g = h->g;
+  const uint32_t *row;
+  int stride;
+  if (level == 0) {
+    row = &g.adj0[(size_t)node * g.deg0_stride];
+    stride = (int)g.deg0_stride;
+  } else {
+    if (level > g.maxlevel || g.upper_slot[node] < 0 || (uint32_t)g.upper_slot[node] >= g.level_count[level])
+      return 0;
+    row = &g.upper_adj[level][(size_t)g.upper_slot[node] * g.upper_stride];
+    stride = (int)g.upper_stride;
+  }
+  for (int i = 0; i < stride && i < cap; ++i) out[i] = row[i];
+  return stride;
+}
+
+int hs_debug_node(const hs_host_graph *h, uint32_t node, int *level, uint32_t *label, float *vec_out) {
+  if (!h || node >= h->g.n) return HS_ERR_ARG;
+  const HostGraph &g = h->g;
+  if (level) *level = g.levels[node];
+  if (label) *label = g.labels[node];
+  if (vec_out && !g.vec.empty()) std::memcpy(vec_out, &g.vec[(size_t)node * g.dim_padded], g.dim_padded * 4);
+  return HS_OK;
+}
+
+int hs_stats(hs_index *ix, uint64_t *n_dist, uint64_t *n_hops, uint64_t *n_rerank) {
+  if (!ix) {
+    set_error("null argument");
+    return HS_ERR_ARG;
+  }
+  unsigned long long h[4] = {0, 0, 0, 0};
+  HS_CUDA(cudaSetDevice(ix->device));
+  HS_CUDA(cudaDeviceSynchronize());
+  HS_CUDA(cudaMemcpy(h, ix->d_stats, sizeof h, cudaMemcpyDeviceToHost));
+  if (n_dist) *n_dist = h[0];
+  if (n_hops) *n_hops = h[1];
+  if (n_rerank) *n_rerank = h[2];
+  return HS_OK;
+}
+
+int hs_reset_stats(hs_index *ix) {
+  if (!ix) {
+    set_error("null argument");
+    return HS_ERR_ARG;
+  }
+  HS_CUDA(cudaSetDevice(ix->device));
+  HS_CUDA(cudaDeviceSynchronize());
+  HS_CUDA(cudaMemset(ix->d_stats, 0, 4 * sizeof(unsigned long long)));
+  return HS_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,56 @@
+// Internal declarations shared by the host loader, the C ABI and the kernels.
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "../../include/hnswslim_b200.h"
+
+namespace hs {
+
+constexpr uint32_t kInvalid = 0xFFFFFFFFu;
+constexpr int kMaxLevels = 32;   // upper levels addressable by the kernels
+constexpr int kTeam = 8;         // lanes cooperating on one vector row
+constexpr int kRowAlignFloats = 32;   // 128-byte rows: dim padded to a multiple of 32 floats
+
+void set_error(const std::string &msg);
+
+// A .graph file flattened on the host, ready to upload (see DESIGN.md "HBM layout").
+struct HostGraph {
+  // header, as stored by saveIndex (slim.h:717-739 / slimq.h:1161-1190)
+  uint64_t n = 0, size_data_per_element = 0, label_offset = 0, offset_total = 0, offset_data = 0,
+           offset_nbr = 0, maxM = 0, maxM0 = 0, M = 0, ef_construction = 0;
+  int32_t maxlevel = 0, threshold_level = 0;
+  uint32_t enterpoint = 0;
+  bool has_deleted = false;
+  int kind = HS_KIND_SLIM;
+  size_t dim = 0, dim_padded = 0;
+
+  // flattened graph
+  uint32_t deg0_stride = 32, max_deg0 = 0, upper_stride = 16, max_deg_upper = 0, n_upper = 0;
+  uint64_t sum_deg0 = 0;
+  std::vector<float> vec;             // n x dim_padded (hnsw_slim); empty for slimq
+  std::vector<uint32_t> adj0;         // n x deg0_stride, kInvalid-padded
+  std::vector<int32_t> upper_slot;    // n; -1 for level-0-only nodes; slots sorted by level desc
+  std::vector<uint32_t> level_count;  // [maxlevel+1]: nodes with level >= l
+  std::vector<std::vector<uint32_t>> upper_adj;  // [l] : level_count[l] x upper_stride (l >= 1)
+  std::vector<uint32_t> labels;       // n, external labels truncated to 32 bit (slim.h:2129)
+  std::vector<int8_t> levels;         // n
+  std::vector<uint8_t> deleted;       // n, bit 0 of record byte 6 (slim.h:1776-1781); all 0 in practice
+
+  // hnsw_slimq payload (slimq.h:1187-1206, data_layout.hpp:171-194)
+  uint64_t num_cluster = 0, padded_dim_q = 0, ex_bits = 0;
+  uint8_t metric_type_q = 0;
+  std::vector<float> centroids;       // num_cluster x padded_dim_q (already rotated)
+  std::vector<uint8_t> rotator_flip;  // 4 * padded_dim_q / 8 bytes (rotator.hpp:263-275)
+  std::vector<uint32_t> cluster_id;   // n
+  std::vector<uint64_t> bin_code;     // n x padded_dim_q/64 (MSB-first bit order)
+  std::vector<float> f_add, f_rescale, f_error;   // n each
+};
+
+// Parses a reference .graph image.  Returns HS_OK or a negative hs_status (message via set_error).
+int parse_graph(const uint8_t *bytes, size_t size, int kind, size_t dim, HostGraph *out);
+int read_file(const char *path, std::vector<uint8_t> *out);
+
+}  // namespace hs

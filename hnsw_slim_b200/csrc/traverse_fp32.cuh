@@ -1,0 +1,46 @@
+// Launch interface of the fp32 traversal kernel (traverse_fp32.cu).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "hs_internal.h"
+
+namespace hs {
+
+struct TraverseParams {
+  // HBM-resident index
+  const float4 *vec;                       // n x row_chunks float4
+  const uint32_t *adj0;                    // n x deg0_stride
+  const int32_t *upper_slot;               // n
+  const uint32_t *upper_adj[kMaxLevels];   // [l] -> level_count[l] x upper_stride
+  const uint32_t *labels;                  // n
+  const uint8_t *deleted;                  // n (only read when has_deleted)
+  uint32_t n, row_chunks, deg0_stride, upper_stride, enterpoint;
+  int32_t maxlevel, threshold_level, has_deleted;
+  // query batch
+  const float *queries;                    // nq x dim
+  uint32_t nq, dim, k, ef;
+  uint32_t *out_labels;                    // nq x k
+  float *out_dists;                        // nq x k or null
+  // scratch / counters
+  unsigned int *work_counter;              // zeroed before launch
+  unsigned long long *stats;               // [0] n_dist  [1] n_hops
+  uint32_t *per_query;                     // optional nq x 2 (n_dist, n_hops) or null
+  // shared-memory carve-up per warp (bytes)
+  uint32_t hash_bits, smem_per_warp, off_hash, off_stage, off_query;
+};
+
+struct TraverseLaunch {
+  int warps_per_cta;
+  int grid;
+  size_t smem_bytes;
+};
+
+// Fills the smem carve-up fields of `p` and returns the launch shape.
+// hash_bits_override = 0 picks the default for p.ef.
+int plan_traverse(TraverseParams &p, int metric, int hash_bits_override, int sm_count, int nq,
+                  TraverseLaunch *out);
+int launch_traverse(const TraverseParams &p, int metric, const TraverseLaunch &l, cudaStream_t stream);
+
+}  // namespace hs

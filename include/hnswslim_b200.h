@@ -1,0 +1,166 @@
+/* hnswslim_b200 — C ABI of the B200-native batched query engine for the HNSW-Slim
+ * search hot path.  Built into hnsw_slim_b200/_build/libhnswslim_b200.so.
+ *
+ * Every entry point names the reference interface it replaces
+ * (reference = InfiniteNightmare/HNSW-Slim; slim.h = third_party/hnswlib/hnswalg_slim.h,
+ * slimq.h = third_party/hnswlib/hnswalg_slimq.h).  Plain pointers and sizes only:
+ * the reference side binds it with a 20-line C++ shim.
+ *
+ * All functions return HS_OK (0) or a negative hs_status; hs_last_error() returns
+ * the message of the calling thread's last failure (the reference throws
+ * std::runtime_error at the same places: slim.h:757-758,785-788,804-806).
+ * There is NO CPU fallback: without a CUDA device every compute entry point fails
+ * with HS_ERR_CUDA.
+ */
+#ifndef HNSWSLIM_B200_H
+#define HNSWSLIM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HS_ABI_VERSION 1
+
+typedef enum {
+  HS_OK = 0,
+  HS_ERR_ARG = -1,     /* bad argument */
+  HS_ERR_IO = -2,      /* cannot open / truncated / inconsistent .graph file */
+  HS_ERR_CUDA = -3,    /* CUDA runtime error (incl. no device) */
+  HS_ERR_NOMEM = -4,   /* host or device allocation failed */
+  HS_ERR_UNSUPPORTED = -5
+} hs_status;
+
+/* --solve_strategy values of main.cc:111-139 that have a GPU engine */
+typedef enum { HS_KIND_SLIM = 0 /* hnsw_slim, hnsw_slimzero */, HS_KIND_SLIMQ = 1 /* hnsw_slimq */ } hs_kind;
+
+/* hnswlib::L2Space (space_l2.h:214-251) / hnswlib::InnerProductSpace (space_ip.h:342-398) */
+typedef enum { HS_METRIC_L2 = 0, HS_METRIC_IP = 1 } hs_metric;
+
+typedef struct hs_index hs_index;   /* owns the HBM-resident copy of one .graph */
+
+typedef struct {
+  uint64_t n;                /* cur_element_count_                      slim.h:34  */
+  uint64_t dim;
+  uint64_t dim_padded;       /* floats per HBM row (128-byte multiple)             */
+  uint64_t M, maxM, maxM0, ef_construction;      /*                      slim.h:38-41 */
+  int32_t maxlevel;          /*                                         slim.h:44  */
+  int32_t threshold_level;   /*                                         slim.h:45  */
+  uint32_t enterpoint;       /* enterpoint_node_                        slim.h:49  */
+  int32_t has_deleted;       /* has_deleted_elements_                   slim.h:36  */
+  int32_t kind, metric;
+  uint32_t deg0_stride;      /* ids per level-0 adjacency row in HBM (multiple of 32) */
+  uint32_t max_deg0;         /* largest level-0 degree found in the file            */
+  uint32_t upper_stride;     /* ids per upper-level adjacency row                   */
+  uint32_t n_upper;          /* nodes with level > 0                                */
+  uint64_t sum_deg0;         /* total level-0 edges (avg degree = sum_deg0 / n)     */
+  uint64_t device_bytes;     /* HBM held by this handle                             */
+  uint64_t ef;               /* current ef_ (hs_set_ef)                             */
+  /* hnsw_slimq only (slimq.h:1187-1200), 0 otherwise */
+  uint64_t padded_dim_q;     /* RaBitQ padded_dim (multiple of 64)                  */
+  uint64_t num_cluster;
+} hs_index_info;
+
+/* Replaces HierarchicalNSWSlim::loadIndex (slim.h:753-815) and
+ * HierarchicalNSWSlimQ::loadIndex + setDataset (slimq.h:1218-1313, :303-305):
+ * parses the reference's .graph byte for byte, flattens it (fixed-stride,
+ * 128-byte-aligned adjacency + vector store) and uploads it to `device`.
+ *   dim       vector dimension (the reference takes it from the SpaceInterface)
+ *   raw_base  hnsw_slimq only: the n_raw x dim float rows used for the exact
+ *             rerank (slimq.h:747-749), indexed by internal id; copied to HBM.
+ *             NULL for hnsw_slim (vectors live in the .graph). */
+int hs_load(const char *graph_path, int kind, int metric, size_t dim, const float *raw_base,
+            size_t n_raw, int device, hs_index **out);
+
+/* Same, from a .graph image already in host memory (what a server holds after
+ * patchFromStream; also used by tests).  */
+int hs_load_memory(const void *graph_bytes, size_t graph_size, int kind, int metric, size_t dim,
+                   const float *raw_base, size_t n_raw, int device, hs_index **out);
+
+/* ~HierarchicalNSWSlim / clear() (slim.h:147-167) */
+void hs_free(hs_index *);
+
+/* setEf (slim.h:193, slimq.h:346-349) */
+int hs_set_ef(hs_index *, size_t ef);
+
+int hs_get_info(const hs_index *, hs_index_info *out);
+
+/* Replaces the query loop of HnswSlimStrategy::solve / HnswSlimQStrategy::solve
+ * (hnsw_slim_strategy.h:112-114, hnsw_slimq_strategy.h:157-159), i.e. nq calls of
+ * searchKnn(const void*, size_t k, tableint*) (slim.h:2030-2131, slimq.h:1810-1924),
+ * with HOST buffers: queries nq x dim row-major in, labels_out nq x k out
+ * (external labels truncated to 32 bit as slim.h:2129).  Unlike the reference
+ * (unordered k-subset, no distances) each row is sorted by (distance, id)
+ * ascending and dists_out (nq x k, may be NULL) receives the distances.  Rows
+ * with fewer than k reachable results are padded with 0xFFFFFFFF / +inf (the
+ * reference reads uninitialised memory there).  Copies host->device, runs the
+ * traversal kernel, copies back; synchronous. */
+int hs_search_batch(hs_index *, const float *queries, size_t nq, size_t k, uint32_t *labels_out,
+                    float *dists_out);
+
+/* hs_search_batch that also returns per-query counters: per_query_counts[2*i] = distances
+ * evaluated for query i, [2*i+1] = nodes expanded (the per-query split of hs_stats). */
+int hs_search_batch_counts(hs_index *, const float *queries, size_t nq, size_t k, uint32_t *labels_out,
+                           float *dists_out, uint32_t *per_query_counts);
+
+/* Same with DEVICE buffers (d_queries nq x dim, d_labels nq x k, d_dists nq x k or
+ * NULL) on CUDA stream `stream` (a cudaStream_t, 0 = legacy default stream);
+ * asynchronous, no host<->device copies.  This is what the device-resident
+ * benchmark number and multi-GPU sharding use. */
+int hs_search_batch_device(hs_index *, const float *d_queries, size_t nq, size_t k,
+                           uint32_t *d_labels, float *d_dists, void *stream);
+
+/* Counters accumulated since the last hs_reset_stats, with the meaning of
+ * metric_distance_computations / metric_hops (slim.h:70-71,371-374,2064-2065):
+ * n_dist = distances evaluated, n_hops = nodes expanded (upper + base layer).
+ * hnsw_slimq: n_dist counts 1-bit estimates, *n_rerank exact reranks. */
+int hs_stats(hs_index *, uint64_t *n_dist, uint64_t *n_hops, uint64_t *n_rerank);
+int hs_reset_stats(hs_index *);
+
+/* Replaces BruteForce::solve (brute_force_strategy.h:15-45) =
+ * BruteforceSearch<float>::searchKnn per query (bruteforce.h:106-135): exact kNN of
+ * nq queries over n base rows (label of row i = i).  Row order: NEAREST first,
+ * ties -> smaller label (the reference writes farthest-first; reverse to compare).
+ * Host buffers; dists_out may be NULL. */
+int hs_bruteforce_knn(const float *base, size_t n, size_t dim, const float *queries, size_t nq,
+                      size_t k, int metric, int device, uint32_t *labels_out, float *dists_out);
+
+/* Same with device buffers, asynchronous on `stream`. */
+int hs_bruteforce_knn_device(const float *d_base, size_t n, size_t dim, const float *d_queries,
+                             size_t nq, size_t k, int metric, uint32_t *d_labels, float *d_dists,
+                             void *stream);
+
+/* Cross-shard top-k merge for sharded corpora (no reference analogue: the
+ * reference builds one graph).  d_labels_in / d_dists_in hold
+ * n_parts consecutive [nq x k] tables (e.g. the output of an NCCL all-gather);
+ * writes the global top-k per query sorted by (dist, label).  Asynchronous. */
+int hs_topk_merge_device(const uint32_t *d_labels_in, const float *d_dists_in, size_t n_parts,
+                         size_t nq, size_t k, uint32_t *d_labels_out, float *d_dists_out,
+                         void *stream);
+
+/* SolveStrategy::recall (solve_strategy.h:67-103) on the device: recall@K of knn
+ * (nq x K labels, any order) against gt (nq x gt_k ids, any order, gt_k >= K),
+ * GT re-ranked by exact distance to `base` rows (ties -> smaller id). Host buffers. */
+int hs_recall(const float *base, size_t n, size_t dim, const float *queries, size_t nq,
+              const uint32_t *knn, size_t K, const uint32_t *gt, size_t gt_k, int metric, int device,
+              double *recall_out);
+
+/* Host-only inspection of the flattened form of a .graph (no CUDA needed): what
+ * hs_load uploads.  Used by the CPU test-suite to check the loader against the
+ * reference's accessors (slim.h:620-661). */
+typedef struct hs_host_graph hs_host_graph;
+int hs_debug_flatten(const char *graph_path, int kind, size_t dim, hs_host_graph **out);
+void hs_debug_free(hs_host_graph *);
+int hs_debug_info(const hs_host_graph *, hs_index_info *out);
+int hs_debug_row(const hs_host_graph *, uint32_t node, int level, uint32_t *out, int cap);
+int hs_debug_node(const hs_host_graph *, uint32_t node, int *level, uint32_t *label, float *vec_out);
+
+const char *hs_last_error(void);
+int hs_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HNSWSLIM_B200_H */

@@ -1,0 +1,577 @@
+/* TEST INFRASTRUCTURE — NOT PRODUCT CODE.  See hs_oracle.h.
+ *
+ * Plain-C restatement of the reference's HNSW-Slim search path.  Written from the
+ * algorithm; every function names the reference file:line it follows
+ * (slim.h = third_party/hnswlib/hnswalg_slim.h).
+ */
+#include "hs_oracle.h"
+
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+static _Thread_local char g_err[256];
+const char *hso_last_error(void) { return g_err; }
+
+/* ------------------------------------------------------------------ index -- */
+/* In-memory image identical to the reference's: one record per node
+ * [int32 level @0][uint32 total_nbr @4][uint64 label @8][ptr @16][float vec @24]
+ * (slim.h:127-131) plus one blob per node [uint16 offsets[level]][uint32 ids[total]]
+ * (slim.h:1096-1106). */
+struct hso_index {
+  uint64_t n, size_data_per_element, label_offset, offset_total, offset_data, offset_nbr;
+  uint64_t maxM, maxM0, M, ef_construction;
+  int32_t maxlevel, threshold_level;
+  uint32_t enterpoint;
+  uint8_t has_deleted;
+  size_t dim;
+  int metric;
+  char *elements;
+  char **blobs;
+};
+
+static int rd(FILE *f, void *p, size_t n) { return fread(p, 1, n, f) == n ? 0 : -1; }
+
+/* slim.h:753-815 */
+hso_index *hso_load(const char *path, size_t dim, int metric) {
+  FILE *f = fopen(path, "rb");
+  if (!f) {
+    snprintf(g_err, sizeof g_err, "Cannot open file %s", path);
+    return NULL;
+  }
+  hso_index *ix = (hso_index *)calloc(1, sizeof *ix);
+  ix->dim = dim;
+  ix->metric = metric;
+  int bad = 0;
+  bad |= rd(f, &ix->n, 8);
+  bad |= rd(f, &ix->size_data_per_element, 8);
+  bad |= rd(f, &ix->label_offset, 8);
+  bad |= rd(f, &ix->offset_total, 8);
+  bad |= rd(f, &ix->offset_data, 8);
+  bad |= rd(f, &ix->offset_nbr, 8);
+  bad |= rd(f, &ix->maxlevel, 4);
+  bad |= rd(f, &ix->threshold_level, 4);
+  bad |= rd(f, &ix->enterpoint, 4);
+  bad |= rd(f, &ix->maxM, 8);
+  bad |= rd(f, &ix->maxM0, 8);
+  bad |= rd(f, &ix->M, 8);
+  bad |= rd(f, &ix->ef_construction, 8);
+  bad |= rd(f, &ix->has_deleted, 1);
+  if (bad || ix->size_data_per_element != ix->offset_data + 4 * dim) {
+    snprintf(g_err, sizeof g_err, "bad header in %s (size_data_per_element=%llu, dim=%zu)", path,
+             (unsigned long long)ix->size_data_per_element, dim);
+    fclose(f);
+    free(ix);
+    return NULL;
+  }
+  ix->elements = (char *)malloc(ix->n * ix->size_data_per_element + 1);
+  ix->blobs = (char **)calloc(ix->n + 1, sizeof(char *));
+  if (rd(f, ix->elements, ix->n * ix->size_data_per_element)) bad = 1;
+  for (uint64_t i = 0; i < ix->n && !bad; i++) {
+    uint32_t sz;
+    if (rd(f, &sz, 4)) { bad = 1; break; }
+    uint32_t total = *(uint32_t *)(ix->elements + i * ix->size_data_per_element + ix->offset_total);
+    if (sz == 0 || total == 0) continue;      /* slim.h:800-802 */
+    ix->blobs[i] = (char *)malloc(sz);
+    if (rd(f, ix->blobs[i], sz)) bad = 1;
+  }
+  fclose(f);
+  if (bad) {
+    snprintf(g_err, sizeof g_err, "truncated graph file %s", path);
+    hso_free(ix);
+    return NULL;
+  }
+  return ix;
+}
+
+void hso_free(hso_index *ix) {
+  if (!ix) return;
+  if (ix->blobs) {
+    for (uint64_t i = 0; i < ix->n; i++) free(ix->blobs[i]);
+    free(ix->blobs);
+  }
+  free(ix->elements);
+  free(ix);
+}
+
+void hso_get_info(const hso_index *ix, hso_info *o) {
+  o->n = ix->n;
+  o->size_data_per_element = ix->size_data_per_element;
+  o->maxM = ix->maxM;
+  o->maxM0 = ix->maxM0;
+  o->M = ix->M;
+  o->ef_construction = ix->ef_construction;
+  o->dim = ix->dim;
+  o->maxlevel = ix->maxlevel;
+  o->threshold_level = ix->threshold_level;
+  o->enterpoint = ix->enterpoint;
+  o->has_deleted = ix->has_deleted;
+}
+
+static inline const char *elem(const hso_index *ix, uint32_t i) {
+  return ix->elements + (size_t)i * ix->size_data_per_element;
+}
+int hso_node_level(const hso_index *ix, uint32_t i) { return *(const int32_t *)elem(ix, i); }
+static inline uint32_t node_total(const hso_index *ix, uint32_t i) {
+  return *(const uint32_t *)(elem(ix, i) + ix->offset_total);
+}
+uint64_t hso_node_label(const hso_index *ix, uint32_t i) {
+  uint64_t l;
+  memcpy(&l, elem(ix, i) + ix->label_offset, 8);
+  return l;
+}
+const float *hso_node_vector(const hso_index *ix, uint32_t i) {
+  return (const float *)(elem(ix, i) + ix->offset_data);
+}
+/* slim.h:1776-1781: bit 0 of byte 6 of the record */
+static inline int node_deleted(const hso_index *ix, uint32_t i) {
+  return ((const unsigned char *)elem(ix, i))[6] & 1;
+}
+
+/* slim.h:245-260 (level slice) and :363-369 (level-0 slice) */
+int hso_node_neighbors(const hso_index *ix, uint32_t i, int level, const uint32_t **ids) {
+  const char *blob = ix->blobs[i];
+  *ids = NULL;
+  if (!blob) return 0;
+  int el = hso_node_level(ix, i);
+  if (level > el) return 0;
+  const uint16_t *offs = (const uint16_t *)blob;
+  uint32_t begin = level == 0 ? 0 : offs[level - 1];
+  uint32_t end = level == el ? node_total(ix, i) : offs[level];
+  *ids = (const uint32_t *)(blob + 2 * (size_t)el) + begin;
+  return (int)(end - begin);
+}
+
+/* -------------------------------------------------------------- distances -- */
+/* space_l2.h:6-20 / space_ip.h:6-19 */
+static float dist_seq(const float *a, const float *b, size_t dim, int metric) {
+  float res = 0;
+  if (metric == HSO_IP) {
+    for (size_t i = 0; i < dim; i++) res += a[i] * b[i];
+    return 1.0f - res;
+  }
+  for (size_t i = 0; i < dim; i++) {
+    float t = a[i] - b[i];
+    res += t * t;
+  }
+  return res;
+}
+
+/* space_l2.h:25-54 (mul then add, lanes summed in index order) and
+ * space_ip.h:146-204 (fma).  Requires dim % 16 == 0, else falls back to SEQ. */
+static float dist_ref(const float *a, const float *b, size_t dim, int metric) {
+  if (dim % 16) return dist_seq(a, b, dim, metric);
+  float lane[16];
+  for (int j = 0; j < 16; j++) lane[j] = 0.f;
+  for (size_t i = 0; i < dim; i += 16)
+    for (int j = 0; j < 16; j++) {
+      if (metric == HSO_IP) {
+        lane[j] = fmaf(a[i + j], b[i + j], lane[j]);
+      } else {
+        float d = a[i + j] - b[i + j];
+        lane[j] = lane[j] + d * d;
+      }
+    }
+  float res = lane[0];
+  for (int j = 1; j < 16; j++) res += lane[j];
+  return metric == HSO_IP ? 1.0f - res : res;
+}
+
+/* The CUDA kernel's association: `team` lanes per row, lane t owns the 4-float
+ * chunks t, t+team, ...; elements past dim are zeros (rows are zero-padded in HBM). */
+static float dist_gpu(const float *a, const float *b, size_t dim, int metric, int team) {
+  float lane[32];
+  size_t chunks = (dim + 3) / 4;
+  for (int t = 0; t < team; t++) {
+    float acc = 0.f;
+    for (size_t c = (size_t)t; c < chunks; c += (size_t)team)
+      for (int e = 0; e < 4; e++) {
+        size_t i = 4 * c + e;
+        float x = i < dim ? a[i] : 0.f, y = i < dim ? b[i] : 0.f;
+        if (metric == HSO_IP) {
+          acc = fmaf(x, y, acc);
+        } else {
+          float d = x - y;
+          acc = fmaf(d, d, acc);
+        }
+      }
+    lane[t] = acc;
+  }
+  for (int off = team / 2; off >= 1; off >>= 1) {
+    float nxt[32];
+    for (int t = 0; t < team; t++) nxt[t] = lane[t] + lane[t ^ off];
+    memcpy(lane, nxt, sizeof(float) * team);
+  }
+  return metric == HSO_IP ? 1.0f - lane[0] : lane[0];
+}
+
+/* one fp32 fma chain in index order: the association of the exact-kNN CUDA kernel
+ * (hnsw_slim_b200/csrc/bruteforce.cu) */
+static float dist_seqfma(const float *a, const float *b, size_t dim, int metric) {
+  float acc = 0.f;
+  if (metric == HSO_IP) {
+    for (size_t i = 0; i < dim; i++) acc = fmaf(a[i], b[i], acc);
+    return 1.0f - acc;
+  }
+  for (size_t i = 0; i < dim; i++) {
+    float t = a[i] - b[i];
+    acc = fmaf(t, t, acc);
+  }
+  return acc;
+}
+
+float hso_dist(const float *a, const float *b, size_t dim, int metric, int order, int team) {
+  if (order == HSO_ORDER_SEQFMA) return dist_seqfma(a, b, dim, metric);
+  if (order == HSO_ORDER_REF) return dist_ref(a, b, dim, metric);
+  if (order == HSO_ORDER_GPU) return dist_gpu(a, b, dim, metric, team > 0 ? team : 8);
+  return dist_seq(a, b, dim, metric);
+}
+
+/* ------------------------------------------------------------------ heaps -- */
+typedef struct {
+  float d;
+  uint32_t id;
+} pairfu;
+
+/* Binary heap on an array with "less" = (a.d < b.d) for a max-heap (maxheap=1)
+ * or (a.d > b.d) for a min-heap, as std::push_heap / std::pop_heap with
+ * compare_by_first / compare_by_first_rev (slim.h:169-183). */
+static inline int heap_less(pairfu a, pairfu b, int maxheap) { return maxheap ? a.d < b.d : a.d > b.d; }
+
+static void heap_push(pairfu *h, size_t n /* new size, value at h[n-1] */, int maxheap) {
+  pairfu v = h[n - 1];
+  size_t hole = n - 1;
+  while (hole > 0) {
+    size_t parent = (hole - 1) / 2;
+    if (!heap_less(h[parent], v, maxheap)) break;
+    h[hole] = h[parent];
+    hole = parent;
+  }
+  h[hole] = v;
+}
+
+/* moves the top to h[n-1], leaves a heap in h[0..n-1) */
+static void heap_pop(pairfu *h, size_t n, int maxheap) {
+  if (n <= 1) return;
+  pairfu top = h[0], v = h[n - 1];
+  size_t len = n - 1, hole = 0, child = 0;
+  while (child < (len - 1) / 2) {       /* walk the hole down along the better child */
+    child = 2 * (child + 1);
+    if (heap_less(h[child], h[child - 1], maxheap)) child--;
+    h[hole] = h[child];
+    hole = child;
+  }
+  if ((len & 1) == 0 && child == (len - 2) / 2) {
+    child = 2 * (child + 1);
+    h[hole] = h[child - 1];
+    hole = child - 1;
+  }
+  while (hole > 0) {                     /* then sift the displaced value up */
+    size_t parent = (hole - 1) / 2;
+    if (!heap_less(h[parent], v, maxheap)) break;
+    h[hole] = h[parent];
+    hole = parent;
+  }
+  h[hole] = v;
+  h[n - 1] = top;
+}
+
+/* ----------------------------------------------------------------- search -- */
+typedef struct {
+  pairfu *top;     /* max-heap, ef+1 */
+  pairfu *cand;    /* min-heap, grows */
+  size_t cand_cap;
+  uint16_t *visited;
+  uint16_t tag;
+  size_t n;
+} scratch;
+
+static void cand_reserve(scratch *s, size_t need) {
+  if (need <= s->cand_cap) return;
+  size_t c = s->cand_cap ? s->cand_cap : 1024;
+  while (c < need) c *= 2;
+  s->cand = (pairfu *)realloc(s->cand, c * sizeof(pairfu));
+  s->cand_cap = c;
+}
+
+/* One beam pass over `layer` (slim.h:222-316 for layer > 0; slim.h:321-457 for
+ * layer 0).  stop_needs_full: the stop rule also requires |top| == ef
+ * (slim.h:237 and the non-bare-bone rule :346-347).  check_deleted: skip
+ * delete-marked nodes when filling `top` (slim.h:297, :418). */
+static void beam_layer(const hso_index *ix, const float *q, int layer, scratch *s, size_t *top_size,
+                       size_t ef, float *lower_bound, int stop_needs_full, int check_deleted,
+                       int order, int team, uint32_t *n_dist, uint32_t *n_hops) {
+  size_t csz = *top_size;
+  cand_reserve(s, csz + 1);
+  memcpy(s->cand, s->top, csz * sizeof(pairfu));
+  /* std::make_heap on the copy */
+  for (size_t i = 1; i <= csz; i++) heap_push(s->cand, i, 0);
+
+  while (csz > 0) {
+    pairfu cur = s->cand[0];
+    int stop = cur.d > *lower_bound;
+    if (stop_needs_full) stop = stop && (*top_size == ef);
+    if (stop) break;
+    heap_pop(s->cand, csz, 0);
+    csz--;
+
+    const uint32_t *ids;
+    int cnt = hso_node_neighbors(ix, cur.id, layer, &ids);
+    if (cnt == 0) continue;
+    if (n_hops) (*n_hops)++;
+    for (int j = 0; j < cnt; j++) {
+      uint32_t c = ids[j];
+      if (s->visited[c] == s->tag) continue;
+      s->visited[c] = s->tag;
+      float d = hso_dist(q, hso_node_vector(ix, c), ix->dim, ix->metric, order, team);
+      if (n_dist) (*n_dist)++;
+      if (*top_size < ef || *lower_bound > d) {
+        cand_reserve(s, csz + 1);
+        s->cand[csz].d = d;
+        s->cand[csz].id = c;
+        csz++;
+        heap_push(s->cand, csz, 0);
+        if (!check_deleted || !node_deleted(ix, c)) {
+          s->top[*top_size].d = d;
+          s->top[*top_size].id = c;
+          (*top_size)++;
+          heap_push(s->top, *top_size, 1);
+        }
+        while (*top_size > ef) {
+          heap_pop(s->top, *top_size, 1);
+          (*top_size)--;
+        }
+        if (*top_size > 0) *lower_bound = s->top[0].d;
+      }
+    }
+  }
+}
+
+static int cmp_pair(const void *a, const void *b) {
+  const pairfu *x = (const pairfu *)a, *y = (const pairfu *)b;
+  if (x->d < y->d) return -1;
+  if (x->d > y->d) return 1;
+  return x->id < y->id ? -1 : (x->id > y->id);
+}
+
+/* slim.h:2030-2131 */
+static void search_one(const hso_index *ix, const float *q, size_t k, size_t ef_in, scratch *s,
+                       int order, int team, uint32_t *out_labels, float *out_dists,
+                       uint32_t *n_dist, uint32_t *n_hops) {
+  uint32_t nd = 0, nh = 0;
+  uint32_t cur = ix->enterpoint;
+  float curdist = hso_dist(q, hso_node_vector(ix, cur), ix->dim, ix->metric, order, team);
+  nd++;
+  /* VisitedList::reset, visited_list_pool.h:22-28 */
+  s->tag++;
+  if (s->tag == 0) {
+    memset(s->visited, 0, sizeof(uint16_t) * s->n);
+    s->tag++;
+  }
+  /* greedy descent, slim.h:2040-2078: strict improvement, rescan while improved,
+   * no visited marking */
+  for (int level = ix->maxlevel; level > ix->threshold_level; level--) {
+    int changed = 1;
+    while (changed) {
+      changed = 0;
+      const uint32_t *ids;
+      int cnt = hso_node_neighbors(ix, cur, level, &ids);
+      if (cnt == 0) continue;
+      nh++;
+      for (int i = 0; i < cnt; i++) {
+        float d = hso_dist(q, hso_node_vector(ix, ids[i]), ix->dim, ix->metric, order, team);
+        nd++;
+        if (d < curdist) {
+          curdist = d;
+          cur = ids[i];
+          changed = 1;
+        }
+      }
+    }
+  }
+  size_t ef = ef_in > k ? ef_in : k;     /* slim.h:2080 */
+  size_t top_size = 1;
+  s->top[0].d = curdist;
+  s->top[0].id = cur;
+  s->visited[cur] = s->tag;
+  float lower = node_deleted(ix, cur) ? 3.402823466e+38f : curdist;   /* slim.h:2104-2106 */
+
+  int thr = ix->threshold_level < ix->maxlevel ? ix->threshold_level : ix->maxlevel;
+  for (int level = thr; level > 0; level--)     /* slim.h:2108-2113 */
+    beam_layer(ix, q, level, s, &top_size, ef, &lower, 1, 1, order, team, &nd, &nh);
+  int bare = !ix->has_deleted;                  /* slim.h:2114-2123 */
+  beam_layer(ix, q, 0, s, &top_size, ef, &lower, !bare, !bare, order, team, &nd, &nh);
+
+  /* slim.h:2126-2130 returns an unordered k-subset of labels; we sort so that the
+   * result is canonical: (dist, internal id) ascending */
+  qsort(s->top, top_size, sizeof(pairfu), cmp_pair);
+  for (size_t i = 0; i < k; i++) {
+    if (i < top_size) {
+      out_labels[i] = (uint32_t)hso_node_label(ix, s->top[i].id);
+      if (out_dists) out_dists[i] = s->top[i].d;
+    } else {
+      out_labels[i] = 0xFFFFFFFFu;
+      if (out_dists) out_dists[i] = INFINITY;
+    }
+  }
+  if (n_dist) *n_dist = nd;
+  if (n_hops) *n_hops = nh;
+}
+
+int hso_search(const hso_index *ix, const float *queries, size_t nq, size_t k, size_t ef, int order,
+               int team, int threads, uint32_t *out_labels, float *out_dists, uint32_t *n_dist,
+               uint32_t *n_hops) {
+  if (ix->n == 0) return 0;                     /* slim.h:2031-2032 */
+  size_t efx = ef > k ? ef : k;
+#ifdef _OPENMP
+  if (threads <= 0) threads = omp_get_num_procs();
+#else
+  threads = 1;
+#endif
+#pragma omp parallel num_threads(threads)
+  {
+    scratch s;
+    memset(&s, 0, sizeof s);
+    s.n = ix->n;
+    s.top = (pairfu *)malloc((efx + 2) * sizeof(pairfu));
+    s.visited = (uint16_t *)calloc(ix->n, sizeof(uint16_t));
+    s.tag = 0;
+#pragma omp for schedule(dynamic)
+    for (size_t i = 0; i < nq; i++)
+      search_one(ix, queries + i * ix->dim, k, ef, &s, order, team, out_labels + i * k,
+                 out_dists ? out_dists + i * k : NULL, n_dist ? n_dist + i : NULL,
+                 n_hops ? n_hops + i : NULL);
+    free(s.top);
+    free(s.cand);
+    free(s.visited);
+  }
+  return 0;
+}
+
+/* ------------------------------------------------------------ brute force -- */
+/* std::priority_queue<std::pair<float, size_t>>: max-heap ordered by the PAIR
+ * (dist, then label) — bruteforce.h:109.  We keep the pair order explicitly. */
+typedef struct {
+  float d;
+  uint64_t label;
+} pairfl;
+static inline int pl_less(pairfl a, pairfl b) { return a.d < b.d || (a.d == b.d && a.label < b.label); }
+static void pl_push(pairfl *h, size_t n) {
+  pairfl v = h[n - 1];
+  size_t hole = n - 1;
+  while (hole > 0) {
+    size_t p = (hole - 1) / 2;
+    if (!pl_less(h[p], v)) break;
+    h[hole] = h[p];
+    hole = p;
+  }
+  h[hole] = v;
+}
+static void pl_pop(pairfl *h, size_t n) {
+  if (n <= 1) return;
+  pairfl top = h[0], v = h[n - 1];
+  size_t len = n - 1, hole = 0;
+  for (;;) {
+    size_t l = 2 * hole + 1, r = l + 1, c;
+    if (l >= len) break;
+    c = (r < len && pl_less(h[l], h[r])) ? r : l;
+    if (!pl_less(v, h[c])) break;
+    h[hole] = h[c];
+    hole = c;
+  }
+  h[hole] = v;
+  h[n - 1] = top;
+}
+
+/* bruteforce.h:106-135; rows drained farthest-first (brute_force_strategy.h:27-31) */
+int hso_bruteforce(const float *base, size_t n, size_t dim, int metric, int order, int team,
+                   const float *queries, size_t nq, size_t k, int threads, uint32_t *out_labels,
+                   float *out_dists) {
+#ifdef _OPENMP
+  if (threads <= 0) threads = omp_get_num_procs();
+#else
+  threads = 1;
+#endif
+  if (k > n) k = n;
+#pragma omp parallel for schedule(dynamic) num_threads(threads)
+  for (size_t qi = 0; qi < nq; qi++) {
+    const float *q = queries + qi * dim;
+    pairfl *h = (pairfl *)malloc((k + 2) * sizeof(pairfl));
+    size_t sz = 0;
+    for (size_t i = 0; i < k; i++) {           /* first k unconditionally, :112-118 */
+      h[sz].d = hso_dist(q, base + i * dim, dim, metric, order, team);
+      h[sz].label = i;
+      sz++;
+      pl_push(h, sz);
+    }
+    float last = sz ? h[0].d : 3.402823466e+38f;
+    for (size_t i = k; i < n; i++) {           /* :120-133, admits dist <= lastdist */
+      float d = hso_dist(q, base + i * dim, dim, metric, order, team);
+      if (d <= last) {
+        h[sz].d = d;
+        h[sz].label = i;
+        sz++;
+        pl_push(h, sz);
+        if (sz > k) {
+          pl_pop(h, sz);
+          sz--;
+        }
+        if (sz) last = h[0].d;
+      }
+    }
+    size_t j = 0;
+    while (sz > 0) {                           /* drain: farthest first */
+      out_labels[qi * k + j] = (uint32_t)h[0].label;
+      if (out_dists) out_dists[qi * k + j] = h[0].d;
+      pl_pop(h, sz);
+      sz--;
+      j++;
+    }
+    free(h);
+  }
+  return 0;
+}
+
+/* ----------------------------------------------------------------- recall -- */
+static int cmp_u32(const void *a, const void *b) {
+  uint32_t x = *(const uint32_t *)a, y = *(const uint32_t *)b;
+  return x < y ? -1 : x > y;
+}
+
+/* solve_strategy.h:67-103 */
+double hso_recall(const float *base, size_t dim, const float *queries, size_t nq, const uint32_t *knn,
+                  size_t K, const uint32_t *gt, size_t gt_k, int metric) {
+  long hit = 0;
+#pragma omp parallel for schedule(dynamic) reduction(+ : hit)
+  for (size_t i = 0; i < nq; i++) {
+    pairfu *t = (pairfu *)malloc(gt_k * sizeof(pairfu));
+    for (size_t j = 0; j < gt_k; j++) {
+      uint32_t g = gt[i * gt_k + j];
+      t[j].id = g;
+      t[j].d = dist_seq(queries + i * dim, base + (size_t)g * dim, dim, metric);  /* :85 L2Sqr */
+    }
+    qsort(t, gt_k, sizeof(pairfu), cmp_pair);     /* :87 sort pairs: ties -> smaller id */
+    uint32_t *a = (uint32_t *)malloc(K * sizeof(uint32_t)), *b = (uint32_t *)malloc(K * sizeof(uint32_t));
+    for (size_t j = 0; j < K; j++) {
+      a[j] = knn[i * K + j];
+      b[j] = t[j].id;
+    }
+    qsort(a, K, 4, cmp_u32);
+    qsort(b, K, 4, cmp_u32);
+    size_t x = 0, y = 0;                          /* std::set_intersection */
+    while (x < K && y < K) {
+      if (a[x] < b[y]) x++;
+      else if (b[y] < a[x]) y++;
+      else { hit++; x++; y++; }
+    }
+    free(a);
+    free(b);
+    free(t);
+  }
+  return (double)hit / (double)(nq * K);
+}

@@ -1,0 +1,85 @@
+/* TEST INFRASTRUCTURE — NOT PRODUCT CODE.
+ *
+ * hs_oracle: a plain-C CPU restatement of the HNSW-Slim search hot path of the
+ * reference (InfiniteNightmare/HNSW-Slim), written from the algorithm, citing the
+ * reference file:line each function follows.  It is the checker for the CUDA path.
+ * Pinned (tests/test_oracle_vs_reference.py) against the reference itself, compiled
+ * unmodified into oracle/_ref/ by oracle/Makefile.
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may use it.
+ */
+#ifndef HS_ORACLE_H
+#define HS_ORACLE_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct hso_index hso_index;
+
+enum { HSO_L2 = 0, HSO_IP = 1 };
+
+/* Floating-point association of the distance sum.
+ *   HSO_ORDER_SEQ : plain left-to-right scalar loop (space_l2.h:6-20)
+ *   HSO_ORDER_REF : the AVX-512 kernel's association — 16 partial sums, lane j
+ *                   takes elements j, j+16, ...; L2 uses mul+add, IP uses fma;
+ *                   lanes added left to right (space_l2.h:25-54, space_ip.h:146-204)
+ *   HSO_ORDER_GPU : the CUDA kernel's association — `team` lanes, lane t takes the
+ *                   4-float chunks t, t+team, ...; one fma chain per lane; xor
+ *                   butterfly team/2 ... 1 (hnsw_slim_b200/csrc/traverse_fp32.cu)
+ */
+/*   HSO_ORDER_SEQFMA : one fma chain in index order (the exact-kNN CUDA kernel, bruteforce.cu) */
+enum { HSO_ORDER_SEQ = 0, HSO_ORDER_REF = 1, HSO_ORDER_GPU = 2, HSO_ORDER_SEQFMA = 3 };
+
+typedef struct {
+  uint64_t n, size_data_per_element, maxM, maxM0, M, ef_construction, dim;
+  int32_t maxlevel, threshold_level;
+  uint32_t enterpoint;
+  int32_t has_deleted;
+} hso_info;
+
+/* slim.h:753-815 (file written by slim.h:717-751) */
+hso_index *hso_load(const char *graph_path, size_t dim, int metric);
+void hso_free(hso_index *);
+void hso_get_info(const hso_index *, hso_info *out);
+const char *hso_last_error(void);
+
+/* accessors over the reference memory layout (slim.h:195-210,620-661) */
+int hso_node_level(const hso_index *, uint32_t node);
+uint64_t hso_node_label(const hso_index *, uint32_t node);
+const float *hso_node_vector(const hso_index *, uint32_t node);
+/* level-`level` neighbour slice; returns count, *ids points into the blob */
+int hso_node_neighbors(const hso_index *, uint32_t node, int level, const uint32_t **ids);
+
+float hso_dist(const float *a, const float *b, size_t dim, int metric, int order, int team);
+
+/* slim.h:2030-2131.  out_labels/out_dists: nq*k, sorted by (dist, internal id)
+ * ascending (the reference returns the same k-subset unordered and no distances).
+ * Rows with fewer than k results are padded with label 0xFFFFFFFF / dist +inf.
+ * n_dist / n_hops (may be NULL): per-query counters with the meaning of
+ * metric_distance_computations / metric_hops (slim.h:70-71,371-374,2064-2065):
+ * evaluated distances (entry point, upper-layer scans, unvisited base-layer
+ * neighbours) and expanded nodes. */
+int hso_search(const hso_index *, const float *queries, size_t nq, size_t k, size_t ef,
+               int order, int team, int threads, uint32_t *out_labels, float *out_dists,
+               uint32_t *n_dist, uint32_t *n_hops);
+
+/* bruteforce.h:106-135 + brute_force_strategy.h:24-36: k labels per query,
+ * FARTHEST first (the order the strategy writes to *_groundtruth.ivecs);
+ * labels[i] of base row i is i. */
+int hso_bruteforce(const float *base, size_t n, size_t dim, int metric, int order, int team,
+                   const float *queries, size_t nq, size_t k, int threads,
+                   uint32_t *out_labels, float *out_dists);
+
+/* solve_strategy.h:67-103: recall@K of `knn` (nq x K labels, any order) against a
+ * ground-truth table gt (nq x gt_k labels, any order, gt_k >= K): GT rows are
+ * re-ranked with scalar L2Sqr against base, ties -> smaller id, first K taken. */
+double hso_recall(const float *base, size_t dim, const float *queries, size_t nq,
+                  const uint32_t *knn, size_t K, const uint32_t *gt, size_t gt_k, int metric);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,326 @@
+"""TEST INFRASTRUCTURE — ctypes bindings for the checker libraries.
+
+* ``RefSlim`` / ``ref_*``  -> oracle/_ref/libhsref_slim_{v3,v4}.so: the UNMODIFIED
+  reference (hnswlib fork under /root/reference) compiled by oracle/Makefile.
+* ``Oracle``               -> oracle/_build/libhs_oracle.so: our plain-C restatement.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+legs may import this module.  The product path (hnsw_slim_b200/) never does.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF_DIR = os.path.join(HERE, "_ref")
+ORACLE_SO = os.path.join(HERE, "_build", "libhs_oracle.so")
+REFERENCE_ROOT = "/root/reference"
+
+_f32p = np.ctypeslib.ndpointer(dtype=np.float32, flags="C_CONTIGUOUS")
+_u32p = np.ctypeslib.ndpointer(dtype=np.uint32, flags="C_CONTIGUOUS")
+_u64p = np.ctypeslib.ndpointer(dtype=np.uint64, flags="C_CONTIGUOUS")
+
+
+def _cpu_flags() -> set:
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("flags"):
+                    return set(line.split(":", 1)[1].split())
+    except OSError:
+        pass
+    return set()
+
+
+def cpu_level() -> str:
+    """'v4' if the host CPU runs x86-64-v4 (AVX-512 F/BW/CD/DQ/VL) code, else 'v3'."""
+    fl = _cpu_flags()
+    need = {"avx512f", "avx512bw", "avx512cd", "avx512dq", "avx512vl"}
+    return "v4" if need <= fl else "v3"
+
+
+def have_reference_tree() -> bool:
+    return os.path.isdir(os.path.join(REFERENCE_ROOT, "third_party", "hnswlib"))
+
+
+def build(ref: bool = True, oracle: bool = True, quiet: bool = True) -> None:
+    """Compile the checker libraries (make).  `ref` needs /root/reference."""
+    targets = []
+    if oracle:
+        targets.append("oracle")
+    if ref and have_reference_tree():
+        targets.append("ref")
+    if not targets:
+        return
+    subprocess.run(["make", "-C", HERE, "-j4"] + targets, check=True,
+                   stdout=subprocess.DEVNULL if quiet else None)
+
+
+def ref_slim_path() -> str | None:
+    p = os.path.join(REF_DIR, f"libhsref_slim_{cpu_level()}.so")
+    return p if os.path.exists(p) else None
+
+
+def ref_slimq_path() -> str | None:
+    if cpu_level() != "v4" or "avx512_vpopcntdq" not in _cpu_flags():
+        return None
+    p = os.path.join(REF_DIR, "libhsref_slimq_v4.so")
+    return p if os.path.exists(p) else None
+
+
+_slim_lib = None
+
+
+def slim_lib():
+    global _slim_lib
+    if _slim_lib is None:
+        p = ref_slim_path()
+        if p is None:
+            raise RuntimeError("oracle/_ref/libhsref_slim_*.so not built (run `make -C oracle ref` "
+                               "where /root/reference exists)")
+        L = C.CDLL(p)
+        L.ref_last_error.restype = C.c_char_p
+        L.ref_num_procs.restype = C.c_int
+        L.ref_slim_build.restype = C.c_int
+        L.ref_slim_build.argtypes = [_f32p, C.c_size_t, C.c_size_t, C.c_int, C.c_size_t, C.c_size_t,
+                                     C.c_char_p, C.c_int, C.c_float, C.c_float, C.c_size_t, C.c_size_t,
+                                     C.c_size_t, C.c_size_t, C.c_int, C.c_void_p, C.c_char_p, C.c_char_p,
+                                     C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        L.ref_slim_open.restype = C.c_void_p
+        L.ref_slim_open.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.c_size_t, C.c_int]
+        L.ref_slim_close.argtypes = [C.c_void_p]
+        L.ref_slim_info.argtypes = [C.c_void_p, _u64p]
+        L.ref_slim_node.restype = C.c_int
+        L.ref_slim_node.argtypes = [C.c_void_p, C.c_uint32, C.c_int, C.POINTER(C.c_int),
+                                    C.POINTER(C.c_uint64), _u32p, C.c_int]
+        L.ref_slim_search.restype = C.c_int
+        L.ref_slim_search.argtypes = [C.c_void_p, _f32p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_int,
+                                      _u32p, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]
+        L.ref_slim_counts.restype = C.c_int
+        L.ref_slim_counts.argtypes = [C.c_void_p, _f32p, C.c_size_t, C.c_size_t, C.c_size_t, _u32p, _u64p]
+        L.ref_dist.restype = C.c_float
+        L.ref_dist.argtypes = [_f32p, _f32p, C.c_size_t, C.c_int]
+        L.ref_bruteforce.restype = C.c_int
+        L.ref_bruteforce.argtypes = [_f32p, C.c_size_t, C.c_size_t, C.c_int, _f32p, C.c_size_t, C.c_size_t,
+                                     C.c_int, _u32p, C.c_void_p, C.POINTER(C.c_double)]
+        _slim_lib = L
+    return _slim_lib
+
+
+# pruning parameters = main.cc defaults (main.cc:27-35,58-70)
+PRUNE_DEFAULTS = dict(threshold_level=0, top_degree_percent0=0.02, top_degree_percent=0.02,
+                      top_M0=32, low_m0=8, top_M=16, low_m=4)
+
+
+def ref_slim_build(base: np.ndarray, path: str, *, metric: int = 0, M: int = 16, ef_construction: int = 200,
+                   branching: str = "4", threads: int = 0, labels: np.ndarray | None = None,
+                   hnsw_path: str = "", **prune) -> tuple[float, float]:
+    """Reference builder: omp addPoint -> convertFromHNSW -> saveIndex (hnsw_slim_strategy.h:60-95)."""
+    L = slim_lib()
+    p = dict(PRUNE_DEFAULTS)
+    p.update(prune)
+    base = np.ascontiguousarray(base, dtype=np.float32)
+    n, dim = base.shape
+    bs, cs = C.c_double(0), C.c_double(0)
+    lab = None
+    if labels is not None:
+        labels = np.ascontiguousarray(labels, dtype=np.uint64)
+        lab = labels.ctypes.data_as(C.c_void_p)
+    rc = L.ref_slim_build(base, n, dim, metric, M, ef_construction, branching.encode(),
+                          p["threshold_level"], p["top_degree_percent0"], p["top_degree_percent"],
+                          p["top_M0"], p["low_m0"], p["top_M"], p["low_m"], threads, lab,
+                          path.encode(), hnsw_path.encode(), C.byref(bs), C.byref(cs))
+    if rc != 0:
+        raise RuntimeError(L.ref_last_error().decode())
+    return bs.value, cs.value
+
+
+class RefSlim:
+    """The reference's HierarchicalNSWSlim<float> loaded from a .graph file."""
+
+    def __init__(self, path: str, dim: int, n: int, metric: int = 0, counting: bool = False):
+        self.L = slim_lib()
+        self.h = self.L.ref_slim_open(path.encode(), dim, metric, n, int(counting))
+        if not self.h:
+            raise RuntimeError(self.L.ref_last_error().decode())
+        self.dim = dim
+
+    def close(self):
+        if self.h:
+            self.L.ref_slim_close(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
+
+    def info(self) -> dict:
+        a = np.zeros(10, dtype=np.uint64)
+        self.L.ref_slim_info(self.h, a)
+        keys = ["n", "size_data_per_element", "maxlevel", "threshold_level", "enterpoint", "maxM", "maxM0",
+                "M", "ef_construction", "has_deleted"]
+        d = {k: int(v) for k, v in zip(keys, a)}
+        for k in ("maxlevel", "threshold_level"):
+            if d[k] >= 1 << 63:
+                d[k] -= 1 << 64
+        return d
+
+    def node(self, i: int, level: int):
+        out = np.zeros(256, dtype=np.uint32)
+        lvl, lab = C.c_int(0), C.c_uint64(0)
+        cnt = self.L.ref_slim_node(self.h, i, level, C.byref(lvl), C.byref(lab), out, 256)
+        return lvl.value, lab.value, out[:cnt].copy()
+
+    def search(self, q: np.ndarray, k: int, ef: int, threads: int = 1):
+        q = np.ascontiguousarray(q, dtype=np.float32)
+        out = np.zeros((q.shape[0], k), dtype=np.uint32)
+        sec, calls = C.c_double(0), C.c_uint64(0)
+        self.L.ref_slim_search(self.h, q, q.shape[0], k, ef, threads, out, C.byref(sec), C.byref(calls))
+        return out, sec.value, calls.value
+
+    def counts(self, q: np.ndarray, k: int, ef: int):
+        q = np.ascontiguousarray(q, dtype=np.float32)
+        out = np.zeros((q.shape[0], k), dtype=np.uint32)
+        per = np.zeros(q.shape[0], dtype=np.uint64)
+        self.L.ref_slim_counts(self.h, q, q.shape[0], k, ef, out, per)
+        return out, per
+
+
+def ref_dist(a, b, metric=0) -> float:
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    b = np.ascontiguousarray(b, dtype=np.float32)
+    return float(slim_lib().ref_dist(a, b, a.shape[0], metric))
+
+
+def ref_bruteforce(base, q, k, metric=0, threads=0, want_dists=False):
+    """BruteForce::solve rows: k labels per query, FARTHEST first (brute_force_strategy.h:24-36)."""
+    base = np.ascontiguousarray(base, dtype=np.float32)
+    q = np.ascontiguousarray(q, dtype=np.float32)
+    out = np.zeros((q.shape[0], k), dtype=np.uint32)
+    d = np.zeros((q.shape[0], k), dtype=np.float32) if want_dists else None
+    sec = C.c_double(0)
+    rc = slim_lib().ref_bruteforce(base, base.shape[0], base.shape[1], metric, q, q.shape[0], k, threads, out,
+                                   d.ctypes.data_as(C.c_void_p) if want_dists else None, C.byref(sec))
+    if rc != 0:
+        raise RuntimeError(slim_lib().ref_last_error().decode())
+    return (out, d, sec.value) if want_dists else (out, sec.value)
+
+
+# --------------------------------------------------------------------------- C restatement
+ORDER_SEQ, ORDER_REF, ORDER_GPU, ORDER_SEQFMA = 0, 1, 2, 3
+_oracle_lib = None
+
+
+class _HsoInfo(C.Structure):
+    _fields_ = [("n", C.c_uint64), ("size_data_per_element", C.c_uint64), ("maxM", C.c_uint64),
+                ("maxM0", C.c_uint64), ("M", C.c_uint64), ("ef_construction", C.c_uint64), ("dim", C.c_uint64),
+                ("maxlevel", C.c_int32), ("threshold_level", C.c_int32), ("enterpoint", C.c_uint32),
+                ("has_deleted", C.c_int32)]
+
+
+def oracle_lib():
+    global _oracle_lib
+    if _oracle_lib is None:
+        if not os.path.exists(ORACLE_SO):
+            build(ref=False, oracle=True)
+        L = C.CDLL(ORACLE_SO)
+        L.hso_last_error.restype = C.c_char_p
+        L.hso_load.restype = C.c_void_p
+        L.hso_load.argtypes = [C.c_char_p, C.c_size_t, C.c_int]
+        L.hso_free.argtypes = [C.c_void_p]
+        L.hso_get_info.argtypes = [C.c_void_p, C.POINTER(_HsoInfo)]
+        L.hso_node_level.restype = C.c_int
+        L.hso_node_level.argtypes = [C.c_void_p, C.c_uint32]
+        L.hso_node_label.restype = C.c_uint64
+        L.hso_node_label.argtypes = [C.c_void_p, C.c_uint32]
+        L.hso_node_vector.restype = C.POINTER(C.c_float)
+        L.hso_node_vector.argtypes = [C.c_void_p, C.c_uint32]
+        L.hso_node_neighbors.restype = C.c_int
+        L.hso_node_neighbors.argtypes = [C.c_void_p, C.c_uint32, C.c_int, C.POINTER(C.POINTER(C.c_uint32))]
+        L.hso_dist.restype = C.c_float
+        L.hso_dist.argtypes = [_f32p, _f32p, C.c_size_t, C.c_int, C.c_int, C.c_int]
+        L.hso_search.restype = C.c_int
+        L.hso_search.argtypes = [C.c_void_p, _f32p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_int, C.c_int, C.c_int,
+                                 _u32p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.hso_bruteforce.restype = C.c_int
+        L.hso_bruteforce.argtypes = [_f32p, C.c_size_t, C.c_size_t, C.c_int, C.c_int, C.c_int, _f32p, C.c_size_t,
+                                     C.c_size_t, C.c_int, _u32p, C.c_void_p]
+        L.hso_recall.restype = C.c_double
+        L.hso_recall.argtypes = [_f32p, C.c_size_t, _f32p, C.c_size_t, _u32p, C.c_size_t, _u32p, C.c_size_t, C.c_int]
+        _oracle_lib = L
+    return _oracle_lib
+
+
+class Oracle:
+    """oracle/hs_oracle.c: the plain-C restatement of HierarchicalNSWSlim load + searchKnn."""
+
+    def __init__(self, path: str, dim: int, metric: int = 0):
+        self.L = oracle_lib()
+        self.h = self.L.hso_load(path.encode(), dim, metric)
+        if not self.h:
+            raise RuntimeError(self.L.hso_last_error().decode())
+        self.dim, self.metric = dim, metric
+
+    def close(self):
+        if self.h:
+            self.L.hso_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
+
+    def info(self) -> dict:
+        s = _HsoInfo()
+        self.L.hso_get_info(self.h, C.byref(s))
+        return {f: getattr(s, f) for f, _ in s._fields_}
+
+    def node(self, i: int, level: int):
+        p = C.POINTER(C.c_uint32)()
+        cnt = self.L.hso_node_neighbors(self.h, i, level, C.byref(p))
+        ids = np.ctypeslib.as_array(p, shape=(cnt,)).copy() if cnt else np.zeros(0, np.uint32)
+        return self.L.hso_node_level(self.h, i), self.L.hso_node_label(self.h, i), ids
+
+    def vector(self, i: int) -> np.ndarray:
+        return np.ctypeslib.as_array(self.L.hso_node_vector(self.h, i), shape=(self.dim,)).copy()
+
+    def search(self, q, k: int, ef: int, order: int = ORDER_GPU, team: int = 8, threads: int = 0):
+        """-> labels[nq,k], dists[nq,k] sorted by (dist, internal id); n_dist[nq], n_hops[nq]."""
+        q = np.ascontiguousarray(q, dtype=np.float32)
+        nq = q.shape[0]
+        lab = np.zeros((nq, k), np.uint32)
+        dist = np.zeros((nq, k), np.float32)
+        nd = np.zeros(nq, np.uint32)
+        nh = np.zeros(nq, np.uint32)
+        self.L.hso_search(self.h, q, nq, k, ef, order, team, threads, lab, dist.ctypes.data, nd.ctypes.data,
+                          nh.ctypes.data)
+        return lab, dist, nd, nh
+
+
+def oracle_dist(a, b, metric=0, order=ORDER_GPU, team=8) -> float:
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    b = np.ascontiguousarray(b, dtype=np.float32)
+    return float(oracle_lib().hso_dist(a, b, a.shape[0], metric, order, team))
+
+
+def oracle_bruteforce(base, q, k, metric=0, order=ORDER_REF, team=8, threads=0):
+    base = np.ascontiguousarray(base, dtype=np.float32)
+    q = np.ascontiguousarray(q, dtype=np.float32)
+    k = min(k, base.shape[0])
+    lab = np.zeros((q.shape[0], k), np.uint32)
+    dist = np.zeros((q.shape[0], k), np.float32)
+    oracle_lib().hso_bruteforce(base, base.shape[0], base.shape[1], metric, order, team, q, q.shape[0], k, threads,
+                                lab, dist.ctypes.data)
+    return lab, dist
+
+
+def oracle_recall(base, q, knn, gt, K=None, metric=0) -> float:
+    base = np.ascontiguousarray(base, dtype=np.float32)
+    q = np.ascontiguousarray(q, dtype=np.float32)
+    knn = np.ascontiguousarray(knn, dtype=np.uint32)
+    gt = np.ascontiguousarray(gt, dtype=np.uint32)
+    K = K or knn.shape[1]
+    assert knn.shape[1] == K and gt.shape[1] >= K
+    return float(oracle_lib().hso_recall(base, base.shape[1], q, q.shape[0], knn, K, gt, gt.shape[1], metric))

@@ -1,0 +1,163 @@
+"""GPU parity: the CUDA traversal (through the C ABI) against the C oracle and the reference.
+
+Bars (north_star): graph search reproduces the reference's recall@k within 0.5 pp at the same
+graph and ef_search; returned distances within 1e-5 relative.  We assert more: against the
+oracle run with the kernel's own fp32 association (HSO_ORDER_GPU) ids, distances and the
+per-query distance-evaluation counts are BIT-EXACT (integer/index work is exact; only bitwise
+distance ties may differ).
+"""
+import numpy as np
+import pytest
+
+from conftest import get_corpus, needs_ref
+from hnsw_slim_b200 import capi
+from oracle import refharness as rh
+
+pytestmark = pytest.mark.gpu
+
+REL_TOL = 1e-5   # north_star: distances within 1e-5 relative error
+
+
+def _recall(found, gt_sets):
+    return float(np.mean([len(set(f) & g) / len(g) for f, g in zip(found, gt_sets)]))
+
+
+def check_against_oracle(c, k, ef, *, min_exact=0.999):
+    ix = capi.Index(c.graph, c.dim, metric=c.metric)
+    ix.set_ef(ef)
+    lab, dist, cnt = ix.search(c.queries, k, counts=True)
+    orc = rh.Oracle(c.graph, c.dim, c.metric)
+    olab, odist, ond, onh = orc.search(c.queries, k, ef, order=rh.ORDER_GPU, team=8)
+    same_rows = np.all(lab == olab, axis=1)
+    # bit-exact ids, distances and counters (ties aside)
+    assert same_rows.mean() >= min_exact, f"only {same_rows.mean():.4f} of rows identical to the oracle"
+    assert np.array_equal(dist[same_rows].view(np.uint32), odist[same_rows].view(np.uint32))
+    assert (cnt[same_rows, 0] == ond[same_rows]).mean() >= min_exact
+    assert (cnt[same_rows, 1] == onh[same_rows]).mean() >= min_exact
+    # rows that differ must be explainable by ties: same distance multiset within tolerance
+    for i in np.nonzero(~same_rows)[0]:
+        fin = np.isfinite(odist[i])
+        np.testing.assert_allclose(dist[i][fin], odist[i][fin], rtol=REL_TOL)
+    return ix, lab, dist
+
+
+@pytest.mark.parametrize("ef", [10, 50, 100, 200])
+def test_small_l2_matches_oracle_bit_exact(small_corpus, ef):
+    check_against_oracle(small_corpus, 10, ef)
+
+
+@needs_ref
+@pytest.mark.parametrize("ef", [50, 100])
+def test_small_l2_matches_reference(small_corpus, ef):
+    c = small_corpus
+    ix = capi.Index(c.graph, c.dim)
+    ix.set_ef(ef)
+    lab, dist = ix.search(c.queries, 10)
+    ref = rh.RefSlim(c.graph, c.dim, c.n)
+    rlab, _, _ = ref.search(c.queries, 10, ef)
+    gt, _ = rh.ref_bruteforce(c.base, c.queries, 10)
+    gts = [set(r) for r in gt]
+    r_gpu, r_ref = _recall(lab, gts), _recall(rlab, gts)
+    assert abs(r_gpu - r_ref) <= 0.005, (r_gpu, r_ref)          # 0.5 pp
+    same = np.mean([set(a) == set(b) for a, b in zip(lab, rlab)])
+    assert same >= 0.99, same
+    # distances: recompute with the reference's own DISTFUNC
+    for i in range(0, c.nq, 17):
+        for j in range(10):
+            d = rh.ref_dist(c.queries[i], c.base[lab[i, j]], c.metric)
+            assert abs(d - dist[i, j]) <= REL_TOL * max(abs(d), 1e-30)
+
+
+@pytest.mark.parametrize("dim,rank", [(96, 12), (128, 14), (100, 12), (64, 8)])
+def test_dims_l2(dim, rank):
+    c = get_corpus(n=20000, nq=200, dim=dim, rank=rank)
+    check_against_oracle(c, 10, 64)
+
+
+def test_large_dim_generic_kernel():
+    c = get_corpus(n=6000, nq=100, dim=960, rank=16, M=32)     # GIST-shaped rows, M=32 -> deg stride 64
+    ix, lab, dist = check_against_oracle(c, 10, 100)
+    assert ix.info()["deg0_stride"] in (32, 64)
+
+
+def test_inner_product():
+    c = get_corpus(n=20000, nq=200, dim=768, rank=16, M=32, metric=1)   # COHERE-shaped
+    check_against_oracle(c, 10, 100)
+
+
+def test_edge_cases(small_corpus):
+    c = small_corpus
+    ix = capi.Index(c.graph, c.dim)
+    # nq = 0 and empty results buffers
+    lab, dist = ix.search(np.zeros((0, c.dim), np.float32), 10)
+    assert lab.shape == (0, 10)
+    # ef < k -> ef = max(ef, k)   (slim.h:2080)
+    ix.set_ef(3)
+    lab, dist = ix.search(c.queries[:50], 20)
+    orc = rh.Oracle(c.graph, c.dim)
+    olab, odist, _, _ = orc.search(c.queries[:50], 20, 3)
+    assert np.array_equal(lab, olab)
+    assert (np.diff(dist, axis=1) >= 0).all()                     # sortedness
+    # single query, k = 1
+    ix.set_ef(50)
+    lab1, _ = ix.search(c.queries[:1], 1)
+    olab1, _, _, _ = orc.search(c.queries[:1], 1, 50)
+    assert np.array_equal(lab1, olab1)
+    # a query that IS a base vector finds itself at distance 0
+    lab, dist = ix.search(c.base[:64], 1)
+    assert (dist[:, 0] == 0).all() and np.array_equal(lab[:, 0], np.arange(64, dtype=np.uint32))
+    # idempotence + batch-split invariance
+    ix.set_ef(80)
+    a, _ = ix.search(c.queries, 10)
+    b, _ = ix.search(c.queries, 10)
+    h = c.nq // 2
+    c1, _ = ix.search(c.queries[:h], 10)
+    c2, _ = ix.search(c.queries[h:], 10)
+    assert np.array_equal(a, b) and np.array_equal(a, np.vstack([c1, c2]))
+
+
+def test_tiny_graphs():
+    for n in (1, 2, 5, 40):
+        c = get_corpus(n=n, nq=7, dim=32, M=4, efc=20)
+        ix = capi.Index(c.graph, c.dim)
+        ix.set_ef(16)
+        k = 3
+        lab, dist = ix.search(c.queries, k)
+        orc = rh.Oracle(c.graph, c.dim)
+        olab, odist, _, _ = orc.search(c.queries, k, 16)
+        assert np.array_equal(lab, olab), n
+        assert np.array_equal(np.isinf(dist), np.isinf(odist))
+
+
+def test_hash_reset_keeps_results(small_corpus, monkeypatch):
+    """A visited hash far too small forces resets: results must not change (only n_dist grows)."""
+    c = small_corpus
+    ix = capi.Index(c.graph, c.dim)
+    ix.set_ef(100)
+    a, da, ca = ix.search(c.queries, 10, counts=True)
+    monkeypatch.setenv("HS_HASH_BITS", "8")
+    ix2 = capi.Index(c.graph, c.dim)
+    ix2.set_ef(100)
+    b, db, cb = ix2.search(c.queries, 10, counts=True)
+    assert np.array_equal(a, b) and np.array_equal(da, db)
+    assert (cb[:, 0] >= ca[:, 0]).all() and (cb[:, 0] > ca[:, 0]).any()
+
+
+def test_stats_counters(small_corpus):
+    c = small_corpus
+    ix = capi.Index(c.graph, c.dim)
+    ix.set_ef(50)
+    ix.reset_stats()
+    _, _, cnt = ix.search(c.queries, 10, counts=True)
+    st = ix.stats()
+    assert st["n_dist"] == int(cnt[:, 0].sum()) and st["n_hops"] == int(cnt[:, 1].sum())
+
+
+def test_errors_are_loud(tmp_path):
+    with pytest.raises(capi.HsError) as e:
+        capi.Index(str(tmp_path / "missing.graph"), 32)
+    assert e.value.code == -2
+    bad = tmp_path / "bad.graph"
+    bad.write_bytes(b"\x01" * 100)
+    with pytest.raises(capi.HsError):
+        capi.Index(str(bad), 32)
