@@ -118,8 +118,31 @@ PRUNE_DEFAULTS = dict(threshold_level=0, top_degree_percent0=0.02, top_degree_pe
 
 def ref_slim_build(base: np.ndarray, path: str, *, metric: int = 0, M: int = 16, ef_construction: int = 200,
                    branching: str = "4", threads: int = 0, labels: np.ndarray | None = None,
-                   hnsw_path: str = "", **prune) -> tuple[float, float]:
-    """Reference builder: omp addPoint -> convertFromHNSW -> saveIndex (hnsw_slim_strategy.h:60-95)."""
+                   hnsw_path: str = "", isolate: bool = True, **prune) -> tuple[float, float]:
+    """Reference builder: omp addPoint -> convertFromHNSW -> saveIndex (hnsw_slim_strategy.h:60-95).
+
+    isolate=True runs it in a fresh process: convertFromHNSW keeps `thread_local` scratch sized
+    from the FIRST index a thread converts (slim.h:957-959,1008-1011), so a second build with a
+    larger M in the same process overruns it.  The reference never builds twice per process.
+    """
+    if isolate:
+        import json
+        import sys
+        import tempfile
+        with tempfile.TemporaryDirectory(prefix="hsref_") as td:
+            np.save(os.path.join(td, "base.npy"), np.ascontiguousarray(base, dtype=np.float32))
+            if labels is not None:
+                np.save(os.path.join(td, "labels.npy"), np.ascontiguousarray(labels, dtype=np.uint64))
+            args = dict(path=path, metric=metric, M=M, ef_construction=ef_construction, branching=branching,
+                        threads=threads, hnsw_path=hnsw_path, prune=prune, have_labels=labels is not None)
+            with open(os.path.join(td, "args.json"), "w") as f:
+                json.dump(args, f)
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--build-slim", td],
+                               capture_output=True, text=True)
+            if r.returncode != 0:
+                raise RuntimeError(f"reference builder failed (rc={r.returncode}): {r.stderr[-2000:]}")
+            bs, cs = json.loads(r.stdout.strip().splitlines()[-1])
+            return bs, cs
     L = slim_lib()
     p = dict(PRUNE_DEFAULTS)
     p.update(prune)
@@ -324,3 +347,18 @@ def oracle_recall(base, q, knn, gt, K=None, metric=0) -> float:
     K = K or knn.shape[1]
     assert knn.shape[1] == K and gt.shape[1] >= K
     return float(oracle_lib().hso_recall(base, base.shape[1], q, q.shape[0], knn, K, gt, gt.shape[1], metric))
+
+
+if __name__ == "__main__":
+    import json
+    import sys
+    if len(sys.argv) == 3 and sys.argv[1] == "--build-slim":
+        td = sys.argv[2]
+        with open(os.path.join(td, "args.json")) as f:
+            a = json.load(f)
+        base = np.load(os.path.join(td, "base.npy"), mmap_mode="r")
+        labels = np.load(os.path.join(td, "labels.npy")) if a["have_labels"] else None
+        out = ref_slim_build(np.ascontiguousarray(base), a["path"], metric=a["metric"], M=a["M"],
+                             ef_construction=a["ef_construction"], branching=a["branching"], threads=a["threads"],
+                             labels=labels, hnsw_path=a["hnsw_path"], isolate=False, **a["prune"])
+        print(json.dumps(out))

@@ -29,7 +29,7 @@ ap.add_argument("--check", type=int, default=1)
 a = ap.parse_args()
 
 base, q = make_dataset(a.n, a.nq, a.dim, metric=a.metric, rank=a.rank)
-cache = os.path.join(ROOT, "data_cache")
+cache = os.environ.get("HS_DATA_CACHE", "/tmp/hs_data_cache")
 os.makedirs(cache, exist_ok=True)
 graph = os.path.join(cache, f"probe_n{a.n}_d{a.dim}_r{a.rank}_M{a.M}_e{a.efc}_m{a.metric}.graph")
 if not os.path.exists(graph):
