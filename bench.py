@@ -1,0 +1,363 @@
+#!/usr/bin/env python
+"""bench.py — QPS of the HNSW-Slim search hot path on B200 (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # our CUDA engine (C ABI)
+    python bench.py --impl reference --gpus N --steps K ...   # the reference's CPU search
+
+A "step" = one pass of the hot path over one batch of synthetic queries:
+HierarchicalNSWSlim::searchKnn for every query of the batch (hnsw_slim_strategy.h:112-114)
+== ONE hs_search_batch_device launch.  Workload at every N: BASELINE.json configs[0], the
+configuration the north-star target is quoted on — SIFT-shaped synthetic 1M x 128 L2,
+hnsw_slim M=16 ef_construction=200, k=10 ef_search=100, 10k queries per batch.  With N GPUs
+the 1M index is replicated and every rank searches its own 10k-query batch (north_star:
+"1M-scale indices are replicated and queries are split with no collective") => weak scaling,
+value = N * 10k * K / max-over-ranks device time.  `--workload deep-sharded` runs the
+sharded path instead (one sub-graph per shard, NCCL all-gather + top-k merge).
+
+Prints ONE JSON line (rank 0).  Inputs (corpus, queries, .graph) are generated once and cached
+in $HS_DATA_CACHE (default /tmp/hs_data_cache); the .graph is built by the engine's own host
+builder (hs_build_slim_graph), not by anything under oracle/.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CACHE = os.environ.get("HS_DATA_CACHE", "/tmp/hs_data_cache")
+
+WORKLOADS = {
+    # BASELINE.json configs[0]
+    "sift1m": dict(n=1_000_000, dim=128, metric=0, M=16, efc=200, rank=14, nq=10_000, k=10, ef=100,
+                   desc="SIFT-shaped synthetic 1Mx128 L2, hnsw_slim M=16 efc=200 (rank-14 latent Gaussian, seed 1)"),
+    # reduced-size variants for quick local runs (not contract lines)
+    "sift200k": dict(n=200_000, dim=128, metric=0, M=16, efc=200, rank=14, nq=10_000, k=10, ef=100,
+                     desc="SIFT-shaped synthetic 200kx128 L2 (dev size)"),
+}
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def env_rank():
+    return int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+
+
+def prepare_inputs(w: dict, n_query_batches: int, build_rank: bool):
+    """Synthetic corpus + query batches + the .graph over the corpus (cached on disk)."""
+    from hnsw_slim_b200 import capi
+    from hnsw_slim_b200.synth import latent_gaussian
+    os.makedirs(CACHE, exist_ok=True)
+    tag = f"n{w['n']}_d{w['dim']}_m{w['metric']}_r{w['rank']}_M{w['M']}_e{w['efc']}_b4_s1"
+    graph = os.path.join(CACHE, f"hnsw_slim_{tag}.graph")
+    base = None
+    if not os.path.exists(graph) and build_rank:
+        t0 = time.time()
+        base = latent_gaussian(w["n"], w["dim"], rank=w["rank"], seed=1, normalize=(w["metric"] == 1))
+        t1 = time.time()
+        tmp = graph + f".tmp{os.getpid()}"
+        capi.build_slim_graph(base, tmp, metric=w["metric"], M=w["M"], ef_construction=w["efc"], branching="4")
+        os.replace(tmp, graph)
+        log(f"[bench] generated corpus in {t1-t0:.1f}s, built {graph} in {time.time()-t1:.1f}s "
+            f"({os.cpu_count()} host threads)")
+    queries = [latent_gaussian(w["nq"], w["dim"], rank=w["rank"], seed=1, normalize=(w["metric"] == 1),
+                               stream=1 + b) for b in range(n_query_batches)]
+    return graph, base, queries
+
+
+class ClockSampler:
+    """Samples SM clock / throttle reasons through NVML during the timed region."""
+
+    def __init__(self, device_index: int):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception as e:  # pragma: no cover
+            self.nv = None
+            log(f"[bench] NVML unavailable: {e}")
+
+    def _run(self):
+        nv = self.nv
+        names = {
+            nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+            nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+            nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+            nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap",
+            nv.nvmlClocksThrottleReasonHwPowerBrakeSlowdown: "hw_power_brake",
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.02)
+
+    def __enter__(self):
+        if self.nv:
+            self._thr = threading.Thread(target=self._run, daemon=True)
+            self._thr.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self._thr:
+            self._thr.join()
+
+    def summary(self):
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f), "measured (MEASURED_PEAKS.json)"
+    return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md)"
+
+
+def cpu_reference_qps(graph: str, w: dict, queries: np.ndarray, threads: int, passes: int):
+    """The reference's own search (oracle/_ref, compiled unmodified) on this host's cores."""
+    from oracle import refharness as rh
+    if rh.ref_slim_path() is not None:
+        ix = rh.RefSlim(graph, w["dim"], w["n"], w["metric"])
+        ix.search(queries[: min(2000, len(queries))], w["k"], w["ef"], threads)      # warm-up: per-thread visited lists
+        t = 0.0
+        for _ in range(passes):
+            _, sec, _ = ix.search(queries, w["k"], w["ef"], threads)
+            t += sec
+        return len(queries) * passes / t, "reference", t
+    orc = rh.Oracle(graph, w["dim"], w["metric"])                              # plain-C port
+    t0 = time.time()
+    for _ in range(passes):
+        orc.search(queries, w["k"], w["ef"], order=rh.ORDER_REF, threads=threads if threads != 1 else 1)
+    t = time.time() - t0
+    return len(queries) * passes / t, "port", t
+
+
+def run_reference(args, w):
+    rank, _, world = env_rank()
+    if rank != 0:
+        return
+    from oracle import refharness as rh
+    graph, _, qb = prepare_inputs(w, 1, True)
+    q = qb[0]
+    cores = os.cpu_count() or 1
+    ix = rh.RefSlim(graph, w["dim"], w["n"], w["metric"]) if rh.ref_slim_path() else None
+    kind = "reference" if ix is not None else "port"
+    orc = None if ix is not None else rh.Oracle(graph, w["dim"], w["metric"])
+
+    def step():
+        if ix is not None:
+            _, sec, _ = ix.search(q, w["k"], w["ef"], 0)         # omp dynamic, all cores
+            return sec
+        t0 = time.time()
+        orc.search(q, w["k"], w["ef"], order=rh.ORDER_REF, threads=0)
+        return time.time() - t0
+
+    for _ in range(max(1, args.warmup)):
+        step()
+    total = sum(step() for _ in range(args.steps))
+    qps = len(q) * args.steps / total
+    sample = (f"{args.steps} x {len(q)} queries, ef={w['ef']}, k={w['k']}, omp parallel for schedule(dynamic) over "
+              f"queries (hnsw_slim_client_update_patch.cc:223-226), {cores} threads")
+    out = {
+        "impl": "reference", "metric": "QPS at recall@10>=0.95", "value": qps, "unit": "queries/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": w["desc"], "k": w["k"], "ef_search": w["ef"], "queries_per_step": len(q)},
+        "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(out), flush=True)
+
+
+def run_gpu(args, w):
+    import torch
+    rank, local_rank, world = env_rank()
+    from hnsw_slim_b200 import capi
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the engine has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    distributed = world > 1
+    if distributed:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if distributed:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    n_batches = min(8, args.warmup + args.steps)
+    # rank 0 builds the graph (all host threads); the others wait, then read the cache
+    if rank == 0:
+        graph, base, qbatches = prepare_inputs(w, n_batches, True)
+    barrier()
+    if rank != 0:
+        graph, base, qbatches = prepare_inputs(w, n_batches, False)
+    # each rank takes its own batches (different streams) in the replicated/weak-scaling mode
+    if distributed:
+        from hnsw_slim_b200.synth import latent_gaussian
+        qbatches = [latent_gaussian(w["nq"], w["dim"], rank=w["rank"], seed=1, normalize=(w["metric"] == 1),
+                                    stream=1 + b + 100 * rank) for b in range(n_batches)]
+
+    t0 = time.time()
+    ix = capi.Index(graph, w["dim"], metric=w["metric"], device=local_rank)
+    ix.set_ef(w["ef"])
+    info = ix.info()
+    log(f"[bench] rank {rank}: index resident in {time.time()-t0:.1f}s, {info['device_bytes']/2**20:.0f} MiB HBM, "
+        f"maxlevel {info['maxlevel']}, avg deg0 {info['sum_deg0']/info['n']:.2f}")
+
+    nq, k, dim = w["nq"], w["k"], w["dim"]
+    stream = torch.cuda.Stream()
+    d_q = [torch.from_numpy(q).cuda() for q in qbatches]
+    d_lab = torch.empty((nq, k), dtype=torch.int32, device="cuda")
+    d_dist = torch.empty((nq, k), dtype=torch.float32, device="cuda")
+    torch.cuda.synchronize()
+
+    def step(i):
+        ix.search_device(d_q[i % n_batches].data_ptr(), nq, k, d_lab.data_ptr(), d_dist.data_ptr(), stream.cuda_stream)
+
+    # ---- device-resident number ----
+    for i in range(args.warmup):
+        step(i)
+    stream.synchronize()
+    ix.reset_stats()
+    barrier()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    with ClockSampler(local_rank) as clocks:
+        ev[0].record(stream)
+        for i in range(args.steps):
+            step(args.warmup + i)
+            ev[i + 1].record(stream)
+        stream.synchronize()
+    barrier()
+    ms_total = ev[0].elapsed_time(ev[-1])
+    st = ix.stats()
+    if distributed:
+        t = torch.tensor([ms_total], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    value = world * nq * args.steps / (ms_total * 1e-3)
+
+    # ---- roofline of the traversal kernel (the only kernel in the step) ----
+    launch_ms = ev[0].elapsed_time(ev[-1]) / args.steps
+    n_dist = st["n_dist"] / args.steps
+    n_hops = st["n_hops"] / args.steps
+    avg_deg0 = info["sum_deg0"] / info["n"]
+    alg_bytes = n_dist * 4 * info["dim_padded"] + n_hops * (8 + 4 * avg_deg0)
+    peaks, peak_src = measured_peaks()
+    achieved = alg_bytes / (launch_ms * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")     # dram bytes/launch from the committed ncu capture
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic = json.load(f).get(args.workload, {}).get("dram_bytes_per_launch")
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_source": peak_src,
+                "kernel": "hs::traverse_kernel", "algorithmic_bytes_per_launch": alg_bytes,
+                "dist_evals_per_query": n_dist / nq, "hops_per_query": n_hops / nq, "launch_ms": launch_ms}
+
+    # ---- end to end through the host-buffer C-ABI call (pinned host memory) ----
+    h_q = [torch.from_numpy(q).pin_memory() for q in qbatches]
+    h_lab = torch.empty((nq, k), dtype=torch.int32).pin_memory()
+    h_dist = torch.empty((nq, k), dtype=torch.float32).pin_memory()
+    for i in range(args.warmup):
+        ix.search_ptr(h_q[i % n_batches].data_ptr(), nq, k, h_lab.data_ptr(), h_dist.data_ptr())
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        ix.search_ptr(h_q[(args.warmup + i) % n_batches].data_ptr(), nq, k, h_lab.data_ptr(), h_dist.data_ptr())
+    e2e_s = time.perf_counter() - t0
+    if distributed:
+        t = torch.tensor([e2e_s], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e = {"value": world * nq * args.steps / e2e_s, "unit": "queries/s", "h2d_bytes_per_step": nq * dim * 4,
+           "d2h_bytes_per_step": nq * k * 8, "timing": "host wall clock around the synchronous hs_search_batch call"}
+
+    # ---- recall of what was just measured (exact kNN on the GPU, outside the timed regions) ----
+    recall = None
+    if rank == 0 and not args.no_recall:
+        if base is None:
+            from hnsw_slim_b200.synth import latent_gaussian
+            base = latent_gaussian(w["n"], dim, rank=w["rank"], seed=1, normalize=(w["metric"] == 1))
+        ns = min(1000, nq)
+        gt, _ = capi.bruteforce_knn(base, qbatches[0][:ns], k, metric=w["metric"], device=local_rank)
+        lab, _ = ix.search(qbatches[0][:ns], k)
+        recall = float(np.mean([len(set(a) & set(b)) / k for a, b in zip(lab, gt)]))
+
+    # ---- the reference's CPU search on this host, bounded sample (rank 0, N=1 only) ----
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        qps_all, kind, secs = cpu_reference_qps(graph, w, qbatches[0], 0, 4)
+        qps_1, _, secs1 = cpu_reference_qps(graph, w, qbatches[0][:2000], 1, 1)
+        cpu = {"value": qps_all, "unit": "queries/s", "cores": cores, "kind": kind,
+               "sample": f"4 passes x {nq} queries of the same workload, omp dynamic over queries, {cores} threads "
+                         f"({secs:.1f}s); serial 1-thread loop (hnsw_slim_strategy.h:112-114) on 2000 queries: "
+                         f"{qps_1:.0f} queries/s"}
+
+    if rank == 0:
+        out = {
+            "metric": "QPS at recall@10>=0.95", "value": value, "unit": "queries/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": w["desc"], "k": k, "ef_search": w["ef"], "queries_per_step_per_gpu": nq,
+                       "parallelism": f"replicated index x{world}, queries split, no collective",
+                       "recall_at_10": recall,
+                       "l2": "index (vectors+adjacency) %.0f MiB > 126 MB L2; a different query batch every step"
+                             % (info["device_bytes"] / 2**20)},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": args.steps,
+            "clocks": clocks.summary(),
+        }
+        print(json.dumps(out), flush=True)
+    if distributed:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="sift1m", choices=sorted(WORKLOADS))
+    ap.add_argument("--ef", type=int, default=None)
+    ap.add_argument("--no-recall", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(3, args.warmup) if args.impl == "ours" else max(1, args.warmup)
+    w = dict(WORKLOADS[args.workload])
+    if args.ef:
+        w["ef"] = args.ef
+    if args.impl == "reference":
+        run_reference(args, w)
+    else:
+        run_gpu(args, w)
+
+
+if __name__ == "__main__":
+    main()

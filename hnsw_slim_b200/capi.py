@@ -21,6 +21,7 @@ EXPORTS = [
     "hs_search_batch_counts", "hs_search_batch_device", "hs_stats", "hs_reset_stats", "hs_bruteforce_knn",
     "hs_bruteforce_knn_device", "hs_topk_merge_device", "hs_recall", "hs_last_error", "hs_abi_version",
     "hs_debug_flatten", "hs_debug_free", "hs_debug_info", "hs_debug_row", "hs_debug_node",
+    "hs_build_params_default", "hs_build_slim_graph",
 ]
 
 
@@ -41,6 +42,13 @@ class IndexInfo(C.Structure):
 
     def as_dict(self) -> dict:
         return {f: getattr(self, f) for f, _ in self._fields_}
+
+
+class BuildParams(C.Structure):
+    _fields_ = [("M", C.c_uint64), ("ef_construction", C.c_uint64), ("branching_factor", C.c_char_p),
+                ("threshold_level", C.c_int32), ("top_degree_percent0", C.c_float),
+                ("top_degree_percent", C.c_float), ("top_M0", C.c_uint64), ("low_m0", C.c_uint64),
+                ("top_M", C.c_uint64), ("low_m", C.c_uint64), ("threads", C.c_int32), ("seed", C.c_uint64)]
 
 
 _lib = None
@@ -83,8 +91,11 @@ def lib():
         L.hs_debug_info.argtypes = [vp, C.POINTER(IndexInfo)]
         L.hs_debug_row.argtypes = [vp, C.c_uint32, i32, vp, i32]
         L.hs_debug_node.argtypes = [vp, C.c_uint32, C.POINTER(i32), C.POINTER(C.c_uint32), vp]
+        L.hs_build_params_default.argtypes = [C.POINTER(BuildParams)]
+        L.hs_build_params_default.restype = None
+        L.hs_build_slim_graph.argtypes = [vp, sz, sz, i32, C.POINTER(BuildParams), vp, C.c_char_p]
         for name in EXPORTS:
-            if name not in ("hs_last_error", "hs_free", "hs_debug_free"):
+            if name not in ("hs_last_error", "hs_free", "hs_debug_free", "hs_build_params_default"):
                 getattr(L, name).restype = i32
         _lib = L
     return _lib
@@ -177,6 +188,23 @@ class Index:
 
     def reset_stats(self) -> None:
         _check(lib().hs_reset_stats(self._h))
+
+
+def build_slim_graph(base, path: str, *, metric: int = HS_METRIC_L2, M: int = 16, ef_construction: int = 200,
+                     branching: str = "4", threads: int = 0, labels=None, seed: int = 100, **prune) -> None:
+    """hs_build_slim_graph: host-side HNSW build + HNSW-Slim pruning -> reference-format .graph."""
+    b = _f32(base)
+    p = BuildParams()
+    lib().hs_build_params_default(C.byref(p))
+    p.M, p.ef_construction, p.branching_factor = M, ef_construction, branching.encode()
+    p.threads, p.seed = threads, seed
+    for k_, v in prune.items():
+        setattr(p, k_, v)
+    lab = None
+    if labels is not None:
+        labels = np.ascontiguousarray(labels, dtype=np.uint64)
+        lab = labels.ctypes.data
+    _check(lib().hs_build_slim_graph(b.ctypes.data, b.shape[0], b.shape[1], metric, C.byref(p), lab, path.encode()))
 
 
 class HostGraph:

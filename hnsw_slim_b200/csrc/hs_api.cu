@@ -1,6 +1,7 @@
 // C ABI of libhnswslim_b200.so (include/hnswslim_b200.h): index lifetime, batched search.
 #include <cuda_runtime.h>
 
+#include <cmath>
 #include <cstdlib>
 #include <cstring>
 #include <memory>
@@ -449,6 +450,45 @@ int hs_recall(const float *base, size_t n, size_t dim, const float *queries, siz
   }
   cleanup();
   return rc;
+}
+
+void hs_build_params_default(hs_build_params *p) {
+  if (!p) return;
+  p->M = 32;                       // core.h:31
+  p->ef_construction = 128;        // main.cc:16
+  p->branching_factor = "4";       // core.h:36
+  p->threshold_level = 0;          // core.h:38
+  p->top_degree_percent0 = 0.02f;  // main.cc:27
+  p->top_degree_percent = 0.02f;
+  p->top_M0 = 32;                  // main.cc:29
+  p->low_m0 = 8;                   // top_M0 * Mm_ratio / 100, main.cc:64
+  p->top_M = 16;                   // level_ratio% * top_M0, main.cc:65
+  p->low_m = 4;                    // main.cc:66
+  p->threads = 0;
+  p->seed = 100;                   // hnsw.h:85 random_seed
+}
+
+int hs_build_slim_graph(const float *base, size_t n, size_t dim, int metric, const hs_build_params *p,
+                        const uint64_t *labels, const char *out_graph_path) {
+  if (!p || !p->branching_factor) {
+    set_error("null build params");
+    return HS_ERR_ARG;
+  }
+  double bf;
+  const std::string b = p->branching_factor;     // hnsw.h:143-158
+  if (b == "e") bf = M_E;
+  else if (b == "sqrt") bf = std::sqrt(2.0) / (std::sqrt(2.0) - 1.0);
+  else {
+    char *end = nullptr;
+    bf = std::strtod(b.c_str(), &end);
+    if (end == b.c_str() || bf <= 1.0) {
+      set_error("Invalid branching factor: " + b);
+      return HS_ERR_ARG;
+    }
+  }
+  return build_slim_graph(base, n, dim, metric, p->M, p->ef_construction, bf, p->threshold_level,
+                          p->top_degree_percent0, p->top_degree_percent, p->top_M0, p->low_m0, p->top_M, p->low_m,
+                          p->threads, p->seed, labels, out_graph_path);
 }
 
 // ---- host-only inspection of the flattened graph (used by the CPU test-suite; no CUDA) ----

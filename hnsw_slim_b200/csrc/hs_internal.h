@@ -53,4 +53,10 @@ struct HostGraph {
 int parse_graph(const uint8_t *bytes, size_t size, int kind, size_t dim, HostGraph *out);
 int read_file(const char *path, std::vector<uint8_t> *out);
 
+// graph_build.cpp — HNSW construction + HNSW-Slim pruning + saveIndex file format
+int build_slim_graph(const float *base, size_t n, size_t dim, int metric, size_t M, size_t ef_construction,
+                     double branching, int threshold_level, float top_pct0, float top_pct, size_t top_M0,
+                     size_t low_m0, size_t top_M, size_t low_m, int threads, uint64_t seed,
+                     const uint64_t *labels, const char *out_path);
+
 }  // namespace hs

@@ -147,6 +147,30 @@ int hs_recall(const float *base, size_t n, size_t dim, const float *queries, siz
               const uint32_t *knn, size_t K, const uint32_t *gt, size_t gt_k, int metric, int device,
               double *recall_out);
 
+/* Index construction parameters = the flags of main.cc:10-38 and the values derived
+ * from them at main.cc:58-70. */
+typedef struct {
+  uint64_t M;                  /* --m               (HierarchicalNSW M, hnsw.h:84)            */
+  uint64_t ef_construction;    /* --ef_construction                                           */
+  const char *branching_factor;/* --branching_factor: "4", "16", "e", "sqrt" (hnsw.h:143-158) */
+  int32_t threshold_level;     /* --threshold_level                                           */
+  float top_degree_percent0;   /* --top_degree_percent0 (alpha_0)                             */
+  float top_degree_percent;    /* alpha (main.cc:62 copies alpha_0)                           */
+  uint64_t top_M0, low_m0, top_M, low_m;   /* M_h0, M_l0, M_h, M_l (main.cc:63-66)             */
+  int32_t threads;             /* <= 0: all hardware threads                                  */
+  uint64_t seed;
+} hs_build_params;
+
+/* Fills `p` with the defaults of main.cc:10-38 (M=32 there; pass your own). */
+void hs_build_params_default(hs_build_params *p);
+
+/* Host-side builder of the engine's input: HNSW construction (the omp addPoint loop of
+ * hnsw_slim_strategy.h:66-69), HNSW-Slim pruning (convertFromHNSW, slim.h:867-1108) and
+ * saveIndex (slim.h:717-751).  Writes a .graph that both hs_load and the reference's
+ * loadIndex read.  labels may be NULL (label of row i = i).  CPU only, multi-threaded. */
+int hs_build_slim_graph(const float *base, size_t n, size_t dim, int metric, const hs_build_params *p,
+                        const uint64_t *labels, const char *out_graph_path);
+
 /* Host-only inspection of the flattened form of a .graph (no CUDA needed): what
  * hs_load uploads.  Used by the CPU test-suite to check the loader against the
  * reference's accessors (slim.h:620-661). */
