@@ -30,6 +30,27 @@ def needs_build() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+def build_variant(tag: str, defs: list[str]) -> str:
+    """Developer helper: an extra copy of the library compiled with -D flags (tuning sweeps);
+    selected at run time with HS_LIB_PATH."""
+    out = os.path.join(OUT_DIR, f"variant_{tag}")
+    os.makedirs(out, exist_ok=True)
+    lib = os.path.join(out, "libhnswslim_b200.so")
+    objs = []
+    procs = []
+    for src in SOURCES:
+        obj = os.path.join(out, os.path.splitext(src)[0] + ".o")
+        cmd = [_nvcc()] + NVCC_FLAGS + [f"-D{d}" for d in defs] + ["-c", os.path.join(CSRC, src), "-o", obj]
+        procs.append(subprocess.Popen(cmd))
+        objs.append(obj)
+    for pr in procs:
+        if pr.wait() != 0:
+            raise RuntimeError("nvcc failed")
+    subprocess.run([_nvcc(), "-shared", "-o", lib] + objs + ["-gencode", "arch=compute_100a,code=sm_100a",
+                                                            "-ccbin", "/usr/bin/g++"], check=True)
+    return lib
+
+
 def build(force: bool = False, verbose: bool = False, ptxas_v: bool = False) -> str:
     if not force and not needs_build():
         return LIB
@@ -57,4 +78,7 @@ def build(force: bool = False, verbose: bool = False, ptxas_v: bool = False) -> 
 
 
 if __name__ == "__main__":
+    if len(sys.argv) >= 3 and sys.argv[1] == "--variant":
+        print(build_variant(sys.argv[2], sys.argv[3:]))
+        sys.exit(0)
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, ptxas_v="--ptxas" in sys.argv))

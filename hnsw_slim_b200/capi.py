@@ -62,11 +62,12 @@ def lib():
     """The loaded shared library (raises if it was not built — no fallback)."""
     global _lib
     if _lib is None:
-        if not os.path.exists(_build.LIB):
+        path = os.environ.get("HS_LIB_PATH", _build.LIB)     # HS_LIB_PATH: tuning variants (build.py --variant)
+        if not os.path.exists(path):
             raise FileNotFoundError(
-                f"{_build.LIB} is missing: run `python -m hnsw_slim_b200.build` (nvcc, sm_100a). "
+                f"{path} is missing: run `python -m hnsw_slim_b200.build` (nvcc, sm_100a). "
                 "hnsw_slim_b200 has no CPU / PyTorch fallback.")
-        L = C.CDLL(_build.LIB)
+        L = C.CDLL(path)
         vp, sz, i32 = C.c_void_p, C.c_size_t, C.c_int
         L.hs_last_error.restype = C.c_char_p
         L.hs_abi_version.restype = i32

@@ -50,6 +50,7 @@ struct hs_index {
   uint32_t *d_perq = nullptr;
   size_t cap_q = 0, cap_out = 0, cap_perq = 0;
   int hash_bits_override = 0;
+  uint32_t traverse_flags = 3;
   std::mutex mu;
 };
 
@@ -98,6 +99,7 @@ int build_index(const HostGraph &g, int metric, int device, hs_index **out) {
   HS_CUDA(cudaGetDeviceProperties(&prop, device));
   ix->sm_count = prop.multiProcessorCount;
   if (const char *hb = std::getenv("HS_HASH_BITS")) ix->hash_bits_override = std::atoi(hb);
+  if (const char *tf = std::getenv("HS_TRAVERSE_FLAGS")) ix->traverse_flags = (uint32_t)std::atoi(tf);
 
   size_t bytes = 0;
   auto fail = [&](int code) {
@@ -232,6 +234,7 @@ int search_device(hs_index *ix, const float *d_queries, size_t nq, size_t k, uin
   p.work_counter = ix->d_work;
   p.stats = ix->d_stats;
   p.per_query = d_perq;
+  p.flags = ix->traverse_flags;
   TraverseLaunch l{};
   int rc = plan_traverse(p, ix->info.metric, ix->hash_bits_override, ix->sm_count, (int)nq, &l);
   if (rc != HS_OK) return rc;

@@ -7,17 +7,20 @@
 //
 // Equivalence with the CPU algorithm (DESIGN.md "Sequential semantics"): the reference
 // keeps a min-heap of candidates and an ef-bounded max-heap of results and tightens
-// lowerBound after every admitted neighbour.  Here both are ONE ascending list of at
-// most ef (distance,id) keys with an "expanded" bit; a hop scores all unvisited
-// neighbours of the closest unexpanded entry at once and merges them.  Keeping the ef
-// smallest of (list U neighbours) is exactly what the neighbour-by-neighbour admission
-// produces, and an entry pushed out of the list can never be expanded by the reference
-// either (its distance exceeds lowerBound from then on), so visited sets, distance
-// counts and results coincide except where two distances tie bit-for-bit.
+// lowerBound after every admitted neighbour.  Here both are ONE pool of at most ef
+// (distance,id) keys with an "expanded" bit; a hop scores all unvisited neighbours of the
+// closest unexpanded entry at once and admits each one iff it beats the pool's current
+// worst entry (which it replaces) — the reference's `top_size < ef || lowerBound > dist`
+// followed by the trim to ef.  An entry pushed out of the pool can never be expanded by
+// the reference either (its distance exceeds lowerBound from then on), so visited sets,
+// distance counts and results coincide except where two distances tie bit-for-bit.
 //
-// Per-warp shared memory: the sorted list, an open-addressing visited hash (replaces the
-// N-entry tag array of visited_list_pool.h), a 32-entry staging area and — for large dim —
-// the query.  Vector rows are read with 128-bit loads, 8 lanes per row (4 rows per warp
+// The pool is UNSORTED and column-distributed: lane l owns entries l, l+32, ... and caches
+// its column's closest-unexpanded and worst keys in registers; the warp-wide best / worst
+// are single REDUX (__reduce_min/max_sync) instructions plus a ballot, so a hop needs no
+// binary search and no shifting.  Per-warp shared memory: the pool, an open-addressing
+// visited hash (replaces the N-entry tag array of visited_list_pool.h), 32 staging ids and
+// — for large dim — the query.  Vector rows are read with 128-bit loads, 8 lanes per row (4 rows per warp
 // instruction), fp32 FMA chains per lane, xor-shuffle reduction 4,2,1.
 #include <cuda_runtime.h>
 
@@ -30,10 +33,10 @@ namespace {
 
 // tuning knobs (see profiles/ for the measurements behind the defaults)
 #ifndef HS_TRAVERSE_MIN_CTAS
-#define HS_TRAVERSE_MIN_CTAS 4     // 128-thread CTAs per SM the register budget must allow
+#define HS_TRAVERSE_MIN_CTAS 6     // 128-thread CTAs per SM the register budget must allow
 #endif
 #ifndef HS_TRAVERSE_U
-#define HS_TRAVERSE_U 2            // x4 rows whose loads are in flight per warp
+#define HS_TRAVERSE_U 1            // x4 rows whose loads are in flight per warp
 #endif
 
 constexpr unsigned FULL = 0xffffffffu;
@@ -61,7 +64,6 @@ __device__ __forceinline__ uint64_t warp_min_u64(uint64_t v) {
   }
   return v;
 }
-__device__ __forceinline__ int warp_min_i32(int v) { return __reduce_min_sync(FULL, v); }
 
 template <int METRIC>
 __device__ __forceinline__ float acc4(float acc, const float4 q, const float4 x) {
@@ -184,60 +186,109 @@ __device__ __forceinline__ void hash_clear(uint32_t *hash, uint32_t hsize, int l
 __device__ __forceinline__ void prefetch_l2(const void *p) {
   asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }
+// one instruction pulls a whole vector row (bytes % 16 == 0) into L2; no registers are held
+__device__ __forceinline__ void prefetch_row_l2(const void *p, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+constexpr uint64_t NONE = ~0ull;
 
-// Merge up to 32 scored neighbours (one per lane, `valid`) into the ascending list.
-// Equivalent to admitting them one by one with `top_size < ef || lowerBound > dist`
-// and trimming to ef after each (slim.h:403-452).  Returns the smallest insert position
-// (or INT_MAX) and sets *admitted for lanes whose candidate entered the list.
-__device__ __forceinline__ int list_merge(uint64_t *list, uint32_t &size, uint32_t ef, bool valid,
-                                          uint64_t key, uint64_t *stage_key, uint32_t *stage_pos,
-                                          int lane, bool *admitted) {
-  *admitted = false;
-  const uint64_t worst = (size == ef) ? (list[size - 1] & KEYMASK) : ~0ull;
-  const bool adm = valid && key < worst;
-  const unsigned m = __ballot_sync(FULL, adm);
-  if (m == 0) return 0x7fffffff;
-  const int n_adm = __popc(m);
-  int pos = 0;
-  if (adm) {   // number of list entries below key
-    int lo = 0, hi = (int)size;
-    while (lo < hi) {
-      const int mid = (lo + hi) >> 1;
-      if ((list[mid] & KEYMASK) < key) lo = mid + 1; else hi = mid;
+// per-lane summary of the pool column this lane owns (entries lane, lane+32, ...)
+struct ColStat {
+  uint64_t min_un;    // smallest key among unexpanded entries, NONE if there is none
+  uint64_t max_all;   // largest key in the column, 0 if the column is empty
+  uint32_t min_e, max_e;   // their pool indices
+};
+
+__device__ __forceinline__ void col_rescan(const uint64_t *pool, uint32_t size, int lane, ColStat &cs) {
+  cs.min_un = NONE;
+  cs.max_all = 0;
+  cs.min_e = cs.max_e = 0;
+  for (uint32_t e = lane; e < size; e += 32) {
+    const uint64_t k = pool[e];
+    const uint64_t km = k & KEYMASK;
+    if (!((uint32_t)k & FLAG) && km < cs.min_un) {
+      cs.min_un = km;
+      cs.min_e = e;
     }
-    pos = lo;
-    const int slot = __popc(m & ((1u << lane) - 1));
-    stage_key[slot] = key;
-    stage_pos[slot] = (uint32_t)pos;
+    if (km >= cs.max_all) {
+      cs.max_all = km;
+      cs.max_e = e;
+    }
   }
-  __syncwarp();
-  int rank = 0;
-  if (adm)
-    for (int i = 0; i < n_adm; ++i) rank += stage_key[i] < key;
-  const int fp = pos + rank;
-  const int pmin = warp_min_i32(adm ? pos : 0x7fffffff);
-  // shift the tail [pmin, size) up, highest 32-block first so the move is safe in place
-  if (size > 0 && pmin < (int)size) {
-    for (int blk = (int)((size - 1) & ~31u); blk >= (pmin & ~31); blk -= 32) {
-      const int t = blk + lane;
-      const bool have = t < (int)size && t >= pmin;
-      uint64_t e = 0;
-      int s = 0;
-      if (have) {
-        e = list[t];
-        for (int i = 0; i < n_adm; ++i) s += (int)stage_pos[i] <= t;
+}
+
+// lane holding the warp-wide smallest `key` ((dist,id) order; NONE = no entry); -1 if none
+__device__ __forceinline__ int warp_argmin_key(uint64_t key) {
+  const uint32_t hi = (uint32_t)(key >> 32);
+  const uint32_t ghi = __reduce_min_sync(FULL, hi);
+  if (ghi == 0xffffffffu) return -1;
+  unsigned b = __ballot_sync(FULL, hi == ghi);
+  if (b & (b - 1)) {   // equal distances in several lanes: smaller id first
+    const uint32_t lo = hi == ghi ? (uint32_t)key : 0xffffffffu;
+    const uint32_t glo = __reduce_min_sync(FULL, lo);
+    b = __ballot_sync(FULL, hi == ghi && lo == glo);
+  }
+  return __ffs(b) - 1;
+}
+// lane holding the warp-wide largest `key` (0 = no entry)
+__device__ __forceinline__ int warp_argmax_key(uint64_t key) {
+  const uint32_t hi = (uint32_t)(key >> 32);
+  const uint32_t ghi = __reduce_max_sync(FULL, hi);
+  unsigned b = __ballot_sync(FULL, hi == ghi);
+  if (b & (b - 1)) {
+    const uint32_t lo = hi == ghi ? (uint32_t)key : 0u;
+    const uint32_t glo = __reduce_max_sync(FULL, lo);
+    b = __ballot_sync(FULL, hi == ghi && lo == glo);
+  }
+  return __ffs(b) - 1;
+}
+
+// Admit up to 32 scored neighbours (one per lane, `valid`) into the pool: each enters iff the
+// pool is not full or it beats the current worst entry, which it then replaces — exactly
+// `top_size < ef || lowerBound > dist` + trim (slim.h:403-452), candidate by candidate.
+// Returns the ballot of lanes whose candidate entered (it may be displaced again later).
+__device__ __forceinline__ unsigned pool_admit(uint64_t *pool, uint32_t &size, uint32_t ef, bool valid,
+                                               uint64_t key, ColStat &cs, int lane) {
+  unsigned entered = 0;
+  const unsigned vmask = __ballot_sync(FULL, valid);
+  if (vmask == 0) return 0;
+  const uint32_t n_valid = (uint32_t)__popc(vmask);
+  unsigned todo = vmask;
+  if (size < ef) {
+    // room left: the first (ef - size) candidates are appended unconditionally
+    const uint32_t room = ef - size;
+    const uint32_t rank = (uint32_t)__popc(vmask & ((1u << lane) - 1));
+    const bool app = valid && rank < room;
+    if (app) pool[size + rank] = key;
+    const unsigned am = __ballot_sync(FULL, app);
+    entered |= am;
+    todo &= ~am;
+    size += min(room, n_valid);
+    __syncwarp();
+    col_rescan(pool, size, lane, cs);
+    if (todo == 0) return entered;
+  }
+  // pool full: pre-filter against the current worst (it only gets smaller), then one by one
+  int owner = warp_argmax_key(cs.max_all);
+  uint64_t worst = __shfl_sync(FULL, cs.max_all, owner);
+  todo &= __ballot_sync(FULL, valid && key < worst);
+  while (todo) {
+    const int src = __ffs(todo) - 1;
+    todo &= todo - 1;
+    const uint64_t ck = __shfl_sync(FULL, key, src);
+    if (ck < worst) {
+      if (lane == owner) {
+        pool[cs.max_e] = ck;
+        col_rescan(pool, size, lane, cs);
       }
-      __syncwarp();
-      if (have && t + s < (int)ef) list[t + s] = e;
-      __syncwarp();
+      entered |= 1u << src;
+      if (todo) {
+        owner = warp_argmax_key(cs.max_all);
+        worst = __shfl_sync(FULL, cs.max_all, owner);
+      }
     }
   }
-  const bool in = adm && fp < (int)ef;
-  if (in) list[fp] = key;
-  __syncwarp();
-  size = min(ef, size + (uint32_t)n_adm);
-  *admitted = in;
-  return warp_min_i32(in ? fp : 0x7fffffff);
+  return entered;
 }
 
 template <int CPL, int METRIC>
@@ -246,11 +297,9 @@ __global__ void __launch_bounds__(128, HS_TRAVERSE_MIN_CTAS) traverse_kernel(con
   const int lane = threadIdx.x & 31;
   const int wid = threadIdx.x >> 5;
   unsigned char *wbase = smem + (size_t)wid * p.smem_per_warp;
-  uint64_t *list = reinterpret_cast<uint64_t *>(wbase);
+  uint64_t *pool = reinterpret_cast<uint64_t *>(wbase);
   uint32_t *hash = reinterpret_cast<uint32_t *>(wbase + p.off_hash);
-  uint64_t *stage_key = reinterpret_cast<uint64_t *>(wbase + p.off_stage);
-  uint32_t *stage_pos = reinterpret_cast<uint32_t *>(wbase + p.off_stage + 32 * 8);
-  uint32_t *stage_ids = stage_pos + 32;
+  uint32_t *stage_ids = reinterpret_cast<uint32_t *>(wbase + p.off_stage);
   float4 *qs = reinterpret_cast<float4 *>(wbase + p.off_query);
 
   const uint32_t hbits = p.hash_bits, hsize = 1u << hbits, hmask = hsize - 1;
@@ -338,55 +387,51 @@ __global__ void __launch_bounds__(128, HS_TRAVERSE_MIN_CTAS) traverse_kernel(con
     }
 
     // ---- seed, slim.h:2100-2106 ----
-    uint32_t size = 1, curpos = 0, hcount = 1;
+    uint32_t size = 1, hcount = 1;
+    ColStat cs;
     if (lane == 0) {
-      list[0] = make_key(curdist, cur);
+      pool[0] = make_key(curdist, cur);
       visited_test_and_set(hash, hbits, hmask, cur);
     }
     __syncwarp();
+    col_rescan(pool, size, lane, cs);
 
     // ---- base layer, slim.h:321-457 ----
+    const uint32_t row_bytes = p.row_chunks * 16u;
+    const bool opt_prefetch = p.flags & 1u;
     for (;;) {
-      bool found = false;
-      while (curpos < size) {
-        const uint32_t t = curpos + lane;
-        const bool un = t < size && !((uint32_t)list[t] & FLAG);
-        const unsigned um = __ballot_sync(FULL, un);
-        if (um) {
-          curpos += __ffs(um) - 1;
-          found = true;
-          break;
-        }
-        curpos += 32;
+      // closest unexpanded entry (the reference pops its candidate min-heap, slim.h:335-354)
+      const int bo = warp_argmin_key(cs.min_un);
+      if (bo < 0) break;
+      const uint32_t node = (uint32_t)__shfl_sync(FULL, (uint32_t)cs.min_un, bo);
+      if (lane == bo) {
+        pool[cs.min_e] |= (uint64_t)FLAG;
+        col_rescan(pool, size, lane, cs);
       }
-      if (!found) break;
-      const uint64_t e = list[curpos];
-      const uint32_t node = (uint32_t)e;
-      __syncwarp();
-      if (lane == 0) list[curpos] = e | FLAG;
-      curpos++;
+      const uint32_t *row = p.adj0 + (size_t)node * p.deg0_stride;
+      uint32_t id = __ldg(row + lane);
 
       if (hcount + p.deg0_stride > hlimit) {
-        // visited hash nearly full: keep only the list entries (results are unchanged:
-        // a node scored before was rejected or evicted and will be again)
+        // visited hash nearly full: keep only the pool entries (results are unchanged:
+        // a node scored before was rejected or displaced and will be again)
         __syncwarp();
         hash_clear(hash, hsize, lane);
         __syncwarp();
         for (uint32_t t = lane; t < size; t += 32)
-          visited_test_and_set(hash, hbits, hmask, (uint32_t)list[t] & ~FLAG);
+          visited_test_and_set(hash, hbits, hmask, (uint32_t)pool[t] & ~FLAG);
         hcount = size;
+        __syncwarp();
       }
-      __syncwarp();
 
-      const uint32_t *row = p.adj0 + (size_t)node * p.deg0_stride;
       bool any = false;
       for (uint32_t seg = 0; seg < p.deg0_stride; seg += 32) {
-        const uint32_t id = __ldg(row + seg + lane);
+        if (seg) id = __ldg(row + seg + lane);
         const unsigned vm = __ballot_sync(FULL, id != kInvalid);
         if (vm == 0) break;
         any = true;
         bool fresh = false;
         if (id != kInvalid) fresh = !visited_test_and_set(hash, hbits, hmask, id);
+        if (fresh && opt_prefetch) prefetch_row_l2(p.vec + (size_t)id * p.row_chunks, row_bytes);
         const unsigned fm = __ballot_sync(FULL, fresh);
         const int count = __popc(fm);
         if (count == 0) continue;
@@ -394,29 +439,41 @@ __global__ void __launch_bounds__(128, HS_TRAVERSE_MIN_CTAS) traverse_kernel(con
         if (fresh) stage_ids[__popc(fm & ((1u << lane) - 1))] = id;
         __syncwarp();
         const uint32_t cid = lane < count ? stage_ids[lane] : 0u;
+        __syncwarp();
         const float d = eval(cid, count);
         nd += (uint32_t)count;
-        bool admitted;
-        const int minfp = list_merge(list, size, ef, lane < count, make_key(d, cid), stage_key,
-                                     stage_pos, lane, &admitted);
-        if (admitted) prefetch_l2(p.adj0 + (size_t)cid * p.deg0_stride);
-        if (minfp < (int)curpos) curpos = (uint32_t)minfp;
+        const unsigned entered = pool_admit(pool, size, ef, lane < count, make_key(d, cid), cs, lane);
+        if ((entered >> lane) & 1u) prefetch_l2(p.adj0 + (size_t)cid * p.deg0_stride);
       }
       if (any) nh++;
     }
 
     // ---- results: the k closest, ascending (the reference nth_element's the same set,
-    //      slim.h:2126-2130) ----
-    for (uint32_t i = lane; i < p.k; i += 32) {
-      uint32_t lab = 0xFFFFFFFFu;
-      float d = __int_as_float(0x7f800000);
-      if (i < size) {
-        const uint64_t e = list[i];
-        lab = __ldg(p.labels + ((uint32_t)e & ~FLAG));
-        d = ord2f((uint32_t)(e >> 32));
+    //      slim.h:2126-2130): k rounds of warp-wide extract-min over the pool ----
+    __syncwarp();
+    {
+      uint64_t last = 0;   // every key is > 0 (f2ord(+0.0f) has the top bit set)
+      for (uint32_t i = 0; i < p.k; ++i) {
+        uint64_t mine = NONE;
+        for (uint32_t e = lane; e < size; e += 32) {
+          const uint64_t km = pool[e] & KEYMASK;
+          if (km > last && km < mine) mine = km;
+        }
+        const int o = warp_argmin_key(mine);
+        uint32_t lab = 0xFFFFFFFFu;
+        float d = __int_as_float(0x7f800000);
+        if (o >= 0) {
+          last = __shfl_sync(FULL, mine, o);
+          lab = (uint32_t)last;
+          d = ord2f((uint32_t)(last >> 32));
+        } else {
+          last = NONE;
+        }
+        if (lane == 0) {
+          p.out_labels[(size_t)qi * p.k + i] = o >= 0 ? __ldg(p.labels + lab) : 0xFFFFFFFFu;
+          if (p.out_dists) p.out_dists[(size_t)qi * p.k + i] = d;
+        }
       }
-      p.out_labels[(size_t)qi * p.k + i] = lab;
-      if (p.out_dists) p.out_dists[(size_t)qi * p.k + i] = d;
     }
     if (lane == 0) {
       atomicAdd(p.stats + 0, (unsigned long long)nd);
@@ -495,7 +552,7 @@ int plan_traverse(TraverseParams &p, int metric, int hash_bits_override, int sm_
   p.hash_bits = bits;
   const uint32_t list_bytes = align_up(p.ef * 8u, 16);
   const uint32_t hash_bytes = 4u << bits;
-  const uint32_t stage_bytes = 32 * 8 + 32 * 4 + 32 * 4;
+  const uint32_t stage_bytes = 32 * 4;
   const bool generic = (p.row_chunks / kTeam) > 4 || (p.row_chunks / kTeam) == 0;
   const uint32_t query_bytes = generic ? p.row_chunks * 16u : 0u;
   p.off_hash = list_bytes;

@@ -29,6 +29,7 @@ struct TraverseParams {
   uint32_t *per_query;                     // optional nq x 2 (n_dist, n_hops) or null
   // shared-memory carve-up per warp (bytes)
   uint32_t hash_bits, smem_per_warp, off_hash, off_stage, off_query;
+  uint32_t flags;                          // bit0: L2 row prefetch, bit1: speculative next-hop prefetch
 };
 
 struct TraverseLaunch {
