@@ -25,6 +25,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <type_traits>
 
 #include "traverse_fp32.cuh"
 
@@ -186,36 +187,7 @@ __device__ __forceinline__ void hash_clear(uint32_t *hash, uint32_t hsize, int l
 __device__ __forceinline__ void prefetch_l2(const void *p) {
   asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }
-// one instruction pulls a whole vector row (bytes % 16 == 0) into L2; no registers are held
-__device__ __forceinline__ void prefetch_row_l2(const void *p, uint32_t bytes) {
-  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
-}
 constexpr uint64_t NONE = ~0ull;
-
-// per-lane summary of the pool column this lane owns (entries lane, lane+32, ...)
-struct ColStat {
-  uint64_t min_un;    // smallest key among unexpanded entries, NONE if there is none
-  uint64_t max_all;   // largest key in the column, 0 if the column is empty
-  uint32_t min_e, max_e;   // their pool indices
-};
-
-__device__ __forceinline__ void col_rescan(const uint64_t *pool, uint32_t size, int lane, ColStat &cs) {
-  cs.min_un = NONE;
-  cs.max_all = 0;
-  cs.min_e = cs.max_e = 0;
-  for (uint32_t e = lane; e < size; e += 32) {
-    const uint64_t k = pool[e];
-    const uint64_t km = k & KEYMASK;
-    if (!((uint32_t)k & FLAG) && km < cs.min_un) {
-      cs.min_un = km;
-      cs.min_e = e;
-    }
-    if (km >= cs.max_all) {
-      cs.max_all = km;
-      cs.max_e = e;
-    }
-  }
-}
 
 // lane holding the warp-wide smallest `key` ((dist,id) order; NONE = no entry); -1 if none
 __device__ __forceinline__ int warp_argmin_key(uint64_t key) {
@@ -243,61 +215,256 @@ __device__ __forceinline__ int warp_argmax_key(uint64_t key) {
   return __ffs(b) - 1;
 }
 
-// Admit up to 32 scored neighbours (one per lane, `valid`) into the pool: each enters iff the
-// pool is not full or it beats the current worst entry, which it then replaces — exactly
-// `top_size < ef || lowerBound > dist` + trim (slim.h:403-452), candidate by candidate.
-// Returns the ballot of lanes whose candidate entered (it may be displaced again later).
-__device__ __forceinline__ unsigned pool_admit(uint64_t *pool, uint32_t &size, uint32_t ef, bool valid,
-                                               uint64_t key, ColStat &cs, int lane) {
-  unsigned entered = 0;
-  const unsigned vmask = __ballot_sync(FULL, valid);
-  if (vmask == 0) return 0;
-  const uint32_t n_valid = (uint32_t)__popc(vmask);
-  unsigned todo = vmask;
-  if (size < ef) {
-    // room left: the first (ef - size) candidates are appended unconditionally
-    const uint32_t room = ef - size;
-    const uint32_t rank = (uint32_t)__popc(vmask & ((1u << lane) - 1));
-    const bool app = valid && rank < room;
-    if (app) pool[size + rank] = key;
-    const unsigned am = __ballot_sync(FULL, app);
-    entered |= am;
-    todo &= ~am;
-    size += min(room, n_valid);
-    __syncwarp();
-    col_rescan(pool, size, lane, cs);
-    if (todo == 0) return entered;
+// The candidate/result pool: at most ef keys, unsorted, column-distributed (entry e lives in
+// lane e % 32).  Two storages with one interface:
+//   RegPool<SLOTS>  ef <= 32*SLOTS: the column sits in registers; column min/max are a few
+//                   compare-selects recomputed on demand by all lanes at once
+//   SmemPool        any ef: the column sits in shared memory, with cached column statistics
+// Interface: seed(), pop_closest_unexpanded(), admit(), for_each_id(), kth().
+template <int SLOTS>
+struct RegPool {
+  uint64_t k[SLOTS];     // empty slots hold NONE (flag set => never "unexpanded", and skipped for max)
+  uint32_t size, ef;
+  int lane;
+
+  __device__ __forceinline__ void init(uint64_t *, uint32_t ef_, int lane_) {
+    ef = ef_;
+    lane = lane_;
+    size = 0;
+#pragma unroll
+    for (int s = 0; s < SLOTS; ++s) k[s] = NONE;
   }
-  // pool full: pre-filter against the current worst (it only gets smaller), then one by one
-  int owner = warp_argmax_key(cs.max_all);
-  uint64_t worst = __shfl_sync(FULL, cs.max_all, owner);
-  todo &= __ballot_sync(FULL, valid && key < worst);
-  while (todo) {
-    const int src = __ffs(todo) - 1;
-    todo &= todo - 1;
-    const uint64_t ck = __shfl_sync(FULL, key, src);
-    if (ck < worst) {
-      if (lane == owner) {
-        pool[cs.max_e] = ck;
-        col_rescan(pool, size, lane, cs);
+  __device__ __forceinline__ void put(uint32_t e, uint64_t key) {   // called by the owner lane only
+#pragma unroll
+    for (int s = 0; s < SLOTS; ++s) k[s] = ((int)(e >> 5) == s) ? key : k[s];   // select, not k[e>>5] = ..: keeps k in registers
+  }
+  __device__ __forceinline__ void seed(uint64_t key) {
+    if (lane == 0) k[0] = key;
+    size = 1;
+  }
+  __device__ __forceinline__ uint64_t col_min_un(int &slot) const {
+    uint64_t m = NONE;
+    slot = 0;
+#pragma unroll
+    for (int s = 0; s < SLOTS; ++s) {
+      const bool un = !((uint32_t)k[s] & FLAG);
+      if (un && k[s] < m) {
+        m = k[s];
+        slot = s;
       }
-      entered |= 1u << src;
-      if (todo) {
-        owner = warp_argmax_key(cs.max_all);
-        worst = __shfl_sync(FULL, cs.max_all, owner);
+    }
+    return m;
+  }
+  __device__ __forceinline__ uint64_t col_max(int &slot) const {
+    uint64_t m = 0;
+    slot = 0;
+#pragma unroll
+    for (int s = 0; s < SLOTS; ++s) {
+      const uint64_t km = k[s] & KEYMASK;
+      const bool used = (uint32_t)(s * 32 + lane) < size;
+      if (used && km >= m) {
+        m = km;
+        slot = s;
+      }
+    }
+    return m;
+  }
+  // closest unexpanded entry: marks it expanded and returns its node id, kInvalid if none
+  __device__ __forceinline__ uint32_t pop_closest_unexpanded() {
+    int slot;
+    const uint64_t m = col_min_un(slot);
+    const int o = warp_argmin_key(m);
+    if (o < 0) return kInvalid;
+    if (lane == o) {
+#pragma unroll
+      for (int s = 0; s < SLOTS; ++s) k[s] = (s == slot) ? (k[s] | (uint64_t)FLAG) : k[s];
+    }
+    return (uint32_t)__shfl_sync(FULL, (uint32_t)m, o);
+  }
+  // admit scored neighbours, one per lane; returns the ballot of lanes whose key entered
+  __device__ __forceinline__ unsigned admit(bool valid, uint64_t key) {
+    unsigned entered = 0;
+    const unsigned vmask = __ballot_sync(FULL, valid);
+    if (vmask == 0) return 0;
+    unsigned todo = vmask;
+    if (size < ef) {   // room left: the first (ef - size) candidates are appended unconditionally
+      const uint32_t room = ef - size;
+      const uint32_t n_app = min(room, (uint32_t)__popc(vmask));
+      for (uint32_t j = 0; j < n_app; ++j) {
+        const int src = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const uint64_t ck = __shfl_sync(FULL, key, src);
+        const uint32_t e = size + j;
+        if ((int)(e & 31) == lane) put(e, ck);
+        entered |= 1u << src;
+      }
+      size += n_app;
+      if (todo == 0) return entered;
+    }
+    int slot;
+    uint64_t cm = col_max(slot);
+    int owner = warp_argmax_key(cm);
+    uint64_t worst = __shfl_sync(FULL, cm, owner);
+    todo &= __ballot_sync(FULL, valid && key < worst);   // the worst only gets smaller
+    while (todo) {
+      const int src = __ffs(todo) - 1;
+      todo &= todo - 1;
+      const uint64_t ck = __shfl_sync(FULL, key, src);
+      if (ck < worst) {
+        if (lane == owner) {
+#pragma unroll
+          for (int s = 0; s < SLOTS; ++s) k[s] = (s == slot) ? ck : k[s];
+        }
+        entered |= 1u << src;
+        if (todo) {
+          cm = col_max(slot);
+          owner = warp_argmax_key(cm);
+          worst = __shfl_sync(FULL, cm, owner);
+        }
+      }
+    }
+    return entered;
+  }
+  template <typename F>
+  __device__ __forceinline__ void for_each_id(F &&f) const {
+#pragma unroll
+    for (int s = 0; s < SLOTS; ++s)
+      if ((uint32_t)(s * 32 + lane) < size) f((uint32_t)k[s] & ~FLAG);
+  }
+  // smallest key strictly above `last` in this lane's column (NONE if none)
+  __device__ __forceinline__ uint64_t col_next_above(uint64_t last) const {
+    uint64_t m = NONE;
+#pragma unroll
+    for (int s = 0; s < SLOTS; ++s) {
+      const uint64_t km = k[s] & KEYMASK;
+      if ((uint32_t)(s * 32 + lane) < size && km > last && km < m) m = km;
+    }
+    return m;
+  }
+};
+
+struct SmemPool {
+  uint64_t *pool;
+  uint32_t size, ef;
+  int lane;
+  uint64_t min_un, max_all;    // cached column statistics
+  uint32_t min_e, max_e;
+
+  __device__ __forceinline__ void init(uint64_t *mem, uint32_t ef_, int lane_) {
+    pool = mem;
+    ef = ef_;
+    lane = lane_;
+    size = 0;
+  }
+  __device__ __forceinline__ void rescan_min() {
+    min_un = NONE;
+    min_e = 0;
+    for (uint32_t e = lane; e < size; e += 32) {
+      const uint64_t k = pool[e];
+      if (!((uint32_t)k & FLAG) && k < min_un) {
+        min_un = k;
+        min_e = e;
       }
     }
   }
-  return entered;
-}
+  __device__ __forceinline__ void rescan_max() {
+    max_all = 0;
+    max_e = 0;
+    for (uint32_t e = lane; e < size; e += 32) {
+      const uint64_t km = pool[e] & KEYMASK;
+      if (km >= max_all) {
+        max_all = km;
+        max_e = e;
+      }
+    }
+  }
+  __device__ __forceinline__ void seed(uint64_t key) {
+    if (lane == 0) pool[0] = key;
+    size = 1;
+    __syncwarp();
+    rescan_min();
+    rescan_max();
+  }
+  __device__ __forceinline__ uint32_t pop_closest_unexpanded() {
+    const int o = warp_argmin_key(min_un);
+    if (o < 0) return kInvalid;
+    const uint32_t node = (uint32_t)__shfl_sync(FULL, (uint32_t)min_un, o);
+    if (lane == o) {
+      pool[min_e] |= (uint64_t)FLAG;
+      rescan_min();
+    }
+    return node;
+  }
+  __device__ __forceinline__ unsigned admit(bool valid, uint64_t key) {
+    unsigned entered = 0;
+    const unsigned vmask = __ballot_sync(FULL, valid);
+    if (vmask == 0) return 0;
+    unsigned todo = vmask;
+    if (size < ef) {
+      const uint32_t room = ef - size;
+      const uint32_t rank = (uint32_t)__popc(vmask & ((1u << lane) - 1));
+      const bool app = valid && rank < room;
+      if (app) pool[size + rank] = key;
+      const unsigned am = __ballot_sync(FULL, app);
+      entered |= am;
+      todo &= ~am;
+      size += min(room, (uint32_t)__popc(vmask));
+      __syncwarp();
+      rescan_min();
+      rescan_max();
+      if (todo == 0) return entered;
+    }
+    int owner = warp_argmax_key(max_all);
+    uint64_t worst = __shfl_sync(FULL, max_all, owner);
+    todo &= __ballot_sync(FULL, valid && key < worst);
+    while (todo) {
+      const int src = __ffs(todo) - 1;
+      todo &= todo - 1;
+      const uint64_t ck = __shfl_sync(FULL, key, src);
+      if (ck < worst) {
+        if (lane == owner) {
+          const bool was_min = max_e == min_e && min_un != NONE;
+          pool[max_e] = ck;
+          if (was_min) {
+            rescan_min();            // the displaced entry was this column's closest unexpanded
+          } else if (ck < min_un) {
+            min_un = ck;
+            min_e = max_e;
+          }
+          rescan_max();
+        }
+        entered |= 1u << src;
+        if (todo) {
+          owner = warp_argmax_key(max_all);
+          worst = __shfl_sync(FULL, max_all, owner);
+        }
+      }
+    }
+    return entered;
+  }
+  template <typename F>
+  __device__ __forceinline__ void for_each_id(F &&f) const {
+    for (uint32_t e = lane; e < size; e += 32) f((uint32_t)pool[e] & ~FLAG);
+  }
+  __device__ __forceinline__ uint64_t col_next_above(uint64_t last) const {
+    uint64_t m = NONE;
+    for (uint32_t e = lane; e < size; e += 32) {
+      const uint64_t km = pool[e] & KEYMASK;
+      if (km > last && km < m) m = km;
+    }
+    return m;
+  }
+};
 
-template <int CPL, int METRIC>
+template <int SLOTS> struct PoolSel { using type = RegPool<SLOTS>; };
+template <> struct PoolSel<0> { using type = SmemPool; };
+
+template <int CPL, int METRIC, int SLOTS>
 __global__ void __launch_bounds__(128, HS_TRAVERSE_MIN_CTAS) traverse_kernel(const __grid_constant__ TraverseParams p) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int lane = threadIdx.x & 31;
   const int wid = threadIdx.x >> 5;
   unsigned char *wbase = smem + (size_t)wid * p.smem_per_warp;
-  uint64_t *pool = reinterpret_cast<uint64_t *>(wbase);
   uint32_t *hash = reinterpret_cast<uint32_t *>(wbase + p.off_hash);
   uint32_t *stage_ids = reinterpret_cast<uint32_t *>(wbase + p.off_stage);
   float4 *qs = reinterpret_cast<float4 *>(wbase + p.off_query);
@@ -387,27 +554,19 @@ __global__ void __launch_bounds__(128, HS_TRAVERSE_MIN_CTAS) traverse_kernel(con
     }
 
     // ---- seed, slim.h:2100-2106 ----
-    uint32_t size = 1, hcount = 1;
-    ColStat cs;
-    if (lane == 0) {
-      pool[0] = make_key(curdist, cur);
-      visited_test_and_set(hash, hbits, hmask, cur);
-    }
+    uint32_t hcount = 1;
+    typename PoolSel<SLOTS>::type pool;
+    pool.init(reinterpret_cast<uint64_t *>(wbase), ef, lane);
+    pool.seed(make_key(curdist, cur));
+    if (lane == 0) visited_test_and_set(hash, hbits, hmask, cur);
     __syncwarp();
-    col_rescan(pool, size, lane, cs);
 
     // ---- base layer, slim.h:321-457 ----
-    const uint32_t row_bytes = p.row_chunks * 16u;
     const bool opt_prefetch = p.flags & 1u;
     for (;;) {
       // closest unexpanded entry (the reference pops its candidate min-heap, slim.h:335-354)
-      const int bo = warp_argmin_key(cs.min_un);
-      if (bo < 0) break;
-      const uint32_t node = (uint32_t)__shfl_sync(FULL, (uint32_t)cs.min_un, bo);
-      if (lane == bo) {
-        pool[cs.min_e] |= (uint64_t)FLAG;
-        col_rescan(pool, size, lane, cs);
-      }
+      const uint32_t node = pool.pop_closest_unexpanded();
+      if (node == kInvalid) break;
       const uint32_t *row = p.adj0 + (size_t)node * p.deg0_stride;
       uint32_t id = __ldg(row + lane);
 
@@ -417,9 +576,8 @@ __global__ void __launch_bounds__(128, HS_TRAVERSE_MIN_CTAS) traverse_kernel(con
         __syncwarp();
         hash_clear(hash, hsize, lane);
         __syncwarp();
-        for (uint32_t t = lane; t < size; t += 32)
-          visited_test_and_set(hash, hbits, hmask, (uint32_t)pool[t] & ~FLAG);
-        hcount = size;
+        pool.for_each_id([&](uint32_t pid) { visited_test_and_set(hash, hbits, hmask, pid); });
+        hcount = pool.size;
         __syncwarp();
       }
 
@@ -431,7 +589,11 @@ __global__ void __launch_bounds__(128, HS_TRAVERSE_MIN_CTAS) traverse_kernel(con
         any = true;
         bool fresh = false;
         if (id != kInvalid) fresh = !visited_test_and_set(hash, hbits, hmask, id);
-        if (fresh && opt_prefetch) prefetch_row_l2(p.vec + (size_t)id * p.row_chunks, row_bytes);
+        if (fresh && opt_prefetch) {
+          // pull the whole row towards L2 now; the scoring loop below then mostly waits on L2
+          const char *r = reinterpret_cast<const char *>(p.vec + (size_t)id * p.row_chunks);
+          for (uint32_t off = 0; off < p.row_chunks * 16u; off += 128) prefetch_l2(r + off);
+        }
         const unsigned fm = __ballot_sync(FULL, fresh);
         const int count = __popc(fm);
         if (count == 0) continue;
@@ -442,7 +604,7 @@ __global__ void __launch_bounds__(128, HS_TRAVERSE_MIN_CTAS) traverse_kernel(con
         __syncwarp();
         const float d = eval(cid, count);
         nd += (uint32_t)count;
-        const unsigned entered = pool_admit(pool, size, ef, lane < count, make_key(d, cid), cs, lane);
+        const unsigned entered = pool.admit(lane < count, make_key(d, cid));
         if ((entered >> lane) & 1u) prefetch_l2(p.adj0 + (size_t)cid * p.deg0_stride);
       }
       if (any) nh++;
@@ -454,24 +616,13 @@ __global__ void __launch_bounds__(128, HS_TRAVERSE_MIN_CTAS) traverse_kernel(con
     {
       uint64_t last = 0;   // every key is > 0 (f2ord(+0.0f) has the top bit set)
       for (uint32_t i = 0; i < p.k; ++i) {
-        uint64_t mine = NONE;
-        for (uint32_t e = lane; e < size; e += 32) {
-          const uint64_t km = pool[e] & KEYMASK;
-          if (km > last && km < mine) mine = km;
-        }
+        const uint64_t mine = last == NONE ? NONE : pool.col_next_above(last);
         const int o = warp_argmin_key(mine);
-        uint32_t lab = 0xFFFFFFFFu;
-        float d = __int_as_float(0x7f800000);
-        if (o >= 0) {
-          last = __shfl_sync(FULL, mine, o);
-          lab = (uint32_t)last;
-          d = ord2f((uint32_t)(last >> 32));
-        } else {
-          last = NONE;
-        }
+        last = o >= 0 ? __shfl_sync(FULL, mine, o) : NONE;
         if (lane == 0) {
-          p.out_labels[(size_t)qi * p.k + i] = o >= 0 ? __ldg(p.labels + lab) : 0xFFFFFFFFu;
-          if (p.out_dists) p.out_dists[(size_t)qi * p.k + i] = d;
+          p.out_labels[(size_t)qi * p.k + i] = o >= 0 ? __ldg(p.labels + (uint32_t)last) : 0xFFFFFFFFu;
+          if (p.out_dists)
+            p.out_dists[(size_t)qi * p.k + i] = o >= 0 ? ord2f((uint32_t)(last >> 32)) : __int_as_float(0x7f800000);
         }
       }
     }
@@ -487,9 +638,9 @@ __global__ void __launch_bounds__(128, HS_TRAVERSE_MIN_CTAS) traverse_kernel(con
   }
 }
 
-template <int CPL, int METRIC>
+template <int CPL, int METRIC, int SLOTS>
 int launch_t(const TraverseParams &p, const TraverseLaunch &l, cudaStream_t stream) {
-  auto kern = traverse_kernel<CPL, METRIC>;
+  auto kern = traverse_kernel<CPL, METRIC, SLOTS>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)l.smem_bytes);
   if (e != cudaSuccess) {
     set_error(std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
@@ -503,35 +654,36 @@ int launch_t(const TraverseParams &p, const TraverseLaunch &l, cudaStream_t stre
   }
   return HS_OK;
 }
-
-template <int METRIC>
-int launch_m(const TraverseParams &p, const TraverseLaunch &l, cudaStream_t stream) {
-  switch (p.row_chunks / kTeam) {
-    case 1: return launch_t<1, METRIC>(p, l, stream);
-    case 2: return launch_t<2, METRIC>(p, l, stream);
-    case 3: return launch_t<3, METRIC>(p, l, stream);   // dim 96  (DEEP / MSTuring)
-    case 4: return launch_t<4, METRIC>(p, l, stream);   // dim 128 (SIFT)
-    default: return launch_t<0, METRIC>(p, l, stream);  // dim 768 / 960 / anything else
-  }
-}
-
-template <int CPL, int METRIC>
+template <int CPL, int METRIC, int SLOTS>
 int occupancy_t(int threads, size_t smem) {
-  auto kern = traverse_kernel<CPL, METRIC>;
+  auto kern = traverse_kernel<CPL, METRIC, SLOTS>;
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   int nb = 0;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, threads, smem) != cudaSuccess) nb = 0;
   return nb;
 }
-template <int METRIC>
-int occupancy_m(uint32_t cpl, int threads, size_t smem) {
-  switch (cpl) {
-    case 1: return occupancy_t<1, METRIC>(threads, smem);
-    case 2: return occupancy_t<2, METRIC>(threads, smem);
-    case 3: return occupancy_t<3, METRIC>(threads, smem);
-    case 4: return occupancy_t<4, METRIC>(threads, smem);
-    default: return occupancy_t<0, METRIC>(threads, smem);
-  }
+
+// kernel variants: CPL 3 (dim 96: DEEP/MSTuring), 4 (dim 128: SIFT) keep the query in
+// registers, everything else runs the generic shared-memory-query path (CPL = 0);
+// pool in registers for ef <= 64 / <= 128, in shared memory above.
+inline int cpl_variant(uint32_t row_chunks) {
+  const uint32_t cpl = row_chunks / kTeam;
+  return (cpl == 3 || cpl == 4) ? (int)cpl : 0;
+}
+inline int slots_variant(uint32_t ef) { return ef <= 64 ? 2 : (ef <= 128 ? 4 : 0); }
+
+template <typename F>
+int dispatch(int cpl, int metric, int slots, F &&f) {
+#define HS_CASE(C, M, S) \
+  if (cpl == C && metric == M && slots == S) return f(std::integral_constant<int, C>{}, std::integral_constant<int, M>{}, std::integral_constant<int, S>{});
+#define HS_CASES_S(C, M) HS_CASE(C, M, 0) HS_CASE(C, M, 2) HS_CASE(C, M, 4)
+#define HS_CASES_M(C) HS_CASES_S(C, HS_METRIC_L2) HS_CASES_S(C, HS_METRIC_IP)
+  HS_CASES_M(0) HS_CASES_M(3) HS_CASES_M(4)
+#undef HS_CASES_M
+#undef HS_CASES_S
+#undef HS_CASE
+  set_error("no traversal kernel variant for this configuration");
+  return HS_ERR_UNSUPPORTED;
 }
 
 inline uint32_t align_up(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
@@ -550,10 +702,10 @@ int plan_traverse(TraverseParams &p, int metric, int hash_bits_override, int sm_
   if (bits > 16) bits = 16;
   while ((1u << bits) - (1u << bits) / 4 < p.ef + 2 * p.deg0_stride + 32 && bits < 16) ++bits;
   p.hash_bits = bits;
-  const uint32_t list_bytes = align_up(p.ef * 8u, 16);
+  const uint32_t list_bytes = slots_variant(p.ef) ? 0u : align_up(p.ef * 8u, 16);
   const uint32_t hash_bytes = 4u << bits;
   const uint32_t stage_bytes = 32 * 4;
-  const bool generic = (p.row_chunks / kTeam) > 4 || (p.row_chunks / kTeam) == 0;
+  const bool generic = cpl_variant(p.row_chunks) == 0;
   const uint32_t query_bytes = generic ? p.row_chunks * 16u : 0u;
   p.off_hash = list_bytes;
   p.off_stage = p.off_hash + hash_bytes;
@@ -567,9 +719,12 @@ int plan_traverse(TraverseParams &p, int metric, int hash_bits_override, int sm_
   while (wpc > 1 && (size_t)wpc * p.smem_per_warp > 227u * 1024u / 2) wpc >>= 1;
   out->warps_per_cta = wpc;
   out->smem_bytes = (size_t)wpc * p.smem_per_warp;
-  const uint32_t cpl = p.row_chunks / kTeam;
-  int per_sm = metric == HS_METRIC_IP ? occupancy_m<HS_METRIC_IP>(cpl, wpc * 32, out->smem_bytes)
-                                      : occupancy_m<HS_METRIC_L2>(cpl, wpc * 32, out->smem_bytes);
+  const int cplv = cpl_variant(p.row_chunks), slv = slots_variant(p.ef);
+  const int threads = wpc * 32;
+  const size_t smem = out->smem_bytes;
+  int per_sm = dispatch(cplv, metric == HS_METRIC_IP ? HS_METRIC_IP : HS_METRIC_L2, slv, [&](auto C, auto M, auto S) {
+    return occupancy_t<decltype(C)::value, decltype(M)::value, decltype(S)::value>(threads, smem);
+  });
   if (per_sm <= 0) {
     set_error("traverse_kernel does not fit on an SM (cudaOccupancyMaxActiveBlocksPerMultiprocessor)");
     return HS_ERR_CUDA;
@@ -581,8 +736,10 @@ int plan_traverse(TraverseParams &p, int metric, int hash_bits_override, int sm_
 }
 
 int launch_traverse(const TraverseParams &p, int metric, const TraverseLaunch &l, cudaStream_t stream) {
-  return metric == HS_METRIC_IP ? launch_m<HS_METRIC_IP>(p, l, stream)
-                                : launch_m<HS_METRIC_L2>(p, l, stream);
+  return dispatch(cpl_variant(p.row_chunks), metric == HS_METRIC_IP ? HS_METRIC_IP : HS_METRIC_L2,
+                  slots_variant(p.ef), [&](auto C, auto M, auto S) {
+                    return launch_t<decltype(C)::value, decltype(M)::value, decltype(S)::value>(p, l, stream);
+                  });
 }
 
 }  // namespace hs
