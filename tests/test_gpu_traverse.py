@@ -11,6 +11,7 @@ import pytest
 
 from conftest import get_corpus, needs_ref
 from hnsw_slim_b200 import capi
+from hnsw_slim_b200.synth import make_dataset
 from oracle import refharness as rh
 
 pytestmark = pytest.mark.gpu
@@ -141,6 +142,51 @@ def test_hash_reset_keeps_results(small_corpus, monkeypatch):
     b, db, cb = ix2.search(c.queries, 10, counts=True)
     assert np.array_equal(a, b) and np.array_equal(da, db)
     assert (cb[:, 0] >= ca[:, 0]).all() and (cb[:, 0] > ca[:, 0]).any()
+
+
+def test_large_ef_shared_memory_pool(small_corpus):
+    """ef > 128 runs the shared-memory pool variant; ef <= 64 / <= 128 the register pools."""
+    for ef in (33, 64, 65, 128, 129, 300):
+        check_against_oracle(small_corpus, 10, ef)
+
+
+def test_k_larger_than_32(small_corpus):
+    check_against_oracle(small_corpus, 100, 100)
+    check_against_oracle(small_corpus, 64, 200)
+
+
+def test_full_size_properties():
+    """Size-independent properties on a 200k x 128 corpus (the oracle would take minutes here):
+    sortedness, self-retrieval, recall monotone in ef, counters consistent, determinism."""
+    n, nq, dim = 200000, 2000, 128
+    base, q = make_dataset(n, nq, dim, rank=14)
+    import tempfile, os
+    with tempfile.TemporaryDirectory() as td:
+        g = os.path.join(td, "g.graph")
+        capi.build_slim_graph(base, g, M=16, ef_construction=100)
+        ix = capi.Index(g, dim)
+        gt, _ = capi.bruteforce_knn(base, q[:500], 10)
+        prev = 0.0
+        for ef in (20, 50, 100, 200):
+            ix.set_ef(ef)
+            lab, dist, cnt = ix.search(q, 10, counts=True)
+            assert (np.diff(dist, axis=1) >= 0).all() and (lab < n).all()
+            assert all(len(set(r)) == 10 for r in lab[:200])
+            rec = np.mean([len(set(a) & set(b)) / 10 for a, b in zip(lab[:500], gt)])
+            assert rec >= prev - 0.002
+            prev = rec
+            assert (cnt[:, 0] >= cnt[:, 1]).all() and (cnt[:, 1] >= 1).all()
+            # returned distances are the true distances of the returned rows
+            i = np.arange(0, nq, 37)
+            true = ((base[lab[i, 0]] - q[i]) ** 2).sum(1)
+            np.testing.assert_allclose(dist[i, 0], true, rtol=1e-5)
+        assert prev >= 0.95
+        self_lab, self_d = ix.search(base[:1000], 1)
+        found = self_lab[:, 0] == np.arange(1000, dtype=np.uint32)      # pruning may orphan a few nodes
+        assert found.mean() >= 0.99 and (self_d[found, 0] == 0).all()
+        a, _ = ix.search(q, 10)
+        b, _ = ix.search(q[::-1].copy(), 10)
+        assert np.array_equal(a, b[::-1])
 
 
 def test_stats_counters(small_corpus):

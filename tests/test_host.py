@@ -1,0 +1,171 @@
+"""CPU suite, part 2: host logic of the engine — loader/flattener, builder, file formats, and that
+the C-ABI library loads and exports every symbol include/hnswslim_b200.h declares.
+No compute entry point is called here (there is no GPU); they must fail loudly instead."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, HAVE_GPU, ROOT, get_corpus, needs_ref
+from hnsw_slim_b200 import capi, vecs_io
+from hnsw_slim_b200.synth import make_dataset
+from oracle import refharness as rh
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "hnswslim_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(hs_[a-z_0-9]+)\s*\(", hdr))
+    assert len(declared) >= 20
+    L = capi.lib()
+    for name in declared:
+        assert hasattr(L, name), f"{name} declared in the header but not exported"
+    assert set(capi.EXPORTS) <= declared
+    assert L.hs_abi_version() == 1
+
+
+@pytest.mark.skipif(HAVE_GPU, reason="checks the no-device error path")
+def test_no_cpu_fallback_without_a_device():
+    with pytest.raises(capi.HsError) as e:
+        capi.Index(os.path.join(GOLDEN, "slim_l2_2k.graph"), 16)
+    assert e.value.code == -3 and "no CPU fallback" in str(e.value)
+    with pytest.raises(capi.HsError) as e:
+        capi.bruteforce_knn(np.zeros((4, 4), np.float32), np.zeros((1, 4), np.float32), 1)
+    assert e.value.code == -3
+
+
+@pytest.mark.parametrize("name,metric", [("slim_l2_2k", 0), ("slim_ip_1k", 1)])
+def test_flattened_graph_matches_reference_layout(name, metric):
+    graph = os.path.join(GOLDEN, name + ".graph")
+    z = np.load(os.path.join(GOLDEN, name + ".npz"))
+    dim = int(z["dim"])
+    hg = capi.HostGraph(graph, dim)
+    orc = rh.Oracle(graph, dim, metric)
+    info, oinfo = hg.info(), orc.info()
+    for key in ("n", "maxlevel", "threshold_level", "enterpoint", "maxM", "maxM0", "M", "ef_construction"):
+        assert info[key] == oinfo[key], key
+    assert info["dim_padded"] % 32 == 0 and info["deg0_stride"] % 32 == 0 and info["upper_stride"] % 8 == 0
+    n_upper = sum_deg0 = max_deg0 = 0
+    for i in range(info["n"]):
+        lvl, lab, vec = hg.node(i)
+        olvl, olab, ids0 = orc.node(i, 0)
+        assert (lvl, lab) == (olvl, olab & 0xFFFFFFFF)
+        assert np.array_equal(vec[:dim], orc.vector(i)) and not vec[dim:].any()
+        for l in range(lvl + 1):
+            assert np.array_equal(hg.row(i, l), orc.node(i, l)[2]), (i, l)
+        assert len(hg.row(i, lvl + 1)) == 0
+        n_upper += lvl > 0
+        sum_deg0 += len(ids0)
+        max_deg0 = max(max_deg0, len(ids0))
+    assert (info["n_upper"], info["sum_deg0"], info["max_deg0"]) == (n_upper, sum_deg0, max_deg0)
+    # golden accessors recorded from the reference itself
+    offs, nbrs, c = z["node_nbr_offsets"], z["node_nbrs"], 0
+    for node in z["node_ids"]:
+        for l in range(info["maxlevel"] + 1):
+            assert np.array_equal(hg.row(int(node), l), nbrs[offs[c]:offs[c + 1]])
+            c += 1
+
+
+def test_loader_rejects_bad_files(tmp_path):
+    good = open(os.path.join(GOLDEN, "slim_l2_2k.graph"), "rb").read()
+    cases = {"empty": b"", "header_only": good[:60], "truncated_records": good[:5000],
+             "truncated_blobs": good[:-7], "garbage": bytes(range(256)) * 8}
+    for name, data in cases.items():
+        p = tmp_path / f"{name}.graph"
+        p.write_bytes(data)
+        with pytest.raises(capi.HsError) as e:
+            capi.HostGraph(str(p), 16)
+        assert e.value.code == -2, name
+    with pytest.raises(capi.HsError) as e:                      # wrong dim
+        capi.HostGraph(os.path.join(GOLDEN, "slim_l2_2k.graph"), 24)
+    assert e.value.code == -2 and "dim" in str(e.value)
+    with pytest.raises(capi.HsError) as e:
+        capi.HostGraph(str(tmp_path / "nope.graph"), 16)
+    assert e.value.code == -2 and "Cannot open" in str(e.value)
+
+
+def test_vecs_io_roundtrip(tmp_path):
+    a = np.random.default_rng(1).standard_normal((17, 5)).astype(np.float32)
+    b = np.arange(34, dtype=np.uint32).reshape(17, 2)
+    vecs_io.write_vecs(str(tmp_path / "a.fvecs"), a)
+    vecs_io.write_vecs(str(tmp_path / "b.ivecs"), b)
+    assert np.array_equal(vecs_io.read_fvecs(str(tmp_path / "a.fvecs")), a)
+    assert np.array_equal(vecs_io.read_ivecs(str(tmp_path / "b.ivecs")), b)
+    raw = np.fromfile(str(tmp_path / "a.fvecs"), dtype=np.int32)
+    assert raw[0] == 5 and raw.size == 17 * 6          # [int32 d][d floats] per row (util.h:149-168)
+
+
+def test_synthetic_generator_is_prefix_stable():
+    a, qa = make_dataset(1000, 10, 24, rank=6)
+    b, qb = make_dataset(70000, 20, 24, rank=6)
+    assert np.array_equal(a, b[:1000]) and np.array_equal(qa, qb[:10])
+    c, _ = make_dataset(100, 1, 24, metric=1, rank=6)
+    np.testing.assert_allclose(np.linalg.norm(c, axis=1), 1.0, rtol=1e-5)
+
+
+def _graph_invariants(path, dim, n, M):
+    orc = rh.Oracle(path, dim)
+    info = orc.info()
+    assert info["n"] == n and info["maxM0"] == 2 * M and info["maxM"] == M
+    assert orc.node(info["enterpoint"], 0)[0] == info["maxlevel"]
+    for i in range(0, n, max(1, n // 500)):
+        lvl, label, _ = orc.node(i, 0)
+        assert label == i
+        for l in range(lvl + 1):
+            ids = orc.node(i, l)[2]
+            assert len(ids) <= (2 * M if l == 0 else M)
+            assert len(set(ids.tolist())) == len(ids) and i not in ids and (ids < n).all()
+            if l > 0:      # hierarchical pruning: upper-level neighbours live exactly on that level
+                assert all(orc.node(int(j), 0)[0] == l for j in ids)
+
+
+def test_builder_writes_the_reference_format(tmp_path):
+    n, dim, M = 4000, 24, 8
+    base, q = make_dataset(n, 100, dim, rank=6)
+    path = str(tmp_path / "mine.graph")
+    capi.build_slim_graph(base, path, M=M, ef_construction=80, threads=2)
+    _graph_invariants(path, dim, n, M)
+    orc = rh.Oracle(path, dim)
+    assert np.array_equal(np.stack([orc.vector(i) for i in range(0, n, 97)]), base[::97])
+    lab, _, _, _ = orc.search(q, 10, 80)
+    gt, _ = rh.oracle_bruteforce(base, q, 10)
+    rec = np.mean([len(set(a) & set(b)) / 10 for a, b in zip(lab, gt)])
+    assert rec > 0.9, rec
+    # levels are a pure function of (seed, node): same seed => same levels whatever the thread timing
+    capi.build_slim_graph(base, str(tmp_path / "again.graph"), M=M, ef_construction=80, threads=3)
+    o2 = rh.Oracle(str(tmp_path / "again.graph"), dim)
+    assert all(orc.node(i, 0)[0] == o2.node(i, 0)[0] for i in range(0, n, 13))
+    # custom labels are stored as given
+    labels = np.arange(n, dtype=np.uint64) + 10_000_000
+    capi.build_slim_graph(base[:500], str(tmp_path / "lab.graph"), M=M, ef_construction=40, labels=labels[:500])
+    o3 = rh.Oracle(str(tmp_path / "lab.graph"), dim)
+    assert o3.node(7, 0)[1] == 10_000_007
+
+
+@needs_ref
+def test_reference_loads_and_searches_our_graph(tmp_path):
+    """Drop-in check in the other direction: the reference's loadIndex + searchKnn on a .graph
+    written by hs_build_slim_graph, with recall on par with a reference-built index."""
+    c = get_corpus(n=20000, nq=300, dim=32)
+    path = str(tmp_path / "mine.graph")
+    capi.build_slim_graph(c.base, path, M=16, ef_construction=200)
+    gt, _ = rh.ref_bruteforce(c.base, c.queries, 10)
+    recalls = {}
+    for name, g in (("ours", path), ("reference", c.graph)):
+        ref = rh.RefSlim(g, c.dim, c.n)
+        lab, _, _ = ref.search(c.queries, 10, 64)
+        recalls[name] = np.mean([len(set(a) & set(b)) / 10 for a, b in zip(lab, gt)])
+    assert abs(recalls["ours"] - recalls["reference"]) < 0.02, recalls
+    hi, ri = capi.HostGraph(path, c.dim).info(), capi.HostGraph(c.graph, c.dim).info()
+    assert abs(hi["sum_deg0"] - ri["sum_deg0"]) / ri["sum_deg0"] < 0.05
+
+
+def test_builder_argument_errors(tmp_path):
+    base = np.zeros((10, 4), np.float32)
+    with pytest.raises(capi.HsError):
+        capi.build_slim_graph(base, str(tmp_path / "x.graph"), M=1)
+    with pytest.raises(capi.HsError):
+        capi.build_slim_graph(base, str(tmp_path / "x.graph"), branching="zero")
+    with pytest.raises(capi.HsError):
+        capi.build_slim_graph(base, "/nonexistent_dir/x.graph", M=4)
