@@ -1,0 +1,63 @@
+"""CPU suite, part 3: the multi-GPU host logic under a real 2-process gloo group
+(shard assignment, all-gather, merge order).  The GPU path swaps in NCCL and the CUDA merge."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import ROOT
+from hnsw_slim_b200 import sharding
+
+
+def test_shard_ranges_and_assignment():
+    assert sharding.shard_ranges(10, 3) == [(0, 4), (4, 7), (7, 10)]
+    r = sharding.shard_ranges(100_000_000, 8)
+    assert r[0] == (0, 12_500_000) and r[-1][1] == 100_000_000
+    assert sharding.shards_of_rank(8, 1, 2) == [4, 5, 6, 7]
+    assert sharding.shards_of_rank(8, 3, 8) == [3]
+    with pytest.raises(ValueError):
+        sharding.shards_of_rank(8, 0, 3)
+
+
+def test_merge_numpy_semantics():
+    lab = np.array([[[1, 5, 0xFFFFFFFF]], [[2, 9, 7]]], dtype=np.uint32)       # parts=2, nq=1, k=3
+    dst = np.array([[[0.5, 0.7, np.inf]], [[0.5, 0.6, 0.9]]], dtype=np.float32)
+    l, d = sharding.merge_numpy(lab, dst, 3)
+    assert l.tolist() == [[1, 2, 9]] and d.tolist() == [[0.5, 0.5, np.float32(0.6)]]
+
+
+def _worker(rank, world, port, tmp):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(5)                      # same stream on every rank
+    nq, k, n = 50, 10, 4000
+    base = rng.standard_normal((n, 8)).astype(np.float32)
+    q = rng.standard_normal((nq, 8)).astype(np.float32)
+    lo, hi = sharding.shard_ranges(n, world)[sharding.shards_of_rank(world, rank, world)[0]]
+    d = ((base[None, lo:hi] - q[:, None]) ** 2).sum(-1).astype(np.float32)   # this rank's shard, exact
+    idx = np.argsort(d, axis=1, kind="stable")[:, :k]
+    loc_l = torch.from_numpy((idx + lo).astype(np.int32))                     # GLOBAL labels
+    loc_d = torch.from_numpy(np.take_along_axis(d, idx, 1))
+
+    def merge(all_l, all_d, kk):
+        return sharding.merge_numpy(all_l.numpy().view(np.uint32), all_d.numpy(), kk)
+
+    got_l, got_d = sharding.gather_and_merge(loc_l, loc_d, k, merge=merge)
+    full = ((base[None] - q[:, None]) ** 2).sum(-1).astype(np.float32)
+    want = np.stack([np.lexsort((np.arange(n), full[i]))[:k] for i in range(nq)])
+    ok = np.array_equal(got_l, want.astype(np.uint32)) and np.allclose(got_d, np.take_along_axis(full, want, 1))
+    with open(os.path.join(tmp, f"ok{rank}"), "w") as f:
+        f.write("1" if ok else "0")
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_gather_and_merge_world_size_2_gloo(tmp_path):
+    port = 29500 + (os.getpid() % 2000)
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert [open(tmp_path / f"ok{r}").read() for r in range(2)] == ["1", "1"]
