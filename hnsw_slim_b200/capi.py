@@ -22,6 +22,7 @@ EXPORTS = [
     "hs_bruteforce_knn_device", "hs_topk_merge_device", "hs_recall", "hs_last_error", "hs_abi_version",
     "hs_debug_flatten", "hs_debug_free", "hs_debug_info", "hs_debug_row", "hs_debug_node",
     "hs_build_params_default", "hs_build_slim_graph",
+    "hs_get_query_tconst", "hs_set_query_tconst", "hs_slimq_prepare",
 ]
 
 
@@ -95,6 +96,9 @@ def lib():
         L.hs_build_params_default.argtypes = [C.POINTER(BuildParams)]
         L.hs_build_params_default.restype = None
         L.hs_build_slim_graph.argtypes = [vp, sz, sz, i32, C.POINTER(BuildParams), vp, C.c_char_p]
+        L.hs_get_query_tconst.argtypes = [vp, C.POINTER(C.c_double)]
+        L.hs_set_query_tconst.argtypes = [vp, C.c_double]
+        L.hs_slimq_prepare.argtypes = [vp, vp, sz, vp, vp, vp, vp]
         for name in EXPORTS:
             if name not in ("hs_last_error", "hs_free", "hs_debug_free", "hs_build_params_default"):
                 getattr(L, name).restype = i32
@@ -181,6 +185,31 @@ class Index:
                       stream: int = 0) -> None:
         """Device pointers, asynchronous on `stream` (hs_search_batch_device)."""
         _check(lib().hs_search_batch_device(self._h, d_queries, nq, k, d_labels, d_dists, stream))
+
+    # ---- hnsw_slimq only ----
+    @property
+    def query_tconst(self) -> float:
+        t = C.c_double(0)
+        _check(lib().hs_get_query_tconst(self._h, C.byref(t)))
+        return t.value
+
+    @query_tconst.setter
+    def query_tconst(self, t: float) -> None:
+        _check(lib().hs_set_query_tconst(self._h, float(t)))
+
+    def slimq_prepare(self, queries):
+        """hs_slimq_prepare -> rotated[nq,pd], planes[nq,pd/64*4] u64, scal[nq,3], q2c[nq,ncl]."""
+        q = _f32(queries)
+        assert q.ndim == 2 and q.shape[1] == self.dim
+        info = self.info()
+        nq, pd, nc = q.shape[0], info["padded_dim_q"], info["num_cluster"]
+        rot = np.zeros((nq, pd), np.float32)
+        planes = np.zeros((nq, pd // 64 * 4), np.uint64)
+        scal = np.zeros((nq, 3), np.float32)
+        q2c = np.zeros((nq, nc), np.float32)
+        _check(lib().hs_slimq_prepare(self._h, q.ctypes.data, nq, rot.ctypes.data, planes.ctypes.data,
+                                      scal.ctypes.data, q2c.ctypes.data))
+        return rot, planes, scal, q2c
 
     def stats(self) -> dict:
         a, b, c = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)

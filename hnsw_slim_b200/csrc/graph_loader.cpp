@@ -20,8 +20,11 @@
 #include <unistd.h>
 
 #include <algorithm>
+#include <cmath>
 #include <cstring>
 #include <numeric>
+#include <queue>
+#include <random>
 
 #include "hs_internal.h"
 
@@ -57,6 +60,69 @@ struct Reader {
 inline uint32_t round_up(uint32_t v, uint32_t m) { return (v + m - 1) / m * m; }
 
 }  // namespace
+
+// The query-quantiser constant of hnsw_slimq.  The reference computes it at load time
+// (slimq.h:1274-1276 -> faster_config, rq/quantization/rabitq.hpp:27-34 ->
+// get_const_scaling_factors, rabitq_impl.hpp:363-377): the mean, over 100 random unit vectors,
+// of the rescale factor t that maximises <o, quantised(t*o)> / |quantised(t*o)|
+// (best_rescale_factor, rabitq_impl.hpp:275-333).  The reference seeds the vectors from
+// std::random_device (a different constant on every load); here the seed is fixed so that an
+// index answers the same way every time, and hs_set_query_tconst can override the value.
+double slimq_default_tconst(size_t padded_dim, size_t ex_bits) {
+  static const double kTightStart[9] = {0, 0.15, 0.20, 0.52, 0.59, 0.71, 0.75, 0.77, 0.81};
+  constexpr int kConstNum = 100, kNEnum = 10;
+  constexpr double kEps = 1e-5;
+  std::mt19937_64 gen(0x5eedULL * 1000003ULL + padded_dim * 31ULL + ex_bits);
+  std::normal_distribution<double> nd(0.0, 1.0);
+  std::vector<double> o(padded_dim);
+  std::vector<int> cur(padded_dim);
+  const int top = (1 << ex_bits) - 1;
+  double sum = 0;
+  for (int v = 0; v < kConstNum; ++v) {
+    double nrm = 0;
+    for (auto &x : o) {
+      x = nd(gen);
+      nrm += x * x;
+    }
+    nrm = std::sqrt(nrm);
+    double max_o = 0;
+    for (auto &x : o) {
+      x = std::fabs(x / nrm);
+      max_o = std::max(max_o, x);
+    }
+    const double t_end = (double)(top + kNEnum) / max_o;
+    const double t_start = t_end * kTightStart[ex_bits];
+    double sqr_den = (double)padded_dim * 0.25, num = 0;
+    using Ev = std::pair<double, size_t>;
+    std::priority_queue<Ev, std::vector<Ev>, std::greater<>> next_t;
+    for (size_t i = 0; i < padded_dim; ++i) {
+      cur[i] = (int)(t_start * o[i] + kEps);
+      sqr_den += (double)cur[i] * cur[i] + cur[i];
+      num += (cur[i] + 0.5) * o[i];
+      next_t.emplace((double)(cur[i] + 1) / o[i], i);
+    }
+    double max_ip = 0, t = 0;
+    while (!next_t.empty()) {
+      const double cur_t = next_t.top().first;
+      const size_t id = next_t.top().second;
+      next_t.pop();
+      cur[id]++;
+      sqr_den += 2 * cur[id];
+      num += o[id];
+      const double ip = num / std::sqrt(sqr_den);
+      if (ip > max_ip) {
+        max_ip = ip;
+        t = cur_t;
+      }
+      if (cur[id] < top) {
+        const double t_next = (double)(cur[id] + 1) / o[id];
+        if (t_next < t_end) next_t.emplace(t_next, id);
+      }
+    }
+    sum += t;
+  }
+  return sum / kConstNum;
+}
 
 int read_file(const char *path, std::vector<uint8_t> *out) {
   int fd = ::open(path, O_RDONLY);

@@ -11,6 +11,7 @@
 #include "bruteforce.cuh"
 #include "hs_internal.h"
 #include "traverse_fp32.cuh"
+#include "traverse_slimq.cuh"
 
 namespace hs {
 static thread_local std::string g_error;
@@ -39,6 +40,12 @@ struct hs_index {
   uint32_t *d_upper_adj[kMaxLevels] = {};
   uint32_t *d_labels = nullptr;
   uint8_t *d_deleted = nullptr;
+  // hnsw_slimq payload
+  uint2 *d_qrec = nullptr;          // n x (words + 2) uint2: code words, (f_add, f_rescale), (cluster, 0)
+  float *d_centroids = nullptr;     // num_cluster x padded_dim (rotated)
+  uint8_t *d_flip = nullptr;        // 4 * padded_dim / 8
+  uint32_t words = 0, trunc_dim = 0;
+  double t_const = 0.0;
   // per-call scratch
   unsigned int *d_work = nullptr;
   unsigned long long *d_stats = nullptr;   // [0] n_dist [1] n_hops [2] n_rerank
@@ -90,7 +97,7 @@ int select_device(int device) {
   return HS_OK;
 }
 
-int build_index(const HostGraph &g, int metric, int device, hs_index **out) {
+int build_index(const HostGraph &g, int metric, int device, const float *raw_base, hs_index **out) {
   int rc = select_device(device);
   if (rc != HS_OK) return rc;
   std::unique_ptr<hs_index> ix(new hs_index);
@@ -106,7 +113,37 @@ int build_index(const HostGraph &g, int metric, int device, hs_index **out) {
     hs_free(ix.release());
     return code;
   };
-  if ((rc = upload(&ix->d_vec, g.vec.data(), g.vec.size(), &bytes)) != HS_OK) return fail(rc);
+  if (g.kind == HS_KIND_SLIMQ) {
+    // raw rows for the exact rerank (slimq.h:747-749), padded like the hnsw_slim vector store
+    std::vector<float> vec(g.n * g.dim_padded, 0.f);
+    for (size_t i = 0; i < g.n; ++i) std::memcpy(&vec[i * g.dim_padded], raw_base + i * g.dim, 4 * g.dim);
+    if ((rc = upload(&ix->d_vec, vec.data(), vec.size(), &bytes)) != HS_OK) return fail(rc);
+    // one record per node: [u64 code[words]][f_add, f_rescale][cluster, 0]; 32 bytes for padded_dim 128
+    const size_t words = g.padded_dim_q / 64, rw = words + 2;
+    std::vector<uint2> rec(g.n * rw);
+    for (size_t i = 0; i < g.n; ++i) {
+      uint2 *r = &rec[i * rw];
+      for (size_t w = 0; w < words; ++w) {
+        const uint64_t c = g.bin_code[i * words + w];
+        r[w] = make_uint2((uint32_t)c, (uint32_t)(c >> 32));
+      }
+      uint32_t fa, fr;
+      std::memcpy(&fa, &g.f_add[i], 4);
+      std::memcpy(&fr, &g.f_rescale[i], 4);
+      r[words] = make_uint2(fa, fr);
+      r[words + 1] = make_uint2(g.cluster_id[i], 0u);
+    }
+    if ((rc = upload(&ix->d_qrec, rec.data(), rec.size(), &bytes)) != HS_OK) return fail(rc);
+    if ((rc = upload(&ix->d_centroids, g.centroids.data(), g.centroids.size(), &bytes)) != HS_OK) return fail(rc);
+    if ((rc = upload(&ix->d_flip, g.rotator_flip.data(), g.rotator_flip.size(), &bytes)) != HS_OK) return fail(rc);
+    ix->words = (uint32_t)words;
+    uint32_t td = 1;                                    // rotator.hpp:233-235
+    while ((size_t)td * 2 <= g.dim) td *= 2;
+    ix->trunc_dim = td;
+    ix->t_const = slimq_default_tconst(g.padded_dim_q, 3);   // kNumBits = 4 (query.hpp:126)
+  } else {
+    if ((rc = upload(&ix->d_vec, g.vec.data(), g.vec.size(), &bytes)) != HS_OK) return fail(rc);
+  }
   if ((rc = upload(&ix->d_adj0, g.adj0.data(), g.adj0.size(), &bytes)) != HS_OK) return fail(rc);
   if ((rc = upload(&ix->d_upper_slot, g.upper_slot.data(), g.upper_slot.size(), &bytes)) != HS_OK) return fail(rc);
   if ((rc = upload(&ix->d_labels, g.labels.data(), g.labels.size(), &bytes)) != HS_OK) return fail(rc);
@@ -164,15 +201,28 @@ int load_common(const uint8_t *bytes, size_t size, int kind, int metric, size_t 
     set_error("dim must be > 0");
     return HS_ERR_ARG;
   }
-  if (kind == HS_KIND_SLIMQ) {
-    (void)raw_base;
-    (void)n_raw;
-    set_error("hnsw_slimq engine not built yet");
+  if (kind == HS_KIND_SLIMQ && metric != HS_METRIC_L2) {
+    // every strategy of the reference builds hnsw_slimq with METRIC_L2 (hnsw_slimq_strategy.h:68)
+    set_error("hnsw_slimq: only the L2 metric is supported");
     return HS_ERR_UNSUPPORTED;
   }
   HostGraph g;
   int rc = parse_graph(bytes, size, kind, dim, &g);
   if (rc != HS_OK) return rc;
+  if (kind == HS_KIND_SLIMQ) {
+    if (!raw_base || n_raw < g.n) {
+      set_error("hnsw_slimq needs raw_base with at least n rows for the exact rerank (setDataset, slimq.h:303-305)");
+      return HS_ERR_ARG;
+    }
+    if (g.metric_type_q != 0 /* rabitqlib::METRIC_L2 */) {
+      set_error("hnsw_slimq index was built with a non-L2 metric: not supported");
+      return HS_ERR_UNSUPPORTED;
+    }
+    if (g.padded_dim_q > 2048 || g.num_cluster == 0 || g.num_cluster > 4096) {
+      set_error("hnsw_slimq: padded_dim > 2048 or cluster count out of range");
+      return HS_ERR_UNSUPPORTED;
+    }
+  }
   if (g.threshold_level > 0) {
     set_error("threshold_level > 0 (layered beam, slim.h:222-316) not supported yet");
     return HS_ERR_UNSUPPORTED;
@@ -181,7 +231,7 @@ int load_common(const uint8_t *bytes, size_t size, int kind, int metric, size_t 
     set_error("indices with deleted elements (slim.h:2119-2122) not supported yet");
     return HS_ERR_UNSUPPORTED;
   }
-  return build_index(g, metric, device, out);
+  return build_index(g, metric, device, raw_base, out);
 }
 
 int ensure(void **p, size_t *cap, size_t need) {
@@ -198,6 +248,60 @@ int ensure(void **p, size_t *cap, size_t need) {
   return HS_OK;
 }
 
+struct PrepDump {
+  float *rotated;
+  unsigned long long *planes;
+  float *scal, *q2c;
+};
+
+int search_device_slimq(hs_index *ix, const float *d_queries, size_t nq, size_t k, uint32_t *d_labels,
+                        float *d_dists, uint32_t *d_perq, cudaStream_t stream, const PrepDump *dump) {
+  TraverseQParams p{};
+  p.qrec = ix->d_qrec;
+  p.vec = reinterpret_cast<const float4 *>(ix->d_vec);
+  p.adj0 = ix->d_adj0;
+  p.upper_slot = ix->d_upper_slot;
+  for (int l = 0; l < kMaxLevels; ++l) p.upper_adj[l] = ix->d_upper_adj[l];
+  p.labels = ix->d_labels;
+  p.centroids = ix->d_centroids;
+  p.flip = ix->d_flip;
+  p.n = (uint32_t)ix->info.n;
+  p.row_chunks = (uint32_t)(ix->info.dim_padded / 4);
+  p.deg0_stride = ix->info.deg0_stride;
+  p.upper_stride = ix->info.upper_stride;
+  p.enterpoint = ix->info.enterpoint;
+  p.maxlevel = ix->info.maxlevel;
+  p.threshold_level = ix->info.threshold_level;
+  p.padded_dim = (uint32_t)ix->info.padded_dim_q;
+  p.trunc_dim = ix->trunc_dim;
+  p.num_cluster = (uint32_t)ix->info.num_cluster;
+  p.words = ix->words;
+  p.rec_words = ix->words + 2;
+  p.fht_fac = 1.0f / std::sqrt((float)ix->trunc_dim);   // rotator.hpp:235
+  p.t_const = ix->t_const;
+  p.queries = d_queries;
+  p.nq = (uint32_t)nq;
+  p.dim = (uint32_t)ix->info.dim;
+  p.k = (uint32_t)k;
+  p.ef = (uint32_t)ix->info.ef;       // pool capacity = ef_ (setEf, slimq.h:346-349), not max(ef, k)
+  p.out_labels = d_labels;
+  p.out_dists = d_dists;
+  if (dump) {
+    p.prep_rotated = dump->rotated;
+    p.prep_planes = dump->planes;
+    p.prep_scal = dump->scal;
+    p.prep_q2c = dump->q2c;
+  }
+  p.work_counter = ix->d_work;
+  p.stats = ix->d_stats;
+  p.per_query = d_perq;
+  TraverseQLaunch l{};
+  int rc = plan_traverse_slimq(p, ix->sm_count, (int)nq, &l);
+  if (rc != HS_OK) return rc;
+  HS_CUDA(cudaMemsetAsync(ix->d_work, 0, sizeof(unsigned int), stream));
+  return launch_traverse_slimq(p, l, stream);
+}
+
 int search_device(hs_index *ix, const float *d_queries, size_t nq, size_t k, uint32_t *d_labels,
                   float *d_dists, uint32_t *d_perq, cudaStream_t stream) {
   if (!ix || (!d_queries && nq) || (!d_labels && nq) || k == 0) {
@@ -209,6 +313,7 @@ int search_device(hs_index *ix, const float *d_queries, size_t nq, size_t k, uin
     set_error("nq or k too large");
     return HS_ERR_ARG;
   }
+  if (ix->info.kind == HS_KIND_SLIMQ) return search_device_slimq(ix, d_queries, nq, k, d_labels, d_dists, d_perq, stream, nullptr);
   TraverseParams p{};
   p.vec = reinterpret_cast<const float4 *>(ix->d_vec);
   p.adj0 = ix->d_adj0;
@@ -305,6 +410,9 @@ void hs_free(hs_index *ix) {
   for (auto *p : ix->d_upper_adj) cudaFree(p);
   cudaFree(ix->d_labels);
   cudaFree(ix->d_deleted);
+  cudaFree(ix->d_qrec);
+  cudaFree(ix->d_centroids);
+  cudaFree(ix->d_flip);
   cudaFree(ix->d_work);
   cudaFree(ix->d_stats);
   cudaFree(ix->d_q);
@@ -321,6 +429,68 @@ int hs_set_ef(hs_index *ix, size_t ef) {
     return HS_ERR_ARG;
   }
   ix->info.ef = ef;
+  return HS_OK;
+}
+
+int hs_set_query_tconst(hs_index *ix, double t_const) {
+  if (!ix || ix->info.kind != HS_KIND_SLIMQ || !(t_const > 0.0)) {
+    set_error("hs_set_query_tconst: hnsw_slimq index and t_const > 0 required");
+    return HS_ERR_ARG;
+  }
+  ix->t_const = t_const;
+  return HS_OK;
+}
+
+int hs_get_query_tconst(const hs_index *ix, double *t_const) {
+  if (!ix || !t_const || ix->info.kind != HS_KIND_SLIMQ) {
+    set_error("hs_get_query_tconst: hnsw_slimq index required");
+    return HS_ERR_ARG;
+  }
+  *t_const = ix->t_const;
+  return HS_OK;
+}
+
+int hs_slimq_prepare(hs_index *ix, const float *queries, size_t nq, float *rotated_out, uint64_t *planes_out,
+                     float *scal_out, float *q2c_out) {
+  if (!ix || ix->info.kind != HS_KIND_SLIMQ || !queries || !rotated_out || !planes_out || !scal_out || !q2c_out) {
+    set_error("hs_slimq_prepare: hnsw_slimq index and non-null buffers required");
+    return HS_ERR_ARG;
+  }
+  if (nq == 0) return HS_OK;
+  std::lock_guard<std::mutex> lock(ix->mu);
+  HS_CUDA(cudaSetDevice(ix->device));
+  const size_t dim = ix->info.dim, pd = ix->info.padded_dim_q, pw = ix->words * 4, nc = ix->info.num_cluster;
+  float *d_q = nullptr, *d_rot = nullptr, *d_scal = nullptr, *d_q2c = nullptr;
+  unsigned long long *d_pl = nullptr;
+  auto cleanup = [&]() {
+    cudaFree(d_q);
+    cudaFree(d_rot);
+    cudaFree(d_scal);
+    cudaFree(d_q2c);
+    cudaFree(d_pl);
+  };
+  if (cudaMalloc(&d_q, nq * dim * 4) != cudaSuccess || cudaMalloc(&d_rot, nq * pd * 4) != cudaSuccess ||
+      cudaMalloc(&d_scal, nq * 12) != cudaSuccess || cudaMalloc(&d_q2c, nq * nc * 4) != cudaSuccess ||
+      cudaMalloc(&d_pl, nq * pw * 8) != cudaSuccess) {
+    cleanup();
+    set_error("hs_slimq_prepare: cudaMalloc failed");
+    return HS_ERR_NOMEM;
+  }
+  PrepDump dump{d_rot, d_pl, d_scal, d_q2c};
+  int rc = HS_OK;
+  cudaError_t e = cudaMemcpyAsync(d_q, queries, nq * dim * 4, cudaMemcpyHostToDevice, ix->stream);
+  if (e == cudaSuccess) rc = search_device_slimq(ix, d_q, nq, 1, nullptr, nullptr, nullptr, ix->stream, &dump);
+  if (e == cudaSuccess && rc == HS_OK) e = cudaMemcpyAsync(rotated_out, d_rot, nq * pd * 4, cudaMemcpyDeviceToHost, ix->stream);
+  if (e == cudaSuccess && rc == HS_OK) e = cudaMemcpyAsync(planes_out, d_pl, nq * pw * 8, cudaMemcpyDeviceToHost, ix->stream);
+  if (e == cudaSuccess && rc == HS_OK) e = cudaMemcpyAsync(scal_out, d_scal, nq * 12, cudaMemcpyDeviceToHost, ix->stream);
+  if (e == cudaSuccess && rc == HS_OK) e = cudaMemcpyAsync(q2c_out, d_q2c, nq * nc * 4, cudaMemcpyDeviceToHost, ix->stream);
+  if (e == cudaSuccess && rc == HS_OK) e = cudaStreamSynchronize(ix->stream);
+  cleanup();
+  if (rc != HS_OK) return rc;
+  if (e != cudaSuccess) {
+    set_error(std::string("hs_slimq_prepare: ") + cudaGetErrorString(e));
+    return HS_ERR_CUDA;
+  }
   return HS_OK;
 }
 

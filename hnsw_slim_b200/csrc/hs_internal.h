@@ -52,6 +52,7 @@ struct HostGraph {
 // Parses a reference .graph image.  Returns HS_OK or a negative hs_status (message via set_error).
 int parse_graph(const uint8_t *bytes, size_t size, int kind, size_t dim, HostGraph *out);
 int read_file(const char *path, std::vector<uint8_t> *out);
+double slimq_default_tconst(size_t padded_dim, size_t ex_bits);
 
 // graph_build.cpp — HNSW construction + HNSW-Slim pruning + saveIndex file format
 int build_slim_graph(const float *base, size_t n, size_t dim, int metric, size_t M, size_t ef_construction,

@@ -1,0 +1,566 @@
+// Device-side building blocks shared by the traversal kernels (traverse_fp32.cu,
+// traverse_slimq.cu): order-preserving (distance,id) keys, warp-wide arg-min/max, the
+// register / shared-memory candidate pools, the fp32 row scorer and the visited hash.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "hs_internal.h"
+
+namespace hs {
+namespace {
+
+constexpr unsigned FULL = 0xffffffffu;
+constexpr uint32_t FLAG = 0x80000000u;             // "expanded" bit inside the id half of a key
+constexpr uint64_t KEYMASK = ~(uint64_t)FLAG;
+constexpr uint32_t EMPTY = 0xFFFFFFFFu;
+
+// monotone float -> uint32 map (IP distances 1 - <a,b> can be negative)
+__device__ __forceinline__ uint32_t f2ord(float f) {
+  uint32_t u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ord2f(uint32_t u) {
+  return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}
+__device__ __forceinline__ uint64_t make_key(float d, uint32_t id) {
+  return ((uint64_t)f2ord(d) << 32) | id;
+}
+
+__device__ __forceinline__ uint64_t warp_min_u64(uint64_t v) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    uint64_t o = __shfl_xor_sync(FULL, v, off);
+    v = o < v ? o : v;
+  }
+  return v;
+}
+
+template <int METRIC>
+__device__ __forceinline__ float acc4(float acc, const float4 q, const float4 x) {
+  if (METRIC == HS_METRIC_L2) {
+    float d;
+    d = __fsub_rn(q.x, x.x); acc = __fmaf_rn(d, d, acc);
+    d = __fsub_rn(q.y, x.y); acc = __fmaf_rn(d, d, acc);
+    d = __fsub_rn(q.z, x.z); acc = __fmaf_rn(d, d, acc);
+    d = __fsub_rn(q.w, x.w); acc = __fmaf_rn(d, d, acc);
+  } else {
+    acc = __fmaf_rn(q.x, x.x, acc);
+    acc = __fmaf_rn(q.y, x.y, acc);
+    acc = __fmaf_rn(q.z, x.z, acc);
+    acc = __fmaf_rn(q.w, x.w, acc);
+  }
+  return acc;
+}
+template <int METRIC>
+__device__ __forceinline__ float finish(float acc) {
+  return METRIC == HS_METRIC_IP ? __fsub_rn(1.0f, acc) : acc;
+}
+__device__ __forceinline__ float team_reduce(float v) {
+  v = __fadd_rn(v, __shfl_xor_sync(FULL, v, 4));
+  v = __fadd_rn(v, __shfl_xor_sync(FULL, v, 2));
+  v = __fadd_rn(v, __shfl_xor_sync(FULL, v, 1));
+  return v;
+}
+
+// Distances from the query to `count` (<= 32) rows; lane j holds id j, gets d_j back.
+// Register-resident query, CPL float4 chunks per lane, U x 4 rows in flight per warp.
+template <int CPL, int METRIC, int U>
+__device__ __forceinline__ float eval_rows_reg(const float4 *__restrict__ vec, uint32_t row_chunks,
+                                               const float4 (&q)[CPL], uint32_t my_id, int count,
+                                               int lane) {
+  const int team = lane >> 3, t = lane & 7;
+  float my_d = 0.f;
+  for (int it0 = 0; it0 * 4 < count; it0 += U) {
+    float4 x[U][CPL];
+    bool act[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int src = (it0 + u) * 4 + team;
+      const uint32_t id = __shfl_sync(FULL, my_id, src & 31);
+      act[u] = src < count;
+      if (act[u]) {
+        const float4 *row = vec + (size_t)id * row_chunks + t;
+#pragma unroll
+        for (int j = 0; j < CPL; ++j) x[u][j] = __ldg(row + 8 * j);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      float acc = 0.f;
+      if (act[u]) {
+#pragma unroll
+        for (int j = 0; j < CPL; ++j) acc = acc4<METRIC>(acc, q[j], x[u][j]);
+      }
+      acc = team_reduce(acc);
+      const float v = __shfl_sync(FULL, acc, (lane & 3) * 8);
+      if ((lane >> 2) == it0 + u) my_d = finish<METRIC>(v);
+    }
+  }
+  return my_d;
+}
+
+// Same with the query in shared memory and a run-time chunk count (large / odd dims).
+template <int METRIC>
+__device__ __forceinline__ float eval_rows_smem(const float4 *__restrict__ vec, uint32_t row_chunks,
+                                                const float4 *qs, uint32_t my_id, int count, int lane) {
+  const int team = lane >> 3, t = lane & 7;
+  const int cpl = (int)(row_chunks >> 3);
+  float my_d = 0.f;
+  for (int it = 0; it * 4 < count; ++it) {
+    const int src = it * 4 + team;
+    const uint32_t id = __shfl_sync(FULL, my_id, src & 31);
+    float acc = 0.f;
+    if (src < count) {
+      const float4 *row = vec + (size_t)id * row_chunks + t;
+      const float4 *qq = qs + t;
+      int j = 0;
+      for (; j + 8 <= cpl; j += 8) {
+        float4 x[8];
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) x[jj] = __ldg(row + 8 * (j + jj));
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) acc = acc4<METRIC>(acc, qq[8 * (j + jj)], x[jj]);
+      }
+      for (; j < cpl; ++j) acc = acc4<METRIC>(acc, qq[8 * j], __ldg(row + 8 * j));
+    }
+    acc = team_reduce(acc);
+    const float v = __shfl_sync(FULL, acc, (lane & 3) * 8);
+    if ((lane >> 2) == it) my_d = finish<METRIC>(v);
+  }
+  return my_d;
+}
+
+// visited set: open addressing, linear probing, 32-bit keys (replaces the per-thread
+// uint16 tag array of visited_list_pool.h:10-31).  Returns true if id was already present.
+__device__ __forceinline__ bool visited_test_and_set(uint32_t *hash, uint32_t hbits, uint32_t hmask,
+                                                     uint32_t id) {
+  uint32_t h = (id * 0x9E3779B1u) >> (32 - hbits);
+  volatile uint32_t *vh = hash;
+  for (;;) {
+    const uint32_t v = vh[h];
+    if (v == id) return true;
+    if (v == EMPTY) {
+      const uint32_t old = atomicCAS(hash + h, EMPTY, id);
+      if (old == EMPTY) return false;
+      if (old == id) return true;
+    }
+    h = (h + 1) & hmask;
+  }
+}
+
+__device__ __forceinline__ void hash_clear(uint32_t *hash, uint32_t hsize, int lane) {
+  const uint4 e = make_uint4(EMPTY, EMPTY, EMPTY, EMPTY);
+  for (uint32_t i = lane * 4; i < hsize; i += 128) *reinterpret_cast<uint4 *>(hash + i) = e;
+}
+
+__device__ __forceinline__ void prefetch_l2(const void *p) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+constexpr uint64_t NONE = ~0ull;
+
+// lane holding the warp-wide smallest `key` ((dist,id) order; NONE = no entry); -1 if none
+__device__ __forceinline__ int warp_argmin_key(uint64_t key) {
+  const uint32_t hi = (uint32_t)(key >> 32);
+  const uint32_t ghi = __reduce_min_sync(FULL, hi);
+  if (ghi == 0xffffffffu) return -1;
+  unsigned b = __ballot_sync(FULL, hi == ghi);
+  if (b & (b - 1)) {   // equal distances in several lanes: smaller id first
+    const uint32_t lo = hi == ghi ? (uint32_t)key : 0xffffffffu;
+    const uint32_t glo = __reduce_min_sync(FULL, lo);
+    b = __ballot_sync(FULL, hi == ghi && lo == glo);
+  }
+  return __ffs(b) - 1;
+}
+// lane holding the warp-wide largest `key` (0 = no entry)
+__device__ __forceinline__ int warp_argmax_key(uint64_t key) {
+  const uint32_t hi = (uint32_t)(key >> 32);
+  const uint32_t ghi = __reduce_max_sync(FULL, hi);
+  unsigned b = __ballot_sync(FULL, hi == ghi);
+  if (b & (b - 1)) {
+    const uint32_t lo = hi == ghi ? (uint32_t)key : 0u;
+    const uint32_t glo = __reduce_max_sync(FULL, lo);
+    b = __ballot_sync(FULL, hi == ghi && lo == glo);
+  }
+  return __ffs(b) - 1;
+}
+
+// The candidate/result pool: at most ef keys, unsorted, column-distributed (entry e lives in
+// lane e % 32).  Two storages with one interface:
+//   RegPool<SLOTS>  ef <= 32*SLOTS: the column sits in registers; column min/max are a few
+//                   compare-selects recomputed on demand by all lanes at once
+//   SmemPool        any ef: the column sits in shared memory, with cached column statistics
+// Interface: seed(), pop_closest_unexpanded(), admit(), for_each_id(), kth().
+template <int SLOTS>
+struct RegPool {
+  uint64_t k[SLOTS];     // empty slots hold NONE (flag set => never "unexpanded", and skipped for max)
+  uint32_t size, ef;
+  int lane;
+
+  __device__ __forceinline__ void init(uint64_t *, uint32_t ef_, int lane_) {
+    ef = ef_;
+    lane = lane_;
+    size = 0;
+#pragma unroll
+    for (int s = 0; s < SLOTS; ++s) k[s] = NONE;
+  }
+  __device__ __forceinline__ void put(uint32_t e, uint64_t key) {   // called by the owner lane only
+#pragma unroll
+    for (int s = 0; s < SLOTS; ++s) k[s] = ((int)(e >> 5) == s) ? key : k[s];   // select, not k[e>>5] = ..: keeps k in registers
+  }
+  __device__ __forceinline__ void seed(uint64_t key) {
+    if (lane == 0) k[0] = key;
+    size = 1;
+  }
+  __device__ __forceinline__ uint64_t col_min_un(int &slot) const {
+    uint64_t m = NONE;
+    slot = 0;
+#pragma unroll
+    for (int s = 0; s < SLOTS; ++s) {
+      const bool un = !((uint32_t)k[s] & FLAG);
+      if (un && k[s] < m) {
+        m = k[s];
+        slot = s;
+      }
+    }
+    return m;
+  }
+  __device__ __forceinline__ uint64_t col_max(int &slot) const {
+    uint64_t m = 0;
+    slot = 0;
+#pragma unroll
+    for (int s = 0; s < SLOTS; ++s) {
+      const uint64_t km = k[s] & KEYMASK;
+      const bool used = (uint32_t)(s * 32 + lane) < size;
+      if (used && km >= m) {
+        m = km;
+        slot = s;
+      }
+    }
+    return m;
+  }
+  // closest unexpanded entry: marks it expanded and returns its node id, kInvalid if none
+  __device__ __forceinline__ uint32_t pop_closest_unexpanded() {
+    int slot;
+    const uint64_t m = col_min_un(slot);
+    const int o = warp_argmin_key(m);
+    if (o < 0) return kInvalid;
+    if (lane == o) {
+#pragma unroll
+      for (int s = 0; s < SLOTS; ++s) k[s] = (s == slot) ? (k[s] | (uint64_t)FLAG) : k[s];
+    }
+    return (uint32_t)__shfl_sync(FULL, (uint32_t)m, o);
+  }
+  // admit scored neighbours, one per lane; returns the ballot of lanes whose key entered
+  __device__ __forceinline__ unsigned admit(bool valid, uint64_t key) {
+    unsigned entered = 0;
+    const unsigned vmask = __ballot_sync(FULL, valid);
+    if (vmask == 0) return 0;
+    unsigned todo = vmask;
+    if (size < ef) {   // room left: the first (ef - size) candidates are appended unconditionally
+      const uint32_t room = ef - size;
+      const uint32_t n_app = min(room, (uint32_t)__popc(vmask));
+      for (uint32_t j = 0; j < n_app; ++j) {
+        const int src = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const uint64_t ck = __shfl_sync(FULL, key, src);
+        const uint32_t e = size + j;
+        if ((int)(e & 31) == lane) put(e, ck);
+        entered |= 1u << src;
+      }
+      size += n_app;
+      if (todo == 0) return entered;
+    }
+    int slot;
+    uint64_t cm = col_max(slot);
+    int owner = warp_argmax_key(cm);
+    uint64_t worst = __shfl_sync(FULL, cm, owner);
+    todo &= __ballot_sync(FULL, valid && key < worst);   // the worst only gets smaller
+    while (todo) {
+      const int src = __ffs(todo) - 1;
+      todo &= todo - 1;
+      const uint64_t ck = __shfl_sync(FULL, key, src);
+      if (ck < worst) {
+        if (lane == owner) {
+#pragma unroll
+          for (int s = 0; s < SLOTS; ++s) k[s] = (s == slot) ? ck : k[s];
+        }
+        entered |= 1u << src;
+        if (todo) {
+          cm = col_max(slot);
+          owner = warp_argmax_key(cm);
+          worst = __shfl_sync(FULL, cm, owner);
+        }
+      }
+    }
+    return entered;
+  }
+  // ---- hnsw_slimq pool semantics (SearchBuffer, slimq.h:80-151): the same (dist,id) may sit
+  //      in the pool several times; "visited" == some copy carries the expanded flag ----
+  // closest unexpanded entry; flags EVERY copy of it (the reference pops the later copies
+  // and skips them as visited, slimq.h:700-702 — a no-op)
+  __device__ __forceinline__ uint32_t pop_closest_unexpanded_dups() {
+    int slot;
+    const uint64_t m = col_min_un(slot);
+    const int o = warp_argmin_key(m);
+    if (o < 0) return kInvalid;
+    const uint64_t g = __shfl_sync(FULL, m, o);
+#pragma unroll
+    for (int s = 0; s < SLOTS; ++s) k[s] = (k[s] == g) ? (k[s] | (uint64_t)FLAG) : k[s];
+    return (uint32_t)g;
+  }
+  // slimq.h:741-745: a scored neighbour enters unless the pool is full and it is worse than
+  // the worst entry, or it was expanded already (== a flagged copy of its key is in the pool:
+  // an expanded entry that left the pool is worse than the worst from then on)
+  __device__ __forceinline__ unsigned admit_q(bool valid, uint64_t key) {
+    unsigned entered = 0;
+    unsigned todo = __ballot_sync(FULL, valid);
+    if (todo == 0) return 0;
+    int slot = 0, owner = 0;
+    uint64_t worst = NONE;
+    if (size >= ef) {
+      const uint64_t cm = col_max(slot);
+      owner = warp_argmax_key(cm);
+      worst = __shfl_sync(FULL, cm, owner);
+      todo &= __ballot_sync(FULL, valid && key < worst);
+    }
+    while (todo) {
+      const int src = __ffs(todo) - 1;
+      todo &= todo - 1;
+      const uint64_t ck = __shfl_sync(FULL, key, src);
+      const uint64_t fk = ck | (uint64_t)FLAG;
+      bool dup = false;
+#pragma unroll
+      for (int s = 0; s < SLOTS; ++s) dup |= (k[s] == fk);
+      if (__any_sync(FULL, dup)) continue;
+      if (size < ef) {
+        if ((int)(size & 31) == lane) put(size, ck);
+        ++size;
+        entered |= 1u << src;
+        if (size == ef && todo) {
+          const uint64_t cm = col_max(slot);
+          owner = warp_argmax_key(cm);
+          worst = __shfl_sync(FULL, cm, owner);
+        }
+      } else if (ck < worst) {
+        if (lane == owner) {
+#pragma unroll
+          for (int s = 0; s < SLOTS; ++s) k[s] = (s == slot) ? ck : k[s];
+        }
+        entered |= 1u << src;
+        if (todo) {
+          const uint64_t cm = col_max(slot);
+          owner = warp_argmax_key(cm);
+          worst = __shfl_sync(FULL, cm, owner);
+        }
+      }
+    }
+    return entered;
+  }
+  template <typename F>
+  __device__ __forceinline__ void for_each_id(F &&f) const {
+#pragma unroll
+    for (int s = 0; s < SLOTS; ++s)
+      if ((uint32_t)(s * 32 + lane) < size) f((uint32_t)k[s] & ~FLAG);
+  }
+  // smallest key strictly above `last` in this lane's column (NONE if none)
+  __device__ __forceinline__ uint64_t col_next_above(uint64_t last) const {
+    uint64_t m = NONE;
+#pragma unroll
+    for (int s = 0; s < SLOTS; ++s) {
+      const uint64_t km = k[s] & KEYMASK;
+      if ((uint32_t)(s * 32 + lane) < size && km > last && km < m) m = km;
+    }
+    return m;
+  }
+};
+
+struct SmemPool {
+  uint64_t *pool;
+  uint32_t size, ef;
+  int lane;
+  uint64_t min_un, max_all;    // cached column statistics
+  uint32_t min_e, max_e;
+
+  __device__ __forceinline__ void init(uint64_t *mem, uint32_t ef_, int lane_) {
+    pool = mem;
+    ef = ef_;
+    lane = lane_;
+    size = 0;
+  }
+  __device__ __forceinline__ void rescan_min() {
+    min_un = NONE;
+    min_e = 0;
+    for (uint32_t e = lane; e < size; e += 32) {
+      const uint64_t k = pool[e];
+      if (!((uint32_t)k & FLAG) && k < min_un) {
+        min_un = k;
+        min_e = e;
+      }
+    }
+  }
+  __device__ __forceinline__ void rescan_max() {
+    max_all = 0;
+    max_e = 0;
+    for (uint32_t e = lane; e < size; e += 32) {
+      const uint64_t km = pool[e] & KEYMASK;
+      if (km >= max_all) {
+        max_all = km;
+        max_e = e;
+      }
+    }
+  }
+  __device__ __forceinline__ void seed(uint64_t key) {
+    if (lane == 0) pool[0] = key;
+    size = 1;
+    __syncwarp();
+    rescan_min();
+    rescan_max();
+  }
+  __device__ __forceinline__ uint32_t pop_closest_unexpanded() {
+    const int o = warp_argmin_key(min_un);
+    if (o < 0) return kInvalid;
+    const uint32_t node = (uint32_t)__shfl_sync(FULL, (uint32_t)min_un, o);
+    if (lane == o) {
+      pool[min_e] |= (uint64_t)FLAG;
+      rescan_min();
+    }
+    return node;
+  }
+  __device__ __forceinline__ unsigned admit(bool valid, uint64_t key) {
+    unsigned entered = 0;
+    const unsigned vmask = __ballot_sync(FULL, valid);
+    if (vmask == 0) return 0;
+    unsigned todo = vmask;
+    if (size < ef) {
+      const uint32_t room = ef - size;
+      const uint32_t rank = (uint32_t)__popc(vmask & ((1u << lane) - 1));
+      const bool app = valid && rank < room;
+      if (app) pool[size + rank] = key;
+      const unsigned am = __ballot_sync(FULL, app);
+      entered |= am;
+      todo &= ~am;
+      size += min(room, (uint32_t)__popc(vmask));
+      __syncwarp();
+      rescan_min();
+      rescan_max();
+      if (todo == 0) return entered;
+    }
+    int owner = warp_argmax_key(max_all);
+    uint64_t worst = __shfl_sync(FULL, max_all, owner);
+    todo &= __ballot_sync(FULL, valid && key < worst);
+    while (todo) {
+      const int src = __ffs(todo) - 1;
+      todo &= todo - 1;
+      const uint64_t ck = __shfl_sync(FULL, key, src);
+      if (ck < worst) {
+        if (lane == owner) {
+          const bool was_min = max_e == min_e && min_un != NONE;
+          pool[max_e] = ck;
+          if (was_min) {
+            rescan_min();            // the displaced entry was this column's closest unexpanded
+          } else if (ck < min_un) {
+            min_un = ck;
+            min_e = max_e;
+          }
+          rescan_max();
+        }
+        entered |= 1u << src;
+        if (todo) {
+          owner = warp_argmax_key(max_all);
+          worst = __shfl_sync(FULL, max_all, owner);
+        }
+      }
+    }
+    return entered;
+  }
+  // ---- hnsw_slimq pool semantics, see RegPool ----
+  __device__ __forceinline__ uint32_t pop_closest_unexpanded_dups() {
+    const int o = warp_argmin_key(min_un);
+    if (o < 0) return kInvalid;
+    const uint64_t g = __shfl_sync(FULL, min_un, o);
+    bool hit = false;
+    for (uint32_t e = lane; e < size; e += 32)
+      if (pool[e] == g) {
+        pool[e] = g | (uint64_t)FLAG;
+        hit = true;
+      }
+    if (hit) rescan_min();
+    return (uint32_t)g;
+  }
+  __device__ __forceinline__ unsigned admit_q(bool valid, uint64_t key) {
+    unsigned entered = 0;
+    unsigned todo = __ballot_sync(FULL, valid);
+    if (todo == 0) return 0;
+    int owner = 0;
+    uint64_t worst = NONE;
+    if (size >= ef) {
+      owner = warp_argmax_key(max_all);
+      worst = __shfl_sync(FULL, max_all, owner);
+      todo &= __ballot_sync(FULL, valid && key < worst);
+    }
+    while (todo) {
+      const int src = __ffs(todo) - 1;
+      todo &= todo - 1;
+      const uint64_t ck = __shfl_sync(FULL, key, src);
+      const uint64_t fk = ck | (uint64_t)FLAG;
+      bool dup = false;
+      for (uint32_t e = lane; e < size; e += 32) dup |= (pool[e] == fk);
+      if (__any_sync(FULL, dup)) continue;
+      if (size < ef) {
+        if ((int)(size & 31) == lane) {
+          pool[size] = ck;
+          if (ck < min_un) {
+            min_un = ck;
+            min_e = size;
+          }
+          if (ck >= max_all) {
+            max_all = ck;
+            max_e = size;
+          }
+        }
+        ++size;
+        entered |= 1u << src;
+        if (size == ef && todo) {
+          owner = warp_argmax_key(max_all);
+          worst = __shfl_sync(FULL, max_all, owner);
+        }
+      } else if (ck < worst) {
+        if (lane == owner) {
+          const bool was_min = max_e == min_e && min_un != NONE;
+          pool[max_e] = ck;
+          if (was_min) {
+            rescan_min();
+          } else if (ck < min_un) {
+            min_un = ck;
+            min_e = max_e;
+          }
+          rescan_max();
+        }
+        entered |= 1u << src;
+        if (todo) {
+          owner = warp_argmax_key(max_all);
+          worst = __shfl_sync(FULL, max_all, owner);
+        }
+      }
+      __syncwarp();
+    }
+    return entered;
+  }
+  template <typename F>
+  __device__ __forceinline__ void for_each_id(F &&f) const {
+    for (uint32_t e = lane; e < size; e += 32) f((uint32_t)pool[e] & ~FLAG);
+  }
+  __device__ __forceinline__ uint64_t col_next_above(uint64_t last) const {
+    uint64_t m = NONE;
+    for (uint32_t e = lane; e < size; e += 32) {
+      const uint64_t km = pool[e] & KEYMASK;
+      if (km > last && km < m) m = km;
+    }
+    return m;
+  }
+};
+
+}  // namespace
+}  // namespace hs

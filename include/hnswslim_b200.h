@@ -87,6 +87,22 @@ int hs_set_ef(hs_index *, size_t ef);
 
 int hs_get_info(const hs_index *, hs_index_info *out);
 
+/* hnsw_slimq only.  The reference draws its query-quantiser constant at random when it loads an
+ * index (slimq.h:1274-1276 -> faster_config, rabitqlib/quantization/rabitq.hpp:27-34 ->
+ * rabitq_impl.hpp:363-377: std::random_device), so its estimates differ in the low bits from
+ * load to load.  The engine derives the constant the same way from a FIXED seed at hs_load;
+ * these read / override it (the parity tests copy the reference's value in). */
+int hs_get_query_tconst(const hs_index *, double *t_const);
+int hs_set_query_tconst(hs_index *, double t_const);
+
+/* hnsw_slimq only, inspection: the per-query preparation of searchKnn (slimq.h:1816-1847) as the
+ * traversal kernel computes it — FhtKacRotator::rotate (rabitqlib/utils/rotator.hpp:370-423),
+ * SplitSingleQuery (rabitqlib/index/query.hpp:127-156) and the centroid distances.  Host buffers:
+ * rotated nq x padded_dim, planes nq x padded_dim/64*4 (plane j of word w at [w*4+j], MSB-first),
+ * scal nq x 3 = (delta, vl, k1xsumq), q2c nq x num_cluster. */
+int hs_slimq_prepare(hs_index *, const float *queries, size_t nq, float *rotated_out,
+                     uint64_t *planes_out, float *scal_out, float *q2c_out);
+
 /* Replaces the query loop of HnswSlimStrategy::solve / HnswSlimQStrategy::solve
  * (hnsw_slim_strategy.h:112-114, hnsw_slimq_strategy.h:157-159), i.e. nq calls of
  * searchKnn(const void*, size_t k, tableint*) (slim.h:2030-2131, slimq.h:1810-1924),

@@ -79,6 +79,52 @@ int hso_bruteforce(const float *base, size_t n, size_t dim, int metric, int orde
 double hso_recall(const float *base, size_t dim, const float *queries, size_t nq,
                   const uint32_t *knn, size_t K, const uint32_t *gt, size_t gt_k, int metric);
 
+/* ------------------------------------------------------------------------------------
+ * hnsw_slimq (hs_oracle_slimq.c): slimq.h = third_party/hnswlib/hnswalg_slimq.h,
+ * rq/ = third_party/rabitqlib/ */
+typedef struct hsoq_index hsoq_index;
+typedef struct {
+  uint64_t n, size_data_per_element, maxM, maxM0, M, ef_construction, dim, padded_dim, num_cluster, ex_bits;
+  int32_t maxlevel, threshold_level;
+  uint32_t enterpoint;
+  int32_t metric_type;
+} hsoq_info;
+
+/* slimq.h:1218-1313 */
+hsoq_index *hsoq_load(const char *graph_path, size_t dim);
+void hsoq_free(hsoq_index *);
+void hsoq_get_info(const hsoq_index *, hsoq_info *out);
+const char *hsoq_last_error(void);
+/* the query-quantiser constant the reference draws at random at load time (slimq.h:1274-1276) */
+void hsoq_set_tconst(hsoq_index *, double t_const);
+/* record accessors (slimq.h:388-405): cluster id, code words, (f_add, f_rescale, f_error),
+ * level-0 neighbour ids; returns the level-0 degree */
+int hsoq_node(const hsoq_index *, uint32_t node, uint32_t *cluster, uint64_t *code, float *factors,
+              uint32_t *nbr_out, int cap);
+/* FhtKacRotator::rotate, rq/utils/rotator.hpp:370-423: q[dim] -> out[padded_dim] */
+void hsoq_rotate(const hsoq_index *, const float *q, float *out);
+/* SplitSingleQuery ctor, rq/index/query.hpp:127-156: rotated query -> planes[padded_dim/64*4],
+ * scal = (delta, vl, k1xsumq); codes_out (may be NULL): the 4-bit code of every dimension */
+void hsoq_quantize_query(const hsoq_index *, const float *rotated, uint64_t *planes, float *scal,
+                         uint16_t *codes_out);
+/* slimq.h:1816-1847: rotate + quantise + distances to the cluster centroids */
+void hsoq_prep(const hsoq_index *, const float *q, float *rotated, uint64_t *planes, float *scal,
+               float *q2c);
+/* get_bin_est, slimq.h:408-440 */
+float hsoq_est(const hsoq_index *, uint32_t node, const uint64_t *planes, const float *scal,
+               const float *q2c);
+/* slimq.h:1810-1924 for a batch.  raw_base: the n x dim rows setDataset() points at (indexed by
+ * internal id, slimq.h:747-749).  inj_* (all or none, may be NULL): per-query preparation to use
+ * instead of hsoq_prep (planes nq x padded_dim/64*4, scal nq x 3, q2c nq x num_cluster) — this is
+ * how the search is pinned to the reference independently of the preparation's rounding.
+ * out rows: the k nearest EXPANDED nodes by exact distance, sorted by (dist, internal id);
+ * padded with 0xFFFFFFFF / +inf.  Counters per query (may be NULL): estimates computed,
+ * nodes expanded (upper scans + base expansions), exact reranks. */
+int hsoq_search(const hsoq_index *, const float *raw_base, const float *queries, size_t nq, size_t k,
+                size_t ef, int order, int team, int threads, const uint64_t *inj_planes,
+                const float *inj_scal, const float *inj_q2c, uint32_t *out_labels, float *out_dists,
+                uint32_t *n_est, uint32_t *n_hops, uint32_t *n_rerank);
+
 #ifdef __cplusplus
 }
 #endif

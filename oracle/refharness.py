@@ -232,6 +232,180 @@ def ref_bruteforce(base, q, k, metric=0, threads=0, want_dists=False):
     return (out, d, sec.value) if want_dists else (out, sec.value)
 
 
+# --------------------------------------------------------------------------- hnsw_slimq reference
+_slimq_lib = None
+
+
+def slimq_lib():
+    global _slimq_lib
+    if _slimq_lib is None:
+        p = ref_slimq_path()
+        if p is None:
+            raise RuntimeError("oracle/_ref/libhsref_slimq_v4.so not built or host CPU lacks AVX-512 VPOPCNTDQ")
+        L = C.CDLL(p)
+        L.refq_last_error.restype = C.c_char_p
+        L.refq_build.restype = C.c_int
+        L.refq_build.argtypes = [_f32p, C.c_size_t, C.c_size_t, _f32p, C.c_size_t, _u32p, C.c_size_t, C.c_size_t,
+                                 C.c_int, C.c_float, C.c_float, C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t,
+                                 C.c_int, C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        L.refq_open.restype = C.c_void_p
+        L.refq_open.argtypes = [C.c_char_p, C.c_size_t, C.c_size_t, _f32p]
+        L.refq_close.argtypes = [C.c_void_p]
+        L.refq_info.argtypes = [C.c_void_p, _u64p]
+        L.refq_get_tconst.restype = C.c_double
+        L.refq_get_tconst.argtypes = [C.c_void_p]
+        L.refq_set_tconst.argtypes = [C.c_void_p, C.c_double]
+        L.refq_search.restype = C.c_int
+        L.refq_search.argtypes = [C.c_void_p, _f32p, C.c_size_t, C.c_size_t, C.c_size_t, _u32p,
+                                  C.POINTER(C.c_double)]
+        L.refq_prep.restype = C.c_int
+        L.refq_prep.argtypes = [C.c_void_p, _f32p, _f32p, _u64p, _f32p, _f32p]
+        L.refq_est.restype = C.c_int
+        L.refq_est.argtypes = [C.c_void_p, _f32p, _u32p, C.c_size_t, _f32p]
+        L.refq_rotate.restype = C.c_int
+        L.refq_rotate.argtypes = [C.c_void_p, _f32p, C.c_size_t, _f32p]
+        L.refq_node.restype = C.c_int
+        L.refq_node.argtypes = [C.c_void_p, C.c_uint32, _u32p, _u64p, _f32p, _u32p, C.c_int]
+        _slimq_lib = L
+    return _slimq_lib
+
+
+def kmeans(base: np.ndarray, k: int = 16, iters: int = 10, seed: int = 7, sample: int = 100000):
+    """Lloyd k-means -> (centroids[k,dim] f32, cluster_ids[n] u32).  The reference has no producer for
+    its *_centroids_16.fvecs / *_clusterids_16.ivecs inputs (hnsw_slimq_strategy.h:42-45)."""
+    rng = np.random.default_rng(seed)
+    base = np.ascontiguousarray(base, dtype=np.float32)
+    n = base.shape[0]
+    train = base[rng.choice(n, size=min(n, sample), replace=False)]
+    cent = train[rng.choice(train.shape[0], size=k, replace=False)].copy()
+
+    def assign(x):
+        d = (x * x).sum(1)[:, None] - 2.0 * x @ cent.T + (cent * cent).sum(1)[None, :]
+        return d.argmin(1)
+    for _ in range(iters):
+        a = assign(train)
+        for c in range(k):
+            m = a == c
+            if m.any():
+                cent[c] = train[m].mean(0)
+    ids = np.concatenate([assign(base[i:i + 262144]) for i in range(0, n, 262144)]).astype(np.uint32)
+    return cent.astype(np.float32), ids
+
+
+def ref_slimq_build(base, centroids, cluster_ids, path: str, *, M: int = 32, ef_construction: int = 128,
+                    threads: int = 1, isolate: bool = True, **prune) -> tuple[float, float]:
+    """rabitqlib HNSW construct -> HierarchicalNSWSlimQ::convertFromHNSW -> saveIndex
+    (hnsw_slimq_strategy.h:100-142).  threads=1 keeps internal id == label."""
+    if isolate:
+        import json
+        import sys
+        import tempfile
+        with tempfile.TemporaryDirectory(prefix="hsrefq_") as td:
+            np.save(os.path.join(td, "base.npy"), np.ascontiguousarray(base, dtype=np.float32))
+            np.save(os.path.join(td, "cent.npy"), np.ascontiguousarray(centroids, dtype=np.float32))
+            np.save(os.path.join(td, "cid.npy"), np.ascontiguousarray(cluster_ids, dtype=np.uint32))
+            with open(os.path.join(td, "args.json"), "w") as f:
+                json.dump(dict(path=path, M=M, ef_construction=ef_construction, threads=threads, prune=prune), f)
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--build-slimq", td],
+                               capture_output=True, text=True)
+            if r.returncode != 0:
+                raise RuntimeError(f"reference slimq builder failed (rc={r.returncode}): {r.stderr[-2000:]}")
+            return tuple(json.loads(r.stdout.strip().splitlines()[-1]))
+    L = slimq_lib()
+    p = dict(PRUNE_DEFAULTS)
+    p.update(prune)
+    base = np.ascontiguousarray(base, dtype=np.float32)
+    centroids = np.ascontiguousarray(centroids, dtype=np.float32)
+    cluster_ids = np.ascontiguousarray(cluster_ids, dtype=np.uint32)
+    n, dim = base.shape
+    bs, cs = C.c_double(0), C.c_double(0)
+    rc = L.refq_build(base, n, dim, centroids, centroids.shape[0], cluster_ids, M, ef_construction,
+                      p["threshold_level"], p["top_degree_percent0"], p["top_degree_percent"], p["top_M0"],
+                      p["low_m0"], p["top_M"], p["low_m"], threads, path.encode(), C.byref(bs), C.byref(cs))
+    if rc != 0:
+        raise RuntimeError(L.refq_last_error().decode())
+    return bs.value, cs.value
+
+
+class RefSlimQ:
+    """The reference's HierarchicalNSWSlimQ<float> loaded from a .graph file + setDataset(base)."""
+
+    INFO_KEYS = ["n", "size_data_per_element", "maxM", "maxM0", "M", "ef_construction", "maxlevel",
+                 "threshold_level", "enterpoint", "num_cluster", "dim", "padded_dim", "ex_bits", "metric_type"]
+
+    def __init__(self, path: str, base: np.ndarray):
+        self.L = slimq_lib()
+        base = np.ascontiguousarray(base, dtype=np.float32)
+        self.dim = base.shape[1]
+        self.h = self.L.refq_open(path.encode(), self.dim, base.shape[0], base)
+        if not self.h:
+            raise RuntimeError(self.L.refq_last_error().decode())
+        a = np.zeros(len(self.INFO_KEYS), dtype=np.uint64)
+        self.L.refq_info(self.h, a)
+        self.info = {k: int(v) for k, v in zip(self.INFO_KEYS, a)}
+        for k in ("maxlevel", "threshold_level"):
+            if self.info[k] >= 1 << 63:
+                self.info[k] -= 1 << 64
+
+    def close(self):
+        if self.h:
+            self.L.refq_close(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
+
+    @property
+    def t_const(self) -> float:
+        return float(self.L.refq_get_tconst(self.h))
+
+    @t_const.setter
+    def t_const(self, v: float):
+        self.L.refq_set_tconst(self.h, float(v))
+
+    def search(self, q, k: int, ef: int):
+        q = np.ascontiguousarray(q, dtype=np.float32)
+        out = np.zeros((q.shape[0], k), dtype=np.uint32)
+        sec = C.c_double(0)
+        if self.L.refq_search(self.h, q, q.shape[0], k, ef, out, C.byref(sec)) != 0:
+            raise RuntimeError(self.L.refq_last_error().decode())
+        return out, sec.value
+
+    def prep(self, q):
+        """-> rotated[nq,pd], planes[nq,pd/64*4] u64, scal[nq,3] (delta, vl, k1xsumq), q2c[nq,ncl]"""
+        q = np.ascontiguousarray(q, dtype=np.float32).reshape(-1, self.dim)
+        pd, nc = self.info["padded_dim"], self.info["num_cluster"]
+        nq = q.shape[0]
+        rot = np.zeros((nq, pd), np.float32)
+        planes = np.zeros((nq, pd // 64 * 4), np.uint64)
+        scal = np.zeros((nq, 3), np.float32)
+        q2c = np.zeros((nq, nc), np.float32)
+        for i in range(nq):
+            self.L.refq_prep(self.h, q[i], rot[i], planes[i], scal[i], q2c[i])
+        return rot, planes, scal, q2c
+
+    def est(self, q, ids):
+        ids = np.ascontiguousarray(ids, dtype=np.uint32)
+        out = np.zeros(ids.shape[0], np.float32)
+        self.L.refq_est(self.h, np.ascontiguousarray(q, dtype=np.float32), ids, ids.shape[0], out)
+        return out
+
+    def rotate(self, v):
+        v = np.ascontiguousarray(v, dtype=np.float32).reshape(-1, self.dim)
+        out = np.zeros((v.shape[0], self.info["padded_dim"]), np.float32)
+        self.L.refq_rotate(self.h, v, v.shape[0], out)
+        return out
+
+    def node(self, i: int):
+        """-> cluster id, code words u64[pd/64], (f_add, f_rescale, f_error), level-0 neighbour ids"""
+        cl = np.zeros(1, np.uint32)
+        code = np.zeros(self.info["padded_dim"] // 64, np.uint64)
+        fac = np.zeros(3, np.float32)
+        nb = np.zeros(256, np.uint32)
+        cnt = self.L.refq_node(self.h, i, cl, code, fac, nb, 256)
+        return int(cl[0]), code, fac, nb[:cnt].copy()
+
+
 # --------------------------------------------------------------------------- C restatement
 ORDER_SEQ, ORDER_REF, ORDER_GPU, ORDER_SEQFMA = 0, 1, 2, 3
 _oracle_lib = None
@@ -242,6 +416,14 @@ class _HsoInfo(C.Structure):
                 ("maxM0", C.c_uint64), ("M", C.c_uint64), ("ef_construction", C.c_uint64), ("dim", C.c_uint64),
                 ("maxlevel", C.c_int32), ("threshold_level", C.c_int32), ("enterpoint", C.c_uint32),
                 ("has_deleted", C.c_int32)]
+
+
+class _HsoqInfo(C.Structure):
+    _fields_ = [("n", C.c_uint64), ("size_data_per_element", C.c_uint64), ("maxM", C.c_uint64),
+                ("maxM0", C.c_uint64), ("M", C.c_uint64), ("ef_construction", C.c_uint64), ("dim", C.c_uint64),
+                ("padded_dim", C.c_uint64), ("num_cluster", C.c_uint64), ("ex_bits", C.c_uint64),
+                ("maxlevel", C.c_int32), ("threshold_level", C.c_int32), ("enterpoint", C.c_uint32),
+                ("metric_type", C.c_int32)]
 
 
 def oracle_lib():
@@ -273,6 +455,23 @@ def oracle_lib():
                                      C.c_size_t, C.c_int, _u32p, C.c_void_p]
         L.hso_recall.restype = C.c_double
         L.hso_recall.argtypes = [_f32p, C.c_size_t, _f32p, C.c_size_t, _u32p, C.c_size_t, _u32p, C.c_size_t, C.c_int]
+        L.hsoq_last_error.restype = C.c_char_p
+        L.hsoq_load.restype = C.c_void_p
+        L.hsoq_load.argtypes = [C.c_char_p, C.c_size_t]
+        L.hsoq_free.argtypes = [C.c_void_p]
+        L.hsoq_get_info.argtypes = [C.c_void_p, C.POINTER(_HsoqInfo)]
+        L.hsoq_set_tconst.argtypes = [C.c_void_p, C.c_double]
+        L.hsoq_node.restype = C.c_int
+        L.hsoq_node.argtypes = [C.c_void_p, C.c_uint32, _u32p, _u64p, _f32p, _u32p, C.c_int]
+        L.hsoq_rotate.argtypes = [C.c_void_p, _f32p, _f32p]
+        L.hsoq_quantize_query.argtypes = [C.c_void_p, _f32p, _u64p, _f32p, C.c_void_p]
+        L.hsoq_prep.argtypes = [C.c_void_p, _f32p, _f32p, _u64p, _f32p, _f32p]
+        L.hsoq_est.restype = C.c_float
+        L.hsoq_est.argtypes = [C.c_void_p, C.c_uint32, _u64p, _f32p, _f32p]
+        L.hsoq_search.restype = C.c_int
+        L.hsoq_search.argtypes = [C.c_void_p, _f32p, _f32p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_int, C.c_int,
+                                  C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, _u32p, C.c_void_p, C.c_void_p,
+                                  C.c_void_p, C.c_void_p]
         _oracle_lib = L
     return _oracle_lib
 
@@ -322,6 +521,96 @@ class Oracle:
         return lab, dist, nd, nh
 
 
+class OracleQ:
+    """oracle/hs_oracle_slimq.c: the plain-C restatement of HierarchicalNSWSlimQ load + searchKnn.
+    `base` are the raw rows the reference reranks with (setDataset, slimq.h:303-305)."""
+
+    def __init__(self, path: str, base: np.ndarray, t_const: float | None = None):
+        self.L = oracle_lib()
+        self.base = np.ascontiguousarray(base, dtype=np.float32)
+        self.dim = self.base.shape[1]
+        self.h = self.L.hsoq_load(path.encode(), self.dim)
+        if not self.h:
+            raise RuntimeError(self.L.hsoq_last_error().decode())
+        s = _HsoqInfo()
+        self.L.hsoq_get_info(self.h, C.byref(s))
+        self.info = {f: getattr(s, f) for f, _ in s._fields_}
+        if t_const is not None:
+            self.set_tconst(t_const)
+
+    def close(self):
+        if self.h:
+            self.L.hsoq_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
+
+    def set_tconst(self, t: float):
+        self.L.hsoq_set_tconst(self.h, float(t))
+
+    def node(self, i: int):
+        cl = np.zeros(1, np.uint32)
+        code = np.zeros(self.info["padded_dim"] // 64, np.uint64)
+        fac = np.zeros(3, np.float32)
+        nb = np.zeros(256, np.uint32)
+        cnt = self.L.hsoq_node(self.h, i, cl, code, fac, nb, 256)
+        return int(cl[0]), code, fac, nb[:cnt].copy()
+
+    def rotate(self, q):
+        q = np.ascontiguousarray(q, dtype=np.float32).reshape(-1, self.dim)
+        out = np.zeros((q.shape[0], self.info["padded_dim"]), np.float32)
+        for i in range(q.shape[0]):
+            self.L.hsoq_rotate(self.h, q[i], out[i])
+        return out
+
+    def quantize(self, rotated):
+        """-> planes[nq, pd/64*4], scal[nq,3], codes[nq,pd] (4-bit code per dimension)"""
+        pd = self.info["padded_dim"]
+        rotated = np.ascontiguousarray(rotated, dtype=np.float32).reshape(-1, pd)
+        nq = rotated.shape[0]
+        planes = np.zeros((nq, pd // 64 * 4), np.uint64)
+        scal = np.zeros((nq, 3), np.float32)
+        codes = np.zeros((nq, pd), np.uint16)
+        for i in range(nq):
+            self.L.hsoq_quantize_query(self.h, rotated[i], planes[i], scal[i], codes[i].ctypes.data)
+        return planes, scal, codes
+
+    def prep(self, q):
+        q = np.ascontiguousarray(q, dtype=np.float32).reshape(-1, self.dim)
+        pd, nc = self.info["padded_dim"], self.info["num_cluster"]
+        nq = q.shape[0]
+        rot = np.zeros((nq, pd), np.float32)
+        planes = np.zeros((nq, pd // 64 * 4), np.uint64)
+        scal = np.zeros((nq, 3), np.float32)
+        q2c = np.zeros((nq, nc), np.float32)
+        for i in range(nq):
+            self.L.hsoq_prep(self.h, q[i], rot[i], planes[i], scal[i], q2c[i])
+        return rot, planes, scal, q2c
+
+    def est(self, ids, planes, scal, q2c):
+        return np.array([self.L.hsoq_est(self.h, int(i), planes, scal, q2c) for i in ids], np.float32)
+
+    def search(self, q, k: int, ef: int, order: int = ORDER_GPU, team: int = 8, threads: int = 0, inject=None):
+        """-> labels[nq,k], dists[nq,k] (sorted by (dist,id)), n_est[nq], n_hops[nq], n_rerank[nq].
+        inject = (planes, scal, q2c) replaces the oracle's own per-query preparation."""
+        q = np.ascontiguousarray(q, dtype=np.float32).reshape(-1, self.dim)
+        nq = q.shape[0]
+        lab = np.zeros((nq, k), np.uint32)
+        dist = np.zeros((nq, k), np.float32)
+        ne, nh, nr = (np.zeros(nq, np.uint32) for _ in range(3))
+        ip = isc = iq = None
+        if inject is not None:
+            pl, sc, qc = (np.ascontiguousarray(a) for a in inject)
+            assert pl.dtype == np.uint64 and sc.dtype == np.float32 and qc.dtype == np.float32
+            ip, isc, iq = pl.ctypes.data, sc.ctypes.data, qc.ctypes.data
+        rc = self.L.hsoq_search(self.h, self.base, q, nq, k, ef, order, team, threads, ip, isc, iq, lab,
+                                dist.ctypes.data, ne.ctypes.data, nh.ctypes.data, nr.ctypes.data)
+        if rc != 0:
+            raise RuntimeError(self.L.hsoq_last_error().decode())
+        return lab, dist, ne, nh, nr
+
+
 def oracle_dist(a, b, metric=0, order=ORDER_GPU, team=8) -> float:
     a = np.ascontiguousarray(a, dtype=np.float32)
     b = np.ascontiguousarray(b, dtype=np.float32)
@@ -361,4 +650,13 @@ if __name__ == "__main__":
         out = ref_slim_build(np.ascontiguousarray(base), a["path"], metric=a["metric"], M=a["M"],
                              ef_construction=a["ef_construction"], branching=a["branching"], threads=a["threads"],
                              labels=labels, hnsw_path=a["hnsw_path"], isolate=False, **a["prune"])
+        print(json.dumps(out))
+    if len(sys.argv) == 3 and sys.argv[1] == "--build-slimq":
+        td = sys.argv[2]
+        with open(os.path.join(td, "args.json")) as f:
+            a = json.load(f)
+        out = ref_slimq_build(np.load(os.path.join(td, "base.npy")), np.load(os.path.join(td, "cent.npy")),
+                              np.load(os.path.join(td, "cid.npy")), a["path"], M=a["M"],
+                              ef_construction=a["ef_construction"], threads=a["threads"], isolate=False,
+                              **a["prune"])
         print(json.dumps(out))
