@@ -22,7 +22,7 @@ EXPORTS = [
     "hs_bruteforce_knn_device", "hs_topk_merge_device", "hs_recall", "hs_last_error", "hs_abi_version",
     "hs_debug_flatten", "hs_debug_free", "hs_debug_info", "hs_debug_row", "hs_debug_node",
     "hs_build_params_default", "hs_build_slim_graph",
-    "hs_get_query_tconst", "hs_set_query_tconst", "hs_slimq_prepare",
+    "hs_get_query_tconst", "hs_set_query_tconst", "hs_slimq_prepare", "hs_build_slimq_graph",
 ]
 
 
@@ -96,6 +96,7 @@ def lib():
         L.hs_build_params_default.argtypes = [C.POINTER(BuildParams)]
         L.hs_build_params_default.restype = None
         L.hs_build_slim_graph.argtypes = [vp, sz, sz, i32, C.POINTER(BuildParams), vp, C.c_char_p]
+        L.hs_build_slimq_graph.argtypes = [vp, sz, sz, C.POINTER(BuildParams), vp, sz, vp, vp, C.c_char_p]
         L.hs_get_query_tconst.argtypes = [vp, C.POINTER(C.c_double)]
         L.hs_set_query_tconst.argtypes = [vp, C.c_double]
         L.hs_slimq_prepare.argtypes = [vp, vp, sz, vp, vp, vp, vp]
@@ -235,6 +236,30 @@ def build_slim_graph(base, path: str, *, metric: int = HS_METRIC_L2, M: int = 16
         labels = np.ascontiguousarray(labels, dtype=np.uint64)
         lab = labels.ctypes.data
     _check(lib().hs_build_slim_graph(b.ctypes.data, b.shape[0], b.shape[1], metric, C.byref(p), lab, path.encode()))
+
+
+def build_slimq_graph(base, path: str, *, M: int = 16, ef_construction: int = 200, branching: str = "4",
+                      threads: int = 0, labels=None, seed: int = 100, centroids=None, cluster_ids=None,
+                      num_cluster: int = 16, **prune) -> None:
+    """hs_build_slimq_graph: HNSW + HNSW-Slim pruning + RaBitQ codes -> reference-format hnsw_slimq .graph."""
+    b = _f32(base)
+    p = BuildParams()
+    lib().hs_build_params_default(C.byref(p))
+    p.M, p.ef_construction, p.branching_factor = M, ef_construction, branching.encode()
+    p.threads, p.seed = threads, seed
+    for k_, v in prune.items():
+        setattr(p, k_, v)
+    lab = cen = cid = None
+    if labels is not None:
+        labels = np.ascontiguousarray(labels, dtype=np.uint64)
+        lab = labels.ctypes.data
+    if centroids is not None:
+        centroids = _f32(centroids)
+        cluster_ids = np.ascontiguousarray(cluster_ids, dtype=np.uint32)
+        num_cluster = centroids.shape[0]
+        cen, cid = centroids.ctypes.data, cluster_ids.ctypes.data
+    _check(lib().hs_build_slimq_graph(b.ctypes.data, b.shape[0], b.shape[1], C.byref(p), cen, num_cluster, cid,
+                                      lab, path.encode()))
 
 
 class HostGraph:

@@ -287,16 +287,23 @@ void parallel_for(size_t begin, size_t end, int threads, F &&fn) {
 
 }  // namespace
 
-int build_slim_graph(const float *base, size_t n, size_t dim, int metric, size_t M, size_t ef_construction,
-                     double branching, int threshold_level, float top_pct0, float top_pct, size_t top_M0,
-                     size_t low_m0, size_t top_M, size_t low_m, int threads, uint64_t seed,
-                     const uint64_t *labels, const char *out_path) {
-  if (!base || n == 0 || dim == 0 || M < 2 || M > 512 || !out_path || branching <= 1.0 || n >= (1ull << 31)) {
+namespace {
+
+// HNSW construction + HNSW-Slim pruning: the pruned per-level out-lists of every node.
+struct Pruned {
+  Hnsw h;
+  std::vector<std::vector<std::vector<uint32_t>>> nbr;
+  int maxlevel = 0;
+};
+
+int build_pruned(const float *base, size_t n, size_t dim, int metric, size_t M, size_t ef_construction,
+                 double branching, int threshold_level, float top_pct0, float top_pct, size_t top_M0,
+                 size_t low_m0, size_t top_M, size_t low_m, int threads, uint64_t seed, Pruned *out) {
+  if (!base || n == 0 || dim == 0 || M < 2 || M > 512 || branching <= 1.0 || n >= (1ull << 31)) {
     set_error("build_slim_graph: bad argument");
     return HS_ERR_ARG;
   }
-  if (threads <= 0) threads = (int)std::max(1u, std::thread::hardware_concurrency());
-  Hnsw h;
+  Hnsw &h = out->h;
   h.data = base;
   h.n = n;
   h.dim = dim;
@@ -364,7 +371,9 @@ int build_slim_graph(const float *base, size_t n, size_t dim, int metric, size_t
     }
   }
   // out-lists after the first prune, then with reverse edges merged in
-  std::vector<std::vector<std::vector<uint32_t>>> nbr(n), rev(n);
+  std::vector<std::vector<std::vector<uint32_t>>> &nbr = out->nbr;
+  std::vector<std::vector<std::vector<uint32_t>>> rev(n);
+  nbr.assign(n, {});
   parallel_for(0, n, threads, [&](size_t v, int) {
     const int lv = h.level[v];
     nbr[v].resize(lv + 1);
@@ -414,6 +423,59 @@ int build_slim_graph(const float *base, size_t n, size_t dim, int metric, size_t
     rev[v].clear();
     rev[v].shrink_to_fit();
   });
+  out->maxlevel = maxlevel;
+  return HS_OK;
+}
+
+// per-node neighbour blobs, shared by both file formats (slim.h:741-748, slimq.h:1205-1214)
+bool write_blobs(FILE *f, const Pruned &P) {
+  const size_t n = P.h.n;
+  auto put = [&](const void *p, size_t sz) { return std::fwrite(p, 1, sz, f) == sz; };
+  bool ok = true;
+  std::vector<uint8_t> blob;
+  for (size_t i = 0; i < n && ok; ++i) {
+    const int lv = P.h.level[i];
+    uint32_t total = 0;
+    for (auto &l : P.nbr[i]) total += (uint32_t)l.size();
+    const uint32_t bsz = (uint32_t)(2 * lv + 4 * total);
+    ok &= put(&bsz, 4);
+    if (bsz == 0 || total == 0) continue;
+    blob.resize(bsz);
+    uint32_t run = 0;
+    for (int l = 0; l < lv; ++l) {
+      run += (uint32_t)P.nbr[i][l].size();
+      const uint16_t o = (uint16_t)run;
+      std::memcpy(&blob[2 * l], &o, 2);
+    }
+    size_t w = 2 * (size_t)lv;
+    for (int l = 0; l <= lv; ++l)
+      for (uint32_t u : P.nbr[i][l]) {
+        std::memcpy(&blob[w], &u, 4);
+        w += 4;
+      }
+    ok &= put(blob.data(), bsz);
+  }
+  return ok;
+}
+
+}  // namespace
+
+int build_slim_graph(const float *base, size_t n, size_t dim, int metric, size_t M, size_t ef_construction,
+                     double branching, int threshold_level, float top_pct0, float top_pct, size_t top_M0,
+                     size_t low_m0, size_t top_M, size_t low_m, int threads, uint64_t seed,
+                     const uint64_t *labels, const char *out_path) {
+  if (!out_path) {
+    set_error("build_slim_graph: bad argument");
+    return HS_ERR_ARG;
+  }
+  if (threads <= 0) threads = (int)std::max(1u, std::thread::hardware_concurrency());
+  Pruned P;
+  int rc = build_pruned(base, n, dim, metric, M, ef_construction, branching, threshold_level, top_pct0, top_pct,
+                        top_M0, low_m0, top_M, low_m, threads, seed, &P);
+  if (rc != HS_OK) return rc;
+  Hnsw &h = P.h;
+  auto &nbr = P.nbr;
+  const int maxlevel = P.maxlevel;
 
   // ---- 3. saveIndex format (slim.h:717-751) ----
   FILE *f = std::fopen(out_path, "wb");
@@ -447,29 +509,209 @@ int build_slim_graph(const float *base, size_t n, size_t dim, int metric, size_t
     std::memcpy(&record[24], h.vec((uint32_t)i), 4 * dim);
     ok &= put(record.data(), rec);
   }
-  std::vector<uint8_t> blob;
-  for (size_t i = 0; i < n && ok; ++i) {
-    const int lv = h.level[i];
-    uint32_t total = 0;
-    for (auto &l : nbr[i]) total += (uint32_t)l.size();
-    const uint32_t bsz = (uint32_t)(2 * lv + 4 * total);
-    ok &= put(&bsz, 4);
-    if (bsz == 0 || total == 0) continue;
-    blob.resize(bsz);
-    uint32_t run = 0;
-    for (int l = 0; l < lv; ++l) {
-      run += (uint32_t)nbr[i][l].size();
-      const uint16_t o = (uint16_t)run;
-      std::memcpy(&blob[2 * l], &o, 2);
-    }
-    size_t w = 2 * (size_t)lv;
-    for (int l = 0; l <= lv; ++l)
-      for (uint32_t u : nbr[i][l]) {
-        std::memcpy(&blob[w], &u, 4);
-        w += 4;
-      }
-    ok &= put(blob.data(), bsz);
+  ok = ok && write_blobs(f, P);
+  ok &= std::fclose(f) == 0;
+  if (!ok) {
+    set_error(std::string("write error on ") + out_path);
+    return HS_ERR_IO;
   }
+  return HS_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// hnsw_slimq builder: the same HNSW + HNSW-Slim pruning over the raw floats, node payload =
+// 1-bit RaBitQ codes + factors, written in HierarchicalNSWSlimQ::saveIndex's format
+// (slimq.h:1161-1216) so both hs_load and the reference's loadIndex read it.
+namespace {
+
+void host_fwht(float *buf, size_t len) {          // natural order, butterfly distance 1, 2, 4, ...
+  for (size_t h = 1; h < len; h *= 2)
+    for (size_t j = 0; j < len; j += 2 * h)
+      for (size_t k = 0; k < h; ++k) {
+        const float u = buf[j + k], v = buf[j + k + h];
+        buf[j + k] = u + v;
+        buf[j + k + h] = u - v;
+      }
+}
+
+// FhtKacRotator::rotate (rabitqlib/utils/rotator.hpp:370-423)
+void host_rotate(const float *x, size_t dim, size_t pd, size_t td, const uint8_t *flip, float *out) {
+  const float fac = 1.0f / std::sqrt((float)td);
+  std::memcpy(out, x, 4 * dim);
+  std::fill(out + dim, out + pd, 0.f);
+  const bool pow2 = td == pd;
+  const size_t start = pd - td;
+  for (int r = 0; r < 4; ++r) {
+    const uint8_t *fl = flip + (size_t)r * pd / 8;
+    for (size_t i = 0; i < pd; ++i)
+      if ((fl[i >> 3] >> (i & 7)) & 1u) out[i] = -out[i];
+    float *seg = (!pow2 && (r & 1)) ? out + start : out;
+    host_fwht(seg, td);
+    for (size_t i = 0; i < td; ++i) seg[i] *= fac;
+    if (!pow2)
+      for (size_t i = 0; i < pd / 2; ++i) {
+        const float a = out[i], b = out[i + pd / 2];
+        out[i] = a + b;
+        out[i + pd / 2] = a - b;
+      }
+  }
+  if (!pow2)
+    for (size_t i = 0; i < pd; ++i) out[i] *= 0.25f;
+}
+
+// Lloyd k-means over the raw rows (the reference reads *_centroids_16.fvecs and
+// *_clusterids_16.ivecs that no code in it produces, hnsw_slimq_strategy.h:42-45)
+void host_kmeans(const float *base, size_t n, size_t dim, size_t k, int iters, uint64_t seed, int threads,
+                 std::vector<float> &cent, std::vector<uint32_t> &ids) {
+  cent.assign(k * dim, 0.f);
+  ids.assign(n, 0);
+  for (size_t c = 0; c < k; ++c) {
+    const size_t pick = (size_t)(mix64(seed * 7919 + c) % n);
+    std::memcpy(&cent[c * dim], base + pick * dim, 4 * dim);
+  }
+  const size_t sample = std::min<size_t>(n, 200000), stride = std::max<size_t>(1, n / sample);
+  auto assign = [&](size_t i) {
+    float best = std::numeric_limits<float>::max();
+    uint32_t arg = 0;
+    for (size_t c = 0; c < k; ++c) {
+      const float d = l2sqr(base + i * dim, &cent[c * dim], dim);
+      if (d < best) {
+        best = d;
+        arg = (uint32_t)c;
+      }
+    }
+    return arg;
+  };
+  for (int it = 0; it < iters; ++it) {
+    std::vector<std::vector<double>> sum(threads, std::vector<double>(k * dim, 0.0));
+    std::vector<std::vector<size_t>> cnt(threads, std::vector<size_t>(k, 0));
+    parallel_for(0, (n + stride - 1) / stride, threads, [&](size_t s, int tid) {
+      const size_t i = s * stride;
+      const uint32_t a = assign(i);
+      cnt[tid][a]++;
+      for (size_t d = 0; d < dim; ++d) sum[tid][a * dim + d] += base[i * dim + d];
+    });
+    for (size_t c = 0; c < k; ++c) {
+      size_t tot = 0;
+      for (int t = 0; t < threads; ++t) tot += cnt[t][c];
+      if (!tot) continue;
+      for (size_t d = 0; d < dim; ++d) {
+        double v = 0;
+        for (int t = 0; t < threads; ++t) v += sum[t][c * dim + d];
+        cent[c * dim + d] = (float)(v / (double)tot);
+      }
+    }
+  }
+  parallel_for(0, n, threads, [&](size_t i, int) { ids[i] = assign(i); });
+}
+
+}  // namespace
+
+int build_slimq_graph(const float *base, size_t n, size_t dim, size_t M, size_t ef_construction, double branching,
+                      int threshold_level, float top_pct0, float top_pct, size_t top_M0, size_t low_m0,
+                      size_t top_M, size_t low_m, int threads, uint64_t seed, const float *centroids,
+                      size_t num_cluster, const uint32_t *cluster_ids, const uint64_t *labels,
+                      const char *out_path) {
+  if (!out_path || num_cluster == 0 || num_cluster > 4096 || (centroids && !cluster_ids)) {
+    set_error("build_slimq_graph: bad argument");
+    return HS_ERR_ARG;
+  }
+  if (threads <= 0) threads = (int)std::max(1u, std::thread::hardware_concurrency());
+  Pruned P;
+  int rc = build_pruned(base, n, dim, HS_METRIC_L2, M, ef_construction, branching, threshold_level, top_pct0,
+                        top_pct, top_M0, low_m0, top_M, low_m, threads, seed, &P);
+  if (rc != HS_OK) return rc;
+  const Hnsw &h = P.h;
+
+  std::vector<float> cent_own;
+  std::vector<uint32_t> cid_own;
+  if (!centroids) {
+    host_kmeans(base, n, dim, num_cluster, 8, seed, threads, cent_own, cid_own);
+    centroids = cent_own.data();
+    cluster_ids = cid_own.data();
+  }
+  // rotator: 4 x padded_dim random sign bits (rotator.hpp:217-229 draws them from random_device)
+  const size_t pd = (dim + 63) / 64 * 64, words = pd / 64;     // rabitqlib/index/hnsw/hnsw.hpp:424-427
+  size_t td = 1;
+  while (td * 2 <= dim) td *= 2;                                // rotator.hpp:233-235
+  if (td < 64 || td > 2048) {
+    set_error("build_slimq_graph: dim must be in [64, 4095] (FhtKacRotator, rotator.hpp:237-258)");
+    return HS_ERR_UNSUPPORTED;
+  }
+  std::vector<uint8_t> flip(4 * pd / 8);
+  for (size_t i = 0; i < flip.size(); ++i) flip[i] = (uint8_t)(mix64(seed * 0xD1B54A32D192ED03ull + i) >> 56);
+  std::vector<float> rcent(num_cluster * pd);
+  for (size_t c = 0; c < num_cluster; ++c) host_rotate(centroids + c * dim, dim, pd, td, flip.data(), &rcent[c * pd]);
+
+  // record layout (slimq.h:1498-1505): [level][total][label][ptr][cluster @24][bin @28][ex]
+  const size_t ex_bits = 3;
+  const uint64_t size_bin = pd / 8 + 12, size_ex = pd * ex_bits / 8 + 8;     // data_layout.hpp
+  const uint64_t off_bin = 28, off_ex = off_bin + size_bin, rec = off_ex + size_ex;
+  std::vector<uint8_t> elements(n * rec, 0);
+  parallel_for(0, n, threads, [&](size_t i, int) {
+    std::vector<float> rot(pd), res(pd);
+    host_rotate(base + i * dim, dim, pd, td, flip.data(), rot.data());
+    const float *cen = &rcent[(size_t)cluster_ids[i] * pd];
+    // one_bit_code_with_factor, rabitq_impl.hpp:76-135 (L2 metric), in double
+    double l2 = 0, ip_resi = 0, ip_cent = 0;
+    std::vector<uint64_t> code(words, 0);
+    for (size_t d = 0; d < pd; ++d) {
+      const float r = rot[d] - cen[d];
+      const int bit = r > 0.f ? 1 : 0;
+      const double xu = bit - 0.5;
+      l2 += (double)r * r;
+      ip_resi += (double)r * xu;
+      ip_cent += (double)cen[d] * xu;
+      if (bit) code[d / 64] |= 1ull << (63 - (d % 64));      // pack_binary, space.hpp:272-286
+    }
+    if (ip_resi == 0) ip_resi = std::numeric_limits<double>::infinity();
+    const double l2n = std::sqrt(l2);
+    const double tmp_err =
+        l2n * 1.9 * std::sqrt(std::max(0.0, (l2 * ((double)pd * 0.25) / (ip_resi * ip_resi) - 1.0) / (double)(pd - 1)));
+    const float f_add = (float)(l2 + 2 * l2 * ip_cent / ip_resi);
+    const float f_rescale = (float)(-2 * l2 / ip_resi);
+    const float f_error = (float)(2 * tmp_err);
+    uint8_t *e = &elements[i * rec];
+    uint32_t total = 0;
+    for (auto &l : P.nbr[i]) total += (uint32_t)l.size();
+    const int32_t lv = h.level[i];
+    const uint64_t label = labels ? labels[i] : (uint64_t)i;
+    std::memcpy(e, &lv, 4);
+    std::memcpy(e + 4, &total, 4);
+    std::memcpy(e + 8, &label, 8);
+    std::memcpy(e + 24, &cluster_ids[i], 4);
+    std::memcpy(e + off_bin, code.data(), 8 * words);
+    std::memcpy(e + off_bin + 8 * words, &f_add, 4);
+    std::memcpy(e + off_bin + 8 * words + 4, &f_rescale, 4);
+    std::memcpy(e + off_bin + 8 * words + 8, &f_error, 4);
+    // the ex-code block (3 extra bits per dimension) is left zero: the search path never reads
+    // it (only get_bin_est is called, slimq.h:737-738)
+  });
+
+  FILE *f = std::fopen(out_path, "wb");
+  if (!f) {
+    set_error(std::string("cannot open ") + out_path + " for writing");
+    return HS_ERR_IO;
+  }
+  auto put = [&](const void *p, size_t sz) { return std::fwrite(p, 1, sz, f) == sz; };
+  bool ok = true;
+  const uint64_t hdr[6] = {n, rec, 8, 4, off_bin /* offsetData_ = offset_bin_data_, slimq.h:1503 */, 16};
+  ok &= put(hdr, sizeof hdr);
+  const int32_t ml = P.maxlevel, thr = threshold_level;
+  const uint32_t ep = h.enter.load();
+  ok &= put(&ml, 4) && put(&thr, 4) && put(&ep, 4);
+  const uint64_t ms[4] = {h.maxM, h.maxM0, h.M, h.efc};
+  ok &= put(ms, sizeof ms);
+  const uint8_t has_deleted = 0;
+  ok &= put(&has_deleted, 1);
+  const uint64_t meta[9] = {num_cluster, dim, pd, 24, off_bin, off_ex, size_bin, size_ex, ex_bits};
+  ok &= put(meta, sizeof meta);
+  const uint8_t metric_type = 0;   // rabitqlib::METRIC_L2
+  ok &= put(&metric_type, 1);
+  ok &= put(rcent.data(), rcent.size() * 4);
+  ok &= put(flip.data(), flip.size());
+  ok &= put(elements.data(), elements.size());
+  ok = ok && write_blobs(f, P);
   ok &= std::fclose(f) == 0;
   if (!ok) {
     set_error(std::string("write error on ") + out_path);

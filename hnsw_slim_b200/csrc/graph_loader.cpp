@@ -173,7 +173,9 @@ int parse_graph(const uint8_t *bytes, size_t size, int kind, size_t dim, HostGra
     set_error("truncated .graph header");
     return HS_ERR_IO;
   }
-  if (g->offset_total != 4 || g->label_offset != 8 || g->offset_nbr != 16 || g->offset_data != 24) {
+  // hnsw_slimq stores offsetData_ = offset_bin_data_ = 28 (slimq.h:1503), hnsw_slim 24 (slim.h:130)
+  const uint64_t want_offset_data = kind == HS_KIND_SLIMQ ? 28 : 24;
+  if (g->offset_total != 4 || g->label_offset != 8 || g->offset_nbr != 16 || g->offset_data != want_offset_data) {
     set_error("unexpected record offsets in .graph header (not a HNSW-Slim index?)");
     return HS_ERR_IO;
   }

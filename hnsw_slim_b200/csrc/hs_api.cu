@@ -641,24 +641,41 @@ void hs_build_params_default(hs_build_params *p) {
   p->seed = 100;                   // hnsw.h:85 random_seed
 }
 
-int hs_build_slim_graph(const float *base, size_t n, size_t dim, int metric, const hs_build_params *p,
-                        const uint64_t *labels, const char *out_graph_path) {
+static int parse_branching(const hs_build_params *p, double *bf) {
   if (!p || !p->branching_factor) {
     set_error("null build params");
     return HS_ERR_ARG;
   }
-  double bf;
   const std::string b = p->branching_factor;     // hnsw.h:143-158
-  if (b == "e") bf = M_E;
-  else if (b == "sqrt") bf = std::sqrt(2.0) / (std::sqrt(2.0) - 1.0);
+  if (b == "e") *bf = M_E;
+  else if (b == "sqrt") *bf = std::sqrt(2.0) / (std::sqrt(2.0) - 1.0);
   else {
     char *end = nullptr;
-    bf = std::strtod(b.c_str(), &end);
-    if (end == b.c_str() || bf <= 1.0) {
+    *bf = std::strtod(b.c_str(), &end);
+    if (end == b.c_str() || *bf <= 1.0) {
       set_error("Invalid branching factor: " + b);
       return HS_ERR_ARG;
     }
   }
+  return HS_OK;
+}
+
+int hs_build_slimq_graph(const float *base, size_t n, size_t dim, const hs_build_params *p, const float *centroids,
+                         size_t num_cluster, const uint32_t *cluster_ids, const uint64_t *labels,
+                         const char *out_graph_path) {
+  double bf;
+  int rc = parse_branching(p, &bf);
+  if (rc != HS_OK) return rc;
+  return build_slimq_graph(base, n, dim, p->M, p->ef_construction, bf, p->threshold_level, p->top_degree_percent0,
+                           p->top_degree_percent, p->top_M0, p->low_m0, p->top_M, p->low_m, p->threads, p->seed,
+                           centroids, num_cluster, cluster_ids, labels, out_graph_path);
+}
+
+int hs_build_slim_graph(const float *base, size_t n, size_t dim, int metric, const hs_build_params *p,
+                        const uint64_t *labels, const char *out_graph_path) {
+  double bf;
+  int rc0 = parse_branching(p, &bf);
+  if (rc0 != HS_OK) return rc0;
   return build_slim_graph(base, n, dim, metric, p->M, p->ef_construction, bf, p->threshold_level,
                           p->top_degree_percent0, p->top_degree_percent, p->top_M0, p->low_m0, p->top_M, p->low_m,
                           p->threads, p->seed, labels, out_graph_path);

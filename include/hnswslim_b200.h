@@ -187,6 +187,20 @@ void hs_build_params_default(hs_build_params *p);
 int hs_build_slim_graph(const float *base, size_t n, size_t dim, int metric, const hs_build_params *p,
                         const uint64_t *labels, const char *out_graph_path);
 
+/* Host-side builder of an hnsw_slimq index: the same HNSW + HNSW-Slim pruning over the raw floats
+ * (the reference builds the graph with rabitqlib's HNSW, hnsw_slimq_strategy.h:100-142, then
+ * convertFromHNSW, slimq.h:1471-1762), node payload = 1-bit RaBitQ code + (f_add, f_rescale,
+ * f_error) against the node's cluster centroid (one_bit_code_with_factor,
+ * rabitqlib/quantization/rabitq_impl.hpp:76-135) after the FHT-Kac rotation, written in
+ * HierarchicalNSWSlimQ::saveIndex's format (slimq.h:1161-1216).  centroids (num_cluster x dim)
+ * and cluster_ids (n) are the reference's *_centroids_16.fvecs / *_clusterids_16.ivecs inputs
+ * (hnsw_slimq_strategy.h:42-45); pass NULL for both to have the builder run k-means with
+ * num_cluster clusters.  The 3-bit ex-code block of each record is zero-filled: no search path
+ * reads it.  L2 metric.  CPU only, multi-threaded. */
+int hs_build_slimq_graph(const float *base, size_t n, size_t dim, const hs_build_params *p,
+                         const float *centroids, size_t num_cluster, const uint32_t *cluster_ids,
+                         const uint64_t *labels, const char *out_graph_path);
+
 /* Host-only inspection of the flattened form of a .graph (no CUDA needed): what
  * hs_load uploads.  Used by the CPU test-suite to check the loader against the
  * reference's accessors (slim.h:620-661). */

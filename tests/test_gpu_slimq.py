@@ -139,3 +139,36 @@ def test_larger_index_vs_oracle_and_reference(tmp_path):
         np.testing.assert_allclose(dist, exact, rtol=1e-5)
     st = ix.stats()
     assert st["n_rerank"] > 0 and st["n_dist"] > st["n_hops"] >= st["n_rerank"]
+
+
+def test_full_size_properties():
+    """Size-independent properties on a 200k x 96 engine-built index (DEEP / MSTuring shape):
+    sortedness, distances are the exact distances of the returned rows, recall monotone in ef and
+    >= 0.95, determinism under query permutation, and bit-exactness against the oracle on a slice."""
+    import tempfile
+    n, nq, dim, k = 200000, 2000, 96, 10
+    base, q = make_dataset(n, nq, dim, rank=14)
+    with tempfile.TemporaryDirectory() as td:
+        graph = os.path.join(td, "q.graph")
+        capi.build_slimq_graph(base, graph, M=16, ef_construction=100)
+        ix = open_index(graph, base)
+        gt, _ = capi.bruteforce_knn(base, q[:500], k)
+        prev = 0.0
+        for ef in (20, 50, 100, 200):
+            ix.set_ef(ef)
+            lab, dist, cnt = ix.search(q, k, counts=True)
+            assert (np.diff(dist, axis=1) >= 0).all() and (lab < n).all()
+            assert all(len(set(r)) == k for r in lab[:200])
+            rec = np.mean([len(set(a) & set(b)) / k for a, b in zip(lab[:500], gt)])
+            assert rec >= prev - 0.002
+            prev = rec
+            i = np.arange(0, nq, 37)
+            true = ((base[lab[i, 0]] - q[i]) ** 2).sum(1)
+            np.testing.assert_allclose(dist[i, 0], true, rtol=1e-5)
+            assert (cnt[:, 0] > cnt[:, 1]).all() and (cnt[:, 1] >= 1).all()
+        assert prev >= 0.95, prev
+        a, _ = ix.search(q, k)
+        b, _ = ix.search(q[::-1].copy(), k)
+        assert np.array_equal(a, b[::-1])
+        o = rh.OracleQ(graph, base, t_const=ix.query_tconst)
+        check_against_oracle(ix, o, q[:300], k, 100)

@@ -169,3 +169,56 @@ def test_builder_argument_errors(tmp_path):
         capi.build_slim_graph(base, str(tmp_path / "x.graph"), branching="zero")
     with pytest.raises(capi.HsError):
         capi.build_slim_graph(base, "/nonexistent_dir/x.graph", M=4)
+
+
+# ---------------------------------------------------------------- hnsw_slimq loader
+@pytest.mark.parametrize("name", ["slimq_d96", "slimq_d128", "slimq_d200"])
+def test_slimq_loader_matches_reference_accessors(name):
+    """hs_debug_flatten on the reference-written hnsw_slimq .graph (slimq.h:1161-1216): header
+    fields and level-0 rows against what the reference's own accessors returned (golden)."""
+    import os
+    from conftest import GOLDEN
+    g = np.load(os.path.join(GOLDEN, f"{name}.npz"))
+    graph = os.path.join(GOLDEN, f"{name}.graph")
+    hg = capi.HostGraph(graph, int(g["dim"]), kind=capi.HS_KIND_SLIMQ)
+    info = hg.info()
+    ref = dict(zip(rh.RefSlimQ.INFO_KEYS, g["info"]))
+    assert info["n"] == ref["n"] and info["maxlevel"] == ref["maxlevel"] and info["enterpoint"] == ref["enterpoint"]
+    assert info["padded_dim_q"] == ref["padded_dim"] and info["num_cluster"] == ref["num_cluster"]
+    assert info["kind"] == capi.HS_KIND_SLIMQ and info["M"] == ref["M"]
+    offs = g["node_nbr_offsets"]
+    for j, i in enumerate(g["node_ids"]):
+        assert np.array_equal(hg.row(int(i), 0), g["node_nbrs"][offs[j]:offs[j + 1]])
+    # a slim loader must refuse the slimq file and vice versa
+    with pytest.raises(capi.HsError):
+        capi.HostGraph(graph, int(g["dim"]), kind=capi.HS_KIND_SLIM)
+    with pytest.raises(capi.HsError):
+        capi.HostGraph(os.path.join(GOLDEN, "slim_l2_2k.graph"), 16, kind=capi.HS_KIND_SLIMQ)
+
+
+@pytest.mark.skipif(rh.ref_slimq_path() is None, reason="needs oracle/_ref/libhsref_slimq_v4.so")
+def test_reference_loads_engine_built_slimq_graph(tmp_path):
+    """hs_build_slimq_graph writes HierarchicalNSWSlimQ::saveIndex's format (slimq.h:1161-1216): the
+    reference loads it, searches it, and the restatement agrees with it id for id."""
+    n, nq, dim, k = 8000, 100, 96, 10
+    base, q = make_dataset(n, nq, dim, rank=10, seed=5)
+    graph = str(tmp_path / "e.graph")
+    capi.build_slimq_graph(base, graph, M=16, ef_construction=100, threads=4)
+    r = rh.RefSlimQ(graph, base)
+    assert r.info["n"] == n and r.info["padded_dim"] == 128 and r.info["num_cluster"] == 16
+    o = rh.OracleQ(graph, base, t_const=r.t_const)
+    gt, _ = rh.ref_bruteforce(base, q, k)
+    rlab, _ = r.search(q, k, 100)
+    olab, *_ = o.search(q, k, 100, order=rh.ORDER_REF)
+    assert np.mean([set(a) == set(b) for a, b in zip(rlab, olab)]) >= 0.98
+    rec = np.mean([len(set(a) & set(b)) / k for a, b in zip(rlab, gt)])
+    assert rec >= 0.95, rec
+    # estimator quality of the engine's codes: estimates track the exact distances
+    ids = np.arange(0, 2000, dtype=np.uint32)
+    est = r.est(q[0], ids)
+    exact = ((base[ids] - q[0]) ** 2).sum(1)
+    assert np.corrcoef(est, exact)[0, 1] > 0.97
+    # loader view
+    hg = capi.HostGraph(graph, dim, kind=capi.HS_KIND_SLIMQ)
+    for i in (0, 17, n - 1):
+        assert np.array_equal(hg.row(i, 0), r.node(i)[3])
