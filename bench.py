@@ -43,9 +43,21 @@ WORKLOADS = {
     "deep-sharded": dict(n=4_000_000, shards=8, dim=96, metric=0, M=16, efc=200, rank=12, nq=10_000, k=10, ef=100,
                          desc="DEEP-shaped synthetic 4Mx96 L2 in 8 sub-graphs of 500k (100M config scaled down), "
                               "hnsw_slim M=16 efc=200, all-gather + top-k merge"),
+    # BASELINE.json configs[4] shape (MSTuring 96-dim, hnsw-slimq = RaBitQ codes + exact rerank) on one GPU
+    "msturing1m-slimq": dict(n=1_000_000, dim=96, metric=0, M=16, efc=200, rank=12, nq=10_000, k=10, ef=100,
+                             kind="slimq",
+                             desc="MSTuring-shaped synthetic 1Mx96 L2, hnsw_slimq (16 clusters, 1-bit RaBitQ codes + exact "
+                                  "rerank) M=16 efc=200 (rank-12 latent Gaussian, seed 1)"),
+    # ... and sharded like configs[4]: 8 sub-graphs over 1/2/4/8 GPUs, scaled from 100M to 8 x 500k rows
+    "msturing-sharded-slimq": dict(n=4_000_000, shards=8, dim=96, metric=0, M=16, efc=200, rank=12, nq=10_000, k=10,
+                                   ef=100, kind="slimq",
+                                   desc="MSTuring-shaped synthetic 4Mx96 L2 in 8 hnsw_slimq sub-graphs of 500k (100M config "
+                                        "scaled down), M=16 efc=200, all-gather + top-k merge"),
     # reduced-size variants for quick local runs (not contract lines)
     "sift200k": dict(n=200_000, dim=128, metric=0, M=16, efc=200, rank=14, nq=10_000, k=10, ef=100,
                      desc="SIFT-shaped synthetic 200kx128 L2 (dev size)"),
+    "msturing200k-slimq": dict(n=200_000, dim=96, metric=0, M=16, efc=200, rank=12, nq=10_000, k=10, ef=100,
+                               kind="slimq", desc="MSTuring-shaped synthetic 200kx96 hnsw_slimq (dev size)"),
 }
 
 
@@ -63,14 +75,21 @@ def prepare_inputs(w: dict, n_query_batches: int, build_rank: bool):
     from hnsw_slim_b200.synth import latent_gaussian
     os.makedirs(CACHE, exist_ok=True)
     tag = f"n{w['n']}_d{w['dim']}_m{w['metric']}_r{w['rank']}_M{w['M']}_e{w['efc']}_b4_s1"
-    graph = os.path.join(CACHE, f"hnsw_slim_{tag}.graph")
+    slimq = w.get("kind") == "slimq"
+    graph = os.path.join(CACHE, f"hnsw_{'slimq' if slimq else 'slim'}_{tag}.graph")
     base = None
+    if slimq:      # the raw rows are part of a hnsw_slimq index (exact rerank, setDataset)
+        base = latent_gaussian(w["n"], w["dim"], rank=w["rank"], seed=1)
     if not os.path.exists(graph) and build_rank:
         t0 = time.time()
-        base = latent_gaussian(w["n"], w["dim"], rank=w["rank"], seed=1, normalize=(w["metric"] == 1))
+        if base is None:
+            base = latent_gaussian(w["n"], w["dim"], rank=w["rank"], seed=1, normalize=(w["metric"] == 1))
         t1 = time.time()
         tmp = graph + f".tmp{os.getpid()}"
-        capi.build_slim_graph(base, tmp, metric=w["metric"], M=w["M"], ef_construction=w["efc"], branching="4")
+        if slimq:
+            capi.build_slimq_graph(base, tmp, M=w["M"], ef_construction=w["efc"], branching="4")
+        else:
+            capi.build_slim_graph(base, tmp, metric=w["metric"], M=w["M"], ef_construction=w["efc"], branching="4")
         os.replace(tmp, graph)
         log(f"[bench] generated corpus in {t1-t0:.1f}s, built {graph} in {time.time()-t1:.1f}s "
             f"({os.cpu_count()} host threads)")
@@ -141,6 +160,32 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md)"
 
 
+def cpu_reference_qps_slimq(graph: str, base: np.ndarray, w: dict, queries: np.ndarray, threads: int, passes: int):
+    """hnsw_slimq: the reference's search is not re-entrant (member search_pool_, slimq.h:220,1814) and its
+    strategy loops serially (hnsw_slimq_strategy.h:157-159): `threads` only applies to the plain-C port."""
+    from oracle import refharness as rh
+    if rh.ref_slimq_path() is not None:
+        ix = rh.RefSlimQ(graph, base)
+        ix.search(queries[:200], w["k"], w["ef"])
+        t = 0.0
+        for _ in range(passes):
+            _, sec = ix.search(queries, w["k"], w["ef"])
+            t += sec
+        return len(queries) * passes / t, "reference", t, 1
+    return None, "port", 0.0, 1
+
+
+def cpu_port_qps_slimq(graph: str, base: np.ndarray, w: dict, queries: np.ndarray, t_const: float, threads: int):
+    """The plain-C restatement (oracle/hs_oracle_slimq.c), one index shared by `threads` OpenMP threads."""
+    from oracle import refharness as rh
+    orc = rh.OracleQ(graph, base, t_const=t_const)
+    orc.search(queries[:200], w["k"], w["ef"], order=rh.ORDER_REF, threads=threads)
+    t0 = time.time()
+    orc.search(queries, w["k"], w["ef"], order=rh.ORDER_REF, threads=threads)
+    t = time.time() - t0
+    return len(queries) / t, t
+
+
 def cpu_reference_qps(graph: str, w: dict, queries: np.ndarray, threads: int, passes: int):
     """The reference's own search (oracle/_ref, compiled unmodified) on this host's cores."""
     from oracle import refharness as rh
@@ -165,14 +210,29 @@ def run_reference(args, w):
     if rank != 0:
         return
     from oracle import refharness as rh
-    graph, _, qb = prepare_inputs(w, 1, True)
+    graph, base, qb = prepare_inputs(w, 1, True)
     q = qb[0]
     cores = os.cpu_count() or 1
-    ix = rh.RefSlim(graph, w["dim"], w["n"], w["metric"]) if rh.ref_slim_path() else None
-    kind = "reference" if ix is not None else "port"
-    orc = None if ix is not None else rh.Oracle(graph, w["dim"], w["metric"])
+    slimq = w.get("kind") == "slimq"
+    how = ("omp parallel for schedule(dynamic) over queries (hnsw_slim_client_update_patch.cc:223-226), "
+           f"{cores} threads")
+    if slimq:
+        from hnsw_slim_b200 import capi
+        if rh.ref_slimq_path():
+            ix, orc, kind, cores = rh.RefSlimQ(graph, base), None, "reference", 1
+            how = ("serial loop of hnsw_slimq_strategy.h:157-159, 1 thread (the reference's hnsw_slimq search is not "
+                   "re-entrant: member search_pool_, slimq.h:220,1814)")
+        else:
+            pd = (w["dim"] + 63) // 64 * 64
+            ix, orc, kind = None, rh.OracleQ(graph, base, t_const=capi.slimq_default_tconst(pd)), "port"
+    else:
+        ix = rh.RefSlim(graph, w["dim"], w["n"], w["metric"]) if rh.ref_slim_path() else None
+        kind = "reference" if ix is not None else "port"
+        orc = None if ix is not None else rh.Oracle(graph, w["dim"], w["metric"])
 
     def step():
+        if ix is not None and slimq:
+            return ix.search(q, w["k"], w["ef"])[1]
         if ix is not None:
             _, sec, _ = ix.search(q, w["k"], w["ef"], 0)         # omp dynamic, all cores
             return sec
@@ -184,8 +244,7 @@ def run_reference(args, w):
         step()
     total = sum(step() for _ in range(args.steps))
     qps = len(q) * args.steps / total
-    sample = (f"{args.steps} x {len(q)} queries, ef={w['ef']}, k={w['k']}, omp parallel for schedule(dynamic) over "
-              f"queries (hnsw_slim_client_update_patch.cc:223-226), {cores} threads")
+    sample = f"{args.steps} x {len(q)} queries, ef={w['ef']}, k={w['k']}, {how}"
     out = {
         "impl": "reference", "metric": "QPS at recall@10>=0.95", "value": qps, "unit": "queries/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total / args.steps * 1e3,
@@ -228,7 +287,11 @@ def run_gpu(args, w):
                                     stream=1 + b + 100 * rank) for b in range(n_batches)]
 
     t0 = time.time()
-    ix = capi.Index(graph, w["dim"], metric=w["metric"], device=local_rank)
+    slimq = w.get("kind") == "slimq"
+    if slimq:
+        ix = capi.Index(graph, w["dim"], kind=capi.HS_KIND_SLIMQ, raw_base=base, device=local_rank)
+    else:
+        ix = capi.Index(graph, w["dim"], metric=w["metric"], device=local_rank)
     ix.set_ef(w["ef"])
     info = ix.info()
     log(f"[bench] rank {rank}: index resident in {time.time()-t0:.1f}s, {info['device_bytes']/2**20:.0f} MiB HBM, "
@@ -271,7 +334,14 @@ def run_gpu(args, w):
     n_dist = st["n_dist"] / args.steps
     n_hops = st["n_hops"] / args.steps
     avg_deg0 = info["sum_deg0"] / info["n"]
-    alg_bytes = n_dist * 4 * info["dim_padded"] + n_hops * (8 + 4 * avg_deg0)
+    if slimq:
+        # per estimate the code record (padded_dim/8 B code + 2 factors + cluster id = one
+        # 32-byte record at padded_dim 128), per expansion the adjacency list and one raw row for the rerank
+        n_rerank = st["n_rerank"] / args.steps
+        alg_bytes = (n_dist * (info["padded_dim_q"] // 8 + 16) + n_rerank * 4 * info["dim_padded"]
+                     + n_hops * (8 + 4 * avg_deg0))
+    else:
+        alg_bytes = n_dist * 4 * info["dim_padded"] + n_hops * (8 + 4 * avg_deg0)
     peaks, peak_src = measured_peaks()
     achieved = alg_bytes / (launch_ms * 1e-3) / 1e9
     traffic = None
@@ -281,7 +351,8 @@ def run_gpu(args, w):
             traffic = json.load(f).get(args.workload, {}).get("dram_bytes_per_launch")
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_source": peak_src,
-                "kernel": "hs::traverse_kernel", "algorithmic_bytes_per_launch": alg_bytes,
+                "kernel": "hs::traverse_slimq_kernel" if slimq else "hs::traverse_kernel",
+                "algorithmic_bytes_per_launch": alg_bytes,
                 "dist_evals_per_query": n_dist / nq, "hops_per_query": n_hops / nq, "launch_ms": launch_ms}
 
     # ---- end to end through the host-buffer C-ABI call (pinned host memory) ----
@@ -317,12 +388,24 @@ def run_gpu(args, w):
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        qps_all, kind, secs = cpu_reference_qps(graph, w, qbatches[0], 0, 4)
-        qps_1, _, secs1 = cpu_reference_qps(graph, w, qbatches[0][:2000], 1, 1)
-        cpu = {"value": qps_all, "unit": "queries/s", "cores": cores, "kind": kind,
-               "sample": f"4 passes x {nq} queries of the same workload, omp dynamic over queries, {cores} threads "
-                         f"({secs:.1f}s); serial 1-thread loop (hnsw_slim_strategy.h:112-114) on 2000 queries: "
-                         f"{qps_1:.0f} queries/s"}
+        if slimq:
+            qps_ref, kind, secs, _ = cpu_reference_qps_slimq(graph, base, w, qbatches[0][:5000], 1, 1)
+            qps_port, secs_p = cpu_port_qps_slimq(graph, base, w, qbatches[0], ix.query_tconst, cores)
+            if qps_ref is None:
+                cpu = {"value": qps_port, "unit": "queries/s", "cores": cores, "kind": "port",
+                       "sample": f"{nq} queries of the same workload, plain-C restatement, omp over queries ({secs_p:.1f}s)"}
+            else:
+                cpu = {"value": qps_ref, "unit": "queries/s", "cores": 1, "kind": kind,
+                       "sample": f"5000 queries of the same workload, serial loop of hnsw_slimq_strategy.h:157-159 "
+                                 f"({secs:.1f}s; the reference's hnsw_slimq search is not re-entrant); the plain-C "
+                                 f"restatement on {cores} threads: {qps_port:.0f} queries/s"}
+        else:
+            qps_all, kind, secs = cpu_reference_qps(graph, w, qbatches[0], 0, 4)
+            qps_1, _, secs1 = cpu_reference_qps(graph, w, qbatches[0][:2000], 1, 1)
+            cpu = {"value": qps_all, "unit": "queries/s", "cores": cores, "kind": kind,
+                   "sample": f"4 passes x {nq} queries of the same workload, omp dynamic over queries, {cores} threads "
+                             f"({secs:.1f}s); serial 1-thread loop (hnsw_slim_strategy.h:112-114) on 2000 queries: "
+                             f"{qps_1:.0f} queries/s"}
 
     if rank == 0:
         out = {

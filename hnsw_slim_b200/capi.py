@@ -23,6 +23,7 @@ EXPORTS = [
     "hs_debug_flatten", "hs_debug_free", "hs_debug_info", "hs_debug_row", "hs_debug_node",
     "hs_build_params_default", "hs_build_slim_graph",
     "hs_get_query_tconst", "hs_set_query_tconst", "hs_slimq_prepare", "hs_build_slimq_graph",
+    "hs_slimq_default_tconst",
 ]
 
 
@@ -97,12 +98,15 @@ def lib():
         L.hs_build_params_default.restype = None
         L.hs_build_slim_graph.argtypes = [vp, sz, sz, i32, C.POINTER(BuildParams), vp, C.c_char_p]
         L.hs_build_slimq_graph.argtypes = [vp, sz, sz, C.POINTER(BuildParams), vp, sz, vp, vp, C.c_char_p]
+        L.hs_slimq_default_tconst.argtypes = [sz]
         L.hs_get_query_tconst.argtypes = [vp, C.POINTER(C.c_double)]
         L.hs_set_query_tconst.argtypes = [vp, C.c_double]
         L.hs_slimq_prepare.argtypes = [vp, vp, sz, vp, vp, vp, vp]
         for name in EXPORTS:
-            if name not in ("hs_last_error", "hs_free", "hs_debug_free", "hs_build_params_default"):
+            if name not in ("hs_last_error", "hs_free", "hs_debug_free", "hs_build_params_default",
+                            "hs_slimq_default_tconst"):
                 getattr(L, name).restype = i32
+        L.hs_slimq_default_tconst.restype = C.c_double
         _lib = L
     return _lib
 
@@ -260,6 +264,10 @@ def build_slimq_graph(base, path: str, *, M: int = 16, ef_construction: int = 20
         cen, cid = centroids.ctypes.data, cluster_ids.ctypes.data
     _check(lib().hs_build_slimq_graph(b.ctypes.data, b.shape[0], b.shape[1], C.byref(p), cen, num_cluster, cid,
                                       lab, path.encode()))
+
+
+def slimq_default_tconst(padded_dim: int) -> float:
+    return float(lib().hs_slimq_default_tconst(padded_dim))
 
 
 class HostGraph:

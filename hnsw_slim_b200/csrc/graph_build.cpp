@@ -329,15 +329,20 @@ int build_pruned(const float *base, size_t n, size_t dim, int metric, size_t M, 
   }
 
   // ---- 1. HNSW construction ----
+  // The first few thousand points go in one at a time: points inserted concurrently into a
+  // near-empty graph see almost no candidates, end up with one or two links and can become
+  // unreachable once their few neighbours turn into hubs and prune them (measured: 0.8 % of the
+  // first 5000 nodes of a 50k graph with 8 threads, none with this serial prefix).
+  const size_t serial_prefix = std::min<size_t>(n, 4096);
   {
     Visited v0(n);
     std::vector<Pair> c0;
-    insert(h, 0, v0, c0);
+    for (size_t i = 0; i < serial_prefix; ++i) insert(h, (uint32_t)i, v0, c0);
   }
   {
     std::vector<std::unique_ptr<Visited>> vis(threads);
     std::vector<std::vector<Pair>> cands(threads);
-    parallel_for(1, n, threads, [&](size_t i, int tid) {
+    parallel_for(serial_prefix, n, threads, [&](size_t i, int tid) {
       if (!vis[tid]) vis[tid].reset(new Visited(n));
       insert(h, (uint32_t)i, *vis[tid], cands[tid]);
     });

@@ -58,6 +58,7 @@ struct hs_index {
   size_t cap_q = 0, cap_out = 0, cap_perq = 0;
   int hash_bits_override = 0;
   uint32_t traverse_flags = 3;
+  uint32_t slimq_flags = 0;
   std::mutex mu;
 };
 
@@ -107,6 +108,7 @@ int build_index(const HostGraph &g, int metric, int device, const float *raw_bas
   ix->sm_count = prop.multiProcessorCount;
   if (const char *hb = std::getenv("HS_HASH_BITS")) ix->hash_bits_override = std::atoi(hb);
   if (const char *tf = std::getenv("HS_TRAVERSE_FLAGS")) ix->traverse_flags = (uint32_t)std::atoi(tf);
+  if (const char *qf = std::getenv("HS_SLIMQ_FLAGS")) ix->slimq_flags = (uint32_t)std::atoi(qf);
 
   size_t bytes = 0;
   auto fail = [&](int code) {
@@ -295,6 +297,7 @@ int search_device_slimq(hs_index *ix, const float *d_queries, size_t nq, size_t 
   p.work_counter = ix->d_work;
   p.stats = ix->d_stats;
   p.per_query = d_perq;
+  p.flags = ix->slimq_flags;
   TraverseQLaunch l{};
   int rc = plan_traverse_slimq(p, ix->sm_count, (int)nq, &l);
   if (rc != HS_OK) return rc;
@@ -440,6 +443,8 @@ int hs_set_query_tconst(hs_index *ix, double t_const) {
   ix->t_const = t_const;
   return HS_OK;
 }
+
+double hs_slimq_default_tconst(size_t padded_dim) { return slimq_default_tconst(padded_dim, 3); }
 
 int hs_get_query_tconst(const hs_index *ix, double *t_const) {
   if (!ix || !t_const || ix->info.kind != HS_KIND_SLIMQ) {

@@ -310,6 +310,14 @@ struct RegPool {
     for (int s = 0; s < SLOTS; ++s) k[s] = (k[s] == g) ? (k[s] | (uint64_t)FLAG) : k[s];
     return (uint32_t)g;
   }
+  // node id of the closest unexpanded entry without popping it (kInvalid if none)
+  __device__ __forceinline__ uint32_t peek_closest_unexpanded() const {
+    int slot;
+    const uint64_t m = col_min_un(slot);
+    const int o = warp_argmin_key(m);
+    if (o < 0) return kInvalid;
+    return (uint32_t)__shfl_sync(FULL, (uint32_t)m, o);
+  }
   // slimq.h:741-745: a scored neighbour enters unless the pool is full and it is worse than
   // the worst entry, or it was expanded already (== a flagged copy of its key is in the pool:
   // an expanded entry that left the pool is worse than the worst from then on)
@@ -488,6 +496,11 @@ struct SmemPool {
       }
     if (hit) rescan_min();
     return (uint32_t)g;
+  }
+  __device__ __forceinline__ uint32_t peek_closest_unexpanded() const {
+    const int o = warp_argmin_key(min_un);
+    if (o < 0) return kInvalid;
+    return (uint32_t)__shfl_sync(FULL, (uint32_t)min_un, o);
   }
   __device__ __forceinline__ unsigned admit_q(bool valid, uint64_t key) {
     unsigned entered = 0;

@@ -255,13 +255,13 @@ inline int cpl_variant(uint32_t row_chunks) {
   const uint32_t cpl = row_chunks / kTeam;
   return (cpl == 3 || cpl == 4) ? (int)cpl : 0;
 }
-inline int slots_variant(uint32_t ef) { return ef <= 64 ? 2 : (ef <= 128 ? 4 : 0); }
+inline int slots_variant(uint32_t ef) { return ef <= 64 ? 2 : (ef <= 128 ? 4 : (ef <= 256 ? 8 : 0)); }
 
 template <typename F>
 int dispatch(int cpl, int metric, int slots, F &&f) {
 #define HS_CASE(C, M, S) \
   if (cpl == C && metric == M && slots == S) return f(std::integral_constant<int, C>{}, std::integral_constant<int, M>{}, std::integral_constant<int, S>{});
-#define HS_CASES_S(C, M) HS_CASE(C, M, 0) HS_CASE(C, M, 2) HS_CASE(C, M, 4)
+#define HS_CASES_S(C, M) HS_CASE(C, M, 0) HS_CASE(C, M, 2) HS_CASE(C, M, 4) HS_CASE(C, M, 8)
 #define HS_CASES_M(C) HS_CASES_S(C, HS_METRIC_L2) HS_CASES_S(C, HS_METRIC_IP)
   HS_CASES_M(0) HS_CASES_M(3) HS_CASES_M(4)
 #undef HS_CASES_M

@@ -302,9 +302,12 @@ traverse_slimq_kernel(const __grid_constant__ TraverseQParams p) {
       if (node == kInvalid) break;
       const uint32_t *row = p.adj0 + (size_t)node * p.deg0_stride;
       uint32_t id = __ldg(row + lane);
-      // the expanded node's raw row, for the exact rerank below (slimq.h:747-749): 8 lanes
-      if ((uint32_t)lane * 128u < p.row_chunks * 16u)
-        prefetch_l2(reinterpret_cast<const char *>(p.vec + (size_t)node * p.row_chunks) + lane * 128);
+      // the expanded node's raw row, for the exact rerank below (slimq.h:747-749): issued now so
+      // that its DRAM latency hides behind the estimates and the pool update.  Lane t owns the
+      // 4-float chunks t, t+32, ... (the oracle's HSO_ORDER_GPU association with team = 32).
+      const float4 *xrow = p.vec + (size_t)node * p.row_chunks;
+      float4 x0 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if ((uint32_t)lane < p.row_chunks) x0 = __ldg(xrow + lane);
 
       bool any = false;
       for (uint32_t seg = 0; seg < p.deg0_stride; seg += 32) {
@@ -318,10 +321,23 @@ traverse_slimq_kernel(const __grid_constant__ TraverseQParams p) {
         const unsigned entered = pool.admit_q(valid, make_key(d, id));
         if ((entered >> lane) & 1u) prefetch_l2(p.adj0 + (size_t)id * p.deg0_stride);
       }
+      if (p.flags & 1u) {
+        // speculation: the entry that is now the closest unexpanded one is the likeliest next
+        // pop; its adjacency row is (mostly) in L2 since its admission — pull the code records
+        // of its neighbours towards L2 while this hop finishes
+        const uint32_t nxt = pool.peek_closest_unexpanded();
+        if (nxt != kInvalid) {
+          const uint32_t nid = __ldg(p.adj0 + (size_t)nxt * p.deg0_stride + lane);
+          if (nid != kInvalid) prefetch_l2(p.qrec + (size_t)nid * p.rec_words);
+        }
+      }
       if (!any) continue;                               // slimq.h:708-715: no neighbours, no rerank
       nh++;
       nr++;
-      const float dx = __shfl_sync(FULL, eval_rows_smem<HS_METRIC_L2>(p.vec, p.row_chunks, qs, node, 1, lane), 0);
+      float acc = 0.f;
+      if ((uint32_t)lane < p.row_chunks) acc = acc4<HS_METRIC_L2>(acc, qs[lane], x0);
+      for (uint32_t c = lane + 32; c < p.row_chunks; c += 32) acc = acc4<HS_METRIC_L2>(acc, qs[c], __ldg(xrow + c));
+      const float dx = warp_sum_f(acc);
       const uint64_t xk = make_key(dx, node);
       if (!top_seeded) {
         top.seed(xk);
@@ -360,7 +376,7 @@ traverse_slimq_kernel(const __grid_constant__ TraverseQParams p) {
 }
 
 inline int wreg_variant(uint32_t words) { return words == 2 ? 2 : 0; }
-inline int slots_variant(uint32_t ef) { return ef <= 64 ? 2 : (ef <= 128 ? 4 : 0); }
+inline int slots_variant(uint32_t ef) { return ef <= 64 ? 2 : (ef <= 128 ? 4 : (ef <= 256 ? 8 : 0)); }
 inline int kreg_variant(uint32_t k) { return k <= 32 ? 1 : 0; }
 
 template <typename F>
@@ -368,7 +384,7 @@ int dispatch(int wreg, int slots, int kreg, F &&f) {
 #define HS_CASE(W, S, K) \
   if (wreg == W && slots == S && kreg == K) return f(std::integral_constant<int, W>{}, std::integral_constant<int, S>{}, std::integral_constant<int, K>{});
 #define HS_CASES_K(W, S) HS_CASE(W, S, 0) HS_CASE(W, S, 1)
-#define HS_CASES_S(W) HS_CASES_K(W, 0) HS_CASES_K(W, 2) HS_CASES_K(W, 4)
+#define HS_CASES_S(W) HS_CASES_K(W, 0) HS_CASES_K(W, 2) HS_CASES_K(W, 4) HS_CASES_K(W, 8)
   HS_CASES_S(0) HS_CASES_S(2)
 #undef HS_CASES_S
 #undef HS_CASES_K

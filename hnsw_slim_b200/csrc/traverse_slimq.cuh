@@ -39,6 +39,7 @@ struct TraverseQParams {
   uint32_t *per_query;                     // optional nq x 2 (n_est, n_hops)
   // shared-memory carve-up per warp (bytes)
   uint32_t smem_per_warp, off_buf, off_g2c, off_planes, off_topk;
+  uint32_t flags;                          // bit0: speculative L2 prefetch of the next hop's code records
 };
 
 struct TraverseQLaunch {

@@ -92,6 +92,7 @@ int hs_get_info(const hs_index *, hs_index_info *out);
  * rabitq_impl.hpp:363-377: std::random_device), so its estimates differ in the low bits from
  * load to load.  The engine derives the constant the same way from a FIXED seed at hs_load;
  * these read / override it (the parity tests copy the reference's value in). */
+double hs_slimq_default_tconst(size_t padded_dim);   /* host only: the value hs_load picks */
 int hs_get_query_tconst(const hs_index *, double *t_const);
 int hs_set_query_tconst(hs_index *, double t_const);
 

@@ -32,7 +32,7 @@ def open_index(graph, base, t_const=None):
 def check_against_oracle(ix, o, q, k, ef, min_exact=0.995):
     ix.set_ef(ef)
     lab, dist, cnt = ix.search(q, k, counts=True)
-    olab, odist, one, onh, onr = o.search(q, k, ef, order=rh.ORDER_GPU, team=8)
+    olab, odist, one, onh, onr = o.search(q, k, ef, order=rh.ORDER_GPU, team=32)
     same = np.all(lab == olab, axis=1)
     assert same.mean() >= min_exact, f"only {same.mean():.4f} of rows identical to the oracle (ef={ef}, k={k})"
     assert np.array_equal(dist[same].view(np.uint32), odist[same].view(np.uint32))

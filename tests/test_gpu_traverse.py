@@ -42,7 +42,7 @@ def check_against_oracle(c, k, ef, *, min_exact=0.999):
     return ix, lab, dist
 
 
-@pytest.mark.parametrize("ef", [10, 50, 100, 200])
+@pytest.mark.parametrize("ef", [10, 50, 100, 200, 300])     # register pools (<= 64 / 128 / 256) and the smem pool
 def test_small_l2_matches_oracle_bit_exact(small_corpus, ef):
     check_against_oracle(small_corpus, 10, ef)
 
@@ -183,7 +183,7 @@ def test_full_size_properties():
         assert prev >= 0.95
         self_lab, self_d = ix.search(base[:1000], 1)
         found = self_lab[:, 0] == np.arange(1000, dtype=np.uint32)      # pruning may orphan a few nodes
-        assert found.mean() >= 0.97, found.mean()   # reference-built graphs reach 1.0; the engine builder orphans ~1-2 %
+        assert found.mean() >= 0.99, found.mean()
         assert (self_d[found, 0] == 0).all()
         a, _ = ix.search(q, 10)
         b, _ = ix.search(q[::-1].copy(), 10)

@@ -46,7 +46,7 @@ print("total samples", tot, "total warp-instructions", totx)
 src = {}
 for k, v in sorted(agg.items(), key=lambda kv: -kv[1][0])[:top]:
     text = str(k)
-    if k and k[0].endswith('.cu'):
+    if k and (k[0].endswith('.cu') or k[0].endswith('.cuh')):
         try:
             src.setdefault(k[0], open('/root/repo/hnsw_slim_b200/csrc/' + k[0]).read().split('\n'))
             text = src[k[0]][k[1] - 1].strip()[:64]

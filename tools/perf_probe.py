@@ -24,7 +24,11 @@ w = dict(bench.WORKLOADS[a.workload])
 if a.nq:
     w["nq"] = a.nq
 graph, base, qb = bench.prepare_inputs(w, 4, True)
-ix = capi.Index(graph, w["dim"], metric=w["metric"])
+slimq = w.get("kind") == "slimq"
+if slimq:
+    ix = capi.Index(graph, w["dim"], kind=capi.HS_KIND_SLIMQ, raw_base=base)
+else:
+    ix = capi.Index(graph, w["dim"], metric=w["metric"])
 info = ix.info()
 nq, k = w["nq"], w["k"]
 dq = [torch.from_numpy(q).cuda() for q in qb]
@@ -52,13 +56,19 @@ for ef in [int(x) for x in a.efs.split(",")]:
     ms = e0.elapsed_time(e1) / a.iters
     st = ix.stats()
     nd, nh = st["n_dist"] / a.iters / nq, st["n_hops"] / a.iters / nq
-    bytes_q = nd * 4 * info["dim_padded"] + nh * (8 + 4 * info["sum_deg0"] / info["n"])
+    if slimq:
+        nr = st["n_rerank"] / a.iters / nq
+        bytes_q = (nd * (info["padded_dim_q"] // 8 + 16) + nr * 4 * info["dim_padded"]
+                   + nh * (8 + 4 * info["sum_deg0"] / info["n"]))
+    else:
+        bytes_q = nd * 4 * info["dim_padded"] + nh * (8 + 4 * info["sum_deg0"] / info["n"])
     rec = -1.0
     if gt is not None:
         ix.search_device(dq[0].data_ptr(), nq, k, dl.data_ptr(), dd.data_ptr(), stream.cuda_stream)
         torch.cuda.synchronize()
         lab = dl[:1000].cpu().numpy().view(np.uint32)
         rec = float(np.mean([len(set(r) & g) / k for r, g in zip(lab, gt)]))
-    print(f"flags={os.environ.get('HS_TRAVERSE_FLAGS','-')} hb={os.environ.get('HS_HASH_BITS','-')} ef={ef:4d} "
+    print(f"lib={os.path.basename(os.path.dirname(os.environ.get('HS_LIB_PATH','default/x')))} "
+          f"flags={os.environ.get('HS_TRAVERSE_FLAGS','-')} hb={os.environ.get('HS_HASH_BITS','-')} ef={ef:4d} "
           f"{ms:8.3f} ms/batch {nq/ms*1e3:11.0f} QPS  n_dist/q={nd:7.1f} n_hops/q={nh:6.1f} "
           f"alg GB/s={bytes_q*nq/ms/1e6:7.1f} recall@{k}={rec:.4f}", flush=True)
