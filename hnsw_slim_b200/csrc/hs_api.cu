@@ -45,6 +45,7 @@ struct hs_index {
   float *d_centroids = nullptr;     // num_cluster x padded_dim (rotated)
   uint8_t *d_flip = nullptr;        // 4 * padded_dim / 8
   uint32_t words = 0, trunc_dim = 0;
+  uint32_t level_count[kMaxLevels] = {};
   double t_const = 0.0;
   // per-call scratch
   unsigned int *d_work = nullptr;
@@ -161,6 +162,7 @@ int build_index(const HostGraph &g, int metric, int device, const float *raw_bas
     return fail(HS_ERR_CUDA);
   }
 
+  for (int l = 0; l <= g.maxlevel && l < kMaxLevels; ++l) ix->level_count[l] = g.level_count[l];
   hs_index_info &I = ix->info;
   I.n = g.n;
   I.dim = g.dim;
@@ -225,9 +227,9 @@ int load_common(const uint8_t *bytes, size_t size, int kind, int metric, size_t 
       return HS_ERR_UNSUPPORTED;
     }
   }
-  if (g.threshold_level > 0) {
-    set_error("threshold_level > 0 (layered beam, slim.h:222-316) not supported yet");
-    return HS_ERR_UNSUPPORTED;
+  if (g.threshold_level < 0) {
+    set_error("negative threshold_level in .graph header");
+    return HS_ERR_IO;
   }
   if (g.has_deleted) {
     set_error("indices with deleted elements (slim.h:2119-2122) not supported yet");
@@ -324,6 +326,7 @@ int search_device(hs_index *ix, const float *d_queries, size_t nq, size_t k, uin
   for (int l = 0; l < kMaxLevels; ++l) p.upper_adj[l] = ix->d_upper_adj[l];
   p.labels = ix->d_labels;
   p.deleted = ix->d_deleted;
+  for (int l = 0; l < kMaxLevels; ++l) p.level_count[l] = ix->level_count[l];
   p.n = (uint32_t)ix->info.n;
   p.row_chunks = (uint32_t)(ix->info.dim_padded / 4);
   p.deg0_stride = ix->info.deg0_stride;

@@ -296,6 +296,11 @@ struct RegPool {
     }
     return entered;
   }
+  // every entry becomes unexpanded again (a new layer of the layered beam, slim.h:228-233)
+  __device__ __forceinline__ void clear_flags() {
+#pragma unroll
+    for (int s = 0; s < SLOTS; ++s) k[s] = ((uint32_t)(s * 32 + lane) < size) ? (k[s] & KEYMASK) : k[s];
+  }
   // ---- hnsw_slimq pool semantics (SearchBuffer, slimq.h:80-151): the same (dist,id) may sit
   //      in the pool several times; "visited" == some copy carries the expanded flag ----
   // closest unexpanded entry; flags EVERY copy of it (the reference pops the later copies
@@ -482,6 +487,12 @@ struct SmemPool {
       }
     }
     return entered;
+  }
+  __device__ __forceinline__ void clear_flags() {
+    __syncwarp();
+    for (uint32_t e = lane; e < size; e += 32) pool[e] &= KEYMASK;
+    __syncwarp();
+    rescan_min();
   }
   // ---- hnsw_slimq pool semantics, see RegPool ----
   __device__ __forceinline__ uint32_t pop_closest_unexpanded_dups() {

@@ -24,6 +24,7 @@
 // instruction), fp32 FMA chains per lane, xor-shuffle reduction 4,2,1.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstdint>
 #include <type_traits>
 
@@ -145,6 +146,55 @@ __global__ void __launch_bounds__(128, HS_TRAVERSE_MIN_CTAS) traverse_kernel(con
     pool.seed(make_key(curdist, cur));
     if (lane == 0) visited_test_and_set(hash, hbits, hmask, cur);
     __syncwarp();
+
+    // ---- layered beam for threshold_level > 0 (searchBaseLayer, slim.h:222-316, called for
+    //      levels min(threshold, maxlevel) .. 1 at slim.h:2108-2113).  Every layer restarts
+    //      from ALL pool entries (the candidate set is re-made from top_candidates, :228-233:
+    //      the expanded flags are cleared) while the visited set carries over.  The stop rule
+    //      `min(cand) > lowerBound && |top| == ef` (:236-238) is "no unexpanded entry left in the
+    //      pool", as on level 0: a candidate outside the pool implies a full pool. ----
+    for (int layer = min(p.threshold_level, p.maxlevel); layer > 0; --layer) {
+      const uint32_t *ladj = p.upper_adj[layer];
+      for (;;) {
+        const uint32_t node = pool.pop_closest_unexpanded();
+        if (node == kInvalid) break;
+        const int slot = __ldg(p.upper_slot + node);
+        // pool entries met on a lower layer may not exist on this one: the reference asserts
+        // element_level >= layer (:247); such an entry has no row here
+        if (slot < 0 || (uint32_t)slot >= p.level_count[layer]) continue;
+        const uint32_t *row = ladj + (size_t)slot * p.upper_stride;
+        if (hcount + p.upper_stride > hlimit) {
+          __syncwarp();
+          hash_clear(hash, hsize, lane);
+          __syncwarp();
+          pool.for_each_id([&](uint32_t pid) { visited_test_and_set(hash, hbits, hmask, pid); });
+          hcount = pool.size;
+          __syncwarp();
+        }
+        bool any = false;
+        for (uint32_t seg = 0; seg < p.upper_stride; seg += 32) {
+          const uint32_t id = (seg + lane < p.upper_stride) ? __ldg(row + seg + lane) : kInvalid;
+          const unsigned vm = __ballot_sync(FULL, id != kInvalid);
+          if (vm == 0) break;
+          any = true;
+          bool fresh = false;
+          if (id != kInvalid) fresh = !visited_test_and_set(hash, hbits, hmask, id);
+          const unsigned fm = __ballot_sync(FULL, fresh);
+          const int count = __popc(fm);
+          if (count == 0) continue;
+          hcount += (uint32_t)count;
+          if (fresh) stage_ids[__popc(fm & ((1u << lane) - 1))] = id;
+          __syncwarp();
+          const uint32_t cid = lane < count ? stage_ids[lane] : 0u;
+          __syncwarp();
+          const float d = eval(cid, count);
+          nd += (uint32_t)count;
+          pool.admit(lane < count, make_key(d, cid));
+        }
+        if (any) nh++;
+      }
+      pool.clear_flags();
+    }
 
     // ---- base layer, slim.h:321-457 ----
     const bool opt_prefetch = p.flags & 1u;
@@ -280,8 +330,10 @@ int plan_traverse(TraverseParams &p, int metric, int hash_bits_override, int sm_
   // visited-hash capacity: ~16 slots per ef entry (measured ~12 evaluations per ef entry on
   // 1M x 128), clamped to [1024, 16384]; the kernel resets the table when it
   // passes 75 % so a smaller table only costs repeated evaluations, never correctness.
+  // With threshold_level > 0 every layer of the layered beam adds its own evaluations.
+  const uint32_t layers = 1u + (uint32_t)std::max(0, std::min(p.threshold_level, p.maxlevel));
   uint32_t bits = 10;
-  while ((1u << bits) < 16u * p.ef && bits < 14) ++bits;
+  while ((1u << bits) < 16u * p.ef * layers && bits < 14) ++bits;
   if (hash_bits_override > 0) bits = (uint32_t)hash_bits_override;
   if (bits < 8) bits = 8;
   if (bits > 16) bits = 16;

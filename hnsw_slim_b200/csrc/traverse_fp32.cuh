@@ -17,6 +17,7 @@ struct TraverseParams {
   const uint32_t *labels;                  // n
   const uint8_t *deleted;                  // n (only read when has_deleted)
   uint32_t n, row_chunks, deg0_stride, upper_stride, enterpoint;
+  uint32_t level_count[kMaxLevels];        // rows of upper_adj[l] (nodes with level >= l)
   int32_t maxlevel, threshold_level, has_deleted;
   // query batch
   const float *queries;                    // nq x dim

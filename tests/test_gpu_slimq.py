@@ -172,3 +172,16 @@ def test_full_size_properties():
         assert np.array_equal(a, b[::-1])
         o = rh.OracleQ(graph, base, t_const=ix.query_tconst)
         check_against_oracle(ix, o, q[:300], k, 100)
+
+
+def test_threshold_level(tmp_path):
+    """threshold_level = 1 index from the engine's builder: bit-exact against the oracle."""
+    n, nq, dim, k = 20000, 200, 96, 10
+    base, q = make_dataset(n, nq, dim, rank=10, seed=4)
+    graph = str(tmp_path / "q.graph")
+    capi.build_slimq_graph(base, graph, M=16, ef_construction=100, threshold_level=1)
+    ix = open_index(graph, base)
+    assert ix.info()["threshold_level"] == 1
+    o = rh.OracleQ(graph, base, t_const=ix.query_tconst)
+    for ef in (40, 120):
+        check_against_oracle(ix, o, q, k, ef)

@@ -150,6 +150,41 @@ def test_large_ef_shared_memory_pool(small_corpus):
         check_against_oracle(small_corpus, 10, ef)
 
 
+@pytest.mark.parametrize("thr", [1, 2, 7])
+def test_threshold_level_layered_beam(thr):
+    """threshold_level > 0: greedy descent stops above the threshold, then searchBaseLayer runs on
+    levels min(thr, maxlevel) .. 1 (slim.h:222-316, 2108-2113) before the base layer.  thr = 7
+    exceeds maxlevel of this corpus: no greedy descent at all."""
+    c = get_corpus(n=20000, nq=300, dim=32, threshold_level=thr)
+    info = capi.Index(c.graph, c.dim).info()
+    assert info["threshold_level"] == thr
+    for ef in (10, 60, 150, 300):
+        check_against_oracle(c, 10, ef)
+    # a visited hash too small for the layered beam is cleared and re-seeded: results identical
+    import os
+    os.environ["HS_HASH_BITS"] = "9"
+    try:
+        ix = capi.Index(c.graph, c.dim)
+    finally:
+        del os.environ["HS_HASH_BITS"]
+    ix.set_ef(60)
+    lab, dist = ix.search(c.queries, 10)
+    olab, odist, _, _ = rh.Oracle(c.graph, c.dim).search(c.queries, 10, 60, order=rh.ORDER_GPU, team=8)
+    assert (lab == olab).all(1).mean() >= 0.999
+
+
+@needs_ref
+def test_threshold_level_matches_reference():
+    c = get_corpus(n=20000, nq=300, dim=32, threshold_level=1)
+    ix = capi.Index(c.graph, c.dim)
+    ix.set_ef(80)
+    lab, _ = ix.search(c.queries, 10)
+    ref = rh.RefSlim(c.graph, c.dim, c.n)
+    rlab, _, _ = ref.search(c.queries, 10, 80)
+    same = np.mean([set(a) == set(b) for a, b in zip(lab, rlab)])
+    assert same >= 0.995, same
+
+
 def test_k_larger_than_32(small_corpus):
     check_against_oracle(small_corpus, 100, 100)
     check_against_oracle(small_corpus, 64, 200)

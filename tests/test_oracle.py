@@ -134,3 +134,20 @@ def test_live_reference_multithreaded_search_is_the_same():
     a, _, _ = ref.search(c.queries, 10, 64, 1)
     b, _, _ = ref.search(c.queries, 10, 64, 4)
     assert all(set(x) == set(y) for x, y in zip(a, b))
+
+
+@needs_ref
+@pytest.mark.parametrize("thr", [1, 2, 7])
+def test_threshold_level_against_live_reference(thr):
+    """threshold_level > 0 (layered beam, slim.h:222-316 + 2108-2113): identical k-subsets and
+    distance-evaluation counts vs the reference on a reference-built index."""
+    c = get_corpus(n=20000, nq=300, dim=32, threshold_level=thr)
+    orc = rh.Oracle(c.graph, c.dim, c.metric)
+    assert orc.info()["threshold_level"] == thr
+    ref = rh.RefSlim(c.graph, c.dim, c.n, c.metric, counting=True)
+    for ef in (10, 60, 150):
+        lab, dist, nd, nh = orc.search(c.queries, 10, ef, order=rh.ORDER_REF, threads=1)
+        rlab, rcnt = ref.counts(c.queries, 10, ef)
+        same = np.array([set(a) == set(b) for a, b in zip(lab, rlab)])
+        assert same.mean() >= 0.995, (thr, ef, same.mean())
+        assert (nd[same] == rcnt[same]).all()
