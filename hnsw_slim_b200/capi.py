@@ -23,7 +23,7 @@ EXPORTS = [
     "hs_debug_flatten", "hs_debug_free", "hs_debug_info", "hs_debug_row", "hs_debug_node",
     "hs_build_params_default", "hs_build_slim_graph",
     "hs_get_query_tconst", "hs_set_query_tconst", "hs_slimq_prepare", "hs_build_slimq_graph",
-    "hs_slimq_default_tconst",
+    "hs_slimq_default_tconst", "hs_debug_bf_tc_fallback",
 ]
 
 
@@ -104,9 +104,11 @@ def lib():
         L.hs_slimq_prepare.argtypes = [vp, vp, sz, vp, vp, vp, vp]
         for name in EXPORTS:
             if name not in ("hs_last_error", "hs_free", "hs_debug_free", "hs_build_params_default",
-                            "hs_slimq_default_tconst"):
+                            "hs_slimq_default_tconst", "hs_debug_bf_tc_fallback"):
                 getattr(L, name).restype = i32
         L.hs_slimq_default_tconst.restype = C.c_double
+        L.hs_debug_bf_tc_fallback.restype = C.c_longlong
+        L.hs_debug_bf_tc_fallback.argtypes = []
         _lib = L
     return _lib
 
@@ -321,6 +323,11 @@ def bruteforce_knn(base, queries, k: int, *, metric: int = HS_METRIC_L2, device:
     _check(lib().hs_bruteforce_knn(b.ctypes.data, b.shape[0], b.shape[1], q.ctypes.data, q.shape[0], k, metric,
                                    device, lab.ctypes.data, dist.ctypes.data))
     return lab, dist
+
+
+def bf_tc_fallback() -> int:
+    """hs_debug_bf_tc_fallback(): see include/hnswslim_b200.h (needs HS_BF_TC_STATS=1)."""
+    return int(lib().hs_debug_bf_tc_fallback())
 
 
 def bruteforce_knn_device(d_base: int, n: int, dim: int, d_queries: int, nq: int, k: int, d_labels: int,

@@ -10,6 +10,7 @@
 
 #include <algorithm>
 #include <cstdint>
+#include <cstdlib>
 #include <string>
 
 #include "bruteforce.cuh"
@@ -67,7 +68,14 @@ __device__ __forceinline__ void heap_replace_top(uint64_t *h, uint32_t sz, uint6
 template <int METRIC>
 __global__ void __launch_bounds__(QT) bf_scan_kernel(const float *__restrict__ base, uint32_t n, uint32_t dim,
                                                       const float *__restrict__ queries, uint32_t nq, uint32_t k,
-                                                      uint32_t rows_per_split, uint64_t *__restrict__ partial) {
+                                                      uint32_t rows_per_split, uint64_t *__restrict__ partial,
+                                                      const uint32_t *__restrict__ qmap,
+                                                      const unsigned int *__restrict__ qcount) {
+  const uint32_t heap_stride_nq = nq;
+  // qmap / qcount (optional): only the *qcount queries listed in qmap are scanned (the fallback
+  // list of the tcgen05 path); heaps are indexed by list position
+  if (qcount) nq = min(nq, *qcount);
+  if (blockIdx.x * QT >= nq) return;
   extern __shared__ __align__(16) float sm[];
   float *qs = sm;                     // [SLAB][QPAD]   qs[d][query]
   float *xs = sm + SLAB * QPAD;       // [RT][SLAB]
@@ -79,7 +87,7 @@ __global__ void __launch_bounds__(QT) bf_scan_kernel(const float *__restrict__ b
   const uint32_t r_end = min(n, r_begin + rows_per_split);
   const uint32_t n_slabs = (dim + SLAB - 1) / SLAB;
 
-  uint64_t *heap = partial + ((size_t)split * nq + min(my_q, nq - 1)) * k;
+  uint64_t *heap = partial + ((size_t)split * heap_stride_nq + min(my_q, nq - 1)) * k;
   uint32_t hsz = 0;
   uint64_t top = ~0ull;
 
@@ -88,7 +96,9 @@ __global__ void __launch_bounds__(QT) bf_scan_kernel(const float *__restrict__ b
     for (uint32_t i = t; i < QT * SLAB; i += QT) {
       const uint32_t qq = i / SLAB, d = i % SLAB;
       const uint32_t gd = s * SLAB + d, gq = q0 + qq;
-      qs[d * QPAD + qq] = (gd < dim && gq < nq) ? __ldg(queries + (size_t)gq * dim + gd) : 0.f;
+      float v = 0.f;
+      if (gd < dim && gq < nq) v = __ldg(queries + (size_t)(qmap ? __ldg(qmap + gq) : gq) * dim + gd);
+      qs[d * QPAD + qq] = v;
     }
   };
   if (n_slabs == 1) load_q_slab(0);
@@ -172,13 +182,19 @@ __device__ __forceinline__ void bitonic_sort(uint64_t *keys, uint32_t P) {
 
 // one CTA per query: sort n_parts*k candidate keys, emit the k smallest
 __global__ void merge_keys_kernel(const uint64_t *__restrict__ partial, uint32_t n_parts, uint32_t nq, uint32_t k,
-                                  uint32_t P, uint32_t *__restrict__ out_labels, float *__restrict__ out_dists) {
+                                  uint32_t P, uint32_t *__restrict__ out_labels, float *__restrict__ out_dists,
+                                  const uint32_t *__restrict__ qmap, const unsigned int *__restrict__ qcount,
+                                  uint32_t heap_stride_nq) {
   extern __shared__ __align__(16) uint64_t keys[];
-  const uint32_t q = blockIdx.x;
+  uint32_t q = blockIdx.x;
+  if (qcount && q >= *qcount) return;
+  const uint32_t slot = q;
+  if (qmap) q = qmap[slot];
+  (void)nq;
   const uint32_t total = n_parts * k;
   for (uint32_t i = threadIdx.x; i < P; i += blockDim.x) {
     uint64_t v = ~0ull;
-    if (i < total) v = partial[((size_t)(i / k) * nq + q) * k + (i % k)];
+    if (i < total) v = partial[((size_t)(i / k) * heap_stride_nq + slot) * k + (i % k)];
     keys[i] = v;
   }
   bitonic_sort(keys, P);
@@ -276,6 +292,15 @@ uint32_t next_pow2(uint32_t v) {
 
 }  // namespace
 
+static int bruteforce_scan_device(const float *d_base, size_t n, size_t dim, const float *d_queries, size_t nq,
+                                  size_t k, int metric, uint32_t *d_labels, float *d_dists, cudaStream_t stream,
+                                  const uint32_t *qmap, const unsigned int *qcount);
+
+// -1: the last call did not take the tcgen05 path (or HS_BF_TC_STATS is unset); else the number
+// of queries that went through the fallback scan
+static long long g_last_tc_fallback = -1;
+long long bruteforce_last_tc_fallback() { return g_last_tc_fallback; }
+
 int bruteforce_device(const float *d_base, size_t n, size_t dim, const float *d_queries, size_t nq, size_t k,
                       int metric, uint32_t *d_labels, float *d_dists, cudaStream_t stream) {
   if (nq == 0 || n == 0) return HS_OK;
@@ -283,6 +308,33 @@ int bruteforce_device(const float *d_base, size_t n, size_t dim, const float *d_
     set_error("bruteforce: k must be in [1, 2048], n < 2^32");
     return HS_ERR_ARG;
   }
+  g_last_tc_fallback = -1;
+  if (bruteforce_tc_applicable(n, dim, nq, k)) {
+    // tensor-core filter + exact re-scoring; queries it could not certify come back in a list
+    // and go through the scan kernel (same results either way)
+    uint32_t *fb_list = nullptr;
+    unsigned int *fb_count = nullptr;
+    void *scratch = nullptr;
+    int rc = bruteforce_tc_device(d_base, n, dim, d_queries, nq, k, metric, d_labels, d_dists, stream, &fb_list,
+                                  &fb_count, &scratch);
+    if (rc == HS_OK)
+      rc = bruteforce_scan_device(d_base, n, dim, d_queries, nq, k, metric, d_labels, d_dists, stream, fb_list,
+                                  fb_count);
+    if (rc == HS_OK && std::getenv("HS_BF_TC_STATS")) {     // debugging aid: synchronous
+      unsigned int c = 0;
+      if (cudaMemcpyAsync(&c, fb_count, sizeof c, cudaMemcpyDeviceToHost, stream) == cudaSuccess &&
+          cudaStreamSynchronize(stream) == cudaSuccess)
+        g_last_tc_fallback = (long long)c;
+    }
+    if (scratch) cudaFreeAsync(scratch, stream);
+    return rc;
+  }
+  return bruteforce_scan_device(d_base, n, dim, d_queries, nq, k, metric, d_labels, d_dists, stream, nullptr, nullptr);
+}
+
+static int bruteforce_scan_device(const float *d_base, size_t n, size_t dim, const float *d_queries, size_t nq,
+                                  size_t k, int metric, uint32_t *d_labels, float *d_dists, cudaStream_t stream,
+                                  const uint32_t *qmap, const unsigned int *qcount) {
   int dev = 0, sms = 148;
   BF_CUDA(cudaGetDevice(&dev));
   BF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -303,17 +355,17 @@ int bruteforce_device(const float *d_base, size_t n, size_t dim, const float *d_
   if (metric == HS_METRIC_IP) {
     BF_CUDA(cudaFuncSetAttribute(bf_scan_kernel<HS_METRIC_IP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     bf_scan_kernel<HS_METRIC_IP><<<grid, QT, smem, stream>>>(d_base, (uint32_t)n, (uint32_t)dim, d_queries,
-                                                             (uint32_t)nq, (uint32_t)k, rows_per_split, partial);
+                                                             (uint32_t)nq, (uint32_t)k, rows_per_split, partial, qmap, qcount);
   } else {
     BF_CUDA(cudaFuncSetAttribute(bf_scan_kernel<HS_METRIC_L2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     bf_scan_kernel<HS_METRIC_L2><<<grid, QT, smem, stream>>>(d_base, (uint32_t)n, (uint32_t)dim, d_queries,
-                                                             (uint32_t)nq, (uint32_t)k, rows_per_split, partial);
+                                                             (uint32_t)nq, (uint32_t)k, rows_per_split, partial, qmap, qcount);
   }
   BF_CUDA(cudaGetLastError());
   const uint32_t P = next_pow2(std::max<uint32_t>(2, splits * (uint32_t)k));
   BF_CUDA(cudaFuncSetAttribute(merge_keys_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(P * 8)));
   merge_keys_kernel<<<(uint32_t)nq, 256, P * 8, stream>>>(partial, splits, (uint32_t)nq, (uint32_t)k, P, d_labels,
-                                                          d_dists);
+                                                          d_dists, qmap, qcount, (uint32_t)nq);
   BF_CUDA(cudaGetLastError());
   BF_CUDA(cudaFreeAsync(partial, stream));
   return HS_OK;

@@ -12,6 +12,16 @@ namespace hs {
 int bruteforce_device(const float *d_base, size_t n, size_t dim, const float *d_queries, size_t nq,
                       size_t k, int metric, uint32_t *d_labels, float *d_dists, cudaStream_t stream);
 
+// tcgen05 path (bruteforce_tc.cu): same results as the scan kernel.  Queries it cannot certify are
+// returned in *fallback_list / *fallback_count (device memory inside *scratch_to_free, which the
+// caller releases with cudaFreeAsync after the fallback scan has been enqueued).
+bool bruteforce_tc_applicable(size_t n, size_t dim, size_t nq, size_t k);
+int bruteforce_tc_device(const float *d_base, size_t n, size_t dim, const float *d_queries, size_t nq, size_t k,
+                         int metric, uint32_t *d_labels, float *d_dists, cudaStream_t stream,
+                         uint32_t **fallback_list, unsigned int **fallback_count, void **scratch_to_free);
+
+long long bruteforce_last_tc_fallback();
+
 // n_parts consecutive [nq x k] (label, dist) tables -> global top-k per query.
 int topk_merge_device(const uint32_t *d_labels_in, const float *d_dists_in, size_t n_parts, size_t nq,
                       size_t k, uint32_t *d_labels_out, float *d_dists_out, cudaStream_t stream);

@@ -580,6 +580,8 @@ int hs_bruteforce_knn(const float *base, size_t n, size_t dim, const float *quer
   return rc;
 }
 
+long long hs_debug_bf_tc_fallback(void) { return bruteforce_last_tc_fallback(); }
+
 int hs_topk_merge_device(const uint32_t *d_labels_in, const float *d_dists_in, size_t n_parts, size_t nq,
                          size_t k, uint32_t *d_labels_out, float *d_dists_out, void *stream) {
   if (!d_labels_in || !d_dists_in || !d_labels_out) {

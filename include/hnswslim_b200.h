@@ -149,6 +149,11 @@ int hs_bruteforce_knn_device(const float *d_base, size_t n, size_t dim, const fl
                              size_t nq, size_t k, int metric, uint32_t *d_labels, float *d_dists,
                              void *stream);
 
+/* Inspection (set HS_BF_TC_STATS=1): after hs_bruteforce_knn*, -1 if the call ran the fp32 scan
+ * kernel only, else the number of queries the tcgen05 path could not certify and handed to the
+ * scan kernel.  Both paths return identical results; HS_BF_TC=0 / 1 forces one or the other. */
+long long hs_debug_bf_tc_fallback(void);
+
 /* Cross-shard top-k merge for sharded corpora (no reference analogue: the
  * reference builds one graph).  d_labels_in / d_dists_in hold
  * n_parts consecutive [nq x k] tables (e.g. the output of an NCCL all-gather);
