@@ -432,20 +432,28 @@ def prepare_shards(w: dict, my_shards, threads: int):
     from hnsw_slim_b200.synth import latent_gaussian
     os.makedirs(CACHE, exist_ok=True)
     ranges = sharding.shard_ranges(w["n"], w["shards"])
-    paths = [os.path.join(CACHE, f"hnsw_slim_shard{s}of{w['shards']}_n{w['n']}_d{w['dim']}_r{w['rank']}_M{w['M']}"
+    slimq = w.get("kind") == "slimq"
+    fam = "hnsw_slimq" if slimq else "hnsw_slim"
+    paths = [os.path.join(CACHE, f"{fam}_shard{s}of{w['shards']}_n{w['n']}_d{w['dim']}_r{w['rank']}_M{w['M']}"
                                  f"_e{w['efc']}_b4_s1.graph") for s in range(w["shards"])]
     missing = [s for s in my_shards if not os.path.exists(paths[s])]
-    if missing:
+    base = None
+    if missing or slimq:
         base = latent_gaussian(w["n"], w["dim"], rank=w["rank"], seed=1)
         for s in missing:
             lo, hi = ranges[s]
             t0 = time.time()
             tmp = paths[s] + f".tmp{os.getpid()}"
-            capi.build_slim_graph(base[lo:hi], tmp, metric=w["metric"], M=w["M"], ef_construction=w["efc"],
-                                  branching="4", threads=threads, labels=np.arange(lo, hi, dtype=np.uint64))
+            if slimq:
+                capi.build_slimq_graph(base[lo:hi], tmp, M=w["M"], ef_construction=w["efc"], branching="4",
+                                       threads=threads, labels=np.arange(lo, hi, dtype=np.uint64))
+            else:
+                capi.build_slim_graph(base[lo:hi], tmp, metric=w["metric"], M=w["M"], ef_construction=w["efc"],
+                                      branching="4", threads=threads, labels=np.arange(lo, hi, dtype=np.uint64))
             os.replace(tmp, paths[s])
             log(f"[bench] built shard {s} [{lo},{hi}) in {time.time()-t0:.1f}s with {threads} threads")
-    return paths
+    raws = [base[ranges[s][0]:ranges[s][1]] for s in my_shards] if slimq else None
+    return paths, raws
 
 
 def run_gpu_sharded(args, w):
@@ -466,9 +474,11 @@ def run_gpu_sharded(args, w):
         torch.cuda.synchronize()
 
     mine = sharding.shards_of_rank(w["shards"], rank, world)
-    paths = prepare_shards(w, mine, max(1, (os.cpu_count() or 1) // world))
+    paths, raws = prepare_shards(w, mine, max(1, (os.cpu_count() or 1) // world))
     barrier()
-    ix = sharding.ShardedIndex([paths[s] for s in mine], w["dim"], metric=w["metric"], device=local_rank)
+    slimq = w.get("kind") == "slimq"
+    ix = sharding.ShardedIndex([paths[s] for s in mine], w["dim"], metric=w["metric"], device=local_rank,
+                               kind=capi.HS_KIND_SLIMQ if slimq else capi.HS_KIND_SLIM, raw_bases=raws)
     ix.set_ef(w["ef"])
     nq, k = w["nq"], w["k"]
     n_batches = min(8, args.warmup + args.steps)
@@ -492,8 +502,12 @@ def run_gpu_sharded(args, w):
     ms = e0.elapsed_time(e1)
     stats = [s_.stats() for s_ in ix.shards]
     infos = [s_.info() for s_ in ix.shards]
-    alg = sum(st["n_dist"] * 4 * inf["dim_padded"] + st["n_hops"] * (8 + 4 * inf["sum_deg0"] / inf["n"])
-              for st, inf in zip(stats, infos)) / args.steps
+    if slimq:
+        alg = sum(st["n_dist"] * (inf["padded_dim_q"] // 8 + 16) + st["n_rerank"] * 4 * inf["dim_padded"]
+                  + st["n_hops"] * (8 + 4 * inf["sum_deg0"] / inf["n"]) for st, inf in zip(stats, infos)) / args.steps
+    else:
+        alg = sum(st["n_dist"] * 4 * inf["dim_padded"] + st["n_hops"] * (8 + 4 * inf["sum_deg0"] / inf["n"])
+                  for st, inf in zip(stats, infos)) / args.steps
     if world > 1:
         t = torch.tensor([ms, alg], device="cuda", dtype=torch.float64)
         tmax = t.clone()
@@ -521,7 +535,8 @@ def run_gpu_sharded(args, w):
                        "recall_at_10": recall, "l2": "shards >> L2; a different query batch every step"},
             "roofline": {"bound": "hbm", "achieved": per_gpu, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                          "frac": per_gpu / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_src,
-                         "kernel": "hs::traverse_kernel (per GPU, whole step incl. merge + all_gather)"},
+                         "kernel": ("hs::traverse_slimq_kernel" if slimq else "hs::traverse_kernel")
+                                   + " (per GPU, whole step incl. merge + all_gather)"},
             "cpu_baseline": None, "e2e": None, "gpu_launches": args.steps * (len(mine) + 2),
             "clocks": clocks.summary(),
         }

@@ -26,7 +26,11 @@ def needs_build() -> bool:
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "hnswslim_b200.h")]
+    host = os.path.join(HERE, "host")
+    deps = ([os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(host, f) for f in os.listdir(host)]
+            + [os.path.join(HERE, "..", "include", "hnswslim_b200.h")])
+    if not os.path.exists(os.path.join(OUT_DIR, "hs_main")):
+        return True
     return any(os.path.getmtime(d) > t for d in deps)
 
 
@@ -74,7 +78,21 @@ def build(force: bool = False, verbose: bool = False, ptxas_v: bool = False) -> 
         raise RuntimeError("nvcc failed")
     cmd = [_nvcc(), "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-ccbin", "/usr/bin/g++"]
     subprocess.run(cmd, check=True)
+    build_host_cli()
     return LIB
+
+
+HOST_CLI = os.path.join(OUT_DIR, "hs_main")
+
+
+def build_host_cli() -> str:
+    """The C++ host layer above the C ABI: hnsw_slim_b200/host/ (SolveStrategy-shaped classes and the
+    reference's command line) -> _build/hs_main, linked against the shared library next to it."""
+    host = os.path.join(HERE, "host")
+    cmd = ["/usr/bin/g++", "-std=c++17", "-O2", "-Wall", "-o", HOST_CLI, os.path.join(host, "main.cc"),
+           "-L" + OUT_DIR, "-lhnswslim_b200", "-Wl,-rpath,$ORIGIN"]
+    subprocess.run(cmd, check=True)
+    return HOST_CLI
 
 
 if __name__ == "__main__":

@@ -85,10 +85,18 @@ def gather_and_merge(local_labels, local_dists, k: int, *, group=None, merge: Ca
 class ShardedIndex:
     """The shards one rank owns, resident on its GPU; search() returns the GLOBAL top-k."""
 
-    def __init__(self, graph_paths: Sequence[str], dim: int, *, metric: int = 0, device: int = 0):
+    def __init__(self, graph_paths: Sequence[str], dim: int, *, metric: int = 0, device: int = 0,
+                 kind: int = 0, raw_bases: Sequence | None = None):
+        """kind = capi.HS_KIND_SLIMQ needs raw_bases[i] = the rows of shard i (exact rerank, indexed
+        by the shard's internal ids)."""
         from . import capi
         self.capi = capi
-        self.shards = [capi.Index(p, dim, metric=metric, device=device) for p in graph_paths]
+        if kind == capi.HS_KIND_SLIMQ:
+            assert raw_bases is not None and len(raw_bases) == len(graph_paths)
+            self.shards = [capi.Index(p, dim, kind=kind, raw_base=rb, device=device)
+                           for p, rb in zip(graph_paths, raw_bases)]
+        else:
+            self.shards = [capi.Index(p, dim, metric=metric, device=device) for p in graph_paths]
         self.dim = dim
 
     def set_ef(self, ef: int) -> None:

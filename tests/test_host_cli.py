@@ -1,0 +1,91 @@
+"""The C++ host layer (hnsw_slim_b200/host/: SolveStrategy-shaped classes + the reference's command
+line, main.cc:10-139) above the C ABI.  CPU: flag surface, index naming, loud failure without a
+GPU.  GPU: the three strategies end to end on .fvecs files, against the Python binding."""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import HAVE_GPU
+from hnsw_slim_b200 import build as hs_build
+from hnsw_slim_b200 import capi, vecs_io
+from hnsw_slim_b200.synth import make_dataset
+
+
+def run_cli(*args, cwd=None):
+    r = subprocess.run([hs_build.HOST_CLI, *args], capture_output=True, text=True, cwd=cwd, timeout=600)
+    return r.returncode, r.stdout, r.stderr
+
+
+def make_files(tmp_path, name="toy", n=20000, nq=200, dim=96):
+    base, q = make_dataset(n, nq, dim, rank=10, seed=9)
+    d = tmp_path / "data" / name
+    d.mkdir(parents=True)
+    vecs_io.write_vecs(str(d / f"{name}_base.fvecs"), base)
+    vecs_io.write_vecs(str(d / f"{name}_query.fvecs"), q)
+    return base, q, str(tmp_path / "data"), str(tmp_path / "index")
+
+
+def test_unknown_strategy_and_flags(tmp_path):
+    rc, out, _ = run_cli("--solve_strategy=annoy", "--data_dir", str(tmp_path))
+    assert rc == 1 and "Unknown strategy: annoy" in out                      # main.cc:134-138
+    rc, out, _ = run_cli("--no_such_flag=1")
+    assert rc == 1 and "unknown command line flag" in out
+    # index file name and derived pruning parameters, main.cc:58-100
+    rc, out, _ = run_cli("--solve_strategy=nope", "--dataset=sift", "--m=16", "--ef_construction=200",
+                         "--branching_factor=4", "--top_M0=32", "--Mm_ratio=25", "--level_ratio=50")
+    assert "Index path: ../statistics/index/sift/nope_200_16_4_0_0.020000_0.020000_32_8_16_4.graph" in out
+    assert "top_m0: 32, top_m: 16, low_m0: 8, low_m: 4" in out
+
+
+def test_missing_dataset_exits_like_the_reference(tmp_path):
+    rc, out, _ = run_cli("--solve_strategy=hnsw_slim", "--dataset=nothing", "--data_dir", str(tmp_path))
+    assert rc != 0 and "open file error" in out                             # util.h:57-60: exit(-1)
+
+
+@pytest.mark.skipif(HAVE_GPU, reason="checks the no-GPU behaviour")
+def test_no_gpu_fails_loudly(tmp_path):
+    base, q, data_dir, index_dir = make_files(tmp_path, n=2000, nq=10, dim=32)
+    rc, out, err = run_cli("--solve_strategy=hnsw_slim", "--dataset=toy", "--data_dir", data_dir, "--index_dir",
+                           index_dir, "--m=8", "--ef_construction=40", "--k=5")
+    assert rc != 0
+    assert "no CUDA device" in err and "no CPU fallback" in err
+    # the index was still built and saved on the host, in the reference's format
+    graphs = list((tmp_path / "index" / "toy").glob("hnsw_slim_40_8_4_*.graph"))
+    assert len(graphs) == 1 and capi.HostGraph(str(graphs[0]), 32).info()["n"] == 2000
+
+
+@pytest.mark.gpu
+def test_cli_end_to_end(tmp_path):
+    base, q, data_dir, index_dir = make_files(tmp_path)
+    common = ["--dataset=toy", "--data_dir", data_dir, "--index_dir", index_dir, "--m=16", "--ef_construction=100",
+              "--k=10", "--ef_search=100"]
+    # 1. ground truth (brute_force_strategy.h:15-45): k=100 rows, farthest first
+    rc, out, err = run_cli("--solve_strategy=bruteforce", *common)
+    assert rc == 0, err
+    gt = vecs_io.read_ivecs(os.path.join(data_dir, "toy", "toy_groundtruth.ivecs"))
+    assert gt.shape == (200, 100)
+    want, _ = capi.bruteforce_knn(base, q, 100)
+    assert np.array_equal(gt, want[:, ::-1])
+    assert float(re.search(r"Recall: ([0-9.]+)", out).group(1)) == 1.0        # its own top-10 against itself
+    # 2. hnsw_slim: builds + saves on the first run, loads on the second; same recall both times
+    recalls = []
+    for _ in range(2):
+        rc, out, err = run_cli("--solve_strategy=hnsw_slim", *common)
+        assert rc == 0, err
+        recalls.append(float(re.search(r"Recall: ([0-9.]+)", out).group(1)))
+    assert recalls[0] == recalls[1] and recalls[0] >= 0.95
+    graph = [p for p in os.listdir(os.path.join(index_dir, "toy")) if p.startswith("hnsw_slim_100_16_4_")]
+    assert len(graph) == 1
+    ix = capi.Index(os.path.join(index_dir, "toy", graph[0]), 96)
+    ix.set_ef(100)
+    lab, _ = ix.search(q, 10)
+    py_recall = np.mean([len(set(a) & set(b)) / 10 for a, b in zip(lab, want[:, :10])])
+    assert abs(py_recall - recalls[0]) < 1e-6
+    # 3. hnsw-slimq (README spelling)
+    rc, out, err = run_cli("--solve_strategy=hnsw-slimq", *common)
+    assert rc == 0, err
+    assert float(re.search(r"Recall: ([0-9.]+)", out).group(1)) >= 0.93
+    assert any(p.startswith("hnsw_slimq_100_16_4_") for p in os.listdir(os.path.join(index_dir, "toy")))
