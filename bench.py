@@ -293,6 +293,7 @@ def run_gpu(args, w):
     else:
         ix = capi.Index(graph, w["dim"], metric=w["metric"], device=local_rank)
     ix.set_ef(w["ef"])
+    ix.set_overlap(not args.no_overlap)
     info = ix.info()
     log(f"[bench] rank {rank}: index resident in {time.time()-t0:.1f}s, {info['device_bytes']/2**20:.0f} MiB HBM, "
         f"maxlevel {info['maxlevel']}, avg deg0 {info['sum_deg0']/info['n']:.2f}")
@@ -415,6 +416,9 @@ def run_gpu(args, w):
             "config": {"workload": w["desc"], "k": k, "ef_search": w["ef"], "queries_per_step_per_gpu": nq,
                        "parallelism": f"replicated index x{world}, queries split, no collective",
                        "recall_at_10": recall,
+                       "batch_overlap": (not args.no_overlap) and "hs_set_overlap: the next step's grid is launched with "
+                                        "programmatic stream serialization and fills SMs while this step's last queries "
+                                        "drain; ms_per_step = timed region / steps",
                        "l2": "index (vectors+adjacency) %.0f MiB > 126 MB L2; a different query batch every step"
                              % (info["device_bytes"] / 2**20)},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": args.steps,
@@ -555,6 +559,8 @@ def main():
     ap.add_argument("--workload", default="sift1m", choices=sorted(WORKLOADS))
     ap.add_argument("--ef", type=int, default=None)
     ap.add_argument("--no-recall", action="store_true")
+    ap.add_argument("--no-overlap", action="store_true",
+                    help="do not let consecutive batches overlap on the stream (hs_set_overlap off)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(3, args.warmup) if args.impl == "ours" else max(1, args.warmup)

@@ -23,7 +23,7 @@ EXPORTS = [
     "hs_debug_flatten", "hs_debug_free", "hs_debug_info", "hs_debug_row", "hs_debug_node",
     "hs_build_params_default", "hs_build_slim_graph",
     "hs_get_query_tconst", "hs_set_query_tconst", "hs_slimq_prepare", "hs_build_slimq_graph",
-    "hs_slimq_default_tconst", "hs_debug_bf_tc_fallback",
+    "hs_slimq_default_tconst", "hs_debug_bf_tc_fallback", "hs_set_overlap",
 ]
 
 
@@ -99,6 +99,7 @@ def lib():
         L.hs_build_slim_graph.argtypes = [vp, sz, sz, i32, C.POINTER(BuildParams), vp, C.c_char_p]
         L.hs_build_slimq_graph.argtypes = [vp, sz, sz, C.POINTER(BuildParams), vp, sz, vp, vp, C.c_char_p]
         L.hs_slimq_default_tconst.argtypes = [sz]
+        L.hs_set_overlap.argtypes = [vp, i32]
         L.hs_get_query_tconst.argtypes = [vp, C.POINTER(C.c_double)]
         L.hs_set_query_tconst.argtypes = [vp, C.c_double]
         L.hs_slimq_prepare.argtypes = [vp, vp, sz, vp, vp, vp, vp]
@@ -167,6 +168,10 @@ class Index:
 
     def set_ef(self, ef: int) -> None:
         _check(lib().hs_set_ef(self._h, ef))
+
+    def set_overlap(self, on: bool) -> None:
+        """hs_set_overlap: consecutive device-buffer batches on one stream may overlap (see the header)."""
+        _check(lib().hs_set_overlap(self._h, int(bool(on))))
 
     def search(self, queries, k: int, *, want_dists: bool = True, counts: bool = False):
         """Host buffers in/out (hs_search_batch).  -> labels[nq,k], dists[nq,k] (, counts[nq,2])."""

@@ -29,6 +29,10 @@ using namespace hs;
     }                                                                                 \
   } while (0)
 
+// Launches in flight at once are bounded by what fits on the GPU (a dozen small grids); a slot is
+// reused only kWorkRing launches later.
+constexpr unsigned int kWorkRing = 1024;
+
 struct hs_index {
   hs_index_info info{};
   int device = 0;
@@ -48,7 +52,9 @@ struct hs_index {
   uint32_t level_count[kMaxLevels] = {};
   double t_const = 0.0;
   // per-call scratch
-  unsigned int *d_work = nullptr;
+  unsigned long long *d_work = nullptr;    // ring of kWorkRing tagged work counters (traverse_common.cuh)
+  unsigned int launch_seq = 1;             // tags start at 1 (slots are initialised to 0xff..ff)
+  int overlap = 0;                         // hs_set_overlap
   unsigned long long *d_stats = nullptr;   // [0] n_dist [1] n_hops [2] n_rerank
   // staging for the host-buffer entry points
   cudaStream_t stream = nullptr;
@@ -154,7 +160,8 @@ int build_index(const HostGraph &g, int metric, int device, const float *raw_bas
   for (int l = 1; l <= g.maxlevel && l < kMaxLevels; ++l)
     if ((rc = upload(&ix->d_upper_adj[l], g.upper_adj[l].data(), g.upper_adj[l].size(), &bytes)) != HS_OK)
       return fail(rc);
-  if (cudaMalloc(&ix->d_work, sizeof(unsigned int)) != cudaSuccess ||
+  if (cudaMalloc(&ix->d_work, kWorkRing * sizeof(unsigned long long)) != cudaSuccess ||
+      cudaMemset(ix->d_work, 0xff, kWorkRing * sizeof(unsigned long long)) != cudaSuccess ||
       cudaMalloc(&ix->d_stats, 4 * sizeof(unsigned long long)) != cudaSuccess ||
       cudaMemset(ix->d_stats, 0, 4 * sizeof(unsigned long long)) != cudaSuccess ||
       cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking) != cudaSuccess) {
@@ -296,14 +303,16 @@ int search_device_slimq(hs_index *ix, const float *d_queries, size_t nq, size_t 
     p.prep_scal = dump->scal;
     p.prep_q2c = dump->q2c;
   }
-  p.work_counter = ix->d_work;
+  const unsigned int seq = ix->launch_seq++;
+  p.work_counter = ix->d_work + (seq % kWorkRing);
+  p.launch_tag = seq;
+  p.overlap = ix->overlap ? 1u : 0u;
   p.stats = ix->d_stats;
   p.per_query = d_perq;
   p.flags = ix->slimq_flags;
   TraverseQLaunch l{};
   int rc = plan_traverse_slimq(p, ix->sm_count, (int)nq, &l);
   if (rc != HS_OK) return rc;
-  HS_CUDA(cudaMemsetAsync(ix->d_work, 0, sizeof(unsigned int), stream));
   return launch_traverse_slimq(p, l, stream);
 }
 
@@ -342,14 +351,16 @@ int search_device(hs_index *ix, const float *d_queries, size_t nq, size_t k, uin
   p.ef = (uint32_t)std::max<size_t>(ix->info.ef, k);   // slim.h:2080
   p.out_labels = d_labels;
   p.out_dists = d_dists;
-  p.work_counter = ix->d_work;
+  const unsigned int seq = ix->launch_seq++;
+  p.work_counter = ix->d_work + (seq % kWorkRing);
+  p.launch_tag = seq;
+  p.overlap = ix->overlap ? 1u : 0u;
   p.stats = ix->d_stats;
   p.per_query = d_perq;
   p.flags = ix->traverse_flags;
   TraverseLaunch l{};
   int rc = plan_traverse(p, ix->info.metric, ix->hash_bits_override, ix->sm_count, (int)nq, &l);
   if (rc != HS_OK) return rc;
-  HS_CUDA(cudaMemsetAsync(ix->d_work, 0, sizeof(unsigned int), stream));
   return launch_traverse(p, ix->info.metric, l, stream);
 }
 
@@ -435,6 +446,15 @@ int hs_set_ef(hs_index *ix, size_t ef) {
     return HS_ERR_ARG;
   }
   ix->info.ef = ef;
+  return HS_OK;
+}
+
+int hs_set_overlap(hs_index *ix, int on) {
+  if (!ix) {
+    set_error("null argument");
+    return HS_ERR_ARG;
+  }
+  ix->overlap = on ? 1 : 0;
   return HS_OK;
 }
 

@@ -160,6 +160,26 @@ __device__ __forceinline__ void prefetch_l2(const void *p) {
 }
 constexpr uint64_t NONE = ~0ull;
 
+// Dynamic work distribution: the next query index of THIS launch.  The counter is one slot of a
+// ring that the host walks (hs_api.cu), tagged in its high half with the launch sequence number,
+// so it never needs a reset between launches — which lets consecutive launches overlap
+// (hs_set_overlap) without a memset node between them.  The first warp of a launch to arrive
+// finds a foreign tag and claims the slot.
+__device__ __forceinline__ uint32_t next_ticket(unsigned long long *ctr, uint32_t tag) {
+  unsigned long long old = atomicAdd(ctr, 1ull);
+  while ((uint32_t)(old >> 32) != tag) {
+    const unsigned long long cur = *reinterpret_cast<volatile unsigned long long *>(ctr);
+    if ((uint32_t)(cur >> 32) == tag) {
+      old = atomicAdd(ctr, 1ull);
+    } else if (atomicCAS(ctr, cur, ((unsigned long long)tag << 32) | 1ull) == cur) {
+      old = (unsigned long long)tag << 32;       // ticket 0 is mine
+    } else {
+      old = cur;                                  // lost the race: look again
+    }
+  }
+  return (uint32_t)old;
+}
+
 // lane holding the warp-wide smallest `key` ((dist,id) order; NONE = no entry); -1 if none
 __device__ __forceinline__ int warp_argmin_key(uint64_t key) {
   const uint32_t hi = (uint32_t)(key >> 32);

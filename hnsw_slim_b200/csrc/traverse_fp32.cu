@@ -55,6 +55,12 @@ __global__ void __launch_bounds__(128, HS_TRAVERSE_MIN_CTAS) traverse_kernel(con
   uint32_t *stage_ids = reinterpret_cast<uint32_t *>(wbase + p.off_stage);
   float4 *qs = reinterpret_cast<float4 *>(wbase + p.off_query);
 
+  if (p.overlap) {
+    // consecutive batches may overlap (programmatic dependent launch): this grid needs nothing
+    // from its predecessor, so the next launch may fill SM slots as soon as they free up
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  }
+
   const uint32_t hbits = p.hash_bits, hsize = 1u << hbits, hmask = hsize - 1;
   const uint32_t hlimit = hsize - hsize / 4;
   const uint32_t ef = p.ef;
@@ -63,7 +69,7 @@ __global__ void __launch_bounds__(128, HS_TRAVERSE_MIN_CTAS) traverse_kernel(con
 
   for (;;) {
     uint32_t qi = 0;
-    if (lane == 0) qi = atomicAdd(p.work_counter, 1u);
+    if (lane == 0) qi = next_ticket(p.work_counter, p.launch_tag);
     qi = __shfl_sync(FULL, qi, 0);
     if (qi >= p.nq) break;
 
@@ -281,7 +287,17 @@ int launch_t(const TraverseParams &p, const TraverseLaunch &l, cudaStream_t stre
     set_error(std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
     return HS_ERR_CUDA;
   }
-  kern<<<l.grid, l.warps_per_cta * 32, l.smem_bytes, stream>>>(p);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(l.grid);
+  cfg.blockDim = dim3(l.warps_per_cta * 32);
+  cfg.dynamicSmemBytes = l.smem_bytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = p.overlap ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, kern, p);
   e = cudaGetLastError();
   if (e != cudaSuccess) {
     set_error(std::string("traverse_kernel launch: ") + cudaGetErrorString(e));

@@ -25,7 +25,9 @@ struct TraverseParams {
   uint32_t *out_labels;                    // nq x k
   float *out_dists;                        // nq x k or null
   // scratch / counters
-  unsigned int *work_counter;              // zeroed before launch
+  unsigned long long *work_counter;        // one slot of the ring of tagged counters (next_ticket)
+  uint32_t launch_tag;                     // launch sequence number: the counter's tag
+  uint32_t overlap;                        // 1: launched with programmatic stream serialization
   unsigned long long *stats;               // [0] n_dist  [1] n_hops
   uint32_t *per_query;                     // optional nq x 2 (n_dist, n_hops) or null
   // shared-memory carve-up per warp (bytes)

@@ -209,10 +209,11 @@ traverse_slimq_kernel(const __grid_constant__ TraverseQParams p) {
   float *g2c = reinterpret_cast<float *>(wbase + p.off_g2c);
   unsigned long long *planes_s = reinterpret_cast<unsigned long long *>(wbase + p.off_planes);
   const uint32_t ef = p.ef;
+  if (p.overlap) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // see traverse_fp32.cu
 
   for (;;) {
     uint32_t qi = 0;
-    if (lane == 0) qi = atomicAdd(p.work_counter, 1u);
+    if (lane == 0) qi = next_ticket(p.work_counter, p.launch_tag);
     qi = __shfl_sync(FULL, qi, 0);
     if (qi >= p.nq) break;
     const float *qptr = p.queries + (size_t)qi * p.dim;
@@ -442,7 +443,17 @@ int launch_traverse_slimq(const TraverseQParams &p, const TraverseQLaunch &l, cu
       set_error(std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
       return (int)HS_ERR_CUDA;
     }
-    kern<<<l.grid, l.warps_per_cta * 32, l.smem_bytes, stream>>>(p);
+    cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(l.grid);
+  cfg.blockDim = dim3(l.warps_per_cta * 32);
+  cfg.dynamicSmemBytes = l.smem_bytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = p.overlap ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, kern, p);
     e = cudaGetLastError();
     if (e != cudaSuccess) {
       set_error(std::string("traverse_slimq_kernel launch: ") + cudaGetErrorString(e));

@@ -34,7 +34,9 @@ struct TraverseQParams {
   float *prep_scal;                        // nq x 3
   float *prep_q2c;                         // nq x num_cluster
   // scratch / counters
-  unsigned int *work_counter;
+  unsigned long long *work_counter;        // one slot of the ring of tagged counters (next_ticket)
+  uint32_t launch_tag;                     // launch sequence number: the counter's tag
+  uint32_t overlap;                        // 1: launched with programmatic stream serialization
   unsigned long long *stats;               // [0] n_est [1] n_hops [2] n_rerank
   uint32_t *per_query;                     // optional nq x 2 (n_est, n_hops)
   // shared-memory carve-up per warp (bytes)

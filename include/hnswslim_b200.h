@@ -87,6 +87,16 @@ int hs_set_ef(hs_index *, size_t ef);
 
 int hs_get_info(const hs_index *, hs_index_info *out);
 
+/* Batch overlap (off by default).  When on, the traversal kernel of one hs_search_batch_device
+ * call is launched with programmatic stream serialization, so on ONE stream the next call's grid
+ * starts filling SMs while the previous call's last queries are still draining (a batch otherwise
+ * ends with a tail of about one query latency during which most of the GPU idles).  The caller
+ * promises that the query buffer of a call is complete when the call is enqueued unless it was
+ * produced by a non-kernel operation (copy, memset) on the same stream: a kernel of the caller
+ * that writes the queries must have finished (event / stream sync) first.  Results are
+ * unchanged. */
+int hs_set_overlap(hs_index *, int on);
+
 /* hnsw_slimq only.  The reference draws its query-quantiser constant at random when it loads an
  * index (slimq.h:1274-1276 -> faster_config, rabitqlib/quantization/rabitq.hpp:27-34 ->
  * rabitq_impl.hpp:363-377: std::random_device), so its estimates differ in the low bits from

@@ -243,3 +243,28 @@ def test_errors_are_loud(tmp_path):
     bad.write_bytes(b"\x01" * 100)
     with pytest.raises(capi.HsError):
         capi.Index(str(bad), 32)
+
+
+def test_batch_overlap_keeps_results(small_corpus):
+    """hs_set_overlap: consecutive device-buffer batches on one stream may overlap (programmatic
+    dependent launch + a ring of work counters); every batch still gets exactly its own results."""
+    import torch
+    c = small_corpus
+    ix = capi.Index(c.graph, c.dim)
+    ix.set_ef(60)
+    k, nq = 10, c.queries.shape[0]
+    batches = [np.ascontiguousarray(np.roll(c.queries, s, axis=0)) for s in range(12)]
+    want = [ix.search(b, k) for b in batches]
+    ix.set_overlap(True)
+    dq = [torch.from_numpy(b).cuda() for b in batches]
+    dl = [torch.empty((nq, k), dtype=torch.int32, device="cuda") for _ in batches]
+    dd = [torch.empty((nq, k), dtype=torch.float32, device="cuda") for _ in batches]
+    torch.cuda.synchronize()
+    s = torch.cuda.current_stream().cuda_stream
+    for rep in range(3):
+        for i in range(len(batches)):
+            ix.search_device(dq[i].data_ptr(), nq, k, dl[i].data_ptr(), dd[i].data_ptr(), s)
+    torch.cuda.synchronize()
+    for i, (wl, wd) in enumerate(want):
+        assert np.array_equal(dl[i].cpu().numpy().view(np.uint32), wl), i
+        assert np.array_equal(dd[i].cpu().numpy().view(np.uint32), wd.view(np.uint32)), i

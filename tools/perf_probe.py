@@ -19,6 +19,7 @@ ap.add_argument("--efs", type=str, default="100")
 ap.add_argument("--iters", type=int, default=10)
 ap.add_argument("--check", type=int, default=0)
 ap.add_argument("--nq", type=int, default=0)
+ap.add_argument("--overlap", type=int, default=0)
 a = ap.parse_args()
 w = dict(bench.WORKLOADS[a.workload])
 if a.nq:
@@ -29,6 +30,7 @@ if slimq:
     ix = capi.Index(graph, w["dim"], kind=capi.HS_KIND_SLIMQ, raw_base=base)
 else:
     ix = capi.Index(graph, w["dim"], metric=w["metric"])
+ix.set_overlap(bool(a.overlap))
 info = ix.info()
 nq, k = w["nq"], w["k"]
 dq = [torch.from_numpy(q).cuda() for q in qb]
@@ -68,7 +70,7 @@ for ef in [int(x) for x in a.efs.split(",")]:
         torch.cuda.synchronize()
         lab = dl[:1000].cpu().numpy().view(np.uint32)
         rec = float(np.mean([len(set(r) & g) / k for r, g in zip(lab, gt)]))
-    print(f"lib={os.path.basename(os.path.dirname(os.environ.get('HS_LIB_PATH','default/x')))} "
+    print(f"overlap={a.overlap} lib={os.path.basename(os.path.dirname(os.environ.get('HS_LIB_PATH','default/x')))} "
           f"flags={os.environ.get('HS_TRAVERSE_FLAGS','-')} hb={os.environ.get('HS_HASH_BITS','-')} ef={ef:4d} "
           f"{ms:8.3f} ms/batch {nq/ms*1e3:11.0f} QPS  n_dist/q={nd:7.1f} n_hops/q={nh:6.1f} "
           f"alg GB/s={bytes_q*nq/ms/1e6:7.1f} recall@{k}={rec:.4f}", flush=True)
