@@ -43,6 +43,13 @@ WORKLOADS = {
     "deep-sharded": dict(n=4_000_000, shards=8, dim=96, metric=0, M=16, efc=200, rank=12, nq=10_000, k=10, ef=100,
                          desc="DEEP-shaped synthetic 4Mx96 L2 in 8 sub-graphs of 500k (100M config scaled down), "
                               "hnsw_slim M=16 efc=200, all-gather + top-k merge"),
+    # BASELINE.json configs[1]: GIST-shaped, ef_search sweep 50-400 (tools/perf_probe.py --efs ...)
+    "gist1m": dict(n=1_000_000, dim=960, metric=0, M=32, efc=200, rank=24, nq=10_000, k=10, ef=100,
+                   desc="GIST-shaped synthetic 1Mx960 L2, hnsw_slim M=32 efc=200 (rank-24 latent Gaussian, seed 1)"),
+    # BASELINE.json configs[2]: COHERE-shaped, inner product on unit vectors
+    "cohere1m": dict(n=1_000_000, dim=768, metric=1, M=32, efc=200, rank=24, nq=10_000, k=10, ef=100,
+                     desc="COHERE-shaped synthetic 1Mx768 inner product (unit rows), hnsw_slim M=32 efc=200 "
+                          "(rank-24 latent Gaussian, seed 1)"),
     # BASELINE.json configs[4] shape (MSTuring 96-dim, hnsw-slimq = RaBitQ codes + exact rerank) on one GPU
     "msturing1m-slimq": dict(n=1_000_000, dim=96, metric=0, M=16, efc=200, rank=12, nq=10_000, k=10, ef=100,
                              kind="slimq",

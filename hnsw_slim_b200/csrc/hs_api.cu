@@ -66,6 +66,7 @@ struct hs_index {
   int hash_bits_override = 0;
   uint32_t traverse_flags = 3;
   uint32_t slimq_flags = 0;
+  bool zero_copy = true;                   // hs_search_batch reads/writes pinned+mapped host buffers in place
   std::mutex mu;
 };
 
@@ -116,6 +117,7 @@ int build_index(const HostGraph &g, int metric, int device, const float *raw_bas
   if (const char *hb = std::getenv("HS_HASH_BITS")) ix->hash_bits_override = std::atoi(hb);
   if (const char *tf = std::getenv("HS_TRAVERSE_FLAGS")) ix->traverse_flags = (uint32_t)std::atoi(tf);
   if (const char *qf = std::getenv("HS_SLIMQ_FLAGS")) ix->slimq_flags = (uint32_t)std::atoi(qf);
+  if (const char *zc = std::getenv("HS_ZERO_COPY")) ix->zero_copy = std::atoi(zc) != 0;
 
   size_t bytes = 0;
   auto fail = [&](int code) {
@@ -364,6 +366,24 @@ int search_device(hs_index *ix, const float *d_queries, size_t nq, size_t k, uin
   return launch_traverse(p, ix->info.metric, l, stream);
 }
 
+// Device-visible alias of a host buffer when the whole range [p, p + bytes) is page-locked
+// (cudaHostAlloc / cudaHostRegister, e.g. torch pin_memory) and mapped into this device's address
+// space; nullptr otherwise (pageable memory, or pinned without mapping).
+void *mapped_alias(const void *p, size_t bytes) {
+  if (!p || bytes == 0) return nullptr;
+  cudaPointerAttributes a0{}, a1{};
+  if (cudaPointerGetAttributes(&a0, p) != cudaSuccess ||
+      cudaPointerGetAttributes(&a1, static_cast<const char *>(p) + bytes - 1) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  if (a0.type != cudaMemoryTypeHost || a1.type != cudaMemoryTypeHost || !a0.devicePointer || !a1.devicePointer)
+    return nullptr;
+  if (static_cast<char *>(a1.devicePointer) - static_cast<char *>(a0.devicePointer) != (ptrdiff_t)(bytes - 1))
+    return nullptr;
+  return a0.devicePointer;
+}
+
 int search_host(hs_index *ix, const float *queries, size_t nq, size_t k, uint32_t *labels_out,
                 float *dists_out, uint32_t *perq_out) {
   if (!ix || (!queries && nq) || (!labels_out && nq)) {
@@ -375,6 +395,23 @@ int search_host(hs_index *ix, const float *queries, size_t nq, size_t k, uint32_
   HS_CUDA(cudaSetDevice(ix->device));
   const size_t dim = ix->info.dim;
   int rc;
+  // Zero-copy: when the caller's buffers are pinned and mapped, the traversal kernel reads every
+  // query straight from host memory (one 4*dim-byte read per query, issued by the warp that owns
+  // the query and hidden behind the other warps' work) and writes the k results of a query back in
+  // one coalesced store — no staging copies, no copy->kernel->copy serialisation: the host<->device
+  // transfers overlap the traversal itself.  HS_ZERO_COPY=0 forces the staged path.
+  if (ix->zero_copy) {
+    const float *zq = static_cast<const float *>(mapped_alias(queries, nq * dim * sizeof(float)));
+    uint32_t *zl = static_cast<uint32_t *>(mapped_alias(labels_out, nq * k * 4));
+    float *zd = dists_out ? static_cast<float *>(mapped_alias(dists_out, nq * k * 4)) : nullptr;
+    uint32_t *zp = perq_out ? static_cast<uint32_t *>(mapped_alias(perq_out, nq * 8)) : nullptr;
+    if (zq && zl && (!dists_out || zd) && (!perq_out || zp)) {
+      rc = search_device(ix, zq, nq, k, zl, zd, zp, ix->stream);
+      if (rc != HS_OK) return rc;
+      HS_CUDA(cudaStreamSynchronize(ix->stream));
+      return HS_OK;
+    }
+  }
   if ((rc = ensure((void **)&ix->d_q, &ix->cap_q, nq * dim * sizeof(float))) != HS_OK) return rc;
   size_t cap_lab = ix->cap_out, cap_dist = ix->cap_out;
   if ((rc = ensure((void **)&ix->d_lab, &cap_lab, nq * k * 4)) != HS_OK) return rc;

@@ -37,19 +37,43 @@ __device__ __forceinline__ uint64_t warp_min_u64(uint64_t v) {
   return v;
 }
 
+// Per-lane partial sums live as TWO fp32 accumulators packed in one 64-bit register pair and are
+// updated with the packed FADD2 / FFMA2 instructions of sm_100 (sub.rn.f32x2, fma.rn.f32x2: two
+// IEEE fp32 operations per issue slot).  `lo` accumulates elements x and z of the lane's float4
+// chunks, `hi` elements y and w, both in chunk order; the lane's sum is lo + hi.  The oracle's
+// HSO_ORDER_GPU association (oracle/hs_oracle.c dist_gpu) restates exactly this.
+typedef unsigned long long acc2_t;
+__device__ __forceinline__ acc2_t pack2(float lo, float hi) {
+  acc2_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ float sum2(acc2_t a) {
+  float lo, hi;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a));
+  return __fadd_rn(lo, hi);
+}
+__device__ __forceinline__ acc2_t sub2(acc2_t a, acc2_t b) {
+  acc2_t r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ acc2_t fma2(acc2_t a, acc2_t b, acc2_t c) {
+  acc2_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
 template <int METRIC>
-__device__ __forceinline__ float acc4(float acc, const float4 q, const float4 x) {
+__device__ __forceinline__ acc2_t acc4(acc2_t acc, const float4 q, const float4 x) {
+  const acc2_t q01 = pack2(q.x, q.y), q23 = pack2(q.z, q.w);
+  const acc2_t x01 = pack2(x.x, x.y), x23 = pack2(x.z, x.w);
   if (METRIC == HS_METRIC_L2) {
-    float d;
-    d = __fsub_rn(q.x, x.x); acc = __fmaf_rn(d, d, acc);
-    d = __fsub_rn(q.y, x.y); acc = __fmaf_rn(d, d, acc);
-    d = __fsub_rn(q.z, x.z); acc = __fmaf_rn(d, d, acc);
-    d = __fsub_rn(q.w, x.w); acc = __fmaf_rn(d, d, acc);
+    const acc2_t d01 = sub2(q01, x01), d23 = sub2(q23, x23);
+    acc = fma2(d01, d01, acc);
+    acc = fma2(d23, d23, acc);
   } else {
-    acc = __fmaf_rn(q.x, x.x, acc);
-    acc = __fmaf_rn(q.y, x.y, acc);
-    acc = __fmaf_rn(q.z, x.z, acc);
-    acc = __fmaf_rn(q.w, x.w, acc);
+    acc = fma2(q01, x01, acc);
+    acc = fma2(q23, x23, acc);
   }
   return acc;
 }
@@ -88,12 +112,12 @@ __device__ __forceinline__ float eval_rows_reg(const float4 *__restrict__ vec, u
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      float acc = 0.f;
+      acc2_t acc2 = 0ull;
       if (act[u]) {
 #pragma unroll
-        for (int j = 0; j < CPL; ++j) acc = acc4<METRIC>(acc, q[j], x[u][j]);
+        for (int j = 0; j < CPL; ++j) acc2 = acc4<METRIC>(acc2, q[j], x[u][j]);
       }
-      acc = team_reduce(acc);
+      const float acc = team_reduce(sum2(acc2));
       const float v = __shfl_sync(FULL, acc, (lane & 3) * 8);
       if ((lane >> 2) == it0 + u) my_d = finish<METRIC>(v);
     }
@@ -111,7 +135,7 @@ __device__ __forceinline__ float eval_rows_smem(const float4 *__restrict__ vec, 
   for (int it = 0; it * 4 < count; ++it) {
     const int src = it * 4 + team;
     const uint32_t id = __shfl_sync(FULL, my_id, src & 31);
-    float acc = 0.f;
+    acc2_t acc2 = 0ull;
     if (src < count) {
       const float4 *row = vec + (size_t)id * row_chunks + t;
       const float4 *qq = qs + t;
@@ -121,11 +145,11 @@ __device__ __forceinline__ float eval_rows_smem(const float4 *__restrict__ vec, 
 #pragma unroll
         for (int jj = 0; jj < 8; ++jj) x[jj] = __ldg(row + 8 * (j + jj));
 #pragma unroll
-        for (int jj = 0; jj < 8; ++jj) acc = acc4<METRIC>(acc, qq[8 * (j + jj)], x[jj]);
+        for (int jj = 0; jj < 8; ++jj) acc2 = acc4<METRIC>(acc2, qq[8 * (j + jj)], x[jj]);
       }
-      for (; j < cpl; ++j) acc = acc4<METRIC>(acc, qq[8 * j], __ldg(row + 8 * j));
+      for (; j < cpl; ++j) acc2 = acc4<METRIC>(acc2, qq[8 * j], __ldg(row + 8 * j));
     }
-    acc = team_reduce(acc);
+    const float acc = team_reduce(sum2(acc2));
     const float v = __shfl_sync(FULL, acc, (lane & 3) * 8);
     if ((lane >> 2) == it) my_d = finish<METRIC>(v);
   }
@@ -404,6 +428,143 @@ struct RegPool {
     for (int s = 0; s < SLOTS; ++s) {
       const uint64_t km = k[s] & KEYMASK;
       if ((uint32_t)(s * 32 + lane) < size && km > last && km < m) m = km;
+    }
+    return m;
+  }
+};
+
+// RegPool with 32-bit comparisons — the pool of the fp32 traversal kernel.  Distances and ids sit
+// in separate registers; every comparison on the hot path (closest unexpanded, worst, admission
+// test) is on the 32-bit distance word alone: a 3-instruction min/max per lane, ONE REDUX per warp
+// and a ballot.  Entries of equal distance are taken in (lane, slot) order; the admission test is
+// the reference's strict `lowerBound > dist` (slim.h:403-404) on the distance alone.
+//   kd[s]  ord(distance) of a used slot, 0 for an empty one          (worst = max kd)
+//   ku[s]  ord(distance) while the entry is unexpanded, else ~0       (closest unexpanded = min ku)
+//   id[s]  node id
+template <int SLOTS>
+struct RegPool32 {
+  uint32_t kd[SLOTS], ku[SLOTS], id[SLOTS];
+  uint32_t size, ef;
+  int lane;
+
+  __device__ __forceinline__ void init(uint64_t *, uint32_t ef_, int lane_) {
+    ef = ef_;
+    lane = lane_;
+    size = 0;
+#pragma unroll
+    for (int s = 0; s < SLOTS; ++s) {
+      kd[s] = 0u;
+      ku[s] = 0xffffffffu;
+      id[s] = 0xffffffffu;
+    }
+  }
+  __device__ __forceinline__ void put(uint32_t e, uint32_t d, uint32_t i) {   // owner lane only
+#pragma unroll
+    for (int s = 0; s < SLOTS; ++s) {
+      const bool h = (int)(e >> 5) == s;
+      kd[s] = h ? d : kd[s];
+      ku[s] = h ? d : ku[s];
+      id[s] = h ? i : id[s];
+    }
+  }
+  __device__ __forceinline__ void seed(uint64_t key) {
+    if (lane == 0) put(0, (uint32_t)(key >> 32), (uint32_t)key);
+    size = 1;
+  }
+  __device__ __forceinline__ uint32_t col_min_un() const {
+    uint32_t m = ku[0];
+#pragma unroll
+    for (int s = 1; s < SLOTS; ++s) m = min(m, ku[s]);
+    return m;
+  }
+  __device__ __forceinline__ uint32_t col_max() const {
+    uint32_t m = kd[0];
+#pragma unroll
+    for (int s = 1; s < SLOTS; ++s) m = max(m, kd[s]);
+    return m;
+  }
+  __device__ __forceinline__ uint32_t pop_closest_unexpanded() {
+    const uint32_t m = col_min_un();
+    const uint32_t g = __reduce_min_sync(FULL, m);
+    if (g == 0xffffffffu) return kInvalid;
+    const int o = __ffs(__ballot_sync(FULL, m == g)) - 1;
+    uint32_t node = 0;
+    bool open = lane == o;
+#pragma unroll
+    for (int s = 0; s < SLOTS; ++s) {
+      const bool h = open && ku[s] == g;
+      node = h ? id[s] : node;
+      ku[s] = h ? 0xffffffffu : ku[s];
+      open = open && !h;
+    }
+    return __shfl_sync(FULL, node, o);
+  }
+  __device__ __forceinline__ unsigned admit(bool valid, uint64_t key) {
+    const uint32_t d = (uint32_t)(key >> 32), cid = (uint32_t)key;
+    unsigned entered = 0;
+    const unsigned vmask = __ballot_sync(FULL, valid);
+    if (vmask == 0) return 0;
+    unsigned todo = vmask;
+    if (size < ef) {   // room left: the first (ef - size) candidates are appended unconditionally
+      const uint32_t room = ef - size;
+      const uint32_t n_app = min(room, (uint32_t)__popc(vmask));
+      for (uint32_t j = 0; j < n_app; ++j) {
+        const int src = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const uint32_t cd = __shfl_sync(FULL, d, src), ci = __shfl_sync(FULL, cid, src);
+        const uint32_t e = size + j;
+        if ((int)(e & 31) == lane) put(e, cd, ci);
+        entered |= 1u << src;
+      }
+      size += n_app;
+      if (todo == 0) return entered;
+    }
+    uint32_t cm = col_max();
+    uint32_t worst = __reduce_max_sync(FULL, cm);
+    todo &= __ballot_sync(FULL, valid && d < worst);   // the worst only gets smaller
+    while (todo) {
+      const int src = __ffs(todo) - 1;
+      todo &= todo - 1;
+      const uint32_t cd = __shfl_sync(FULL, d, src);
+      if (cd < worst) {
+        const uint32_t ci = __shfl_sync(FULL, cid, src);
+        const int owner = __ffs(__ballot_sync(FULL, cm == worst)) - 1;
+        bool open = lane == owner;
+#pragma unroll
+        for (int s = 0; s < SLOTS; ++s) {
+          const bool h = open && kd[s] == worst;
+          kd[s] = h ? cd : kd[s];
+          ku[s] = h ? cd : ku[s];
+          id[s] = h ? ci : id[s];
+          open = open && !h;
+        }
+        entered |= 1u << src;
+        if (todo) {
+          cm = col_max();
+          worst = __reduce_max_sync(FULL, cm);
+        }
+      }
+    }
+    return entered;
+  }
+  // every entry becomes unexpanded again (a new layer of the layered beam, slim.h:228-233)
+  __device__ __forceinline__ void clear_flags() {
+#pragma unroll
+    for (int s = 0; s < SLOTS; ++s) ku[s] = kd[s] ? kd[s] : 0xffffffffu;
+  }
+  template <typename F>
+  __device__ __forceinline__ void for_each_id(F &&f) const {
+#pragma unroll
+    for (int s = 0; s < SLOTS; ++s)
+      if (kd[s]) f(id[s]);
+  }
+  // smallest (distance,id) key strictly above `last` in this lane's column (NONE if none)
+  __device__ __forceinline__ uint64_t col_next_above(uint64_t last) const {
+    uint64_t m = NONE;
+#pragma unroll
+    for (int s = 0; s < SLOTS; ++s) {
+      const uint64_t km = ((uint64_t)kd[s] << 32) | id[s];
+      if (kd[s] && km > last && km < m) m = km;
     }
     return m;
   }

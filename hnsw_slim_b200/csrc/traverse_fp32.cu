@@ -42,7 +42,7 @@ namespace {
 #define HS_TRAVERSE_U 1            // x4 rows whose loads are in flight per warp
 #endif
 
-template <int SLOTS> struct PoolSel { using type = RegPool<SLOTS>; };
+template <int SLOTS> struct PoolSel { using type = RegPool32<SLOTS>; };
 template <> struct PoolSel<0> { using type = SmemPool; };
 
 template <int CPL, int METRIC, int SLOTS>
@@ -66,6 +66,7 @@ __global__ void __launch_bounds__(128, HS_TRAVERSE_MIN_CTAS) traverse_kernel(con
   const uint32_t ef = p.ef;
   const int t8 = lane & 7;
   constexpr int QN = CPL > 0 ? CPL : 1;
+  const bool qvec = ((reinterpret_cast<uintptr_t>(p.queries) & 15u) == 0) && (p.dim & 3u) == 0;
 
   for (;;) {
     uint32_t qi = 0;
@@ -73,28 +74,36 @@ __global__ void __launch_bounds__(128, HS_TRAVERSE_MIN_CTAS) traverse_kernel(con
     qi = __shfl_sync(FULL, qi, 0);
     if (qi >= p.nq) break;
 
-    // ---- query: lane t of each team owns chunks t, t+8, ... (zero-padded past dim) ----
+    // ---- query: lane t of each team owns chunks t, t+8, ... (zero-padded past dim).  Each
+    //      chunk is read ONCE per warp (one 16-byte load per lane when the batch is 16-byte
+    //      aligned) and handed to the four teams by shuffles: the batch may sit in pinned host
+    //      memory (zero-copy hs_search_batch), where every request crosses PCIe ----
     const float *qptr = p.queries + (size_t)qi * p.dim;
-    float4 q[QN];
-    if (CPL > 0) {
-#pragma unroll
-      for (int j = 0; j < QN; ++j) {
-        const uint32_t c = 4u * (uint32_t)(t8 + 8 * j);
-        q[j].x = c + 0 < p.dim ? __ldg(qptr + c + 0) : 0.f;
-        q[j].y = c + 1 < p.dim ? __ldg(qptr + c + 1) : 0.f;
-        q[j].z = c + 2 < p.dim ? __ldg(qptr + c + 2) : 0.f;
-        q[j].w = c + 3 < p.dim ? __ldg(qptr + c + 3) : 0.f;
-      }
-    } else {
-      for (uint32_t ch = lane; ch < p.row_chunks; ch += 32) {
-        const uint32_t c = 4u * ch;
-        float4 v;
+    auto load_chunk = [&](uint32_t ch) -> float4 {
+      const uint32_t c = 4u * ch;
+      float4 v;
+      if (qvec && c + 3 < p.dim) {
+        v = __ldg(reinterpret_cast<const float4 *>(qptr) + ch);
+      } else {
         v.x = c + 0 < p.dim ? __ldg(qptr + c + 0) : 0.f;
         v.y = c + 1 < p.dim ? __ldg(qptr + c + 1) : 0.f;
         v.z = c + 2 < p.dim ? __ldg(qptr + c + 2) : 0.f;
         v.w = c + 3 < p.dim ? __ldg(qptr + c + 3) : 0.f;
-        qs[ch] = v;
       }
+      return v;
+    };
+    float4 q[QN];
+    if (CPL > 0) {
+      const float4 mine = load_chunk((uint32_t)lane);      // row_chunks = 8 * CPL <= 32
+#pragma unroll
+      for (int j = 0; j < QN; ++j) {
+        q[j].x = __shfl_sync(FULL, mine.x, t8 + 8 * j);
+        q[j].y = __shfl_sync(FULL, mine.y, t8 + 8 * j);
+        q[j].z = __shfl_sync(FULL, mine.z, t8 + 8 * j);
+        q[j].w = __shfl_sync(FULL, mine.w, t8 + 8 * j);
+      }
+    } else {
+      for (uint32_t ch = lane; ch < p.row_chunks; ch += 32) qs[ch] = load_chunk(ch);
     }
     hash_clear(hash, hsize, lane);
     __syncwarp();
@@ -233,7 +242,12 @@ __global__ void __launch_bounds__(128, HS_TRAVERSE_MIN_CTAS) traverse_kernel(con
         if (fresh && opt_prefetch) {
           // pull the whole row towards L2 now; the scoring loop below then mostly waits on L2
           const char *r = reinterpret_cast<const char *>(p.vec + (size_t)id * p.row_chunks);
-          for (uint32_t off = 0; off < p.row_chunks * 16u; off += 128) prefetch_l2(r + off);
+          if constexpr (CPL > 0) {
+#pragma unroll
+            for (int j = 0; j < CPL; ++j) prefetch_l2(r + 128 * j);      // row = CPL x 128 B
+          } else {
+            for (uint32_t off = 0; off < p.row_chunks * 16u; off += 128) prefetch_l2(r + off);
+          }
         }
         const unsigned fm = __ballot_sync(FULL, fresh);
         const int count = __popc(fm);
@@ -255,15 +269,24 @@ __global__ void __launch_bounds__(128, HS_TRAVERSE_MIN_CTAS) traverse_kernel(con
     //      slim.h:2126-2130): k rounds of warp-wide extract-min over the pool ----
     __syncwarp();
     {
+      // lane i keeps result i; labels are looked up and rows written 32 results at a time
+      // (one coalesced store per row for k <= 32: the output may be pinned host memory)
       uint64_t last = 0;   // every key is > 0 (f2ord(+0.0f) has the top bit set)
+      uint64_t mine_out = NONE;
       for (uint32_t i = 0; i < p.k; ++i) {
         const uint64_t mine = last == NONE ? NONE : pool.col_next_above(last);
         const int o = warp_argmin_key(mine);
         last = o >= 0 ? __shfl_sync(FULL, mine, o) : NONE;
-        if (lane == 0) {
-          p.out_labels[(size_t)qi * p.k + i] = o >= 0 ? __ldg(p.labels + (uint32_t)last) : 0xFFFFFFFFu;
-          if (p.out_dists)
-            p.out_dists[(size_t)qi * p.k + i] = o >= 0 ? ord2f((uint32_t)(last >> 32)) : __int_as_float(0x7f800000);
+        if ((uint32_t)lane == (i & 31u)) mine_out = last;
+        if ((i & 31u) == 31u || i + 1 == p.k) {
+          const uint32_t r = (i & ~31u) + (uint32_t)lane;
+          if (r <= i) {
+            const bool have = mine_out != NONE;
+            p.out_labels[(size_t)qi * p.k + r] = have ? __ldg(p.labels + (uint32_t)mine_out) : 0xFFFFFFFFu;
+            if (p.out_dists)
+              p.out_dists[(size_t)qi * p.k + r] = have ? ord2f((uint32_t)(mine_out >> 32)) : __int_as_float(0x7f800000);
+          }
+          mine_out = NONE;
         }
       }
     }

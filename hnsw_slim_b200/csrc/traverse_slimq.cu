@@ -335,10 +335,10 @@ traverse_slimq_kernel(const __grid_constant__ TraverseQParams p) {
       if (!any) continue;                               // slimq.h:708-715: no neighbours, no rerank
       nh++;
       nr++;
-      float acc = 0.f;
-      if ((uint32_t)lane < p.row_chunks) acc = acc4<HS_METRIC_L2>(acc, qs[lane], x0);
-      for (uint32_t c = lane + 32; c < p.row_chunks; c += 32) acc = acc4<HS_METRIC_L2>(acc, qs[c], __ldg(xrow + c));
-      const float dx = warp_sum_f(acc);
+      acc2_t acc2 = 0ull;
+      if ((uint32_t)lane < p.row_chunks) acc2 = acc4<HS_METRIC_L2>(acc2, qs[lane], x0);
+      for (uint32_t c = lane + 32; c < p.row_chunks; c += 32) acc2 = acc4<HS_METRIC_L2>(acc2, qs[c], __ldg(xrow + c));
+      const float dx = warp_sum_f(sum2(acc2));
       const uint64_t xk = make_key(dx, node);
       if (!top_seeded) {
         top.seed(xk);
@@ -351,15 +351,23 @@ traverse_slimq_kernel(const __grid_constant__ TraverseQParams p) {
     // ---- results: the k closest expanded nodes by exact distance, ascending ----
     __syncwarp();
     {
+      // lane i keeps result i; one coalesced store per row for k <= 32 (see traverse_fp32.cu)
       uint64_t last = 0;
+      uint64_t mine_out = NONE;
       for (uint32_t i = 0; i < p.k; ++i) {
         const uint64_t mine = (last == NONE || !top_seeded) ? NONE : top.col_next_above(last);
         const int o = warp_argmin_key(mine);
         last = o >= 0 ? __shfl_sync(FULL, mine, o) : NONE;
-        if (lane == 0) {
-          p.out_labels[(size_t)qi * p.k + i] = o >= 0 ? __ldg(p.labels + (uint32_t)last) : 0xFFFFFFFFu;
-          if (p.out_dists)
-            p.out_dists[(size_t)qi * p.k + i] = o >= 0 ? ord2f((uint32_t)(last >> 32)) : __int_as_float(0x7f800000);
+        if ((uint32_t)lane == (i & 31u)) mine_out = last;
+        if ((i & 31u) == 31u || i + 1 == p.k) {
+          const uint32_t r = (i & ~31u) + (uint32_t)lane;
+          if (r <= i) {
+            const bool have = mine_out != NONE;
+            p.out_labels[(size_t)qi * p.k + r] = have ? __ldg(p.labels + (uint32_t)mine_out) : 0xFFFFFFFFu;
+            if (p.out_dists)
+              p.out_dists[(size_t)qi * p.k + r] = have ? ord2f((uint32_t)(mine_out >> 32)) : __int_as_float(0x7f800000);
+          }
+          mine_out = NONE;
         }
       }
     }

@@ -183,24 +183,27 @@ static float dist_ref(const float *a, const float *b, size_t dim, int metric) {
 }
 
 /* The CUDA kernel's association: `team` lanes per row, lane t owns the 4-float
- * chunks t, t+team, ...; elements past dim are zeros (rows are zero-padded in HBM). */
+ * chunks t, t+team, ...; elements past dim are zeros (rows are zero-padded in HBM).
+ * Every lane keeps TWO partial sums (the packed FADD2/FFMA2 pair of traverse_common.cuh
+ * acc4): `lo` takes elements 0 and 2 of each chunk, `hi` elements 1 and 3, in chunk order;
+ * the lane sum is lo + hi; lanes are then combined by xor-shuffles team/2 ... 1. */
 static float dist_gpu(const float *a, const float *b, size_t dim, int metric, int team) {
   float lane[32];
   size_t chunks = (dim + 3) / 4;
   for (int t = 0; t < team; t++) {
-    float acc = 0.f;
+    float acc[2] = {0.f, 0.f};
     for (size_t c = (size_t)t; c < chunks; c += (size_t)team)
       for (int e = 0; e < 4; e++) {
         size_t i = 4 * c + e;
         float x = i < dim ? a[i] : 0.f, y = i < dim ? b[i] : 0.f;
         if (metric == HSO_IP) {
-          acc = fmaf(x, y, acc);
+          acc[e & 1] = fmaf(x, y, acc[e & 1]);
         } else {
           float d = x - y;
-          acc = fmaf(d, d, acc);
+          acc[e & 1] = fmaf(d, d, acc[e & 1]);
         }
       }
-    lane[t] = acc;
+    lane[t] = acc[0] + acc[1];
   }
   for (int off = team / 2; off >= 1; off >>= 1) {
     float nxt[32];

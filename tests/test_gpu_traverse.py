@@ -268,3 +268,28 @@ def test_batch_overlap_keeps_results(small_corpus):
     for i, (wl, wd) in enumerate(want):
         assert np.array_equal(dl[i].cpu().numpy().view(np.uint32), wl), i
         assert np.array_equal(dd[i].cpu().numpy().view(np.uint32), wd.view(np.uint32)), i
+
+
+@pytest.mark.parametrize("dim,k", [(128, 10), (100, 10), (128, 40), (30, 7)])
+def test_zero_copy_host_buffers_match_staged(dim, k):
+    """hs_search_batch with pinned + mapped host buffers runs the kernel directly on them (no staging
+    copies); pageable buffers go through the staged path.  Same results either way, also for a
+    dimension that is not a multiple of 4 (scalar query loads) and k > 32 (two result flushes)."""
+    import torch
+    c = get_corpus(n=20000, nq=333, dim=dim)
+    ix = capi.Index(c.graph, c.dim)
+    ix.set_ef(80)
+    want_l, want_d = ix.search(c.queries, k)                      # pageable numpy -> staged path
+    nq = c.queries.shape[0]
+    hq = torch.from_numpy(c.queries).pin_memory()
+    hl = torch.full((nq, k), -1, dtype=torch.int32).pin_memory()
+    hd = torch.zeros((nq, k), dtype=torch.float32).pin_memory()
+    ix.search_ptr(hq.data_ptr(), nq, k, hl.data_ptr(), hd.data_ptr())
+    assert np.array_equal(hl.numpy().view(np.uint32), want_l)
+    assert np.array_equal(hd.numpy().view(np.uint32), want_d.view(np.uint32))
+    # an unaligned view of a pinned buffer (queries start 4 bytes in): scalar loads, same results
+    flat = torch.zeros(nq * dim + 1, dtype=torch.float32).pin_memory()
+    flat[1:] = torch.from_numpy(c.queries).reshape(-1)
+    hl.fill_(-1)
+    ix.search_ptr(flat.data_ptr() + 4, nq, k, hl.data_ptr(), hd.data_ptr())
+    assert np.array_equal(hl.numpy().view(np.uint32), want_l)
