@@ -64,8 +64,17 @@ struct hs_index {
   uint32_t *d_perq = nullptr;
   size_t cap_q = 0, cap_out = 0, cap_perq = 0;
   int hash_bits_override = 0;
-  uint32_t traverse_flags = 3;
+  int ghash_mode = -1;                     // HS_GHASH: -1 auto, 0 shared-memory visited tables, 1 global-memory
+  uint32_t *d_ghash = nullptr;             // two halves, alternated by consecutive (possibly overlapping) launches
+  size_t cap_ghash = 0;
+  uint32_t traverse_flags = 1;             // bit0: L2 row prefetch; bit1: speculative next-pop adjacency load (measured: a loss)
   uint32_t slimq_flags = 0;
+  // the launch plan of the last fp32 traversal (occupancy queries are not free on the host)
+  bool plan_ok = false;
+  uint32_t plan_ef = 0;
+  size_t plan_nq = 0;
+  TraverseLaunch plan_l{};
+  TraverseParams plan_p{};
   bool zero_copy = true;                   // hs_search_batch reads/writes pinned+mapped host buffers in place
   std::mutex mu;
 };
@@ -115,6 +124,7 @@ int build_index(const HostGraph &g, int metric, int device, const float *raw_bas
   HS_CUDA(cudaGetDeviceProperties(&prop, device));
   ix->sm_count = prop.multiProcessorCount;
   if (const char *hb = std::getenv("HS_HASH_BITS")) ix->hash_bits_override = std::atoi(hb);
+  if (const char *gh = std::getenv("HS_GHASH")) ix->ghash_mode = std::atoi(gh);
   if (const char *tf = std::getenv("HS_TRAVERSE_FLAGS")) ix->traverse_flags = (uint32_t)std::atoi(tf);
   if (const char *qf = std::getenv("HS_SLIMQ_FLAGS")) ix->slimq_flags = (uint32_t)std::atoi(qf);
   if (const char *zc = std::getenv("HS_ZERO_COPY")) ix->zero_copy = std::atoi(zc) != 0;
@@ -361,8 +371,28 @@ int search_device(hs_index *ix, const float *d_queries, size_t nq, size_t k, uin
   p.per_query = d_perq;
   p.flags = ix->traverse_flags;
   TraverseLaunch l{};
-  int rc = plan_traverse(p, ix->info.metric, ix->hash_bits_override, ix->sm_count, (int)nq, &l);
-  if (rc != HS_OK) return rc;
+  int rc = HS_OK;
+  if (ix->plan_ok && ix->plan_ef == p.ef && ix->plan_nq == nq) {   // same shape as the last call: reuse its plan
+    l = ix->plan_l;
+    p.hash_bits = ix->plan_p.hash_bits;
+    p.smem_per_warp = ix->plan_p.smem_per_warp;
+    p.off_hash = ix->plan_p.off_hash;
+    p.off_stage = ix->plan_p.off_stage;
+    p.off_query = ix->plan_p.off_query;
+  } else {
+    rc = plan_traverse(p, ix->info.metric, ix->hash_bits_override, ix->ghash_mode, ix->sm_count, (int)nq, &l);
+    if (rc != HS_OK) return rc;
+    ix->plan_ok = true;
+    ix->plan_ef = p.ef;
+    ix->plan_nq = nq;
+    ix->plan_l = l;
+    ix->plan_p = p;
+  }
+  if (l.ghash) {
+    if ((rc = ensure((void **)&ix->d_ghash, &ix->cap_ghash, 2 * l.ghash_bytes)) != HS_OK) return rc;
+    p.ghash = ix->d_ghash + (seq & 1u) * (l.ghash_bytes / 4);
+  }
+  if (!l.may_overlap) p.overlap = 0;
   return launch_traverse(p, ix->info.metric, l, stream);
 }
 
@@ -385,7 +415,7 @@ void *mapped_alias(const void *p, size_t bytes) {
 }
 
 int search_host(hs_index *ix, const float *queries, size_t nq, size_t k, uint32_t *labels_out,
-                float *dists_out, uint32_t *perq_out) {
+                float *dists_out, uint32_t *perq_out, bool sync = true) {
   if (!ix || (!queries && nq) || (!labels_out && nq)) {
     set_error("null argument");
     return HS_ERR_ARG;
@@ -408,7 +438,7 @@ int search_host(hs_index *ix, const float *queries, size_t nq, size_t k, uint32_
     if (zq && zl && (!dists_out || zd) && (!perq_out || zp)) {
       rc = search_device(ix, zq, nq, k, zl, zd, zp, ix->stream);
       if (rc != HS_OK) return rc;
-      HS_CUDA(cudaStreamSynchronize(ix->stream));
+      if (sync) HS_CUDA(cudaStreamSynchronize(ix->stream));
       return HS_OK;
     }
   }
@@ -425,7 +455,7 @@ int search_host(hs_index *ix, const float *queries, size_t nq, size_t k, uint32_
   if (dists_out)
     HS_CUDA(cudaMemcpyAsync(dists_out, ix->d_dist, nq * k * 4, cudaMemcpyDeviceToHost, ix->stream));
   if (perq_out) HS_CUDA(cudaMemcpyAsync(perq_out, ix->d_perq, nq * 8, cudaMemcpyDeviceToHost, ix->stream));
-  HS_CUDA(cudaStreamSynchronize(ix->stream));
+  if (sync) HS_CUDA(cudaStreamSynchronize(ix->stream));
   return HS_OK;
 }
 
@@ -473,6 +503,7 @@ void hs_free(hs_index *ix) {
   cudaFree(ix->d_lab);
   cudaFree(ix->d_dist);
   cudaFree(ix->d_perq);
+  cudaFree(ix->d_ghash);
   if (ix->stream) cudaStreamDestroy(ix->stream);
   delete ix;
 }
@@ -571,6 +602,22 @@ int hs_get_info(const hs_index *ix, hs_index_info *out) {
 int hs_search_batch(hs_index *ix, const float *queries, size_t nq, size_t k, uint32_t *labels_out,
                     float *dists_out) {
   return search_host(ix, queries, nq, k, labels_out, dists_out, nullptr);
+}
+
+int hs_search_batch_submit(hs_index *ix, const float *queries, size_t nq, size_t k, uint32_t *labels_out,
+                           float *dists_out) {
+  return search_host(ix, queries, nq, k, labels_out, dists_out, nullptr, false);
+}
+
+int hs_search_batch_wait(hs_index *ix) {
+  if (!ix) {
+    set_error("null argument");
+    return HS_ERR_ARG;
+  }
+  std::lock_guard<std::mutex> lock(ix->mu);
+  HS_CUDA(cudaSetDevice(ix->device));
+  HS_CUDA(cudaStreamSynchronize(ix->stream));
+  return HS_OK;
 }
 
 int hs_search_batch_counts(hs_index *ix, const float *queries, size_t nq, size_t k, uint32_t *labels_out,

@@ -158,25 +158,43 @@ __device__ __forceinline__ float eval_rows_smem(const float4 *__restrict__ vec, 
 
 // visited set: open addressing, linear probing, 32-bit keys (replaces the per-thread
 // uint16 tag array of visited_list_pool.h:10-31).  Returns true if id was already present.
+template <bool GLOBAL_TABLE = false>
 __device__ __forceinline__ bool visited_test_and_set(uint32_t *hash, uint32_t hbits, uint32_t hmask,
                                                      uint32_t id) {
   uint32_t h = (id * 0x9E3779B1u) >> (32 - hbits);
-  volatile uint32_t *vh = hash;
-  for (;;) {
-    const uint32_t v = vh[h];
-    if (v == id) return true;
-    if (v == EMPTY) {
-      const uint32_t old = atomicCAS(hash + h, EMPTY, id);
-      if (old == EMPTY) return false;
-      if (old == id) return true;
+  if (GLOBAL_TABLE) {
+    // table in global memory: look before the atomic (most probes of a long search end on an
+    // occupied slot, and a load is cheaper than a compare-and-swap at L2)
+    volatile uint32_t *vh = hash;
+    for (;;) {
+      const uint32_t v = vh[h];
+      if (v == id) return true;
+      if (v == EMPTY) {
+        const uint32_t old = atomicCAS(hash + h, EMPTY, id);
+        if (old == EMPTY) return false;
+        if (old == id) return true;
+      }
+      h = (h + 1) & hmask;
     }
+  }
+  // table in shared memory: compare-and-swap FIRST — a fresh id whose home slot is empty (the
+  // common case, the table is at most 75 % full) costs one shared-memory round trip instead of a
+  // load, a branch and a CAS
+  for (;;) {
+    const uint32_t old = atomicCAS(hash + h, EMPTY, id);
+    if (old == EMPTY) return false;
+    if (old == id) return true;
     h = (h + 1) & hmask;
   }
 }
 
+// Callers follow with __syncwarp().  A table in global memory is probed with atomics that execute
+// at L2: the clearing stores must have landed there first (GLOBAL_TABLE: device-scope fence).
+template <bool GLOBAL_TABLE = false>
 __device__ __forceinline__ void hash_clear(uint32_t *hash, uint32_t hsize, int lane) {
   const uint4 e = make_uint4(EMPTY, EMPTY, EMPTY, EMPTY);
   for (uint32_t i = lane * 4; i < hsize; i += 128) *reinterpret_cast<uint4 *>(hash + i) = e;
+  if (GLOBAL_TABLE) __threadfence();
 }
 
 __device__ __forceinline__ void prefetch_l2(const void *p) {
@@ -497,6 +515,17 @@ struct RegPool32 {
       ku[s] = h ? 0xffffffffu : ku[s];
       open = open && !h;
     }
+    return __shfl_sync(FULL, node, o);
+  }
+  // node id of the closest unexpanded entry without popping it (kInvalid if none)
+  __device__ __forceinline__ uint32_t peek_closest_unexpanded() const {
+    const uint32_t m = col_min_un();
+    const uint32_t g = __reduce_min_sync(FULL, m);
+    if (g == 0xffffffffu) return kInvalid;
+    const int o = __ffs(__ballot_sync(FULL, m == g)) - 1;
+    uint32_t node = id[SLOTS - 1];
+#pragma unroll
+    for (int s = SLOTS - 2; s >= 0; --s) node = ku[s] == g ? id[s] : node;     // first matching slot wins
     return __shfl_sync(FULL, node, o);
   }
   __device__ __forceinline__ unsigned admit(bool valid, uint64_t key) {

@@ -25,11 +25,18 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstdint>
 #include <type_traits>
 
 #include "traverse_common.cuh"
 #include "traverse_fp32.cuh"
+
+// This file is compiled twice: as is (visited hash in shared memory) and through
+// traverse_fp32_g.cu with HS_GHASH = 1 (visited hash in global memory, L2-resident).
+#ifndef HS_GHASH
+#define HS_GHASH 0
+#endif
 
 namespace hs {
 namespace {
@@ -51,7 +58,16 @@ __global__ void __launch_bounds__(128, HS_TRAVERSE_MIN_CTAS) traverse_kernel(con
   const int lane = threadIdx.x & 31;
   const int wid = threadIdx.x >> 5;
   unsigned char *wbase = smem + (size_t)wid * p.smem_per_warp;
-  uint32_t *hash = reinterpret_cast<uint32_t *>(wbase + p.off_hash);
+  // the visited table: shared memory, or (HS_GHASH) this warp's slice of a global scratch array.
+  // A hop's probes then cost an L2 round trip instead of a shared-memory one, which is nothing
+  // next to the row reads of a large-dim / large-ef hop, and the shared memory it frees is what
+  // bounds the number of resident warps there.
+  uint32_t *hash;
+  if constexpr (HS_GHASH) {
+    hash = p.ghash + ((size_t)(blockIdx.x * (blockDim.x >> 5) + wid) << p.hash_bits);
+  } else {
+    hash = reinterpret_cast<uint32_t *>(wbase + p.off_hash);
+  }
   uint32_t *stage_ids = reinterpret_cast<uint32_t *>(wbase + p.off_stage);
   float4 *qs = reinterpret_cast<float4 *>(wbase + p.off_query);
 
@@ -105,7 +121,7 @@ __global__ void __launch_bounds__(128, HS_TRAVERSE_MIN_CTAS) traverse_kernel(con
     } else {
       for (uint32_t ch = lane; ch < p.row_chunks; ch += 32) qs[ch] = load_chunk(ch);
     }
-    hash_clear(hash, hsize, lane);
+    hash_clear<HS_GHASH != 0>(hash, hsize, lane);
     __syncwarp();
 
     auto eval = [&](uint32_t my_id, int count) -> float {
@@ -159,7 +175,7 @@ __global__ void __launch_bounds__(128, HS_TRAVERSE_MIN_CTAS) traverse_kernel(con
     typename PoolSel<SLOTS>::type pool;
     pool.init(reinterpret_cast<uint64_t *>(wbase), ef, lane);
     pool.seed(make_key(curdist, cur));
-    if (lane == 0) visited_test_and_set(hash, hbits, hmask, cur);
+    if (lane == 0) visited_test_and_set<HS_GHASH != 0>(hash, hbits, hmask, cur);
     __syncwarp();
 
     // ---- layered beam for threshold_level > 0 (searchBaseLayer, slim.h:222-316, called for
@@ -180,9 +196,9 @@ __global__ void __launch_bounds__(128, HS_TRAVERSE_MIN_CTAS) traverse_kernel(con
         const uint32_t *row = ladj + (size_t)slot * p.upper_stride;
         if (hcount + p.upper_stride > hlimit) {
           __syncwarp();
-          hash_clear(hash, hsize, lane);
+          hash_clear<HS_GHASH != 0>(hash, hsize, lane);
           __syncwarp();
-          pool.for_each_id([&](uint32_t pid) { visited_test_and_set(hash, hbits, hmask, pid); });
+          pool.for_each_id([&](uint32_t pid) { visited_test_and_set<HS_GHASH != 0>(hash, hbits, hmask, pid); });
           hcount = pool.size;
           __syncwarp();
         }
@@ -193,7 +209,7 @@ __global__ void __launch_bounds__(128, HS_TRAVERSE_MIN_CTAS) traverse_kernel(con
           if (vm == 0) break;
           any = true;
           bool fresh = false;
-          if (id != kInvalid) fresh = !visited_test_and_set(hash, hbits, hmask, id);
+          if (id != kInvalid) fresh = !visited_test_and_set<HS_GHASH != 0>(hash, hbits, hmask, id);
           const unsigned fm = __ballot_sync(FULL, fresh);
           const int count = __popc(fm);
           if (count == 0) continue;
@@ -212,21 +228,35 @@ __global__ void __launch_bounds__(128, HS_TRAVERSE_MIN_CTAS) traverse_kernel(con
     }
 
     // ---- base layer, slim.h:321-457 ----
-    const bool opt_prefetch = p.flags & 1u;
+    const bool opt_prefetch = p.flags & 1u, opt_spec = p.flags & 2u;
+    uint32_t spec_node = kInvalid, spec_ids = kInvalid;
     for (;;) {
       // closest unexpanded entry (the reference pops its candidate min-heap, slim.h:335-354)
       const uint32_t node = pool.pop_closest_unexpanded();
       if (node == kInvalid) break;
       const uint32_t *row = p.adj0 + (size_t)node * p.deg0_stride;
-      uint32_t id = __ldg(row + lane);
+      uint32_t id = node == spec_node ? spec_ids : __ldg(row + lane);
+      // Speculation on the NEXT pop: unless this hop admits something closer, it is the entry that
+      // is now the closest unexpanded one.  It usually entered the pool many hops ago, so the L2
+      // prefetch of its adjacency row at admission time has long been evicted and the row would
+      // cost a full DRAM round trip right after the pop; loading it now hides that behind this
+      // hop.  Results do not depend on it: a wrong guess just loads the row on demand.
+      if (opt_spec) {
+        spec_node = pool.peek_closest_unexpanded();
+        if (spec_node != kInvalid) {
+          const uint32_t *srow = p.adj0 + (size_t)spec_node * p.deg0_stride;
+          spec_ids = __ldg(srow + lane);
+          if (p.deg0_stride > 32 && lane * 32u + 32u < p.deg0_stride) prefetch_l2(srow + 32 + lane * 32);
+        }
+      }
 
       if (hcount + p.deg0_stride > hlimit) {
         // visited hash nearly full: keep only the pool entries (results are unchanged:
         // a node scored before was rejected or displaced and will be again)
         __syncwarp();
-        hash_clear(hash, hsize, lane);
+        hash_clear<HS_GHASH != 0>(hash, hsize, lane);
         __syncwarp();
-        pool.for_each_id([&](uint32_t pid) { visited_test_and_set(hash, hbits, hmask, pid); });
+        pool.for_each_id([&](uint32_t pid) { visited_test_and_set<HS_GHASH != 0>(hash, hbits, hmask, pid); });
         hcount = pool.size;
         __syncwarp();
       }
@@ -238,7 +268,7 @@ __global__ void __launch_bounds__(128, HS_TRAVERSE_MIN_CTAS) traverse_kernel(con
         if (vm == 0) break;
         any = true;
         bool fresh = false;
-        if (id != kInvalid) fresh = !visited_test_and_set(hash, hbits, hmask, id);
+        if (id != kInvalid) fresh = !visited_test_and_set<HS_GHASH != 0>(hash, hbits, hmask, id);
         if (fresh && opt_prefetch) {
           // pull the whole row towards L2 now; the scoring loop below then mostly waits on L2
           const char *r = reinterpret_cast<const char *>(p.vec + (size_t)id * p.row_chunks);
@@ -337,15 +367,6 @@ int occupancy_t(int threads, size_t smem) {
   return nb;
 }
 
-// kernel variants: CPL 3 (dim 96: DEEP/MSTuring), 4 (dim 128: SIFT) keep the query in
-// registers, everything else runs the generic shared-memory-query path (CPL = 0);
-// pool in registers for ef <= 64 / <= 128, in shared memory above.
-inline int cpl_variant(uint32_t row_chunks) {
-  const uint32_t cpl = row_chunks / kTeam;
-  return (cpl == 3 || cpl == 4) ? (int)cpl : 0;
-}
-inline int slots_variant(uint32_t ef) { return ef <= 64 ? 2 : (ef <= 128 ? 4 : (ef <= 256 ? 8 : 0)); }
-
 template <typename F>
 int dispatch(int cpl, int metric, int slots, F &&f) {
 #define HS_CASE(C, M, S) \
@@ -360,47 +381,111 @@ int dispatch(int cpl, int metric, int slots, F &&f) {
   return HS_ERR_UNSUPPORTED;
 }
 
-inline uint32_t align_up(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
-
 }  // namespace
 
-int plan_traverse(TraverseParams &p, int metric, int hash_bits_override, int sm_count, int nq,
+// one pair of entry points per copy of this file (shared-memory / global-memory visited hash)
+#if HS_GHASH
+#define HS_VARIANT(name) name##_g
+#else
+#define HS_VARIANT(name) name##_s
+#endif
+int HS_VARIANT(traverse_occupancy)(int cpl, int metric, int slots, int threads, size_t smem) {
+  return dispatch(cpl, metric, slots, [&](auto C, auto M, auto S) {
+    return occupancy_t<decltype(C)::value, decltype(M)::value, decltype(S)::value>(threads, smem);
+  });
+}
+int HS_VARIANT(traverse_launch)(int cpl, int metric, int slots, const TraverseParams &p, const TraverseLaunch &l,
+                                cudaStream_t stream) {
+  return dispatch(cpl, metric, slots, [&](auto C, auto M, auto S) {
+    return launch_t<decltype(C)::value, decltype(M)::value, decltype(S)::value>(p, l, stream);
+  });
+}
+
+#if !HS_GHASH
+int traverse_occupancy_g(int cpl, int metric, int slots, int threads, size_t smem);
+int traverse_launch_g(int cpl, int metric, int slots, const TraverseParams &p, const TraverseLaunch &l,
+                      cudaStream_t stream);
+
+namespace {
+// kernel variants: CPL 3 (dim 96: DEEP/MSTuring), 4 (dim 128: SIFT) keep the query in
+// registers, everything else runs the generic shared-memory-query path (CPL = 0);
+// pool in registers for ef <= 64 / <= 128 / <= 256, in shared memory above.
+inline int cpl_variant(uint32_t row_chunks) {
+  const uint32_t cpl = row_chunks / kTeam;
+  return (cpl == 3 || cpl == 4) ? (int)cpl : 0;
+}
+inline int slots_variant(uint32_t ef) { return ef <= 64 ? 2 : (ef <= 128 ? 4 : (ef <= 256 ? 8 : 0)); }
+inline uint32_t align_up(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
+constexpr uint32_t kSmemPerSm = 227u * 1024u;
+}  // namespace
+
+int plan_traverse(TraverseParams &p, int metric, int hash_bits_override, int ghash_mode, int sm_count, int nq,
                   TraverseLaunch *out) {
   // visited-hash capacity: ~16 slots per ef entry (measured ~12 evaluations per ef entry on
-  // 1M x 128), clamped to [1024, 16384]; the kernel resets the table when it
-  // passes 75 % so a smaller table only costs repeated evaluations, never correctness.
-  // With threshold_level > 0 every layer of the layered beam adds its own evaluations.
+  // 1M x 128); the kernel resets the table when it passes 75 % so a smaller table
+  // only costs repeated evaluations, never correctness.  With threshold_level > 0 every layer of
+  // the layered beam adds its own evaluations.
   const uint32_t layers = 1u + (uint32_t)std::max(0, std::min(p.threshold_level, p.maxlevel));
-  uint32_t bits = 10;
-  while ((1u << bits) < 16u * p.ef * layers && bits < 14) ++bits;
-  if (hash_bits_override > 0) bits = (uint32_t)hash_bits_override;
-  if (bits < 8) bits = 8;
-  if (bits > 16) bits = 16;
-  while ((1u << bits) - (1u << bits) / 4 < p.ef + 2 * p.deg0_stride + 32 && bits < 16) ++bits;
-  p.hash_bits = bits;
-  const uint32_t list_bytes = slots_variant(p.ef) ? 0u : align_up(p.ef * 8u, 16);
-  const uint32_t hash_bytes = 4u << bits;
+  const uint32_t min_slots = p.ef + 2 * std::max(p.deg0_stride, p.upper_stride) + 32;   // the reset must make room
+  auto pick_bits = [&](uint32_t cap) {
+    uint32_t bits = 10;
+    while ((1u << bits) < 16u * p.ef * layers && bits < cap) ++bits;
+    if (hash_bits_override > 0) bits = (uint32_t)hash_bits_override;
+    if (bits < 8) bits = 8;
+    if (bits > 16) bits = 16;
+    while ((1u << bits) - (1u << bits) / 4 < min_slots && bits < 16) ++bits;
+    return bits;
+  };
+  const int cplv = cpl_variant(p.row_chunks), slv = slots_variant(p.ef);
+  const int met = metric == HS_METRIC_IP ? HS_METRIC_IP : HS_METRIC_L2;
+  const uint32_t list_bytes = slv ? 0u : align_up(p.ef * 8u, 16);
   const uint32_t stage_bytes = 32 * 4;
-  const bool generic = cpl_variant(p.row_chunks) == 0;
-  const uint32_t query_bytes = generic ? p.row_chunks * 16u : 0u;
+  const uint32_t query_bytes = cplv == 0 ? p.row_chunks * 16u : 0u;
+
+  // Shared-memory tables first.  They bound the resident warps: 24 per SM (what the register file
+  // allows) needs <= 9.4 KB per warp.  When the table of this ef (plus the query of a large dim)
+  // pushes a warp past ~14 KB (fewer than 16 warps per SM), the tables move to global memory:
+  // they stay L2-resident and a probe's extra latency is small next to a hop's row reads.
+  const uint32_t bits_s = pick_bits(14);
+  const uint32_t per_warp_s = align_up(list_bytes + (4u << bits_s) + stage_bytes + query_bytes, 16);
+  bool ghash = ghash_mode == 1 || (ghash_mode < 0 && kSmemPerSm / per_warp_s < 16);
+  if (per_warp_s > kSmemPerSm) ghash = true;
+  const uint32_t bits = ghash ? pick_bits(16) : bits_s;
+  p.hash_bits = bits;
+  const uint32_t hash_bytes = ghash ? 0u : (4u << bits);
   p.off_hash = list_bytes;
   p.off_stage = p.off_hash + hash_bytes;
   p.off_query = p.off_stage + stage_bytes;
   p.smem_per_warp = align_up(p.off_query + query_bytes, 16);
-  if (p.smem_per_warp > 227u * 1024u) {
+  if (p.smem_per_warp > kSmemPerSm) {
     set_error("ef / dim too large for the per-warp shared-memory working set");
     return HS_ERR_UNSUPPORTED;
   }
-  int wpc = 4;
-  while (wpc > 1 && (size_t)wpc * p.smem_per_warp > 227u * 1024u / 2) wpc >>= 1;
+  // CTA shape.  Warps never cooperate, so a CTA is only a packaging unit — and the smaller the
+  // better: an SM slot is handed to the next (overlapping) launch when a whole CTA exits, and a CTA
+  // of 4 warps idles 3 of them while its last query drains.  One-warp CTAs are used whenever the
+  // 32-CTAs-per-SM limit and the 1 KB of shared memory the system reserves per CTA do not cost
+  // resident warps (measured +2.5 % at ef=100, +5 % at ef=50 on 1M x 128); else 2 or 4 warps.
+  const int met_ = met;
+  auto occupancy = [&](int w) {
+    const size_t smem = (size_t)w * p.smem_per_warp;
+    if (smem > kSmemPerSm) return 0;
+    return ghash ? traverse_occupancy_g(cplv, met_, slv, w * 32, smem) : traverse_occupancy_s(cplv, met_, slv, w * 32, smem);
+  };
+  int wpc = 1, per_sm = occupancy(1);
+  for (int w = 2; w <= 4; w *= 2) {
+    const int o = occupancy(w);
+    if (o * w > per_sm * wpc) {
+      wpc = w;
+      per_sm = o;
+    }
+  }
+  if (const char *w = std::getenv("HS_WPC")) {          // tuning knob
+    wpc = std::max(1, std::min(4, std::atoi(w)));
+    per_sm = occupancy(wpc);
+  }
   out->warps_per_cta = wpc;
   out->smem_bytes = (size_t)wpc * p.smem_per_warp;
-  const int cplv = cpl_variant(p.row_chunks), slv = slots_variant(p.ef);
-  const int threads = wpc * 32;
-  const size_t smem = out->smem_bytes;
-  int per_sm = dispatch(cplv, metric == HS_METRIC_IP ? HS_METRIC_IP : HS_METRIC_L2, slv, [&](auto C, auto M, auto S) {
-    return occupancy_t<decltype(C)::value, decltype(M)::value, decltype(S)::value>(threads, smem);
-  });
   if (per_sm <= 0) {
     set_error("traverse_kernel does not fit on an SM (cudaOccupancyMaxActiveBlocksPerMultiprocessor)");
     return HS_ERR_CUDA;
@@ -408,14 +493,19 @@ int plan_traverse(TraverseParams &p, int metric, int hash_bits_override, int sm_
   const int resident = sm_count * per_sm;
   const int need = (nq + wpc - 1) / wpc;
   out->grid = need < resident ? (need > 0 ? need : 1) : resident;
+  out->ghash = ghash;
+  out->ghash_bytes = ghash ? ((size_t)out->grid * wpc * 4) << bits : 0;
+  // two overlapping launches alternate between two scratch halves (hs_api.cu); a third launch can
+  // only become resident next to them when a grid does not fill the GPU — no overlap then
+  out->may_overlap = !ghash || out->grid == resident;
   return HS_OK;
 }
 
 int launch_traverse(const TraverseParams &p, int metric, const TraverseLaunch &l, cudaStream_t stream) {
-  return dispatch(cpl_variant(p.row_chunks), metric == HS_METRIC_IP ? HS_METRIC_IP : HS_METRIC_L2,
-                  slots_variant(p.ef), [&](auto C, auto M, auto S) {
-                    return launch_t<decltype(C)::value, decltype(M)::value, decltype(S)::value>(p, l, stream);
-                  });
+  const int cplv = cpl_variant(p.row_chunks), slv = slots_variant(p.ef);
+  const int met = metric == HS_METRIC_IP ? HS_METRIC_IP : HS_METRIC_L2;
+  return l.ghash ? traverse_launch_g(cplv, met, slv, p, l, stream) : traverse_launch_s(cplv, met, slv, p, l, stream);
 }
+#endif   // !HS_GHASH
 
 }  // namespace hs

@@ -33,17 +33,24 @@ struct TraverseParams {
   // shared-memory carve-up per warp (bytes)
   uint32_t hash_bits, smem_per_warp, off_hash, off_stage, off_query;
   uint32_t flags;                          // bit0: L2 row prefetch, bit1: speculative next-hop prefetch
+  // visited hash in global memory (large ef / large dim, see plan_traverse): one table of
+  // 2^hash_bits slots per resident warp; null when the tables live in shared memory
+  uint32_t *ghash;
 };
 
 struct TraverseLaunch {
   int warps_per_cta;
   int grid;
   size_t smem_bytes;
+  bool ghash;            // visited tables in global memory: the caller points p.ghash at ghash_bytes of scratch
+  size_t ghash_bytes;    // grid * warps_per_cta * 4 << hash_bits
+  bool may_overlap;      // programmatic stream serialization allowed for this launch shape
 };
 
 // Fills the smem carve-up fields of `p` and returns the launch shape.
-// hash_bits_override = 0 picks the default for p.ef.
-int plan_traverse(TraverseParams &p, int metric, int hash_bits_override, int sm_count, int nq,
+// hash_bits_override = 0 picks the default for p.ef; ghash_mode: -1 = decide from the shared-memory
+// budget, 0 = visited tables in shared memory, 1 = in global memory.
+int plan_traverse(TraverseParams &p, int metric, int hash_bits_override, int ghash_mode, int sm_count, int nq,
                   TraverseLaunch *out);
 int launch_traverse(const TraverseParams &p, int metric, const TraverseLaunch &l, cudaStream_t stream);
 

@@ -122,10 +122,26 @@ int hs_slimq_prepare(hs_index *, const float *queries, size_t nq, float *rotated
  * (unordered k-subset, no distances) each row is sorted by (distance, id)
  * ascending and dists_out (nq x k, may be NULL) receives the distances.  Rows
  * with fewer than k reachable results are padded with 0xFFFFFFFF / +inf (the
- * reference reads uninitialised memory there).  Copies host->device, runs the
- * traversal kernel, copies back; synchronous. */
+ * reference reads uninitialised memory there).  Synchronous.  Pageable buffers are
+ * copied host->device, searched, copied back.  Buffers that are page-locked and mapped
+ * (cudaHostAlloc / cudaHostRegister) are used IN PLACE: the traversal kernel reads each
+ * query from host memory when the warp that owns it starts (4*dim bytes) and stores each
+ * result row with one coalesced write, so the PCIe/C2C transfers overlap the traversal
+ * instead of bracketing it (HS_ZERO_COPY=0 in the environment forces the staged path). */
 int hs_search_batch(hs_index *, const float *queries, size_t nq, size_t k, uint32_t *labels_out,
                     float *dists_out);
+
+/* hs_search_batch split in two so that a caller with a stream of batches (the reference's
+ * server answers /query requests back to back, hnsw_slim_server.cc:69-142) keeps more than one
+ * batch in flight: submit enqueues the batch on the handle's own stream and returns, wait blocks
+ * until every submitted batch is complete.  Batches run in submission order; with hs_set_overlap
+ * the tail of one batch overlaps the head of the next.  Buffers must stay valid and untouched
+ * until hs_search_batch_wait returns.  Pinned + mapped host buffers (cudaHostAlloc /
+ * cudaHostRegister) are read and written in place by the kernel; pageable buffers are staged
+ * through device memory like hs_search_batch does. */
+int hs_search_batch_submit(hs_index *, const float *queries, size_t nq, size_t k, uint32_t *labels_out,
+                           float *dists_out);
+int hs_search_batch_wait(hs_index *);
 
 /* hs_search_batch that also returns per-query counters: per_query_counts[2*i] = distances
  * evaluated for query i, [2*i+1] = nodes expanded (the per-query split of hs_stats). */

@@ -293,3 +293,82 @@ def test_zero_copy_host_buffers_match_staged(dim, k):
     hl.fill_(-1)
     ix.search_ptr(flat.data_ptr() + 4, nq, k, hl.data_ptr(), hd.data_ptr())
     assert np.array_equal(hl.numpy().view(np.uint32), want_l)
+
+
+@pytest.mark.parametrize("pinned", [True, False])
+def test_submit_wait_pipeline(small_corpus, pinned):
+    """hs_search_batch_submit / hs_search_batch_wait: several host-buffer batches in flight on the
+    handle's stream (zero-copy for pinned buffers, staged for pageable ones), overlap on."""
+    import torch
+    c = small_corpus
+    ix = capi.Index(c.graph, c.dim)
+    ix.set_ef(60)
+    k, nq = 10, c.queries.shape[0]
+    batches = [np.ascontiguousarray(np.roll(c.queries, s, axis=0)) for s in range(6)]
+    want = [ix.search(b, k) for b in batches]
+    ix.set_overlap(True)
+    hq = [torch.from_numpy(b) for b in batches]
+    hl = [torch.full((nq, k), -1, dtype=torch.int32) for _ in batches]
+    hd = [torch.zeros((nq, k), dtype=torch.float32) for _ in batches]
+    if pinned:
+        hq, hl, hd = [t.pin_memory() for t in hq], [t.pin_memory() for t in hl], [t.pin_memory() for t in hd]
+    for rep in range(2):
+        for i in range(len(batches)):
+            ix.submit_ptr(hq[i].data_ptr(), nq, k, hl[i].data_ptr(), hd[i].data_ptr())
+        ix.wait()
+    for i, (wl, wd) in enumerate(want):
+        assert np.array_equal(hl[i].numpy().view(np.uint32), wl), i
+        assert np.array_equal(hd[i].numpy().view(np.uint32), wd.view(np.uint32)), i
+
+
+def _index_with_env(c, **env):
+    import os
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update({k: str(v) for k, v in env.items()})
+    try:
+        return capi.Index(c.graph, c.dim, metric=c.metric)
+    finally:
+        for k, v in old.items():
+            if v is None:
+                del os.environ[k]
+            else:
+                os.environ[k] = v
+
+
+@pytest.mark.parametrize("ef", [40, 100, 200, 400])
+def test_global_memory_visited_hash_same_results(small_corpus, ef):
+    """HS_GHASH: the visited tables in global memory (the plan picks them for large ef / dim) and
+    in shared memory give identical ids, distances and counters."""
+    c = small_corpus
+    a = _index_with_env(c, HS_GHASH=0)
+    b = _index_with_env(c, HS_GHASH=1)
+    a.set_ef(ef)
+    b.set_ef(ef)
+    la, da, ca = a.search(c.queries, 10, counts=True)
+    lb, db, cb = b.search(c.queries, 10, counts=True)
+    assert np.array_equal(la, lb) and np.array_equal(da.view(np.uint32), db.view(np.uint32))
+    assert np.array_equal(ca, cb)
+
+
+def test_global_memory_visited_hash_overlapping_batches(small_corpus):
+    """Overlapping launches alternate between the two halves of the global visited scratch."""
+    import torch
+    c = small_corpus
+    ix = _index_with_env(c, HS_GHASH=1)
+    ix.set_ef(200)
+    k = 10
+    big = np.ascontiguousarray(np.tile(c.queries, (40, 1)))          # 12000 queries: the grid fills the GPU
+    nq = big.shape[0]
+    want_l, want_d = ix.search(big, k)
+    ix.set_overlap(True)
+    dq = torch.from_numpy(big).cuda()
+    outs = [(torch.empty((nq, k), dtype=torch.int32, device="cuda"), torch.empty((nq, k), dtype=torch.float32, device="cuda"))
+            for _ in range(5)]
+    torch.cuda.synchronize()
+    s = torch.cuda.current_stream().cuda_stream
+    for dl, dd in outs:
+        ix.search_device(dq.data_ptr(), nq, k, dl.data_ptr(), dd.data_ptr(), s)
+    torch.cuda.synchronize()
+    for dl, dd in outs:
+        assert np.array_equal(dl.cpu().numpy().view(np.uint32), want_l)
+        assert np.array_equal(dd.cpu().numpy().view(np.uint32), want_d.view(np.uint32))
