@@ -13,7 +13,7 @@ import numpy as np
 
 from . import build as _build
 
-HS_KIND_SLIM, HS_KIND_SLIMQ = 0, 1
+HS_KIND_SLIM, HS_KIND_SLIMQ, HS_KIND_HNSW = 0, 1, 2
 HS_METRIC_L2, HS_METRIC_IP = 0, 1
 
 EXPORTS = [
@@ -21,7 +21,7 @@ EXPORTS = [
     "hs_search_batch_counts", "hs_search_batch_submit", "hs_search_batch_wait", "hs_search_batch_device", "hs_stats", "hs_reset_stats", "hs_bruteforce_knn",
     "hs_bruteforce_knn_device", "hs_topk_merge_device", "hs_recall", "hs_last_error", "hs_abi_version",
     "hs_debug_flatten", "hs_debug_free", "hs_debug_info", "hs_debug_row", "hs_debug_node",
-    "hs_build_params_default", "hs_build_slim_graph",
+    "hs_build_params_default", "hs_build_slim_graph", "hs_build_hnsw_graph",
     "hs_get_query_tconst", "hs_set_query_tconst", "hs_slimq_prepare", "hs_build_slimq_graph",
     "hs_slimq_default_tconst", "hs_debug_bf_tc_fallback", "hs_set_overlap",
 ]
@@ -99,6 +99,7 @@ def lib():
         L.hs_build_params_default.argtypes = [C.POINTER(BuildParams)]
         L.hs_build_params_default.restype = None
         L.hs_build_slim_graph.argtypes = [vp, sz, sz, i32, C.POINTER(BuildParams), vp, C.c_char_p]
+        L.hs_build_hnsw_graph.argtypes = [vp, sz, sz, i32, C.POINTER(BuildParams), vp, C.c_char_p]
         L.hs_build_slimq_graph.argtypes = [vp, sz, sz, C.POINTER(BuildParams), vp, sz, vp, vp, C.c_char_p]
         L.hs_slimq_default_tconst.argtypes = [sz]
         L.hs_set_overlap.argtypes = [vp, i32]
@@ -257,6 +258,21 @@ def build_slim_graph(base, path: str, *, metric: int = HS_METRIC_L2, M: int = 16
         labels = np.ascontiguousarray(labels, dtype=np.uint64)
         lab = labels.ctypes.data
     _check(lib().hs_build_slim_graph(b.ctypes.data, b.shape[0], b.shape[1], metric, C.byref(p), lab, path.encode()))
+
+
+def build_hnsw_graph(base, path: str, *, metric: int = HS_METRIC_L2, M: int = 16, ef_construction: int = 200,
+                     branching: str = "4", threads: int = 0, labels=None, seed: int = 100) -> None:
+    """hs_build_hnsw_graph: host-side HNSW build -> upstream-format .graph of the `hnsw` strategy."""
+    b = _f32(base)
+    p = BuildParams()
+    lib().hs_build_params_default(C.byref(p))
+    p.M, p.ef_construction, p.branching_factor = M, ef_construction, branching.encode()
+    p.threads, p.seed = threads, seed
+    lab = None
+    if labels is not None:
+        labels = np.ascontiguousarray(labels, dtype=np.uint64)
+        lab = labels.ctypes.data
+    _check(lib().hs_build_hnsw_graph(b.ctypes.data, b.shape[0], b.shape[1], metric, C.byref(p), lab, path.encode()))
 
 
 def build_slimq_graph(base, path: str, *, M: int = 16, ef_construction: int = 200, branching: str = "4",

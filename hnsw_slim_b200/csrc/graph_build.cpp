@@ -298,7 +298,8 @@ struct Pruned {
 
 int build_pruned(const float *base, size_t n, size_t dim, int metric, size_t M, size_t ef_construction,
                  double branching, int threshold_level, float top_pct0, float top_pct, size_t top_M0,
-                 size_t low_m0, size_t top_M, size_t low_m, int threads, uint64_t seed, Pruned *out) {
+                 size_t low_m0, size_t top_M, size_t low_m, int threads, uint64_t seed, Pruned *out,
+                 bool prune = true) {
   if (!base || n == 0 || dim == 0 || M < 2 || M > 512 || branching <= 1.0 || n >= (1ull << 31)) {
     set_error("build_slim_graph: bad argument");
     return HS_ERR_ARG;
@@ -348,6 +349,8 @@ int build_pruned(const float *base, size_t n, size_t dim, int metric, size_t M, 
     });
   }
   const int maxlevel = h.maxlevel.load();
+  out->maxlevel = maxlevel;
+  if (!prune) return HS_OK;          // hs_build_hnsw_graph: the un-pruned index is the product
 
   // ---- 2. HNSW-Slim pruning (slim.h:867-1108) ----
   // degree thresholds: a level's top `pct` nodes by out-degree keep top_M* neighbours, the rest
@@ -515,6 +518,74 @@ int build_slim_graph(const float *base, size_t n, size_t dim, int metric, size_t
     ok &= put(record.data(), rec);
   }
   ok = ok && write_blobs(f, P);
+  ok &= std::fclose(f) == 0;
+  if (!ok) {
+    set_error(std::string("write error on ") + out_path);
+    return HS_ERR_IO;
+  }
+  return HS_OK;
+}
+
+// The un-pruned index of the `hnsw` strategy (hnsw_strategy.h:24-45): the same construction, saved
+// in HierarchicalNSW::saveIndex's format (hnsw.h:748-779) — level-0 records
+// [uint32 count][uint32 ids[maxM0]][float vec[dim]][uint64 label], then per node
+// uint32 linkListSize + level lists of [uint32 count][uint32 ids[maxM]].
+int build_hnsw_graph(const float *base, size_t n, size_t dim, int metric, size_t M, size_t ef_construction,
+                     double branching, int threads, uint64_t seed, const uint64_t *labels, const char *out_path) {
+  if (!out_path) {
+    set_error("build_hnsw_graph: bad argument");
+    return HS_ERR_ARG;
+  }
+  if (threads <= 0) threads = (int)std::max(1u, std::thread::hardware_concurrency());
+  Pruned P;
+  int rc = build_pruned(base, n, dim, metric, M, ef_construction, branching, 0, 0.f, 0.f, 0, 0, 0, 0, threads, seed,
+                        &P, false);
+  if (rc != HS_OK) return rc;
+  Hnsw &h = P.h;
+  FILE *f = std::fopen(out_path, "wb");
+  if (!f) {
+    set_error(std::string("cannot open ") + out_path + " for writing");
+    return HS_ERR_IO;
+  }
+  auto put = [&](const void *p, size_t sz) { return std::fwrite(p, 1, sz, f) == sz; };
+  bool ok = true;
+  const uint64_t links0 = 4 + 4 * h.maxM0, links = 4 + 4 * h.maxM, rec = links0 + 4 * dim + 8;
+  const uint64_t hdr[6] = {0 /*offsetLevel0*/, n /*max_elements*/, n, rec, links0 + 4 * dim /*label_offset*/,
+                           links0 /*offsetData*/};
+  ok &= put(hdr, sizeof hdr);
+  const int32_t ml = P.maxlevel;
+  const uint32_t ep = h.enter.load();
+  ok &= put(&ml, 4) && put(&ep, 4);
+  const uint64_t ms[3] = {h.maxM, h.maxM0, h.M};
+  ok &= put(ms, sizeof ms);
+  const double mult = 1.0 / std::log(branching);
+  const uint64_t efc = h.efc;
+  ok &= put(&mult, 8) && put(&efc, 8);
+  std::vector<uint8_t> record(rec);
+  for (size_t i = 0; i < n && ok; ++i) {
+    std::fill(record.begin(), record.end(), 0);
+    const uint32_t c = h.count((uint32_t)i, 0);
+    std::memcpy(&record[0], &c, 4);
+    std::memcpy(&record[4], h.clist((uint32_t)i, 0), 4 * (size_t)c);
+    std::memcpy(&record[links0], h.vec((uint32_t)i), 4 * dim);
+    const uint64_t label = labels ? labels[i] : (uint64_t)i;
+    std::memcpy(&record[links0 + 4 * dim], &label, 8);
+    ok &= put(record.data(), rec);
+  }
+  std::vector<uint8_t> lists;
+  for (size_t i = 0; i < n && ok; ++i) {
+    const int lvl = h.level[i];
+    const uint32_t lsz = (uint32_t)(lvl * links);
+    ok &= put(&lsz, 4);
+    if (!lsz) continue;
+    lists.assign(lsz, 0);
+    for (int l = 1; l <= lvl; ++l) {
+      const uint32_t c = h.count((uint32_t)i, l);
+      std::memcpy(&lists[(size_t)(l - 1) * links], &c, 4);
+      std::memcpy(&lists[(size_t)(l - 1) * links + 4], h.clist((uint32_t)i, l), 4 * (size_t)c);
+    }
+    ok &= put(lists.data(), lsz);
+  }
   ok &= std::fclose(f) == 0;
   if (!ok) {
     set_error(std::string("write error on ") + out_path);

@@ -61,6 +61,8 @@ inline uint32_t round_up(uint32_t v, uint32_t m) { return (v + m - 1) / m * m; }
 
 }  // namespace
 
+int parse_hnsw_graph(const uint8_t *bytes, size_t size, size_t dim, HostGraph *g);
+
 // The query-quantiser constant of hnsw_slimq.  The reference computes it at load time
 // (slimq.h:1274-1276 -> faster_config, rq/quantization/rabitq.hpp:27-34 ->
 // get_const_scaling_factors, rabitq_impl.hpp:363-377): the mean, over 100 random unit vectors,
@@ -151,7 +153,72 @@ int read_file(const char *path, std::vector<uint8_t> *out) {
   return HS_OK;
 }
 
+// Shared tail of the parsers: from "neighbour list of node i on level l" to the fixed-stride
+// rows of DESIGN.md "HBM layout".  list(i, l, &ids) returns the length and points ids at the
+// (unaligned) uint32 ids; levels[] is filled.
+template <typename ListFn>
+int flatten_lists(HostGraph *g, ListFn &&list) {
+  const size_t n = g->n;
+  uint32_t max_deg0 = 0, max_deg_up = 0;
+  uint64_t sum_deg0 = 0;
+  for (size_t i = 0; i < n; ++i) {
+    const uint8_t *ids = nullptr;
+    for (int l = 0; l <= g->levels[i]; ++l) {
+      const uint32_t deg = list(i, l, &ids);
+      if (l == 0) {
+        max_deg0 = std::max(max_deg0, deg);
+        sum_deg0 += deg;
+      } else {
+        max_deg_up = std::max(max_deg_up, deg);
+      }
+    }
+  }
+  g->max_deg0 = max_deg0;
+  g->max_deg_upper = max_deg_up;
+  g->sum_deg0 = sum_deg0;
+  g->deg0_stride = std::max<uint32_t>(32, round_up(max_deg0, 32));
+  g->upper_stride = std::max<uint32_t>(8, round_up(max_deg_up, 8));
+
+  // upper-level slots: nodes sorted by level descending, so the rows of level l are the dense
+  // slot prefix [0, level_count[l])
+  g->level_count.assign(g->maxlevel + 2, 0);
+  std::vector<uint32_t> upper_nodes;
+  for (size_t i = 0; i < n; ++i) {
+    for (int l = 0; l <= g->levels[i]; ++l) g->level_count[l]++;
+    if (g->levels[i] > 0) upper_nodes.push_back((uint32_t)i);
+  }
+  std::stable_sort(upper_nodes.begin(), upper_nodes.end(),
+                   [&](uint32_t a, uint32_t b) { return g->levels[a] > g->levels[b]; });
+  g->n_upper = (uint32_t)upper_nodes.size();
+  g->upper_slot.assign(n, -1);
+  for (uint32_t s = 0; s < upper_nodes.size(); ++s) g->upper_slot[upper_nodes[s]] = (int32_t)s;
+
+  g->adj0.assign(n * (size_t)g->deg0_stride, kInvalid);
+  g->upper_adj.assign(g->maxlevel + 1, {});
+  for (int l = 1; l <= g->maxlevel; ++l)
+    g->upper_adj[l].assign((size_t)g->level_count[l] * g->upper_stride, kInvalid);
+  for (size_t i = 0; i < n; ++i) {
+    for (int l = 0; l <= g->levels[i]; ++l) {
+      const uint8_t *ids = nullptr;
+      const uint32_t deg = list(i, l, &ids);
+      uint32_t *dst = (l == 0) ? &g->adj0[i * (size_t)g->deg0_stride]
+                               : &g->upper_adj[l][(size_t)g->upper_slot[i] * g->upper_stride];
+      for (uint32_t j = 0; j < deg; ++j) {
+        uint32_t id;
+        std::memcpy(&id, ids + 4 * (size_t)j, 4);
+        if (id >= n) {
+          set_error("neighbour id out of range in .graph (node " + std::to_string(i) + ")");
+          return HS_ERR_IO;
+        }
+        dst[j] = id;
+      }
+    }
+  }
+  return HS_OK;
+}
+
 int parse_graph(const uint8_t *bytes, size_t size, int kind, size_t dim, HostGraph *g) {
+  if (kind == HS_KIND_HNSW) return parse_hnsw_graph(bytes, size, dim, g);
   Reader r{bytes, size};
   g->kind = kind;
   g->dim = dim;
@@ -273,14 +340,12 @@ int parse_graph(const uint8_t *bytes, size_t size, int kind, size_t dim, HostGra
     }
   }
 
-  // ---- pass 1 over the blobs: degrees ----
+  // ---- the blobs: one per node, level slices inside ----
   struct BlobRef {
     const uint8_t *p;
     uint32_t size;
   };
   std::vector<BlobRef> blobs(n, BlobRef{nullptr, 0});
-  uint32_t max_deg0 = 0, max_deg_up = 0;
-  uint64_t sum_deg0 = 0;
   for (size_t i = 0; i < n; ++i) {
     uint32_t bsz = r.get<uint32_t>();
     if (!r.ok) {
@@ -303,64 +368,136 @@ int parse_graph(const uint8_t *bytes, size_t size, int kind, size_t dim, HostGra
         set_error("corrupt level offsets in .graph (node " + std::to_string(i) + ")");
         return HS_ERR_IO;
       }
-      uint32_t deg = end - prev;
-      if (l == 0) {
-        max_deg0 = std::max(max_deg0, deg);
-        sum_deg0 += deg;
-      } else {
-        max_deg_up = std::max(max_deg_up, deg);
-      }
       prev = end;
     }
   }
-  g->max_deg0 = max_deg0;
-  g->max_deg_upper = max_deg_up;
-  g->sum_deg0 = sum_deg0;
-  g->deg0_stride = std::max<uint32_t>(32, round_up(max_deg0, 32));
-  g->upper_stride = std::max<uint32_t>(8, round_up(max_deg_up, 8));
-
-  // ---- upper-level slots: nodes sorted by level descending, so the rows of level l are
-  //      the dense slot prefix [0, level_count[l]) ----
-  g->level_count.assign(g->maxlevel + 2, 0);
-  std::vector<uint32_t> upper_nodes;
-  for (size_t i = 0; i < n; ++i) {
-    for (int l = 0; l <= g->levels[i]; ++l) g->level_count[l]++;
-    if (g->levels[i] > 0) upper_nodes.push_back((uint32_t)i);
-  }
-  std::stable_sort(upper_nodes.begin(), upper_nodes.end(),
-                   [&](uint32_t a, uint32_t b) { return g->levels[a] > g->levels[b]; });
-  g->n_upper = (uint32_t)upper_nodes.size();
-  g->upper_slot.assign(n, -1);
-  for (uint32_t s = 0; s < upper_nodes.size(); ++s) g->upper_slot[upper_nodes[s]] = (int32_t)s;
-
-  // ---- pass 2: fill the fixed-stride rows ----
-  g->adj0.assign(n * (size_t)g->deg0_stride, kInvalid);
-  g->upper_adj.assign(g->maxlevel + 1, {});
-  for (int l = 1; l <= g->maxlevel; ++l)
-    g->upper_adj[l].assign((size_t)g->level_count[l] * g->upper_stride, kInvalid);
-  for (size_t i = 0; i < n; ++i) {
-    if (!blobs[i].p) continue;
+  return flatten_lists(g, [&](size_t i, int l, const uint8_t **ids) -> uint32_t {
+    if (!blobs[i].p) return 0;
     const int lvl = g->levels[i];
     const uint16_t *offs = reinterpret_cast<const uint16_t *>(blobs[i].p);
-    const uint8_t *ids = blobs[i].p + 2 * (size_t)lvl;
-    uint32_t prev = 0;
-    for (int l = 0; l <= lvl; ++l) {
-      uint32_t end = (l == lvl) ? total[i] : offs[l];
-      uint32_t *dst = (l == 0) ? &g->adj0[i * (size_t)g->deg0_stride]
-                               : &g->upper_adj[l][(size_t)g->upper_slot[i] * g->upper_stride];
-      for (uint32_t j = prev; j < end; ++j) {
-        uint32_t id;
-        std::memcpy(&id, ids + 4 * (size_t)j, 4);
-        if (id >= n) {
-          set_error("neighbour id out of range in .graph (node " + std::to_string(i) + ")");
+    const uint32_t begin = l == 0 ? 0 : offs[l - 1];
+    const uint32_t end = l == lvl ? total[i] : offs[l];
+    *ids = blobs[i].p + 2 * (size_t)lvl + 4 * (size_t)begin;
+    return end - begin;
+  });
+}
+
+// Upstream-format HNSW index, as this fork's HierarchicalNSW::saveIndex writes it
+// (hnsw.h:748-779; read by loadIndex, hnsw.h:781-893) — the `--solve_strategy=hnsw` baseline of
+// the reference (hnsw_strategy.h:15-61):
+//   size_t offsetLevel0, max_elements, cur_element_count, size_data_per_element, label_offset,
+//          offsetData; int maxlevel; uint32 enterpoint; size_t maxM, maxM0, M; double mult;
+//   size_t ef_construction;
+//   cur_element_count level-0 records of size_data_per_element bytes (hnsw.h:116-121):
+//       [uint32 header: low uint16 = list length, byte 2 bit 0 = deleted (hnsw.h:1007-1018)]
+//       [uint32 ids[maxM0]] [float vec[dim] @offsetData] [uint64 label @label_offset]
+//   per node: uint32 linkListSize, then linkListSize = level * (4 + 4*maxM) bytes: the list of
+//       level l >= 1 at (l-1) * (4 + 4*maxM): [uint32 header][uint32 ids[maxM]]
+// searchKnn (hnsw.h:1378-1440) is the slim search with threshold_level 0 on these lists: the same
+// greedy descent over levels maxlevel..1 and the same bare-bone searchBaseLayerST (hnsw.h:325-480).
+int parse_hnsw_graph(const uint8_t *bytes, size_t size, size_t dim, HostGraph *g) {
+  Reader r{bytes, size};
+  g->kind = HS_KIND_HNSW;
+  g->dim = dim;
+  const uint64_t offset_level0 = r.get<uint64_t>();
+  (void)r.get<uint64_t>();                       // max_elements
+  g->n = r.get<uint64_t>();
+  g->size_data_per_element = r.get<uint64_t>();
+  g->label_offset = r.get<uint64_t>();
+  g->offset_data = r.get<uint64_t>();
+  g->maxlevel = r.get<int32_t>();
+  g->enterpoint = r.get<uint32_t>();
+  g->maxM = r.get<uint64_t>();
+  g->maxM0 = r.get<uint64_t>();
+  g->M = r.get<uint64_t>();
+  (void)r.get<double>();                         // mult_
+  g->ef_construction = r.get<uint64_t>();
+  g->threshold_level = 0;
+  if (!r.ok) {
+    set_error("truncated .graph header");
+    return HS_ERR_IO;
+  }
+  const uint64_t links0 = 4 + 4 * g->maxM0, links = 4 + 4 * g->maxM;
+  if (offset_level0 != 0 || g->offset_data != links0 || g->label_offset != links0 + 4 * dim ||
+      g->size_data_per_element != links0 + 4 * dim + 8 || g->maxM0 == 0 || g->maxM == 0) {
+    set_error("unexpected record layout in .graph header (not an hnswlib HNSW index of this dim?)");
+    return HS_ERR_IO;
+  }
+  if (g->n >= (1ull << 31)) {
+    set_error("index has >= 2^31 nodes");
+    return HS_ERR_UNSUPPORTED;
+  }
+  if (g->n > 0 && (g->maxlevel < 0 || g->maxlevel >= kMaxLevels || g->enterpoint >= g->n)) {
+    set_error("bad maxlevel / enterpoint in .graph header");
+    return HS_ERR_IO;
+  }
+  const size_t n = g->n, rec = g->size_data_per_element;
+  const uint8_t *elements = r.take(n * rec);
+  if (!r.ok) {
+    set_error("truncated level-0 records in .graph");
+    return HS_ERR_IO;
+  }
+  g->dim_padded = (dim + kRowAlignFloats - 1) / kRowAlignFloats * kRowAlignFloats;
+  g->labels.resize(n);
+  g->levels.resize(n);
+  g->deleted.assign(n, 0);
+  g->vec.assign(n * g->dim_padded, 0.f);
+  std::vector<const uint8_t *> upper(n, nullptr);
+  for (size_t i = 0; i < n; ++i) {
+    const uint8_t *e = elements + i * rec;
+    uint64_t label;
+    std::memcpy(&label, e + g->label_offset, 8);
+    g->labels[i] = (uint32_t)label;
+    g->deleted[i] = e[2] & 1;                    // DELETE_MARK, hnsw.h:1007-1018
+    if (g->deleted[i]) g->has_deleted = true;
+    uint16_t cnt;
+    std::memcpy(&cnt, e, 2);
+    if (cnt > g->maxM0) {
+      set_error("level-0 list longer than maxM0 in .graph (node " + std::to_string(i) + ")");
+      return HS_ERR_IO;
+    }
+    std::memcpy(&g->vec[i * g->dim_padded], e + g->offset_data, 4 * dim);
+  }
+  for (size_t i = 0; i < n; ++i) {
+    const uint32_t lsz = r.get<uint32_t>();
+    if (!r.ok) {
+      set_error("truncated link lists in .graph");
+      return HS_ERR_IO;
+    }
+    int lvl = 0;
+    if (lsz) {
+      if (lsz % links != 0 || lsz / links > (uint64_t)g->maxlevel) {
+        set_error("link list size is not a multiple of the per-level size (node " + std::to_string(i) + ")");
+        return HS_ERR_IO;
+      }
+      lvl = (int)(lsz / links);                  // hnsw.h:866
+      upper[i] = r.take(lsz);
+      if (!r.ok) {
+        set_error("truncated link lists in .graph");
+        return HS_ERR_IO;
+      }
+      for (int l = 1; l <= lvl; ++l) {
+        uint16_t cnt;
+        std::memcpy(&cnt, upper[i] + (size_t)(l - 1) * links, 2);
+        if (cnt > g->maxM) {
+          set_error("upper list longer than maxM in .graph (node " + std::to_string(i) + ")");
           return HS_ERR_IO;
         }
-        dst[j - prev] = id;
       }
-      prev = end;
     }
+    g->levels[i] = (int8_t)lvl;
   }
-  return HS_OK;
+  if (r.pos != size) {
+    set_error("Index seems to be corrupted or unsupported");      // hnsw.h:833-835
+    return HS_ERR_IO;
+  }
+  return flatten_lists(g, [&](size_t i, int l, const uint8_t **ids) -> uint32_t {
+    const uint8_t *list = l == 0 ? elements + i * rec : upper[i] + (size_t)(l - 1) * links;
+    uint16_t cnt;
+    std::memcpy(&cnt, list, 2);                  // getListCount: the low uint16, hnsw.h:170-172
+    *ids = list + 4;
+    return cnt;
+  });
 }
 
 }  // namespace hs

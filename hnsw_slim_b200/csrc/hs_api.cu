@@ -795,6 +795,15 @@ int hs_build_slim_graph(const float *base, size_t n, size_t dim, int metric, con
                           p->threads, p->seed, labels, out_graph_path);
 }
 
+int hs_build_hnsw_graph(const float *base, size_t n, size_t dim, int metric, const hs_build_params *p,
+                        const uint64_t *labels, const char *out_graph_path) {
+  double bf;
+  int rc0 = parse_branching(p, &bf);
+  if (rc0 != HS_OK) return rc0;
+  return build_hnsw_graph(base, n, dim, metric, p->M, p->ef_construction, bf, p->threads, p->seed, labels,
+                          out_graph_path);
+}
+
 // ---- host-only inspection of the flattened graph (used by the CPU test-suite; no CUDA) ----
 struct hs_host_graph {
   HostGraph g;

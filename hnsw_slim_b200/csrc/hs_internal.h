@@ -60,6 +60,9 @@ int build_slim_graph(const float *base, size_t n, size_t dim, int metric, size_t
                      size_t low_m0, size_t top_M, size_t low_m, int threads, uint64_t seed,
                      const uint64_t *labels, const char *out_path);
 
+int build_hnsw_graph(const float *base, size_t n, size_t dim, int metric, size_t M, size_t ef_construction,
+                     double branching, int threads, uint64_t seed, const uint64_t *labels, const char *out_path);
+
 int build_slimq_graph(const float *base, size_t n, size_t dim, size_t M, size_t ef_construction, double branching,
                       int threshold_level, float top_pct0, float top_pct, size_t top_M0, size_t low_m0,
                       size_t top_M, size_t low_m, int threads, uint64_t seed, const float *centroids,

@@ -1,6 +1,8 @@
 // GPU strategies behind the reference's strategy names:
 //   hnsw_slim      -> HnswSlimGpuStrategy     (include/strategy/hnsw_slim_strategy.h:34-120)
 //   hnsw_slimq     -> HnswSlimQGpuStrategy    (include/strategy/hnsw_slimq_strategy.h:48-165)
+//   hnsw           -> HnswGpuStrategy         (include/strategy/hnsw_strategy.h:15-61)
+//   hnsw_slimzero  -> HnswSlimZeroGpuStrategy (include/strategy/hnsw_slimzero_strategy.h:38-140; load only)
 //   bruteforce     -> BruteForceGpu           (include/strategy/brute_force_strategy.h:15-45)
 // Each solve() keeps the reference's build-or-load logic and console output; the serial
 // per-query loop becomes ONE hs_search_batch call.
@@ -74,6 +76,77 @@ class HnswSlimGpuStrategy : public SolveStrategy {
 
  private:
   PruneParams pp_;
+};
+
+// hnsw_strategy.h:15-61: the un-pruned hnswlib index.  Same search kernel (HierarchicalNSW::searchKnn,
+// hnsw.h:1378-1440, is the slim search with threshold_level 0 on full lists); the file format is
+// HierarchicalNSW::saveIndex's, read by hs_load(kind = HS_KIND_HNSW) and written by hs_build_hnsw_graph.
+class HnswGpuStrategy : public SolveStrategy {
+ public:
+  HnswGpuStrategy(std::string source_path, std::string query_path, std::string index_path, int device = 0)
+      : SolveStrategy(source_path, query_path, index_path, device) {}
+
+  void solve() override {
+    if (!std::filesystem::exists(index_path_)) {            // hnsw_strategy.h:24-45
+      auto s_build = std::chrono::system_clock::now();
+      std::filesystem::path p(index_path_);
+      if (p.has_parent_path()) std::filesystem::create_directories(p.parent_path());
+      hs_build_params bp = make_build_params(M_, ef_construction_, branching_factor_, PruneParams());
+      check(hs_build_hnsw_graph(data_set_.data(), data_num_, data_dim_, HS_METRIC_L2, &bp, nullptr,
+                                index_path_.c_str()));
+      auto e_build = std::chrono::system_clock::now();
+      std::cout << "build cost: " << time_cost(s_build, e_build) << " (ms)\n";
+      std::cout << "save index: " + index_path_ << std::endl;
+    }
+    hs_index *ix = nullptr;                                  // loadIndex, hnsw.h:781
+    check(hs_load(index_path_.c_str(), HS_KIND_HNSW, HS_METRIC_L2, data_dim_, nullptr, 0, device_, &ix));
+    hs_index_info info;
+    hs_get_info(ix, &info);
+    std::cout << "hnsw index size: " << info.device_bytes << " bytes\n";
+    check(hs_set_ef(ix, ef_search_));
+    auto s_solve = std::chrono::system_clock::now();
+    const int rc = hs_search_batch(ix, query_set_.data(), query_num_, K_, knn_results_.data(), nullptr);
+    auto e_solve = std::chrono::system_clock::now();         // the loop of hnsw_strategy.h:49-58
+    if (rc != HS_OK) {
+      hs_free(ix);
+      check(rc);
+    }
+    std::cout << "solve cost: " << time_cost(s_solve, e_solve) << " (ms)\n";
+    hs_free(ix);
+  }
+};
+
+// hnsw_slimzero_strategy.h:38-140.  The index class differs from hnsw_slim only in how
+// convertFromHNSW prunes (min in-degree, hnswalg_slimzero.h:928-1158) — a build-time step of the
+// reference that stays on the CPU; the file format (:701-735) and searchKnn (:1675-1771) are
+// hnsw_slim's, so an index the reference built is loaded and searched here as HS_KIND_SLIM.
+class HnswSlimZeroGpuStrategy : public SolveStrategy {
+ public:
+  HnswSlimZeroGpuStrategy(std::string source_path, std::string query_path, std::string index_path, int device = 0)
+      : SolveStrategy(source_path, query_path, index_path, device) {}
+
+  void solve() override {
+    std::cout << "index path: " << index_path_ << std::endl;
+    if (!std::filesystem::exists(index_path_))
+      throw std::runtime_error("hnsw_slimzero: " + index_path_ + " not found — build it with the reference "
+                               "(HierarchicalNSWSlimZero::convertFromHNSW); the GPU engine loads and searches it");
+    hs_index *ix = nullptr;                                  // loadIndex, hnswalg_slimzero.h:737
+    check(hs_load(index_path_.c_str(), HS_KIND_SLIM, HS_METRIC_L2, data_dim_, nullptr, 0, device_, &ix));
+    hs_index_info info;
+    hs_get_info(ix, &info);
+    std::cout << "hnsw_slim_zero index size: " << info.device_bytes << " bytes\n";
+    check(hs_set_ef(ix, ef_search_));
+    auto s_solve = std::chrono::system_clock::now();
+    const int rc = hs_search_batch(ix, query_set_.data(), query_num_, K_, knn_results_.data(), nullptr);
+    auto e_solve = std::chrono::system_clock::now();         // the loop of hnsw_slimzero_strategy.h:131-133
+    if (rc != HS_OK) {
+      hs_free(ix);
+      check(rc);
+    }
+    std::cout << "solve cost: " << time_cost(s_solve, e_solve) << " (ms)\n";
+    std::cout << "query cost: " << std::chrono::duration<double>(e_solve - s_solve).count() << "\n";
+    hs_free(ix);
+  }
 };
 
 class HnswSlimQGpuStrategy : public SolveStrategy {

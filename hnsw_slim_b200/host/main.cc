@@ -73,6 +73,7 @@ int main(int argc, char **argv) {
   // README / usage text spell two families with hyphens (README.md:98,114; main.cc:136)
   if (solve_strategy == "hnsw-slimq") solve_strategy = "hnsw_slimq";
   if (solve_strategy == "hnsw-slim") solve_strategy = "hnsw_slim";
+  if (solve_strategy == "hnsw-slimzero") solve_strategy = "hnsw_slimzero";
 
   std::string suffix = solve_strategy + "_";                           // main.cc:80-100
   suffix += std::to_string(EF_CONSTRUCTION) + "_";
@@ -107,13 +108,15 @@ int main(int argc, char **argv) {
       strategy = new HnswSlimGpuStrategy(source_path, query_path, index_path, pp, device);
     } else if (solve_strategy == "hnsw_slimq") {
       strategy = new HnswSlimQGpuStrategy(source_path, query_path, index_path, pp, device);
+    } else if (solve_strategy == "hnsw") {
+      strategy = new HnswGpuStrategy(source_path, query_path, index_path, device);
+    } else if (solve_strategy == "hnsw_slimzero") {
+      strategy = new HnswSlimZeroGpuStrategy(source_path, query_path, index_path, device);
     } else if (solve_strategy == "bruteforce") {
       strategy = new BruteForceGpu(source_path, query_path, index_path, gt_path, 100, device);
     } else {
       std::cout << "Unknown strategy: " << solve_strategy << std::endl;
-      std::cout << "['hnsw_slim', 'bruteforce', 'hnsw-slimq'] (GPU engine; 'hnsw' and 'hnsw-slimzero' are CPU-only "
-                   "strategies of the reference)"
-                << std::endl;
+      std::cout << "['hnsw', 'hnsw_slim', 'bruteforce', 'hnsw-slimq', 'hnsw-slimzero']" << std::endl;
       return 1;
     }
     strategy->solve();

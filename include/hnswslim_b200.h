@@ -34,7 +34,11 @@ typedef enum {
 } hs_status;
 
 /* --solve_strategy values of main.cc:111-139 that have a GPU engine */
-typedef enum { HS_KIND_SLIM = 0 /* hnsw_slim, hnsw_slimzero */, HS_KIND_SLIMQ = 1 /* hnsw_slimq */ } hs_kind;
+typedef enum {
+  HS_KIND_SLIM = 0,   /* hnsw_slim and hnsw_slimzero (same file format, same searchKnn: hnswalg_slimzero.h:701-735,1675-1771) */
+  HS_KIND_SLIMQ = 1,  /* hnsw_slimq */
+  HS_KIND_HNSW = 2    /* hnsw: the un-pruned hnswlib index (hnsw_strategy.h:15-61, hnswalg.h:748-893,1378-1440) */
+} hs_kind;
 
 /* hnswlib::L2Space (space_l2.h:214-251) / hnswlib::InnerProductSpace (space_ip.h:342-398) */
 typedef enum { HS_METRIC_L2 = 0, HS_METRIC_IP = 1 } hs_metric;
@@ -217,6 +221,13 @@ void hs_build_params_default(hs_build_params *p);
  * saveIndex (slim.h:717-751).  Writes a .graph that both hs_load and the reference's
  * loadIndex read.  labels may be NULL (label of row i = i).  CPU only, multi-threaded. */
 int hs_build_slim_graph(const float *base, size_t n, size_t dim, int metric, const hs_build_params *p,
+                        const uint64_t *labels, const char *out_graph_path);
+
+/* Host-side builder of the un-pruned index of the `hnsw` strategy: the omp addPoint loop of
+ * hnsw_strategy.h:24-33 and HierarchicalNSW::saveIndex (hnsw.h:748-779).  Writes a .graph that both
+ * hs_load(kind = HS_KIND_HNSW) and the reference's HierarchicalNSW::loadIndex read.  Only M,
+ * ef_construction, branching_factor, threads and seed of `p` are used.  CPU only, multi-threaded. */
+int hs_build_hnsw_graph(const float *base, size_t n, size_t dim, int metric, const hs_build_params *p,
                         const uint64_t *labels, const char *out_graph_path);
 
 /* Host-side builder of an hnsw_slimq index: the same HNSW + HNSW-Slim pruning over the raw floats

@@ -89,6 +89,109 @@ hso_index *hso_load(const char *path, size_t dim, int metric) {
   return ix;
 }
 
+/* The un-pruned hnswlib index of the `hnsw` strategy (hnsw_strategy.h:15-61): file written by
+ * HierarchicalNSW::saveIndex (hnsw.h:748-779), read by loadIndex (hnsw.h:781-893).  Its
+ * searchKnn (hnsw.h:1378-1440) is the same greedy descent over levels maxlevel..1 followed by the
+ * same bare-bone searchBaseLayerST (hnsw.h:325-480) that hso_search restates for hnsw_slim with
+ * threshold_level 0, so the lists are re-packed into the record + blob image above and searched
+ * by the same code.  Level-0 record: [uint32 header, low uint16 = count][uint32 ids[maxM0]]
+ * [float vec[dim]][uint64 label]; per node `level` upper lists of 4 + 4*maxM bytes each. */
+hso_index *hso_load_hnsw(const char *path, size_t dim, int metric) {
+  FILE *f = fopen(path, "rb");
+  if (!f) {
+    snprintf(g_err, sizeof g_err, "Cannot open file %s", path);
+    return NULL;
+  }
+  uint64_t offset_level0, max_elements, n, sdpe, label_offset, offset_data, maxM, maxM0, M, efc;
+  int32_t maxlevel;
+  uint32_t enterpoint;
+  double mult;
+  int bad = 0;
+  bad |= rd(f, &offset_level0, 8);
+  bad |= rd(f, &max_elements, 8);
+  bad |= rd(f, &n, 8);
+  bad |= rd(f, &sdpe, 8);
+  bad |= rd(f, &label_offset, 8);
+  bad |= rd(f, &offset_data, 8);
+  bad |= rd(f, &maxlevel, 4);
+  bad |= rd(f, &enterpoint, 4);
+  bad |= rd(f, &maxM, 8);
+  bad |= rd(f, &maxM0, 8);
+  bad |= rd(f, &M, 8);
+  bad |= rd(f, &mult, 8);
+  bad |= rd(f, &efc, 8);
+  if (bad || offset_data != 4 + 4 * maxM0 || sdpe != offset_data + 4 * dim + 8 || label_offset != offset_data + 4 * dim) {
+    snprintf(g_err, sizeof g_err, "bad hnsw header in %s", path);
+    fclose(f);
+    return NULL;
+  }
+  char *lvl0 = (char *)malloc(n * sdpe + 1);
+  if (rd(f, lvl0, n * sdpe)) bad = 1;
+  hso_index *ix = (hso_index *)calloc(1, sizeof *ix);
+  ix->dim = dim;
+  ix->metric = metric;
+  ix->n = n;
+  ix->offset_total = 4;
+  ix->label_offset = 8;
+  ix->offset_nbr = 16;
+  ix->offset_data = 24;
+  ix->size_data_per_element = 24 + 4 * dim;
+  ix->maxlevel = maxlevel;
+  ix->threshold_level = 0;
+  ix->enterpoint = enterpoint;
+  ix->maxM = maxM;
+  ix->maxM0 = maxM0;
+  ix->M = M;
+  ix->ef_construction = efc;
+  ix->elements = (char *)calloc(n * ix->size_data_per_element + 1, 1);
+  ix->blobs = (char **)calloc(n + 1, sizeof(char *));
+  const size_t links = 4 + 4 * maxM;
+  char *up = (char *)malloc(links * 64);
+  for (uint64_t i = 0; i < n && !bad; i++) {
+    uint32_t lsz;
+    if (rd(f, &lsz, 4) || lsz % links || lsz / links > 63) { bad = 1; break; }
+    const int level = (int)(lsz / links);                       /* hnsw.h:866 */
+    if (lsz && rd(f, up, lsz)) { bad = 1; break; }
+    const char *rec = lvl0 + i * sdpe;
+    if (((const unsigned char *)rec)[2] & 1) ix->has_deleted = 1;   /* hnsw.h:1007-1018 */
+    uint16_t cnt0;
+    memcpy(&cnt0, rec, 2);                                      /* getListCount, hnsw.h:170-172 */
+    uint32_t total = cnt0;
+    uint16_t cnt[64];
+    for (int l = 1; l <= level; l++) {
+      memcpy(&cnt[l], up + (size_t)(l - 1) * links, 2);
+      total += cnt[l];
+    }
+    char *e = ix->elements + i * ix->size_data_per_element;
+    int32_t lv = level;
+    memcpy(e, &lv, 4);
+    memcpy(e + 4, &total, 4);
+    memcpy(e + 8, rec + label_offset, 8);
+    memcpy(e + 24, rec + offset_data, 4 * dim);
+    if (total == 0) continue;
+    char *b = (char *)malloc(2 * (size_t)level + 4 * (size_t)total);
+    uint16_t *offs = (uint16_t *)b;
+    char *ids = b + 2 * (size_t)level;
+    memcpy(ids, rec + 4, 4 * (size_t)cnt0);
+    uint32_t run = cnt0;
+    for (int l = 1; l <= level; l++) {
+      offs[l - 1] = (uint16_t)run;                              /* cumulative count through level l-1 */
+      memcpy(ids + 4 * (size_t)run, up + (size_t)(l - 1) * links + 4, 4 * (size_t)cnt[l]);
+      run += cnt[l];
+    }
+    ix->blobs[i] = b;
+  }
+  free(up);
+  free(lvl0);
+  fclose(f);
+  if (bad) {
+    snprintf(g_err, sizeof g_err, "truncated or inconsistent hnsw graph file %s", path);
+    hso_free(ix);
+    return NULL;
+  }
+  return ix;
+}
+
 void hso_free(hso_index *ix) {
   if (!ix) return;
   if (ix->blobs) {

@@ -42,6 +42,8 @@ typedef struct {
 
 /* slim.h:753-815 (file written by slim.h:717-751) */
 hso_index *hso_load(const char *graph_path, size_t dim, int metric);
+/* hnsw.h:781-893 (file written by hnsw.h:748-779): the `hnsw` strategy's un-pruned index */
+hso_index *hso_load_hnsw(const char *graph_path, size_t dim, int metric);
 void hso_free(hso_index *);
 void hso_get_info(const hso_index *, hso_info *out);
 const char *hso_last_error(void);

@@ -111,6 +111,140 @@ def slim_lib():
     return _slim_lib
 
 
+def ref_hnsw_path() -> str | None:
+    p = os.path.join(REF_DIR, f"libhsref_hnsw_{cpu_level()}.so")
+    return p if os.path.exists(p) else None
+
+
+_hnsw_lib = None
+
+
+def hnsw_lib():
+    """oracle/_ref/libhsref_hnsw_*.so: the reference's plain HierarchicalNSW and HierarchicalNSWSlimZero."""
+    global _hnsw_lib
+    if _hnsw_lib is None:
+        p = ref_hnsw_path()
+        if p is None:
+            raise RuntimeError("oracle/_ref/libhsref_hnsw_*.so not built (run `make -C oracle ref`)")
+        L = C.CDLL(p)
+        L.refh_last_error.restype = C.c_char_p
+        L.refh_hnsw_build.restype = C.c_int
+        L.refh_hnsw_build.argtypes = [_f32p, C.c_size_t, C.c_size_t, C.c_int, C.c_size_t, C.c_size_t, C.c_char_p,
+                                      C.c_int, C.c_void_p, C.c_char_p]
+        L.refh_hnsw_open.restype = C.c_void_p
+        L.refh_hnsw_open.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.c_size_t]
+        L.refh_hnsw_close.argtypes = [C.c_void_p]
+        L.refh_hnsw_search.restype = C.c_int
+        L.refh_hnsw_search.argtypes = [C.c_void_p, _f32p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_int, _u32p,
+                                       C.c_void_p, C.POINTER(C.c_double)]
+        L.refh_slimzero_build.restype = C.c_int
+        L.refh_slimzero_build.argtypes = [_f32p, C.c_size_t, C.c_size_t, C.c_int, C.c_size_t, C.c_size_t, C.c_char_p,
+                                          C.c_int, C.c_float, C.c_float, C.c_size_t, C.c_size_t, C.c_size_t,
+                                          C.c_size_t, C.c_size_t, C.c_size_t, C.c_int, C.c_void_p, C.c_char_p]
+        L.refh_slimzero_open.restype = C.c_void_p
+        L.refh_slimzero_open.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.c_size_t]
+        L.refh_slimzero_close.argtypes = [C.c_void_p]
+        L.refh_slimzero_search.restype = C.c_int
+        L.refh_slimzero_search.argtypes = [C.c_void_p, _f32p, C.c_size_t, C.c_size_t, C.c_size_t, _u32p,
+                                           C.POINTER(C.c_double)]
+        _hnsw_lib = L
+    return _hnsw_lib
+
+
+def _run_isolated(mode: str, base: np.ndarray, args: dict) -> None:
+    """Reference builders run in a child process (thread_local scratch in convertFromHNSW, see ref_slim_build)."""
+    import json
+    import sys
+    import tempfile
+    with tempfile.TemporaryDirectory(prefix="hsref_") as td:
+        np.save(os.path.join(td, "base.npy"), np.ascontiguousarray(base, dtype=np.float32))
+        with open(os.path.join(td, "args.json"), "w") as f:
+            json.dump(args, f)
+        r = subprocess.run([sys.executable, os.path.abspath(__file__), mode, td], capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"reference builder failed (rc={r.returncode}): {r.stderr[-2000:]}")
+
+
+def ref_hnsw_build(base: np.ndarray, path: str, *, metric: int = 0, M: int = 16, ef_construction: int = 200,
+                   branching: str = "4", threads: int = 0, isolate: bool = True) -> None:
+    """hnsw_strategy.h:24-45: omp addPoint + HierarchicalNSW::saveIndex."""
+    if isolate:
+        return _run_isolated("--build-hnsw", base, dict(path=path, metric=metric, M=M, ef_construction=ef_construction,
+                                                        branching=branching, threads=threads))
+    L = hnsw_lib()
+    base = np.ascontiguousarray(base, dtype=np.float32)
+    if L.refh_hnsw_build(base, base.shape[0], base.shape[1], metric, M, ef_construction, branching.encode(), threads,
+                         None, path.encode()) != 0:
+        raise RuntimeError(L.refh_last_error().decode())
+
+
+def ref_slimzero_build(base: np.ndarray, path: str, *, metric: int = 0, M: int = 16, ef_construction: int = 200,
+                       branching: str = "4", threads: int = 0, min_indegree0: int = 8, min_indegree: int = 4,
+                       isolate: bool = True, **prune) -> None:
+    """hnsw_slimzero_strategy.h:38-103: HNSW build + HierarchicalNSWSlimZero::convertFromHNSW + saveIndex."""
+    if isolate:
+        return _run_isolated("--build-slimzero", base,
+                             dict(path=path, metric=metric, M=M, ef_construction=ef_construction, branching=branching,
+                                  threads=threads, min_indegree0=min_indegree0, min_indegree=min_indegree, prune=prune))
+    L = hnsw_lib()
+    p = dict(PRUNE_DEFAULTS)
+    p.update(prune)
+    base = np.ascontiguousarray(base, dtype=np.float32)
+    rc = L.refh_slimzero_build(base, base.shape[0], base.shape[1], metric, M, ef_construction, branching.encode(),
+                               p["threshold_level"], p["top_degree_percent0"], p["top_degree_percent"], p["top_M0"],
+                               p["low_m0"], p["top_M"], p["low_m"], min_indegree0, min_indegree, threads, None,
+                               path.encode())
+    if rc != 0:
+        raise RuntimeError(L.refh_last_error().decode())
+
+
+class RefHnsw:
+    """The reference's plain HierarchicalNSW<float> (the `hnsw` strategy) loaded from its .graph file."""
+
+    def __init__(self, path: str, dim: int, n: int, metric: int = 0):
+        self.L = hnsw_lib()
+        self.h = self.L.refh_hnsw_open(path.encode(), dim, metric, n)
+        if not self.h:
+            raise RuntimeError(self.L.refh_last_error().decode())
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.refh_hnsw_close(self.h)
+            self.h = None
+
+    def search(self, q: np.ndarray, k: int, ef: int, threads: int = 1):
+        """-> labels[nq,k] nearest first, dists[nq,k], seconds."""
+        q = np.ascontiguousarray(q, dtype=np.float32)
+        lab = np.zeros((q.shape[0], k), dtype=np.uint32)
+        dist = np.zeros((q.shape[0], k), dtype=np.float32)
+        sec = C.c_double(0)
+        self.L.refh_hnsw_search(self.h, q, q.shape[0], k, ef, threads, lab, dist.ctypes.data, C.byref(sec))
+        return lab, dist, sec.value
+
+
+class RefSlimZero:
+    """The reference's HierarchicalNSWSlimZero<float> loaded from its .graph file."""
+
+    def __init__(self, path: str, dim: int, n: int, metric: int = 0):
+        self.L = hnsw_lib()
+        self.h = self.L.refh_slimzero_open(path.encode(), dim, metric, n)
+        if not self.h:
+            raise RuntimeError(self.L.refh_last_error().decode())
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.refh_slimzero_close(self.h)
+            self.h = None
+
+    def search(self, q: np.ndarray, k: int, ef: int):
+        """-> labels[nq,k] (unordered within a row), seconds."""
+        q = np.ascontiguousarray(q, dtype=np.float32)
+        lab = np.zeros((q.shape[0], k), dtype=np.uint32)
+        sec = C.c_double(0)
+        self.L.refh_slimzero_search(self.h, q, q.shape[0], k, ef, lab, C.byref(sec))
+        return lab, sec.value
+
+
 # pruning parameters = main.cc defaults (main.cc:27-35,58-70)
 PRUNE_DEFAULTS = dict(threshold_level=0, top_degree_percent0=0.02, top_degree_percent=0.02,
                       top_M0=32, low_m0=8, top_M=16, low_m=4)
@@ -435,6 +569,8 @@ def oracle_lib():
         L.hso_last_error.restype = C.c_char_p
         L.hso_load.restype = C.c_void_p
         L.hso_load.argtypes = [C.c_char_p, C.c_size_t, C.c_int]
+        L.hso_load_hnsw.restype = C.c_void_p
+        L.hso_load_hnsw.argtypes = [C.c_char_p, C.c_size_t, C.c_int]
         L.hso_free.argtypes = [C.c_void_p]
         L.hso_get_info.argtypes = [C.c_void_p, C.POINTER(_HsoInfo)]
         L.hso_node_level.restype = C.c_int
@@ -479,9 +615,10 @@ def oracle_lib():
 class Oracle:
     """oracle/hs_oracle.c: the plain-C restatement of HierarchicalNSWSlim load + searchKnn."""
 
-    def __init__(self, path: str, dim: int, metric: int = 0):
+    def __init__(self, path: str, dim: int, metric: int = 0, hnsw: bool = False):
+        """hnsw=True: `path` is the un-pruned hnswlib index of the `hnsw` strategy (hso_load_hnsw)."""
         self.L = oracle_lib()
-        self.h = self.L.hso_load(path.encode(), dim, metric)
+        self.h = (self.L.hso_load_hnsw if hnsw else self.L.hso_load)(path.encode(), dim, metric)
         if not self.h:
             raise RuntimeError(self.L.hso_last_error().decode())
         self.dim, self.metric = dim, metric
@@ -660,3 +797,15 @@ if __name__ == "__main__":
                               ef_construction=a["ef_construction"], threads=a["threads"], isolate=False,
                               **a["prune"])
         print(json.dumps(out))
+    if len(sys.argv) == 3 and sys.argv[1] in ("--build-hnsw", "--build-slimzero"):
+        td = sys.argv[2]
+        with open(os.path.join(td, "args.json")) as f:
+            a = json.load(f)
+        base = np.ascontiguousarray(np.load(os.path.join(td, "base.npy")))
+        if sys.argv[1] == "--build-hnsw":
+            ref_hnsw_build(base, a["path"], metric=a["metric"], M=a["M"], ef_construction=a["ef_construction"],
+                           branching=a["branching"], threads=a["threads"], isolate=False)
+        else:
+            ref_slimzero_build(base, a["path"], metric=a["metric"], M=a["M"], ef_construction=a["ef_construction"],
+                               branching=a["branching"], threads=a["threads"], min_indegree0=a["min_indegree0"],
+                               min_indegree=a["min_indegree"], isolate=False, **a["prune"])

@@ -54,11 +54,12 @@ def pytest_collection_modifyitems(config, items):
 def _built_libraries():
     """The engine (.so) and the C oracle must exist; build them if the tree is fresh."""
     hs_build.build()
-    rh.build(ref=rh.have_reference_tree() and not HAVE_REF, oracle=True)
+    rh.build(ref=rh.have_reference_tree() and not (HAVE_REF and rh.ref_hnsw_path()), oracle=True)
     yield
 
 
 needs_ref = pytest.mark.skipif(not HAVE_REF, reason="oracle/_ref (compiled reference) not available on this host")
+needs_ref_hnsw = pytest.mark.skipif(rh.ref_hnsw_path() is None, reason="oracle/_ref/libhsref_hnsw_*.so not available on this host")
 
 
 class Corpus:

@@ -89,3 +89,49 @@ def test_cli_end_to_end(tmp_path):
     assert rc == 0, err
     assert float(re.search(r"Recall: ([0-9.]+)", out).group(1)) >= 0.93
     assert any(p.startswith("hnsw_slimq_100_16_4_") for p in os.listdir(os.path.join(index_dir, "toy")))
+
+
+def test_hnsw_builder_writes_the_reference_format(tmp_path):
+    """hs_build_hnsw_graph -> HierarchicalNSW::saveIndex's format: the engine's loader, the oracle and
+    (where it is available) the reference's own loadIndex read the file; searching it with the
+    reference gives a working index (recall)."""
+    from oracle import refharness as rh
+    base, q = make_dataset(5000, 100, 24, rank=8, seed=5)
+    g = str(tmp_path / "h.graph")
+    capi.build_hnsw_graph(base, g, M=12, ef_construction=80)
+    info = capi.HostGraph(g, 24, kind=capi.HS_KIND_HNSW).info()
+    assert (info["n"], info["maxM"], info["maxM0"], info["M"], info["threshold_level"]) == (5000, 12, 24, 12, 0)
+    orc = rh.Oracle(g, 24, 0, hnsw=True)
+    ol, _, _, _ = orc.search(q, 10, 80, order=rh.ORDER_REF)
+    gt, _ = rh.oracle_bruteforce(base, q, 10)
+    rec = np.mean([len(set(a) & set(b)) / 10 for a, b in zip(ol, gt)])
+    assert rec >= 0.95, rec
+    if rh.ref_hnsw_path():
+        rl, _, _ = rh.RefHnsw(g, 24, 5000).search(q, 10, 80)
+        assert np.mean([set(a) == set(b) for a, b in zip(ol, rl)]) >= 0.99
+
+
+@pytest.mark.gpu
+def test_cli_hnsw_and_slimzero(tmp_path):
+    from oracle import refharness as rh
+    base, q, data_dir, index_dir = make_files(tmp_path, n=10000, nq=100, dim=32)
+    common = ["--dataset=toy", "--data_dir", data_dir, "--index_dir", index_dir, "--m=16", "--ef_construction=100",
+              "--k=10", "--ef_search=100"]
+    rc, out, err = run_cli("--solve_strategy=bruteforce", *common)
+    assert rc == 0, err
+    recalls = []
+    for _ in range(2):                                   # builds + saves, then loads (hnsw_strategy.h:21-45)
+        rc, out, err = run_cli("--solve_strategy=hnsw", *common)
+        assert rc == 0, err
+        recalls.append(float(re.search(r"Recall: ([0-9.]+)", out).group(1)))
+    assert recalls[0] == recalls[1] and recalls[0] >= 0.97
+    assert any(p.startswith("hnsw_100_16_4_") for p in os.listdir(os.path.join(index_dir, "toy")))
+    # hnsw_slimzero: load-only — without the file a loud error, with a reference-built file a search
+    rc, out, err = run_cli("--solve_strategy=hnsw-slimzero", *common)
+    assert rc != 0 and "build it with the reference" in err
+    if rh.ref_hnsw_path():
+        path = re.search(r"Index path: (\S+)", out).group(1)
+        rh.ref_slimzero_build(base, path, M=16, ef_construction=100)
+        rc, out, err = run_cli("--solve_strategy=hnsw-slimzero", *common)
+        assert rc == 0, err
+        assert float(re.search(r"Recall: ([0-9.]+)", out).group(1)) >= 0.9
