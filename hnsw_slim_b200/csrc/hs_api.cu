@@ -75,6 +75,11 @@ struct hs_index {
   size_t plan_nq = 0;
   TraverseLaunch plan_l{};
   TraverseParams plan_p{};
+  bool planq_ok = false;
+  uint32_t planq_ef = 0;
+  size_t planq_nq = 0, planq_k = 0;
+  TraverseQLaunch planq_l{};
+  TraverseQParams planq_p{};
   bool zero_copy = true;                   // hs_search_batch reads/writes pinned+mapped host buffers in place
   std::mutex mu;
 };
@@ -323,8 +328,23 @@ int search_device_slimq(hs_index *ix, const float *d_queries, size_t nq, size_t 
   p.per_query = d_perq;
   p.flags = ix->slimq_flags;
   TraverseQLaunch l{};
-  int rc = plan_traverse_slimq(p, ix->sm_count, (int)nq, &l);
-  if (rc != HS_OK) return rc;
+  if (ix->planq_ok && ix->planq_ef == p.ef && ix->planq_nq == nq && ix->planq_k == k) {
+    l = ix->planq_l;
+    p.smem_per_warp = ix->planq_p.smem_per_warp;
+    p.off_buf = ix->planq_p.off_buf;
+    p.off_g2c = ix->planq_p.off_g2c;
+    p.off_planes = ix->planq_p.off_planes;
+    p.off_topk = ix->planq_p.off_topk;
+  } else {
+    int rc = plan_traverse_slimq(p, ix->sm_count, (int)nq, &l);
+    if (rc != HS_OK) return rc;
+    ix->planq_ok = true;
+    ix->planq_ef = p.ef;
+    ix->planq_nq = nq;
+    ix->planq_k = k;
+    ix->planq_l = l;
+    ix->planq_p = p;
+  }
   return launch_traverse_slimq(p, l, stream);
 }
 

@@ -581,6 +581,74 @@ struct RegPool32 {
 #pragma unroll
     for (int s = 0; s < SLOTS; ++s) ku[s] = kd[s] ? kd[s] : 0xffffffffu;
   }
+  // ---- hnsw_slimq pool semantics (SearchBuffer, slimq.h:80-151): the same (estimate, id) may sit
+  //      in the pool several times; "visited" == some copy of the node is marked expanded ----
+  // closest unexpanded entry; marks EVERY copy of that node (the reference pops the later copies
+  // and skips them as visited, slimq.h:700-702 — a no-op).  A node's estimate is a function of
+  // the node, so copies share the distance word.
+  __device__ __forceinline__ uint32_t pop_closest_unexpanded_dups() {
+    const uint32_t m = col_min_un();
+    const uint32_t g = __reduce_min_sync(FULL, m);
+    if (g == 0xffffffffu) return kInvalid;
+    const int o = __ffs(__ballot_sync(FULL, m == g)) - 1;
+    uint32_t node = id[SLOTS - 1];
+#pragma unroll
+    for (int s = SLOTS - 2; s >= 0; --s) node = ku[s] == g ? id[s] : node;
+    node = __shfl_sync(FULL, node, o);
+#pragma unroll
+    for (int s = 0; s < SLOTS; ++s) ku[s] = (ku[s] == g && id[s] == node) ? 0xffffffffu : ku[s];
+    return node;
+  }
+  // slimq.h:741-745: a scored neighbour enters unless the pool is full and it is worse than the
+  // worst entry, or it was expanded already (== an expanded copy of the node is in the pool: an
+  // expanded entry that left the pool is worse than the worst from then on)
+  __device__ __forceinline__ unsigned admit_q(bool valid, uint64_t key) {
+    const uint32_t d = (uint32_t)(key >> 32), cid = (uint32_t)key;
+    unsigned entered = 0;
+    unsigned todo = __ballot_sync(FULL, valid);
+    if (todo == 0) return 0;
+    uint32_t cm = 0, worst = 0xffffffffu;
+    if (size >= ef) {
+      cm = col_max();
+      worst = __reduce_max_sync(FULL, cm);
+      todo &= __ballot_sync(FULL, valid && d < worst);
+    }
+    while (todo) {
+      const int src = __ffs(todo) - 1;
+      todo &= todo - 1;
+      const uint32_t cd = __shfl_sync(FULL, d, src), ci = __shfl_sync(FULL, cid, src);
+      bool dup = false;
+#pragma unroll
+      for (int s = 0; s < SLOTS; ++s) dup |= (id[s] == ci && ku[s] == 0xffffffffu && kd[s] != 0u);
+      if (__any_sync(FULL, dup)) continue;
+      if (size < ef) {
+        if ((int)(size & 31) == lane) put(size, cd, ci);
+        ++size;
+        entered |= 1u << src;
+        if (size == ef && todo) {
+          cm = col_max();
+          worst = __reduce_max_sync(FULL, cm);
+        }
+      } else if (cd < worst) {
+        const int owner = __ffs(__ballot_sync(FULL, cm == worst)) - 1;
+        bool open = lane == owner;
+#pragma unroll
+        for (int s = 0; s < SLOTS; ++s) {
+          const bool h = open && kd[s] == worst;
+          kd[s] = h ? cd : kd[s];
+          ku[s] = h ? cd : ku[s];
+          id[s] = h ? ci : id[s];
+          open = open && !h;
+        }
+        entered |= 1u << src;
+        if (todo) {
+          cm = col_max();
+          worst = __reduce_max_sync(FULL, cm);
+        }
+      }
+    }
+    return entered;
+  }
   template <typename F>
   __device__ __forceinline__ void for_each_id(F &&f) const {
 #pragma unroll

@@ -231,6 +231,7 @@ __global__ void __launch_bounds__(128, HS_TRAVERSE_MIN_CTAS) traverse_kernel(con
     const bool opt_prefetch = p.flags & 1u, opt_spec = p.flags & 2u;
     uint32_t spec_node = kInvalid, spec_ids = kInvalid;
     for (;;) {
+      if (p.flags & 4u) break;    // profiling aid (HS_TRAVERSE_FLAGS bit 2): time the descent alone
       // closest unexpanded entry (the reference pops its candidate min-heap, slim.h:335-354)
       const uint32_t node = pool.pop_closest_unexpanded();
       if (node == kInvalid) break;

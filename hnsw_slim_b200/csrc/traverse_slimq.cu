@@ -28,7 +28,9 @@
 // preparation, the estimates and the results are bit-identical to the oracle.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstdint>
+#include <cstdlib>
 #include <type_traits>
 
 #include "traverse_common.cuh"
@@ -41,7 +43,7 @@ namespace {
 #define HS_SLIMQ_MIN_CTAS 8
 #endif
 
-template <int SLOTS> struct QPoolSel { using type = RegPool<SLOTS>; };
+template <int SLOTS> struct QPoolSel { using type = RegPool32<SLOTS>; };
 template <> struct QPoolSel<0> { using type = SmemPool; };
 
 __device__ __forceinline__ float warp_sum_f(float v) {
@@ -420,19 +422,32 @@ int plan_traverse_slimq(TraverseQParams &p, int sm_count, int nq, TraverseQLaunc
     set_error("ef / dim too large for the per-warp shared-memory working set");
     return HS_ERR_UNSUPPORTED;
   }
-  int wpc = 4;
-  while (wpc > 1 && (size_t)wpc * p.smem_per_warp > 227u * 1024u / 2) wpc >>= 1;
+  // CTA shape: the smallest CTA that does not cost resident warps (see plan_traverse, traverse_fp32.cu)
+  auto occupancy = [&](int w) {
+    const size_t smem = (size_t)w * p.smem_per_warp;
+    if (smem > 227u * 1024u) return 0;
+    return dispatch(wrv, slv, krv, [&](auto W, auto S, auto K) {
+      auto kern = traverse_slimq_kernel<decltype(W)::value, decltype(S)::value, decltype(K)::value>;
+      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      int nb = 0;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, w * 32, smem) != cudaSuccess) nb = 0;
+      return nb;
+    });
+  };
+  int wpc = 1, per_sm = occupancy(1);
+  for (int w = 2; w <= 4; w *= 2) {
+    const int o = occupancy(w);
+    if (o * w > per_sm * wpc) {
+      wpc = w;
+      per_sm = o;
+    }
+  }
+  if (const char *w = std::getenv("HS_WPC")) {          // tuning knob
+    wpc = std::max(1, std::min(4, std::atoi(w)));
+    per_sm = occupancy(wpc);
+  }
   out->warps_per_cta = wpc;
   out->smem_bytes = (size_t)wpc * p.smem_per_warp;
-  const int threads = wpc * 32;
-  const size_t smem = out->smem_bytes;
-  int per_sm = dispatch(wrv, slv, krv, [&](auto W, auto S, auto K) {
-    auto kern = traverse_slimq_kernel<decltype(W)::value, decltype(S)::value, decltype(K)::value>;
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    int nb = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, threads, smem) != cudaSuccess) nb = 0;
-    return nb;
-  });
   if (per_sm <= 0) {
     set_error("traverse_slimq_kernel does not fit on an SM (cudaOccupancyMaxActiveBlocksPerMultiprocessor)");
     return HS_ERR_CUDA;
