@@ -80,6 +80,10 @@ struct hs_index {
   size_t planq_nq = 0, planq_k = 0;
   TraverseQLaunch planq_l{};
   TraverseQParams planq_p{};
+  // completion events of the batches handed to hs_search_batch_submit and not yet waited for (FIFO)
+  static constexpr int kEventRing = 16;
+  cudaEvent_t ev_ring[kEventRing] = {};
+  unsigned long long ev_head = 0, ev_tail = 0;      // [head, tail) are outstanding
   bool zero_copy = true;                   // hs_search_batch reads/writes pinned+mapped host buffers in place
   std::mutex mu;
 };
@@ -256,8 +260,18 @@ int load_common(const uint8_t *bytes, size_t size, int kind, int metric, size_t 
     return HS_ERR_IO;
   }
   if (g.has_deleted) {
-    set_error("indices with deleted elements (slim.h:2119-2122) not supported yet");
-    return HS_ERR_UNSUPPORTED;
+    // has_deleted_elements_ switches the reference to searchBaseLayerST<false> (slim.h:2114-2123),
+    // whose stop rule adds `&& top_size == ef` (:346-347) and which keeps delete-marked nodes out
+    // of the result heap (:418).  While the pool is not full every scored neighbour is admitted, so
+    // the closest candidate is never beyond lowerBound and the extra clause changes nothing: an
+    // index that only carries the flag is searched exactly like one without it.  Nodes that are
+    // actually marked (convertFromHNSW never writes the mark, slim.h:1088-1089) are not supported.
+    bool any_marked = false;
+    for (uint8_t d : g.deleted) any_marked |= d != 0;
+    if (any_marked || kind == HS_KIND_HNSW) {
+      set_error("index contains delete-marked elements (slim.h:1776-1781 / hnsw.h:1007-1018): not supported");
+      return HS_ERR_UNSUPPORTED;
+    }
   }
   return build_index(g, metric, device, raw_base, out);
 }
@@ -524,6 +538,8 @@ void hs_free(hs_index *ix) {
   cudaFree(ix->d_dist);
   cudaFree(ix->d_perq);
   cudaFree(ix->d_ghash);
+  for (auto &ev : ix->ev_ring)
+    if (ev) cudaEventDestroy(ev);
   if (ix->stream) cudaStreamDestroy(ix->stream);
   delete ix;
 }
@@ -626,7 +642,18 @@ int hs_search_batch(hs_index *ix, const float *queries, size_t nq, size_t k, uin
 
 int hs_search_batch_submit(hs_index *ix, const float *queries, size_t nq, size_t k, uint32_t *labels_out,
                            float *dists_out) {
-  return search_host(ix, queries, nq, k, labels_out, dists_out, nullptr, false);
+  int rc = search_host(ix, queries, nq, k, labels_out, dists_out, nullptr, false);
+  if (rc != HS_OK || !ix) return rc;
+  std::lock_guard<std::mutex> lock(ix->mu);
+  if (ix->ev_tail - ix->ev_head == hs_index::kEventRing) {       // ring full: retire the oldest batch
+    HS_CUDA(cudaEventSynchronize(ix->ev_ring[ix->ev_head % hs_index::kEventRing]));
+    ix->ev_head++;
+  }
+  cudaEvent_t &ev = ix->ev_ring[ix->ev_tail % hs_index::kEventRing];
+  if (!ev) HS_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  HS_CUDA(cudaEventRecord(ev, ix->stream));
+  ix->ev_tail++;
+  return HS_OK;
 }
 
 int hs_search_batch_wait(hs_index *ix) {
@@ -637,6 +664,20 @@ int hs_search_batch_wait(hs_index *ix) {
   std::lock_guard<std::mutex> lock(ix->mu);
   HS_CUDA(cudaSetDevice(ix->device));
   HS_CUDA(cudaStreamSynchronize(ix->stream));
+  ix->ev_head = ix->ev_tail;
+  return HS_OK;
+}
+
+int hs_search_batch_wait_oldest(hs_index *ix) {
+  if (!ix) {
+    set_error("null argument");
+    return HS_ERR_ARG;
+  }
+  std::lock_guard<std::mutex> lock(ix->mu);
+  if (ix->ev_head == ix->ev_tail) return HS_OK;                    // nothing outstanding
+  HS_CUDA(cudaSetDevice(ix->device));
+  HS_CUDA(cudaEventSynchronize(ix->ev_ring[ix->ev_head % hs_index::kEventRing]));
+  ix->ev_head++;
   return HS_OK;
 }
 

@@ -97,6 +97,10 @@ class ShardedIndex:
                            for p, rb in zip(graph_paths, raw_bases)]
         else:
             self.shards = [capi.Index(p, dim, metric=metric, device=device) for p in graph_paths]
+        # the shard launches of one batch are independent (same queries, own outputs): let each one's
+        # tail overlap the next one's head on the stream (hs_set_overlap)
+        for s in self.shards:
+            s.set_overlap(True)
         self.dim = dim
 
     def set_ef(self, ef: int) -> None:

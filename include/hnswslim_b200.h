@@ -146,6 +146,10 @@ int hs_search_batch(hs_index *, const float *queries, size_t nq, size_t k, uint3
 int hs_search_batch_submit(hs_index *, const float *queries, size_t nq, size_t k, uint32_t *labels_out,
                            float *dists_out);
 int hs_search_batch_wait(hs_index *);
+/* Blocks until the OLDEST batch that was submitted and not yet waited for is complete (batches
+ * complete in submission order), so a caller can keep a fixed number of batches in flight:
+ * submit, submit, { wait_oldest, consume, submit } ...  Returns at once when nothing is outstanding. */
+int hs_search_batch_wait_oldest(hs_index *);
 
 /* hs_search_batch that also returns per-query counters: per_query_counts[2*i] = distances
  * evaluated for query i, [2*i+1] = nodes expanded (the per-query split of hs_stats). */

@@ -372,3 +372,73 @@ def test_global_memory_visited_hash_overlapping_batches(small_corpus):
     for dl, dd in outs:
         assert np.array_equal(dl.cpu().numpy().view(np.uint32), want_l)
         assert np.array_equal(dd.cpu().numpy().view(np.uint32), want_d.view(np.uint32))
+
+
+def test_has_deleted_flag_without_marks(tmp_path):
+    """has_deleted_elements_ = true in the header, no node marked: the reference runs the
+    non-bare-bone template (slim.h:2114-2123), whose extra stop clause cannot fire — same results
+    as the oracle's restatement of that template, and as the unflagged file."""
+    import os
+    from conftest import GOLDEN
+    src = os.path.join(GOLDEN, "slim_l2_2k.graph")
+    z = np.load(os.path.join(GOLDEN, "slim_l2_2k.npz"))
+    img = bytearray(open(src, "rb").read())
+    off = 6 * 8 + 3 * 4 + 4 * 8            # the bool after ef_construction (slim.h:717-739)
+    assert img[off] == 0
+    img[off] = 1
+    flagged = str(tmp_path / "flagged.graph")
+    open(flagged, "wb").write(bytes(img))
+    dim, q = int(z["dim"]), z["queries"]
+    ix = capi.Index(flagged, dim)
+    assert ix.info()["has_deleted"] == 1
+    plain = capi.Index(src, dim)
+    for ef in (10, 40, 100):
+        ix.set_ef(ef)
+        plain.set_ef(ef)
+        lab, dist = ix.search(q, 10)
+        pl, pd = plain.search(q, 10)
+        assert np.array_equal(lab, pl) and np.array_equal(dist.view(np.uint32), pd.view(np.uint32))
+        ol, od, _, _ = rh.Oracle(flagged, dim).search(q, 10, ef, order=rh.ORDER_GPU, team=8)
+        assert (np.all(lab == ol, axis=1)).mean() >= 0.98
+    # a node that really carries the mark (byte 6 of its record, slim.h:1776-1781) is refused loudly
+    hdr = off + 1
+    img[hdr + 6] |= 1
+    marked = str(tmp_path / "marked.graph")
+    open(marked, "wb").write(bytes(img))
+    with pytest.raises(capi.HsError):
+        capi.Index(marked, dim)
+
+
+def test_submit_wait_oldest_ring(small_corpus):
+    """hs_search_batch_wait_oldest retires batches in submission order, also past the 16-entry
+    completion ring."""
+    import torch
+    c = small_corpus
+    ix = capi.Index(c.graph, c.dim)
+    ix.set_ef(40)
+    ix.set_overlap(True)
+    k, nq = 10, c.queries.shape[0]
+    nb, depth = 40, 3
+    batches = [np.ascontiguousarray(np.roll(c.queries, s, axis=0)) for s in range(nb)]
+    want = [ix.search(b, k)[0] for b in batches]
+    hq = [torch.from_numpy(b).pin_memory() for b in batches]
+    hl = [torch.full((nq, k), -1, dtype=torch.int32).pin_memory() for _ in range(depth)]
+    got = []
+    for i in range(nb):
+        if i >= depth:
+            ix.wait_oldest()
+            got.append(hl[i % depth].numpy().view(np.uint32).copy())
+        ix.submit_ptr(hq[i].data_ptr(), nq, k, hl[i % depth].data_ptr(), None)
+    for i in range(nb - depth, nb):
+        ix.wait_oldest()
+        got.append(hl[i % depth].numpy().view(np.uint32).copy())
+    ix.wait_oldest()                                   # nothing outstanding: returns at once
+    for i in range(nb):
+        assert np.array_equal(got[i], want[i]), i
+    # 20 submits without any wait: the ring retires the oldest ones itself
+    outs = [torch.full((nq, k), -1, dtype=torch.int32).pin_memory() for _ in range(20)]
+    for i in range(20):
+        ix.submit_ptr(hq[i].data_ptr(), nq, k, outs[i].data_ptr(), None)
+    ix.wait()
+    for i in range(20):
+        assert np.array_equal(outs[i].numpy().view(np.uint32), want[i]), i
