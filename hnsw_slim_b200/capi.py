@@ -18,7 +18,7 @@ HS_METRIC_L2, HS_METRIC_IP = 0, 1
 
 EXPORTS = [
     "hs_load", "hs_load_memory", "hs_free", "hs_set_ef", "hs_get_info", "hs_search_batch",
-    "hs_search_batch_counts", "hs_search_batch_submit", "hs_search_batch_wait", "hs_search_batch_wait_oldest", "hs_search_batch_device", "hs_stats", "hs_reset_stats", "hs_bruteforce_knn",
+    "hs_search_batch_counts", "hs_search_batch_submit", "hs_search_batch_wait", "hs_search_batch_wait_oldest", "hs_pin_host", "hs_unpin_host", "hs_search_batch_device", "hs_stats", "hs_reset_stats", "hs_bruteforce_knn",
     "hs_bruteforce_knn_device", "hs_topk_merge_device", "hs_recall", "hs_last_error", "hs_abi_version",
     "hs_debug_flatten", "hs_debug_free", "hs_debug_info", "hs_debug_row", "hs_debug_node",
     "hs_build_params_default", "hs_build_slim_graph", "hs_build_hnsw_graph",
@@ -84,6 +84,8 @@ def lib():
         L.hs_search_batch_submit.argtypes = [vp, vp, sz, sz, vp, vp]
         L.hs_search_batch_wait.argtypes = [vp]
         L.hs_search_batch_wait_oldest.argtypes = [vp]
+        L.hs_pin_host.argtypes = [vp, sz]
+        L.hs_unpin_host.argtypes = [vp]
         L.hs_search_batch_device.argtypes = [vp, vp, sz, sz, vp, vp, vp]
         L.hs_stats.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
         L.hs_reset_stats.argtypes = [vp]

@@ -67,7 +67,7 @@ struct hs_index {
   int ghash_mode = -1;                     // HS_GHASH: -1 auto, 0 shared-memory visited tables, 1 global-memory
   uint32_t *d_ghash = nullptr;             // two halves, alternated by consecutive (possibly overlapping) launches
   size_t cap_ghash = 0;
-  uint32_t traverse_flags = 1;             // bit0: L2 row prefetch; bit1: speculative next-pop adjacency load (measured: a loss)
+  uint32_t traverse_flags = 9;             // bit0: L2 row prefetch; bit1: speculative next-pop adjacency load (measured: a loss); bit3: evict_last adjacency prefetch
   uint32_t slimq_flags = 0;
   // the launch plan of the last fp32 traversal (occupancy queries are not free on the host)
   bool plan_ok = false;
@@ -678,6 +678,36 @@ int hs_search_batch_wait_oldest(hs_index *ix) {
   HS_CUDA(cudaSetDevice(ix->device));
   HS_CUDA(cudaEventSynchronize(ix->ev_ring[ix->ev_head % hs_index::kEventRing]));
   ix->ev_head++;
+  return HS_OK;
+}
+
+int hs_pin_host(void *ptr, size_t bytes) {
+  if (!ptr || bytes == 0) {
+    set_error("hs_pin_host: null / empty range");
+    return HS_ERR_ARG;
+  }
+  cudaError_t e = cudaHostRegister(ptr, bytes, cudaHostRegisterPortable | cudaHostRegisterMapped);
+  if (e == cudaErrorHostMemoryAlreadyRegistered) {
+    cudaGetLastError();
+    return HS_OK;
+  }
+  if (e != cudaSuccess) {
+    set_error(std::string("cudaHostRegister: ") + cudaGetErrorString(e));
+    cudaGetLastError();
+    return HS_ERR_CUDA;
+  }
+  return HS_OK;
+}
+
+int hs_unpin_host(void *ptr) {
+  if (!ptr) return HS_OK;
+  cudaError_t e = cudaHostUnregister(ptr);
+  if (e != cudaSuccess && e != cudaErrorHostMemoryNotRegistered) {
+    set_error(std::string("cudaHostUnregister: ") + cudaGetErrorString(e));
+    cudaGetLastError();
+    return HS_ERR_CUDA;
+  }
+  cudaGetLastError();
   return HS_OK;
 }
 

@@ -200,6 +200,11 @@ __device__ __forceinline__ void hash_clear(uint32_t *hash, uint32_t hsize, int l
 __device__ __forceinline__ void prefetch_l2(const void *p) {
   asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }
+// same, asking L2 to evict the line last: adjacency rows of pool entries are needed again when the
+// entry is popped, typically long after the streaming row reads would have pushed them out
+__device__ __forceinline__ void prefetch_l2_keep(const void *p) {
+  asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(p));
+}
 constexpr uint64_t NONE = ~0ull;
 
 // Dynamic work distribution: the next query index of THIS launch.  The counter is one slot of a

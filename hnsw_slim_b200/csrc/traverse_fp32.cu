@@ -228,7 +228,7 @@ __global__ void __launch_bounds__(128, HS_TRAVERSE_MIN_CTAS) traverse_kernel(con
     }
 
     // ---- base layer, slim.h:321-457 ----
-    const bool opt_prefetch = p.flags & 1u, opt_spec = p.flags & 2u;
+    const bool opt_prefetch = p.flags & 1u, opt_spec = p.flags & 2u, opt_keep = p.flags & 8u;
     uint32_t spec_node = kInvalid, spec_ids = kInvalid;
     for (;;) {
       if (p.flags & 4u) break;    // profiling aid (HS_TRAVERSE_FLAGS bit 2): time the descent alone
@@ -291,7 +291,10 @@ __global__ void __launch_bounds__(128, HS_TRAVERSE_MIN_CTAS) traverse_kernel(con
         const float d = eval(cid, count);
         nd += (uint32_t)count;
         const unsigned entered = pool.admit(lane < count, make_key(d, cid));
-        if ((entered >> lane) & 1u) prefetch_l2(p.adj0 + (size_t)cid * p.deg0_stride);
+        if ((entered >> lane) & 1u) {
+          if (opt_keep) prefetch_l2_keep(p.adj0 + (size_t)cid * p.deg0_stride);
+          else prefetch_l2(p.adj0 + (size_t)cid * p.deg0_stride);
+        }
       }
       if (any) nh++;
     }

@@ -17,6 +17,10 @@ class SolveStrategy {
     ReadData(source_path, data_set_, data_num_, data_dim_);
     ReadData(query_path, query_set_, query_num_, query_dim_);
     knn_results_.resize((size_t)query_num_ * K);
+    // page-lock the query and result blocks once: hs_search_batch then reads / writes them in place
+    // (no staging copies).  Best effort — without a device the search itself reports the error.
+    pinned_ = hs_pin_host(query_set_.data(), query_set_.size() * sizeof(float)) == HS_OK &&
+              hs_pin_host(knn_results_.data(), knn_results_.size() * sizeof(uint32_t)) == HS_OK;
     M_ = M;
     M0_ = M0;
     ef_construction_ = EF_CONSTRUCTION;
@@ -26,7 +30,10 @@ class SolveStrategy {
     threshold_level_ = THRESHOLD_LEVEL;
     index_path_ = index_path;
   }
-  virtual ~SolveStrategy() = default;
+  virtual ~SolveStrategy() {
+    hs_unpin_host(query_set_.data());
+    hs_unpin_host(knn_results_.data());
+  }
 
   virtual void solve() = 0;
 
@@ -34,7 +41,9 @@ class SolveStrategy {
 
   void read_knn(std::string knn_path) {
     uint32_t num, dim;
+    hs_unpin_host(knn_results_.data());              // ReadData may reallocate the block
     ReadData(knn_path, knn_results_, num, dim);
+    hs_pin_host(knn_results_.data(), knn_results_.size() * sizeof(uint32_t));
   }
   void save_knn(std::string knn_path) { WriteData(knn_path, knn_results_, query_num_, (uint32_t)K_); }
 
@@ -64,6 +73,7 @@ class SolveStrategy {
   uint32_t query_num_ = 0, query_dim_ = 0;
   size_t ef_search_;
   std::vector<uint32_t> knn_results_;   // query_num_ x K_
+  bool pinned_ = false;
   size_t K_;
   std::string index_path_;
   int device_;

@@ -135,6 +135,14 @@ int hs_slimq_prepare(hs_index *, const float *queries, size_t nq, float *rotated
 int hs_search_batch(hs_index *, const float *queries, size_t nq, size_t k, uint32_t *labels_out,
                     float *dists_out);
 
+/* Page-lock and map a host range the caller owns (cudaHostRegister, portable + mapped) so that
+ * hs_search_batch / hs_search_batch_submit use it in place; hs_unpin_host undoes it before the
+ * memory is freed.  For callers that do not link the CUDA runtime themselves (the reference's
+ * strategies keep queries and results in std::vector).  Registering costs about a millisecond per
+ * few MB: do it once per buffer, not per call. */
+int hs_pin_host(void *ptr, size_t bytes);
+int hs_unpin_host(void *ptr);
+
 /* hs_search_batch split in two so that a caller with a stream of batches (the reference's
  * server answers /query requests back to back, hnsw_slim_server.cc:69-142) keeps more than one
  * batch in flight: submit enqueues the batch on the handle's own stream and returns, wait blocks
