@@ -479,7 +479,9 @@ int plan_traverse(TraverseParams &p, int metric, int hash_bits_override, int gha
   int wpc = 1, per_sm = occupancy(1);
   for (int w = 2; w <= 4; w *= 2) {
     const int o = occupancy(w);
-    if (o * w > per_sm * wpc) {
+    // large dims (query in shared memory): four-warp CTAs measured better or equal (GIST-shaped
+    // 200k x 960: ef=50 6.2 vs 7.3 ms per 10k queries, ef=100 equal), so they win ties there
+    if (o * w > per_sm * wpc || (cplv == 0 && o * w >= per_sm * wpc)) {
       wpc = w;
       per_sm = o;
     }

@@ -442,3 +442,44 @@ def test_submit_wait_oldest_ring(small_corpus):
     ix.wait()
     for i in range(20):
         assert np.array_equal(outs[i].numpy().view(np.uint32), want[i]), i
+
+
+FUZZ = [
+    # n,    dim, M,  metric, thr, branching, ef,  k,   kind,   prune
+    (3000,  5,   4,  0,      0,   "4",       17,  3,   "slim", {}),     # tiny dim (scalar query loads), tiny M
+    (3000,  17,  6,  1,      0,   "e",       33,  33,  "slim", {}),     # k > 32 with ef == k, inner product, odd dim
+    (5000,  96,  24, 0,      0,   "16",      64,  10,  "slim", {}),     # CPL=3 register variant
+    (5000,  128, 48, 0,      0,   "4",       128, 10,  "slim", dict(top_M0=96, low_m0=80, top_M=48, low_m=40)),  # 3 adjacency segments
+    (4000,  64,  16, 1,      1,   "4",       100, 10,  "slim", {}),     # layered beam + inner product
+    (4000,  200, 12, 0,      2,   "sqrt",    257, 20,  "slim", {}),     # shared-memory pool (ef > 256), generic dim
+    (2000,  33,  8,  0,      0,   "4",       1000, 100, "slim", {}),    # ef half the index: hash resets likely, large k
+    (300,   8,   8,  0,      0,   "4",       400, 10,  "slim", {}),     # ef larger than the index: every node visited
+    (5000,  48,  24, 0,      0,   "4",       90,  10,  "hnsw", {}),     # un-pruned index, maxM0 = 48 -> two segments
+    (3000,  20,  40, 1,      0,   "16",      200, 50,  "hnsw", {}),     # un-pruned, maxM0 = 80, upper rows of 40 ids
+]
+
+
+@pytest.mark.parametrize("n,dim,M,metric,thr,branching,ef,k,kind,prune", FUZZ)
+def test_unusual_shapes_match_oracle(n, dim, M, metric, thr, branching, ef, k, kind, prune, tmp_path):
+    """Bit-exact parity on shapes away from the benchmark configurations, graphs from the engine's
+    own builders (also exercises them: the oracle must be able to read what they wrote)."""
+    base, q = make_dataset(n, 150, dim, metric=metric, rank=min(dim, 6), seed=n + dim)
+    g = str(tmp_path / "f.graph")
+    if kind == "hnsw":
+        capi.build_hnsw_graph(base, g, metric=metric, M=M, ef_construction=60, branching=branching)
+        ix = capi.Index(g, dim, kind=capi.HS_KIND_HNSW, metric=metric)
+        orc = rh.Oracle(g, dim, metric, hnsw=True)
+    else:
+        capi.build_slim_graph(base, g, metric=metric, M=M, ef_construction=60, branching=branching,
+                              threshold_level=thr, **prune)
+        ix = capi.Index(g, dim, metric=metric)
+        orc = rh.Oracle(g, dim, metric)
+    ix.set_ef(ef)
+    lab, dist, cnt = ix.search(q, k, counts=True)
+    ol, od, ond, onh = orc.search(q, k, ef, order=rh.ORDER_GPU, team=8)
+    same = np.all(lab == ol, axis=1)
+    assert same.mean() >= 0.99, same.mean()
+    assert np.array_equal(dist[same].view(np.uint32), od[same].view(np.uint32))
+    assert (cnt[same, 1] == onh[same]).mean() >= 0.99
+    fin = np.isfinite(od)
+    np.testing.assert_allclose(dist[fin], od[fin], rtol=REL_TOL, atol=1e-6)
