@@ -462,6 +462,10 @@ int launch_traverse_slimq(const TraverseQParams &p, const TraverseQLaunch &l, cu
   return dispatch(wreg_variant(p.words), slots_variant(p.ef), kreg_variant(p.k), [&](auto W, auto S, auto K) {
     auto kern = traverse_slimq_kernel<decltype(W)::value, decltype(S)::value, decltype(K)::value>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)l.smem_bytes);
+    // HS_SLIMQ_CARVEOUT (tuning knob): preferred shared-memory carve-out in percent; the rest of the
+    // 256 KB array is L1, which serves about half of this kernel's sector requests
+    static const int carve = [] { const char *c = std::getenv("HS_SLIMQ_CARVEOUT"); return c ? std::atoi(c) : -2; }();
+    if (carve >= -1) cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
     if (e != cudaSuccess) {
       set_error(std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
       return (int)HS_ERR_CUDA;
