@@ -231,6 +231,11 @@ struct TcParams {
   uint32_t n, nq, kblocks, rows_per_split, kp;   // n = rows to scan (a prefix of the base)
   int metric;
   uint32_t smem_heap;        // 1: heaps live in shared memory during the scan (kp <= kMaxSmemKp)
+  // Resident-query mode (few k-blocks, i.e. dim <= ~128): the CTA's query tiles q_hi | q_lo of ALL
+  // k-blocks are loaded once and stay in shared memory; only the base tiles x_hi | x_lo stream
+  // through `xstages` pipeline slots.  Halves the L2 -> shared-memory fill per MMA, which is what
+  // bounds this kernel (ncu: tensor pipe 32 % active, fill 7 TB/s in the streaming mode).
+  uint32_t qres, xstages;
 };
 
 __global__ void __launch_bounds__(THREADS, 1)
@@ -239,12 +244,18 @@ bf_tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant__
              const TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t *full = reinterpret_cast<uint64_t *>(smem + STAGES * STAGE_BYTES);
+  // data region: streaming mode  STAGES x [q_hi | q_lo | x_hi | x_lo]
+  //              resident mode   kblocks x [q_hi | q_lo]  then  xstages x [x_hi | x_lo]
+  const uint32_t n_stages = p.qres ? p.xstages : (uint32_t)STAGES;
+  const uint32_t q_region = p.qres ? p.kblocks * 2 * A_BYTES : 0u;
+  const uint32_t data_bytes = p.qres ? q_region + p.xstages * 2 * B_BYTES : (uint32_t)(STAGES * STAGE_BYTES);
+  uint64_t *full = reinterpret_cast<uint64_t *>(smem + data_bytes);
   uint64_t *empty = full + STAGES;
   uint64_t *tfull = empty + STAGES;
   uint64_t *tempty = tfull + ACC;
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + ACC);
-  uint64_t *smem_heaps = reinterpret_cast<uint64_t *>(smem + STAGES * STAGE_BYTES + 256);
+  uint64_t *qfull = tempty + ACC;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(qfull + 1);
+  uint64_t *smem_heaps = reinterpret_cast<uint64_t *>(smem + data_bytes + 256);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t q0 = blockIdx.x * TM;
@@ -263,6 +274,7 @@ bf_tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant__
       mbar_init(&tfull[a], 1);
       mbar_init(&tempty[a], 128);
     }
+    mbar_init(qfull, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {     // TMEM: ACC x TN fp32 columns for 128 lanes
@@ -279,17 +291,31 @@ bf_tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant__
     // ===== TMA producer =====
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
+      if (p.qres && n_tiles) {                      // the query tiles of every k-block, once
+        mbar_expect_tx(qfull, q_region);
+        for (uint32_t kb = 0; kb < k_iters; ++kb) {
+          tma_load_2d(smem + kb * 2 * A_BYTES, &tm_qhi, (int)(kb * KB), (int)q0, qfull);
+          tma_load_2d(smem + kb * 2 * A_BYTES + A_BYTES, &tm_qlo, (int)(kb * KB), (int)q0, qfull);
+        }
+      }
       for (uint32_t t = 0; t < n_tiles; ++t) {
         const int row0 = (int)(r_begin + t * TN);
         for (uint32_t kb = 0; kb < k_iters; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
-          uint8_t *st = smem + stage * STAGE_BYTES;
-          mbar_expect_tx(&full[stage], STAGE_BYTES);
-          tma_load_2d(st, &tm_qhi, (int)(kb * KB), (int)q0, &full[stage]);
-          tma_load_2d(st + A_BYTES, &tm_qlo, (int)(kb * KB), (int)q0, &full[stage]);
-          tma_load_2d(st + 2 * A_BYTES, &tm_xhi, (int)(kb * KB), row0, &full[stage]);
-          tma_load_2d(st + 2 * A_BYTES + B_BYTES, &tm_xlo, (int)(kb * KB), row0, &full[stage]);
-          if (++stage == STAGES) {
+          if (p.qres) {
+            uint8_t *st = smem + q_region + stage * 2 * B_BYTES;
+            mbar_expect_tx(&full[stage], 2 * B_BYTES);
+            tma_load_2d(st, &tm_xhi, (int)(kb * KB), row0, &full[stage]);
+            tma_load_2d(st + B_BYTES, &tm_xlo, (int)(kb * KB), row0, &full[stage]);
+          } else {
+            uint8_t *st = smem + stage * STAGE_BYTES;
+            mbar_expect_tx(&full[stage], STAGE_BYTES);
+            tma_load_2d(st, &tm_qhi, (int)(kb * KB), (int)q0, &full[stage]);
+            tma_load_2d(st + A_BYTES, &tm_qlo, (int)(kb * KB), (int)q0, &full[stage]);
+            tma_load_2d(st + 2 * A_BYTES, &tm_xhi, (int)(kb * KB), row0, &full[stage]);
+            tma_load_2d(st + 2 * A_BYTES + B_BYTES, &tm_xlo, (int)(kb * KB), row0, &full[stage]);
+          }
+          if (++stage == n_stages) {
             stage = 0;
             phase ^= 1;
           }
@@ -301,6 +327,10 @@ bf_tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant__
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_tf32(TM, TN);
       uint32_t stage = 0, phase = 0;
+      if (p.qres && n_tiles) {
+        mbar_wait(qfull, 0);
+        tc_fence_after();
+      }
       for (uint32_t t = 0; t < n_tiles; ++t) {
         const uint32_t acc = t & 1, acc_phase = (t >> 1) & 1;
         mbar_wait(&tempty[acc], acc_phase ^ 1);       // epilogue has drained this accumulator
@@ -309,9 +339,10 @@ bf_tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant__
         for (uint32_t it = 0; it < k_iters; ++it) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
-          const uint32_t a = smem_u32(smem + stage * STAGE_BYTES);
+          const uint32_t a = p.qres ? smem_u32(smem + it * 2 * A_BYTES) : smem_u32(smem + stage * STAGE_BYTES);
+          const uint32_t b = p.qres ? smem_u32(smem + q_region + stage * 2 * B_BYTES) : a + 2 * A_BYTES;
           const uint64_t qhi = umma_desc_sw128(a), qlo = umma_desc_sw128(a + A_BYTES);
-          const uint64_t xhi = umma_desc_sw128(a + 2 * A_BYTES), xlo = umma_desc_sw128(a + 2 * A_BYTES + B_BYTES);
+          const uint64_t xhi = umma_desc_sw128(b), xlo = umma_desc_sw128(b + B_BYTES);
 #pragma unroll
           for (int g = 0; g < 3; ++g) {               // hi.hi, hi.lo, lo.hi
             const uint64_t ad = g == 2 ? qlo : qhi, bd = g == 1 ? xlo : xhi;
@@ -320,7 +351,7 @@ bf_tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant__
               tc_mma_tf32(d, ad + 2 * k, bd + 2 * k, idesc, (it | g | k) != 0 ? 1u : 0u);
           }
           tc_commit(&empty[stage]);                   // frees the smem slot when these MMAs retire
-          if (++stage == STAGES) {
+          if (++stage == n_stages) {
             stage = 0;
             phase ^= 1;
           }
@@ -671,8 +702,20 @@ int bruteforce_tc_device(const float *d_base, size_t n, size_t dim, const float 
       (rc = make_map(&m_xhi, x_hi, n, kpad)) != HS_OK || (rc = make_map(&m_xlo, x_lo, n, kpad)) != HS_OK)
     return rc;
 
-  const size_t smem_heap_bytes = kp <= kMaxSmemKp ? (size_t)128 * kp * 8 : 0;
-  const size_t smem = STAGES * STAGE_BYTES + 1024 /* alignment slack */ + 256 /* barriers */ + smem_heap_bytes;
+  // resident-query mode when the query tiles of all k-blocks plus at least two base-tile slots fit
+  // (dim + 1 <= 160: SIFT / DEEP / MSTuring shapes); the heaps then live in global memory
+  const uint32_t kblocks = kpad / KB;
+  const size_t smem_budget = 227 * 1024 - 1024 - 256;
+  uint32_t qres = 0, xstages = 0;
+  if ((size_t)kblocks * 2 * A_BYTES + 2 * 2 * B_BYTES <= smem_budget) {
+    qres = 1;
+    xstages = (uint32_t)std::min<size_t>(STAGES, (smem_budget - (size_t)kblocks * 2 * A_BYTES) / (2 * B_BYTES));
+  }
+  if (const char *e = std::getenv("HS_BF_QRES")) qres = e[0] == '1' ? qres : 0;
+  const size_t data_bytes = qres ? (size_t)kblocks * 2 * A_BYTES + (size_t)xstages * 2 * B_BYTES : (size_t)STAGES * STAGE_BYTES;
+  size_t smem_heap_bytes = kp <= kMaxSmemKp ? (size_t)128 * kp * 8 : 0;
+  if (data_bytes + 1024 + 256 + smem_heap_bytes > 227 * 1024) smem_heap_bytes = 0;
+  const size_t smem = data_bytes + 1024 /* alignment slack */ + 256 /* barriers */ + smem_heap_bytes;
   TC_CUDA(cudaFuncSetAttribute(bf_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   auto launch_tc = [&](uint32_t rows, uint32_t n_splits, uint32_t rps, const float *thr) {
     TcParams tp{};
@@ -685,6 +728,8 @@ int bruteforce_tc_device(const float *d_base, size_t n, size_t dim, const float 
     tp.kp = kp;
     tp.metric = metric;
     tp.smem_heap = smem_heap_bytes ? 1u : 0u;
+    tp.qres = qres;
+    tp.xstages = xstages;
     bf_tc_kernel<<<dim3(q_tiles, n_splits), THREADS, smem, stream>>>(m_qhi, m_qlo, m_xhi, m_xlo, tp);
   };
   // phase A: a sample (the first rows) yields per-query prefilter thresholds, which keep the

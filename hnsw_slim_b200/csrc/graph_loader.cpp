@@ -58,6 +58,12 @@ struct Reader {
 };
 
 inline uint32_t round_up(uint32_t v, uint32_t m) { return (v + m - 1) / m * m; }
+// the blobs sit at arbitrary byte offsets of the file image: no aligned access
+inline uint32_t load_u16(const uint8_t *p, size_t idx) {
+  uint16_t v;
+  std::memcpy(&v, p + 2 * idx, 2);
+  return v;
+}
 
 }  // namespace
 
@@ -360,10 +366,9 @@ int parse_graph(const uint8_t *bytes, size_t size, int kind, size_t dim, HostGra
       return HS_ERR_IO;
     }
     blobs[i] = BlobRef{b, bsz};
-    const uint16_t *offs = reinterpret_cast<const uint16_t *>(b);
     uint32_t prev = 0;
     for (int l = 0; l <= lvl; ++l) {
-      uint32_t end = (l == lvl) ? total[i] : offs[l];
+      uint32_t end = (l == lvl) ? total[i] : load_u16(b, l);
       if (end < prev || end > total[i]) {
         set_error("corrupt level offsets in .graph (node " + std::to_string(i) + ")");
         return HS_ERR_IO;
@@ -374,9 +379,8 @@ int parse_graph(const uint8_t *bytes, size_t size, int kind, size_t dim, HostGra
   return flatten_lists(g, [&](size_t i, int l, const uint8_t **ids) -> uint32_t {
     if (!blobs[i].p) return 0;
     const int lvl = g->levels[i];
-    const uint16_t *offs = reinterpret_cast<const uint16_t *>(blobs[i].p);
-    const uint32_t begin = l == 0 ? 0 : offs[l - 1];
-    const uint32_t end = l == lvl ? total[i] : offs[l];
+    const uint32_t begin = l == 0 ? 0 : load_u16(blobs[i].p, l - 1);
+    const uint32_t end = l == lvl ? total[i] : load_u16(blobs[i].p, l);
     *ids = blobs[i].p + 2 * (size_t)lvl + 4 * (size_t)begin;
     return end - begin;
   });
