@@ -107,6 +107,17 @@ __device__ __forceinline__ void heap_replace_top(const HeapRef h, uint32_t sz, u
   h[i] = key;
 }
 
+// one out-of-line copy for the epilogue's (rare) insertions
+__device__ __noinline__ void heap_admit(const HeapRef h, uint32_t &sz, uint32_t kp, uint64_t key, float pre,
+                                        float &cur) {
+  if (sz < kp) {
+    heap_push(h, sz, key);
+  } else {
+    heap_replace_top(h, sz, key);
+  }
+  if (sz == kp) cur = fminf(pre, ord2f((uint32_t)(h[0] >> 32)));
+}
+
 // ---------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -231,10 +242,10 @@ struct TcParams {
   uint32_t n, nq, kblocks, rows_per_split, kp;   // n = rows to scan (a prefix of the base)
   int metric;
   uint32_t smem_heap;        // 1: heaps live in shared memory during the scan (kp <= kMaxSmemKp)
-  // Resident-query mode (few k-blocks, i.e. dim <= ~128): the CTA's query tiles q_hi | q_lo of ALL
-  // k-blocks are loaded once and stay in shared memory; only the base tiles x_hi | x_lo stream
-  // through `xstages` pipeline slots.  Halves the L2 -> shared-memory fill per MMA, which is what
-  // bounds this kernel (ncu: tensor pipe 32 % active, fill 7 TB/s in the streaming mode).
+  // Resident-query mode (few k-blocks, i.e. dim <= ~128; opt-in, see bruteforce_tc_device): the CTA's
+  // query tiles q_hi | q_lo of ALL k-blocks are loaded once and stay in shared memory; only the base
+  // tiles x_hi | x_lo stream through `xstages` pipeline slots.  Halves the L2 -> shared-memory fill
+  // per MMA.
   uint32_t qres, xstages;
 };
 
@@ -367,7 +378,6 @@ bf_tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant__
     uint64_t *gheap = p.cand + ((size_t)split * p.nq + (live ? my_q : 0)) * p.kp;
     const HeapRef heap = p.smem_heap ? HeapRef{smem_heaps + (quad * 32 + lane), 128u} : HeapRef{gheap, 1u};
     uint32_t hsz = 0;
-    uint64_t top = ~0ull;
     // admission threshold on the approximate score: the sampled prefilter (if any) until the
     // heap is full, then also the heap's worst entry.  Rows that tie with it are dropped:
     // bf_finish_kernel treats a full heap whose worst entry is under ITS threshold as
@@ -384,23 +394,21 @@ bf_tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant__
         uint32_t v[32];
         tc_ld32(tmem_base + ((quad * 32u) << 16) + acc * TN + c0, v);
         if (!live) continue;
-        // the accumulator IS the approximate score: one compare per row in the common case
+        // the accumulator IS the approximate score.  Common case: none of the 32 scores passes the
+        // threshold — 32 predicated compares into a mask and ONE branch.  The rare insertions go
+        // through a single out-of-line copy of the heap code (inlining it per element made the
+        // loop body ~50 KB of SASS: ncu showed the warps starved for instructions).
+        uint32_t mask = 0;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const float s = __uint_as_float(v[j]);
-          if (s < cur) {
-            const uint32_t row = row0 + c0 + j;
-            if (row < r_end) {                       // rows past the edge are TMA zero fill
-              const uint64_t key = ((uint64_t)f2ord(s) << 32) | row;
-              if (hsz < p.kp) {
-                heap_push(heap, hsz, key);
-              } else {
-                heap_replace_top(heap, hsz, key);
-              }
-              if (hsz == p.kp) {
-                top = heap[0];
-                cur = fminf(pre, ord2f((uint32_t)(top >> 32)));
-              }
+        for (int j = 0; j < 32; ++j) mask |= (__uint_as_float(v[j]) < cur) ? (1u << j) : 0u;
+        if (mask) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            if (mask & (1u << j)) {
+              const float s = __uint_as_float(v[j]);
+              const uint32_t row = row0 + c0 + j;
+              if (s < cur && row < r_end)             // cur may have tightened; rows past the edge are TMA zero fill
+                heap_admit(heap, hsz, p.kp, ((uint64_t)f2ord(s) << 32) | row, pre, cur);
             }
           }
         }
@@ -711,7 +719,13 @@ int bruteforce_tc_device(const float *d_base, size_t n, size_t dim, const float 
     qres = 1;
     xstages = (uint32_t)std::min<size_t>(STAGES, (smem_budget - (size_t)kblocks * 2 * A_BYTES) / (2 * B_BYTES));
   }
-  if (const char *e = std::getenv("HS_BF_QRES")) qres = e[0] == '1' ? qres : 0;
+  // Measured on 1M x 128, 10k queries (main launch): streaming 16.5 ms, resident 19.0 ms — with the
+  // query tiles resident only two base-tile slots fit and the heaps move to global memory, which
+  // costs more than the halved fill saves.  Resident mode therefore stays opt-in (HS_BF_QRES=1).
+  {
+    const char *e = std::getenv("HS_BF_QRES");
+    if (!(e && e[0] == '1')) qres = 0;
+  }
   const size_t data_bytes = qres ? (size_t)kblocks * 2 * A_BYTES + (size_t)xstages * 2 * B_BYTES : (size_t)STAGES * STAGE_BYTES;
   size_t smem_heap_bytes = kp <= kMaxSmemKp ? (size_t)128 * kp * 8 : 0;
   if (data_bytes + 1024 + 256 + smem_heap_bytes > 227 * 1024) smem_heap_bytes = 0;
