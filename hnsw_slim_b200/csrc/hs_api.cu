@@ -483,6 +483,9 @@ int search_host(hs_index *ix, const float *queries, size_t nq, size_t k, uint32_
   ix->cap_out = std::min(cap_lab, cap_dist);
   if (perq_out && (rc = ensure((void **)&ix->d_perq, &ix->cap_perq, nq * 8)) != HS_OK) return rc;
   HS_CUDA(cudaMemcpyAsync(ix->d_q, queries, nq * dim * sizeof(float), cudaMemcpyHostToDevice, ix->stream));
+  // the counters variant is a diagnostic entry point: poison its scratch so that a query the kernel
+  // never answered shows up as 0xFFFFFFFF counters instead of whatever an earlier call left there
+  if (perq_out) HS_CUDA(cudaMemsetAsync(ix->d_perq, 0xff, nq * 8, ix->stream));
   rc = search_device(ix, ix->d_q, nq, k, ix->d_lab, ix->d_dist, perq_out ? ix->d_perq : nullptr, ix->stream);
   if (rc != HS_OK) return rc;
   HS_CUDA(cudaMemcpyAsync(labels_out, ix->d_lab, nq * k * 4, cudaMemcpyDeviceToHost, ix->stream));
