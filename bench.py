@@ -142,7 +142,7 @@ class ClockSampler:
                         self.reasons.add(name)
             except Exception:
                 pass
-            self._stop.wait(0.02)
+            self._stop.wait(0.004)
 
     def __enter__(self):
         if self.nv:
