@@ -524,8 +524,14 @@ def run_gpu_sharded(args, w):
     d_q = [torch.from_numpy(q).cuda() for q in qb]
     torch.cuda.synchronize()
     out = None
+    # --pipeline-exchange: the exchange step of batch i (all-gather + merge) runs on a side stream and overlaps
+    # the shard searches of batch i+1 (join() puts the last exchange inside the timed region).  Off by default:
+    # measured SLOWER (2 GPUs, deep-sharded: 2.43 M vs 2.68 M QPS) — the NCCL kernels queue behind the
+    # persistent traversal grid that already owns every SM slot.
+    pipelined = args.pipeline_exchange
     for i in range(args.warmup):
-        out = ix.search(d_q[i % n_batches], nq, k)
+        out = ix.search(d_q[i % n_batches], nq, k, pipelined=pipelined)
+    ix.join()
     for s_ in ix.shards:
         s_.reset_stats()
     barrier()
@@ -533,7 +539,8 @@ def run_gpu_sharded(args, w):
     with ClockSampler(local_rank) as clocks:
         e0.record()
         for i in range(args.steps):
-            out = ix.search(d_q[(args.warmup + i) % n_batches], nq, k)
+            out = ix.search(d_q[(args.warmup + i) % n_batches], nq, k, pipelined=pipelined)
+        ix.join()
         e1.record()
         torch.cuda.synchronize()
     barrier()
@@ -569,7 +576,8 @@ def run_gpu_sharded(args, w):
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": w["desc"], "k": k, "ef_search": w["ef"], "queries_per_step": nq,
                        "parallelism": f"{w['shards']} shards over {world} GPUs ({len(mine)} per GPU), "
-                                      "all_gather(nq*k*8 B per rank) + hs_topk_merge_device",
+                                      "all_gather(nq*k*8 B per rank) + hs_topk_merge_device"
+                                      + (", exchange of batch i overlapped with the searches of batch i+1" if pipelined else ""),
                        "recall_at_10": recall, "l2": "shards >> L2; a different query batch every step"},
             "roofline": {"bound": "hbm", "achieved": per_gpu, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                          "frac": per_gpu / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_src,
@@ -596,6 +604,8 @@ def main():
     ap.add_argument("--no-overlap", action="store_true",
                     help="do not let consecutive batches overlap on the stream (hs_set_overlap off)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--pipeline-exchange", action="store_true",
+                    help="sharded workloads: run all-gather + merge of batch i on a side stream (see run_gpu_sharded)")
     args = ap.parse_args()
     args.warmup = max(3, args.warmup) if args.impl == "ours" else max(1, args.warmup)
     w = dict(WORKLOADS[args.workload])

@@ -102,6 +102,7 @@ class ShardedIndex:
         for s in self.shards:
             s.set_overlap(True)
         self.dim = dim
+        self._side = None                    # stream of the pipelined exchange step (search(pipelined=True))
 
     def set_ef(self, ef: int) -> None:
         for s in self.shards:
@@ -127,6 +128,30 @@ class ShardedIndex:
                                     out_d.data_ptr(), stream)
         return out_l, out_d
 
-    def search(self, d_queries, nq: int, k: int, group=None):
+    def search(self, d_queries, nq: int, k: int, group=None, pipelined: bool = False):
+        """Global top-k of one batch.  pipelined=True runs the exchange step (all-gather + merge) on
+        a side stream, so the NEXT batch's shard searches — enqueued on the caller's stream — do
+        not wait for it: a stream of batches then costs max(search, exchange) per batch instead of
+        their sum — in principle: measured on 2 B200s it is slower (2.43 M vs 2.68 M QPS), because the
+        NCCL kernels queue behind the persistent traversal grid that owns every SM slot, so it is off
+        by default.  The returned tensors are complete once join() (or a device synchronize) has
+        been called."""
         l, d = self.search_local(d_queries, nq, k)
-        return gather_and_merge(l, d, k, group=group)
+        if not pipelined:
+            return gather_and_merge(l, d, k, group=group)
+        import torch
+        if self._side is None:
+            self._side = torch.cuda.Stream()
+        main = torch.cuda.current_stream()
+        self._side.wait_stream(main)
+        with torch.cuda.stream(self._side):
+            out = gather_and_merge(l, d, k, group=group)
+        l.record_stream(self._side)          # allocated on the caller's stream, consumed on the side stream
+        d.record_stream(self._side)
+        return out
+
+    def join(self) -> None:
+        """Make the caller's stream wait for every pipelined exchange issued so far."""
+        import torch
+        if self._side is not None:
+            torch.cuda.current_stream().wait_stream(self._side)

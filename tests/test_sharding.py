@@ -108,3 +108,10 @@ def test_sharded_index_local_shards_on_gpu(kind, tmp_path):
     gt, _ = capi.bruteforce_knn(base, q, k)
     rec = np.mean([len(set(a) & set(b)) / k for a, b in zip(lab, gt)])
     assert rec >= 0.97, rec
+    # a pipelined stream of batches (exchange step on a side stream): same rows after join()
+    outs = [ix.search(dq, nq, k, pipelined=True) for _ in range(4)]
+    ix.join()
+    torch.cuda.current_stream().synchronize()
+    for pl, pd in outs:
+        assert np.array_equal(pl.cpu().numpy().view(np.uint32), want_l)
+        assert np.array_equal(pd.cpu().numpy().view(np.uint32), want_d.view(np.uint32))
