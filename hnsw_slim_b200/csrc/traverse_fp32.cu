@@ -228,7 +228,9 @@ __global__ void __launch_bounds__(128, HS_TRAVERSE_MIN_CTAS) traverse_kernel(con
     }
 
     // ---- base layer, slim.h:321-457 ----
-    const bool opt_prefetch = p.flags & 1u, opt_spec = p.flags & 2u, opt_keep = p.flags & 8u;
+    // evict_last on the adjacency prefetch: +1 % with 512-byte rows, -2 % with 3840-byte rows (200k x 960),
+    // where the lines it pins compete with row lines that other queries would have hit: small dims only
+    const bool opt_prefetch = p.flags & 1u, opt_spec = p.flags & 2u, opt_keep = (p.flags & 8u) && CPL > 0;
     uint32_t spec_node = kInvalid, spec_ids = kInvalid;
     for (;;) {
       if (p.flags & 4u) break;    // profiling aid (HS_TRAVERSE_FLAGS bit 2): time the descent alone
