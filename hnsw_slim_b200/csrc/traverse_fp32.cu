@@ -15,13 +15,14 @@
 // the reference either (its distance exceeds lowerBound from then on), so visited sets,
 // distance counts and results coincide except where two distances tie bit-for-bit.
 //
-// The pool is UNSORTED and column-distributed: lane l owns entries l, l+32, ... and caches
-// its column's closest-unexpanded and worst keys in registers; the warp-wide best / worst
-// are single REDUX (__reduce_min/max_sync) instructions plus a ballot, so a hop needs no
-// binary search and no shifting.  Per-warp shared memory: the pool, an open-addressing
-// visited hash (replaces the N-entry tag array of visited_list_pool.h), 32 staging ids and
-// — for large dim — the query.  Vector rows are read with 128-bit loads, 8 lanes per row (4 rows per warp
-// instruction), fp32 FMA chains per lane, xor-shuffle reduction 4,2,1.
+// The pool is UNSORTED and column-distributed (lane l owns entries l, l+32, ...), in registers
+// for ef <= 256 (RegPool32: 32-bit distance words, one VIMNMX3 per lane + one REDUX per warp for
+// the closest unexpanded / worst entry), in shared memory above (SmemPool); a hop needs no binary
+// search and no shifting.  Per-warp shared memory: an open-addressing visited hash (replaces the
+// N-entry tag array of visited_list_pool.h; it moves to global memory — traverse_fp32_g.cu — when
+// it would cost too many resident warps), 32 staging ids and, for large dims, the query.  Vector
+// rows are read with 128-bit loads, 8 lanes per row (4 rows per warp instruction), two packed
+// fp32 FMA chains per lane (FADD2/FFMA2), xor-shuffle reduction 4,2,1.
 #include <cuda_runtime.h>
 
 #include <algorithm>
