@@ -24,6 +24,8 @@ EXPORTS = [
     "hs_build_params_default", "hs_build_slim_graph", "hs_build_hnsw_graph",
     "hs_get_query_tconst", "hs_set_query_tconst", "hs_slimq_prepare", "hs_build_slimq_graph",
     "hs_slimq_default_tconst", "hs_debug_bf_tc_fallback", "hs_set_overlap",
+    "hs_search_batch_device_scatter", "hs_exchange_create", "hs_exchange_handle", "hs_exchange_connect",
+    "hs_exchange_search", "hs_exchange_signal_and_wait", "hs_exchange_tables", "hs_exchange_free",
 ]
 
 
@@ -106,11 +108,20 @@ def lib():
         L.hs_build_slimq_graph.argtypes = [vp, sz, sz, C.POINTER(BuildParams), vp, sz, vp, vp, C.c_char_p]
         L.hs_slimq_default_tconst.argtypes = [sz]
         L.hs_set_overlap.argtypes = [vp, i32]
+        L.hs_search_batch_device_scatter.argtypes = [vp, vp, sz, sz, vp, vp, sz, sz, vp]
+        L.hs_exchange_create.argtypes = [i32, i32, i32, sz, sz, sz, C.POINTER(vp)]
+        L.hs_exchange_handle.argtypes = [vp, vp]
+        L.hs_exchange_connect.argtypes = [vp, vp]
+        L.hs_exchange_search.argtypes = [vp, vp, vp, sz, sz, sz, C.c_uint32, vp]
+        L.hs_exchange_signal_and_wait.argtypes = [vp, C.c_uint32, vp]
+        L.hs_exchange_tables.argtypes = [vp, C.c_uint32, C.POINTER(vp), C.POINTER(vp)]
+        L.hs_exchange_free.argtypes = [vp]
+        L.hs_exchange_free.restype = None
         L.hs_get_query_tconst.argtypes = [vp, C.POINTER(C.c_double)]
         L.hs_set_query_tconst.argtypes = [vp, C.c_double]
         L.hs_slimq_prepare.argtypes = [vp, vp, sz, vp, vp, vp, vp]
         for name in EXPORTS:
-            if name not in ("hs_last_error", "hs_free", "hs_debug_free", "hs_build_params_default",
+            if name not in ("hs_last_error", "hs_free", "hs_debug_free", "hs_build_params_default", "hs_exchange_free",
                             "hs_slimq_default_tconst", "hs_debug_bf_tc_fallback"):
                 getattr(L, name).restype = i32
         L.hs_slimq_default_tconst.restype = C.c_double
@@ -248,6 +259,55 @@ class Index:
 
     def reset_stats(self) -> None:
         _check(lib().hs_reset_stats(self._h))
+
+
+class Exchange:
+    """hs_exchange: the gather tables + flags of one rank for the fused sharded exchange."""
+
+    def __init__(self, device: int, world: int, rank: int, slots: int, nq_max: int, k: int):
+        self._h = C.c_void_p()
+        _check(lib().hs_exchange_create(device, world, rank, slots, nq_max, k, C.byref(self._h)))
+        self.world, self.rank, self.slots, self.k = world, rank, slots, k
+
+    def handle(self) -> bytes:
+        buf = C.create_string_buffer(64)
+        _check(lib().hs_exchange_handle(self._h, buf))
+        return buf.raw
+
+    def connect(self, handles: bytes) -> None:
+        assert len(handles) == 64 * self.world
+        _check(lib().hs_exchange_connect(self._h, handles))
+
+    def search(self, index: "Index", d_queries: int, nq: int, slot: int, seq: int, stream: int = 0) -> None:
+        _check(lib().hs_exchange_search(self._h, index.handle, d_queries, nq, self.k, slot, seq, stream))
+
+    def signal_and_wait(self, seq: int, stream: int = 0) -> None:
+        _check(lib().hs_exchange_signal_and_wait(self._h, seq, stream))
+
+    def tables(self, seq: int):
+        l, d = C.c_void_p(), C.c_void_p()
+        _check(lib().hs_exchange_tables(self._h, seq, C.byref(l), C.byref(d)))
+        return l.value, d.value
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            lib().hs_exchange_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def search_device_scatter(index: "Index", d_queries: int, nq: int, k: int, label_dsts, dist_dsts, slot: int,
+                          stream: int = 0) -> None:
+    """hs_search_batch_device_scatter: rows go to slot `slot` of every destination table."""
+    n = len(label_dsts)
+    la = (C.c_void_p * n)(*label_dsts)
+    da = (C.c_void_p * n)(*dist_dsts)
+    _check(lib().hs_search_batch_device_scatter(index.handle, d_queries, nq, k, la, da, n, slot, stream))
 
 
 def build_slim_graph(base, path: str, *, metric: int = HS_METRIC_L2, M: int = 16, ef_construction: int = 200,

@@ -1,4 +1,5 @@
 // C ABI of libhnswslim_b200.so (include/hnswslim_b200.h): index lifetime, batched search.
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include <cmath>
@@ -7,6 +8,7 @@
 #include <memory>
 #include <mutex>
 #include <string>
+#include <vector>
 
 #include "bruteforce.cuh"
 #include "hs_internal.h"
@@ -297,7 +299,8 @@ struct PrepDump {
 };
 
 int search_device_slimq(hs_index *ix, const float *d_queries, size_t nq, size_t k, uint32_t *d_labels,
-                        float *d_dists, uint32_t *d_perq, cudaStream_t stream, const PrepDump *dump) {
+                        float *d_dists, uint32_t *d_perq, cudaStream_t stream, const PrepDump *dump,
+                        const ScatterDst *scatter = nullptr) {
   TraverseQParams p{};
   p.qrec = ix->d_qrec;
   p.vec = reinterpret_cast<const float4 *>(ix->d_vec);
@@ -328,6 +331,7 @@ int search_device_slimq(hs_index *ix, const float *d_queries, size_t nq, size_t 
   p.ef = (uint32_t)ix->info.ef;       // pool capacity = ef_ (setEf, slimq.h:346-349), not max(ef, k)
   p.out_labels = d_labels;
   p.out_dists = d_dists;
+  if (scatter) p.scatter = *scatter;
   if (dump) {
     p.prep_rotated = dump->rotated;
     p.prep_planes = dump->planes;
@@ -363,8 +367,8 @@ int search_device_slimq(hs_index *ix, const float *d_queries, size_t nq, size_t 
 }
 
 int search_device(hs_index *ix, const float *d_queries, size_t nq, size_t k, uint32_t *d_labels,
-                  float *d_dists, uint32_t *d_perq, cudaStream_t stream) {
-  if (!ix || (!d_queries && nq) || (!d_labels && nq) || k == 0) {
+                  float *d_dists, uint32_t *d_perq, cudaStream_t stream, const ScatterDst *scatter = nullptr) {
+  if (!ix || (!d_queries && nq) || (!d_labels && nq && !(scatter && scatter->n)) || k == 0) {
     set_error("null argument / k == 0");
     return HS_ERR_ARG;
   }
@@ -373,7 +377,8 @@ int search_device(hs_index *ix, const float *d_queries, size_t nq, size_t k, uin
     set_error("nq or k too large");
     return HS_ERR_ARG;
   }
-  if (ix->info.kind == HS_KIND_SLIMQ) return search_device_slimq(ix, d_queries, nq, k, d_labels, d_dists, d_perq, stream, nullptr);
+  if (ix->info.kind == HS_KIND_SLIMQ)
+    return search_device_slimq(ix, d_queries, nq, k, d_labels, d_dists, d_perq, stream, nullptr, scatter);
   TraverseParams p{};
   p.vec = reinterpret_cast<const float4 *>(ix->d_vec);
   p.adj0 = ix->d_adj0;
@@ -397,6 +402,7 @@ int search_device(hs_index *ix, const float *d_queries, size_t nq, size_t k, uin
   p.ef = (uint32_t)std::max<size_t>(ix->info.ef, k);   // slim.h:2080
   p.out_labels = d_labels;
   p.out_dists = d_dists;
+  if (scatter) p.scatter = *scatter;
   const unsigned int seq = ix->launch_seq++;
   p.work_counter = ix->d_work + (seq % kWorkRing);
   p.launch_tag = seq;
@@ -722,6 +728,186 @@ int hs_search_batch_counts(hs_index *ix, const float *queries, size_t nq, size_t
 int hs_search_batch_device(hs_index *ix, const float *d_queries, size_t nq, size_t k, uint32_t *d_labels,
                            float *d_dists, void *stream) {
   return search_device(ix, d_queries, nq, k, d_labels, d_dists, nullptr, static_cast<cudaStream_t>(stream));
+}
+
+int hs_search_batch_device_scatter(hs_index *ix, const float *d_queries, size_t nq, size_t k,
+                                   uint32_t *const *d_labels_dsts, float *const *d_dists_dsts, size_t n_dsts,
+                                   size_t slot, void *stream) {
+  if (!d_labels_dsts || !d_dists_dsts || n_dsts == 0 || n_dsts > (size_t)kMaxScatter) {
+    set_error("hs_search_batch_device_scatter: 1.." + std::to_string(kMaxScatter) + " destinations required");
+    return HS_ERR_ARG;
+  }
+  ScatterDst sc;
+  sc.n = (uint32_t)n_dsts;
+  sc.row0 = (unsigned long long)slot * nq;
+  for (size_t i = 0; i < n_dsts; ++i) {
+    if (!d_labels_dsts[i] || !d_dists_dsts[i]) {
+      set_error("hs_search_batch_device_scatter: null destination");
+      return HS_ERR_ARG;
+    }
+    sc.labels[i] = d_labels_dsts[i];
+    sc.dists[i] = d_dists_dsts[i];
+  }
+  return search_device(ix, d_queries, nq, k, nullptr, nullptr, nullptr, static_cast<cudaStream_t>(stream), &sc);
+}
+
+// ---- hs_exchange: the gather buffers of the sharded path, shared between the ranks of one box ----
+}  // extern "C"
+
+struct hs_exchange {
+  int device = 0, world = 1, rank = 0;
+  size_t rows = 0, k = 0;                  // rows = slots * nq_max per table
+  uint8_t *base = nullptr;                 // own allocation: [2 x labels][2 x dists][flags]
+  size_t bytes = 0;
+  std::vector<uint8_t *> peer;             // base address of every rank's allocation in THIS process
+  CUresult (*write32)(CUstream, CUdeviceptr, cuuint32_t, unsigned int) = nullptr;
+  CUresult (*wait32)(CUstream, CUdeviceptr, cuuint32_t, unsigned int) = nullptr;
+  size_t off_labels(int parity) const { return (size_t)parity * rows * k * 4; }
+  size_t off_dists(int parity) const { return 2 * rows * k * 4 + (size_t)parity * rows * k * 4; }
+  size_t off_flags() const { return 4 * rows * k * 4; }
+};
+
+extern "C" {
+
+int hs_exchange_create(int device, int world, int rank, size_t slots, size_t nq_max, size_t k, hs_exchange **out) {
+  if (!out || world < 1 || world > kMaxScatter || rank < 0 || rank >= world || slots == 0 || nq_max == 0 || k == 0) {
+    set_error("hs_exchange_create: bad argument (world <= " + std::to_string(kMaxScatter) + ")");
+    return HS_ERR_ARG;
+  }
+  *out = nullptr;
+  int rc = select_device(device);
+  if (rc != HS_OK) return rc;
+  std::unique_ptr<hs_exchange> ex(new hs_exchange);
+  ex->device = device;
+  ex->world = world;
+  ex->rank = rank;
+  ex->rows = slots * nq_max;
+  ex->k = k;
+  ex->bytes = ex->off_flags() + 256;
+  void *fn = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuStreamWriteValue32", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn) {
+    set_error("cuStreamWriteValue32 is not available from this driver");
+    return HS_ERR_CUDA;
+  }
+  ex->write32 = reinterpret_cast<decltype(ex->write32)>(fn);
+  if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn) {
+    set_error("cuStreamWaitValue32 is not available from this driver");
+    return HS_ERR_CUDA;
+  }
+  ex->wait32 = reinterpret_cast<decltype(ex->wait32)>(fn);
+  cudaError_t e = cudaMalloc(reinterpret_cast<void **>(&ex->base), ex->bytes);
+  if (e != cudaSuccess) {
+    set_error(std::string("hs_exchange_create: cudaMalloc: ") + cudaGetErrorString(e));
+    return HS_ERR_NOMEM;
+  }
+  HS_CUDA(cudaMemset(ex->base, 0, ex->bytes));
+  ex->peer.assign(world, nullptr);
+  ex->peer[rank] = ex->base;
+  *out = ex.release();
+  return HS_OK;
+}
+
+int hs_exchange_handle(hs_exchange *ex, void *handle64) {
+  if (!ex || !handle64) {
+    set_error("null argument");
+    return HS_ERR_ARG;
+  }
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  cudaIpcMemHandle_t h;
+  HS_CUDA(cudaSetDevice(ex->device));
+  HS_CUDA(cudaIpcGetMemHandle(&h, ex->base));
+  std::memcpy(handle64, &h, 64);
+  return HS_OK;
+}
+
+int hs_exchange_connect(hs_exchange *ex, const void *handles) {
+  if (!ex || !handles) {
+    set_error("null argument");
+    return HS_ERR_ARG;
+  }
+  HS_CUDA(cudaSetDevice(ex->device));
+  for (int r = 0; r < ex->world; ++r) {
+    if (r == ex->rank) continue;
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, static_cast<const uint8_t *>(handles) + 64 * (size_t)r, 64);
+    void *p = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+      set_error("cudaIpcOpenMemHandle(rank " + std::to_string(r) + "): " + cudaGetErrorString(e));
+      cudaGetLastError();
+      return HS_ERR_CUDA;
+    }
+    ex->peer[r] = static_cast<uint8_t *>(p);
+  }
+  return HS_OK;
+}
+
+int hs_exchange_search(hs_exchange *ex, hs_index *ix, const float *d_queries, size_t nq, size_t k, size_t slot,
+                       unsigned int seq, void *stream) {
+  if (!ex || nq * (slot + 1) > ex->rows || k != ex->k) {
+    set_error("hs_exchange_search: slot / nq / k outside the exchange's shape");
+    return HS_ERR_ARG;
+  }
+  uint32_t *labs[kMaxScatter];
+  float *dsts[kMaxScatter];
+  for (int r = 0; r < ex->world; ++r) {
+    if (!ex->peer[r]) {
+      set_error("hs_exchange_search: exchange not connected");
+      return HS_ERR_ARG;
+    }
+    labs[r] = reinterpret_cast<uint32_t *>(ex->peer[r] + ex->off_labels(seq & 1));
+    dsts[r] = reinterpret_cast<float *>(ex->peer[r] + ex->off_dists(seq & 1));
+  }
+  // the tables of one batch are laid out [slot][nq][k] with the CALL's nq (all ranks use the same)
+  return hs_search_batch_device_scatter(ix, d_queries, nq, k, labs, dsts, (size_t)ex->world, slot, stream);
+}
+
+int hs_exchange_signal_and_wait(hs_exchange *ex, unsigned int seq, void *stream) {
+  if (!ex || seq == 0) {
+    set_error("hs_exchange_signal_and_wait: sequence numbers start at 1");
+    return HS_ERR_ARG;
+  }
+  CUstream s = static_cast<CUstream>(stream);
+  // stream-ordered: after this rank's shard searches of batch `seq`, tell every rank (flag word
+  // [this rank] in ITS allocation, release semantics), then hold the stream until every rank has
+  // told us — copy-engine-free and SM-free: the traversal grids keep the SMs
+  for (int r = 0; r < ex->world; ++r) {
+    const CUdeviceptr a = reinterpret_cast<CUdeviceptr>(ex->peer[r] + ex->off_flags()) + 4u * (unsigned)ex->rank;
+    const CUresult cr = ex->write32(s, a, seq, 0 /* CU_STREAM_WRITE_VALUE_DEFAULT */);
+    if (cr != CUDA_SUCCESS) {
+      set_error("cuStreamWriteValue32 failed (" + std::to_string((int)cr) + ")");
+      return HS_ERR_CUDA;
+    }
+  }
+  for (int r = 0; r < ex->world; ++r) {
+    const CUdeviceptr a = reinterpret_cast<CUdeviceptr>(ex->base + ex->off_flags()) + 4u * (unsigned)r;
+    const CUresult cr = ex->wait32(s, a, seq, 0 /* CU_STREAM_WAIT_VALUE_GEQ */);
+    if (cr != CUDA_SUCCESS) {
+      set_error("cuStreamWaitValue32 failed (" + std::to_string((int)cr) + ")");
+      return HS_ERR_CUDA;
+    }
+  }
+  return HS_OK;
+}
+
+int hs_exchange_tables(hs_exchange *ex, unsigned int seq, uint32_t **d_labels, float **d_dists) {
+  if (!ex || !d_labels || !d_dists) {
+    set_error("null argument");
+    return HS_ERR_ARG;
+  }
+  *d_labels = reinterpret_cast<uint32_t *>(ex->base + ex->off_labels(seq & 1));
+  *d_dists = reinterpret_cast<float *>(ex->base + ex->off_dists(seq & 1));
+  return HS_OK;
+}
+
+void hs_exchange_free(hs_exchange *ex) {
+  if (!ex) return;
+  cudaSetDevice(ex->device);
+  for (int r = 0; r < ex->world; ++r)
+    if (r != ex->rank && ex->peer[r]) cudaIpcCloseMemHandle(ex->peer[r]);
+  cudaFree(ex->base);
+  delete ex;
 }
 
 int hs_bruteforce_knn_device(const float *d_base, size_t n, size_t dim, const float *d_queries, size_t nq,

@@ -16,6 +16,18 @@ constexpr int kRowAlignFloats = 32;   // 128-byte rows: dim padded to a multiple
 
 void set_error(const std::string &msg);
 
+// Fused exchange of the sharded path (hs_search_batch_device_scatter): besides (or instead of) its
+// own output tables a traversal kernel stores every result row into the gather buffers of up to
+// kMaxScatter ranks — local memory, or peer memory mapped over NVLink (CUDA IPC) — at row
+// row0 + query, so the "all-gather" of the per-shard top-k lists costs no collective call at all.
+constexpr int kMaxScatter = 16;
+struct ScatterDst {
+  uint32_t n = 0;                          // 0: plain out_labels / out_dists
+  unsigned long long row0 = 0;             // first row of this shard's slot in every destination table
+  uint32_t *labels[kMaxScatter] = {};
+  float *dists[kMaxScatter] = {};
+};
+
 // A .graph file flattened on the host, ready to upload (see DESIGN.md "HBM layout").
 struct HostGraph {
   // header, as stored by saveIndex (slim.h:717-739 / slimq.h:1161-1190)

@@ -319,9 +319,16 @@ __global__ void __launch_bounds__(128, HS_TRAVERSE_MIN_CTAS) traverse_kernel(con
           const uint32_t r = (i & ~31u) + (uint32_t)lane;
           if (r <= i) {
             const bool have = mine_out != NONE;
-            p.out_labels[(size_t)qi * p.k + r] = have ? __ldg(p.labels + (uint32_t)mine_out) : 0xFFFFFFFFu;
-            if (p.out_dists)
-              p.out_dists[(size_t)qi * p.k + r] = have ? ord2f((uint32_t)(mine_out >> 32)) : __int_as_float(0x7f800000);
+            const uint32_t out_l = have ? __ldg(p.labels + (uint32_t)mine_out) : 0xFFFFFFFFu;
+            const float out_d = have ? ord2f((uint32_t)(mine_out >> 32)) : __int_as_float(0x7f800000);
+            if (p.out_labels) p.out_labels[(size_t)qi * p.k + r] = out_l;
+            if (p.out_dists) p.out_dists[(size_t)qi * p.k + r] = out_d;
+            // sharded path: the same row goes straight into every rank's gather buffer
+            for (uint32_t t = 0; t < p.scatter.n; ++t) {
+              const size_t at = ((size_t)p.scatter.row0 + qi) * p.k + r;
+              p.scatter.labels[t][at] = out_l;
+              p.scatter.dists[t][at] = out_d;
+            }
           }
           mine_out = NONE;
         }

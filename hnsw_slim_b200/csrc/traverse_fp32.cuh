@@ -24,6 +24,7 @@ struct TraverseParams {
   uint32_t nq, dim, k, ef;
   uint32_t *out_labels;                    // nq x k
   float *out_dists;                        // nq x k or null
+  ScatterDst scatter;                      // extra destinations (sharded path), see hs_internal.h
   // scratch / counters
   unsigned long long *work_counter;        // one slot of the ring of tagged counters (next_ticket)
   uint32_t launch_tag;                     // launch sequence number: the counter's tag

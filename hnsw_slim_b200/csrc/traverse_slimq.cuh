@@ -28,6 +28,7 @@ struct TraverseQParams {
   uint32_t nq, dim, k, ef;
   uint32_t *out_labels;                    // nq x k
   float *out_dists;                        // nq x k or null
+  ScatterDst scatter;                      // extra destinations (sharded path), see hs_internal.h
   // optional dump of the per-query preparation (hs_slimq_prepare); search is skipped when set
   float *prep_rotated;                     // nq x padded_dim
   unsigned long long *prep_planes;         // nq x words*4

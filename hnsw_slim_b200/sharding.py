@@ -103,6 +103,7 @@ class ShardedIndex:
             s.set_overlap(True)
         self.dim = dim
         self._side = None                    # stream of the pipelined exchange step (search(pipelined=True))
+        self._ex = None                      # fused exchange (connect_exchange / search_fused)
 
     def set_ef(self, ef: int) -> None:
         for s in self.shards:
@@ -149,6 +150,40 @@ class ShardedIndex:
         l.record_stream(self._side)          # allocated on the caller's stream, consumed on the side stream
         d.record_stream(self._side)
         return out
+
+    # ---- exchange fused into the traversal kernel (no collective) ----
+    def connect_exchange(self, rank: int, world: int, n_shards_total: int, nq_max: int, k: int, device: int,
+                         group=None):
+        """Create this rank's gather tables and map every other rank's (CUDA IPC; the 64-byte handles
+        travel through torch.distributed).  Call once, collectively."""
+        import torch.distributed as dist
+        ex = self.capi.Exchange(device, world, rank, n_shards_total, nq_max, k)
+        if world > 1:
+            handles = [None] * world
+            dist.all_gather_object(handles, ex.handle(), group=group)
+            ex.connect(b"".join(handles))
+        self._ex, self._ex_rank, self._ex_world, self._ex_slots, self._ex_seq = ex, rank, world, n_shards_total, 0
+        return ex
+
+    def search_fused(self, d_queries, nq: int, k: int):
+        """Global top-k of one batch with the exchange fused into the traversal kernels: every local
+        shard's kernel stores its rows into slot (rank * shards_per_rank + i) of EVERY rank's gather
+        table (peer memory over NVLink), a stream-ordered flag exchange tells when all rows of the
+        batch have landed, and hs_topk_merge_device reads the local table.  No all-gather call."""
+        import torch
+        ex = self._ex
+        self._ex_seq += 1
+        seq = self._ex_seq
+        stream = torch.cuda.current_stream().cuda_stream
+        n_loc = len(self.shards)
+        for i, s in enumerate(self.shards):
+            ex.search(s, d_queries.data_ptr(), nq, self._ex_rank * n_loc + i, seq, stream)
+        ex.signal_and_wait(seq, stream)
+        tl, td = ex.tables(seq)
+        out_l = torch.empty((nq, k), dtype=torch.int32, device=d_queries.device)
+        out_d = torch.empty((nq, k), dtype=torch.float32, device=d_queries.device)
+        self.capi.topk_merge_device(tl, td, self._ex_slots, nq, k, out_l.data_ptr(), out_d.data_ptr(), stream)
+        return out_l, out_d
 
     def join(self) -> None:
         """Make the caller's stream wait for every pipelined exchange issued so far."""

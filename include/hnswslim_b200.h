@@ -171,6 +171,40 @@ int hs_search_batch_counts(hs_index *, const float *queries, size_t nq, size_t k
 int hs_search_batch_device(hs_index *, const float *d_queries, size_t nq, size_t k,
                            uint32_t *d_labels, float *d_dists, void *stream);
 
+/* ---- Sharded corpora: the exchange fused into the traversal kernel ------------------------------
+ * (no reference analogue)  Instead of searching, all-gathering and merging, every
+ * rank lets its traversal kernel store each result row of shard `slot` DIRECTLY into the gather
+ * tables of all ranks of the box — its own memory and peer memory mapped over NVLink (CUDA IPC) —
+ * so the exchange costs no collective call and no extra kernel.  A stream-ordered flag write /
+ * flag wait per rank (cuStreamWriteValue32 / cuStreamWaitValue32: no SM, no copy engine) tells
+ * when every rank's rows of a batch have arrived; hs_topk_merge_device then reads the local table.
+ *
+ * hs_search_batch_device_scatter is the kernel-level piece: hs_search_batch_device whose rows go to
+ * n_dsts (<= 16) destination tables of shape [slots x nq x k] at slot `slot` (device pointers
+ * valid in this process).
+ *
+ * hs_exchange owns the tables (double-buffered by batch parity) and the flags of one rank:
+ *   create    allocates them on `device`; slots = total number of shards over all ranks
+ *   handle    64-byte CUDA IPC handle of the allocation, to be all-gathered by the caller
+ *   connect   maps the other ranks' allocations (handles = world x 64 bytes, rank-major)
+ *   search    this rank's shard `slot` for batch `seq` (1, 2, ...), scattered to every rank
+ *   signal_and_wait   after the rank's last shard of batch `seq`: announce, then hold the stream
+ *             until every rank has announced `seq`
+ *   tables    this rank's gathered [slots x nq x k] tables of batch `seq` for hs_topk_merge_device
+ * All ranks must use the same nq and k for a given seq, and merge batch seq before searching seq+2. */
+int hs_search_batch_device_scatter(hs_index *, const float *d_queries, size_t nq, size_t k,
+                                   uint32_t *const *d_labels_dsts, float *const *d_dists_dsts, size_t n_dsts,
+                                   size_t slot, void *stream);
+typedef struct hs_exchange hs_exchange;
+int hs_exchange_create(int device, int world, int rank, size_t slots, size_t nq_max, size_t k, hs_exchange **out);
+int hs_exchange_handle(hs_exchange *, void *handle64);
+int hs_exchange_connect(hs_exchange *, const void *handles);
+int hs_exchange_search(hs_exchange *, hs_index *, const float *d_queries, size_t nq, size_t k, size_t slot,
+                       unsigned int seq, void *stream);
+int hs_exchange_signal_and_wait(hs_exchange *, unsigned int seq, void *stream);
+int hs_exchange_tables(hs_exchange *, unsigned int seq, uint32_t **d_labels, float **d_dists);
+void hs_exchange_free(hs_exchange *);
+
 /* Counters accumulated since the last hs_reset_stats, with the meaning of
  * metric_distance_computations / metric_hops (slim.h:70-71,371-374,2064-2065):
  * n_dist = distances evaluated, n_hops = nodes expanded (upper + base layer).

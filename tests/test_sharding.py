@@ -115,3 +115,109 @@ def test_sharded_index_local_shards_on_gpu(kind, tmp_path):
     for pl, pd in outs:
         assert np.array_equal(pl.cpu().numpy().view(np.uint32), want_l)
         assert np.array_equal(pd.cpu().numpy().view(np.uint32), want_d.view(np.uint32))
+
+
+def _build_shards(tmp, base, S, kind="slim"):
+    from hnsw_slim_b200 import capi
+    paths = []
+    for s, (lo, hi) in enumerate(sharding.shard_ranges(len(base), S)):
+        p = os.path.join(tmp, f"x{s}.graph")
+        capi.build_slim_graph(base[lo:hi], p, M=16, ef_construction=100, labels=np.arange(lo, hi, dtype=np.uint64))
+        paths.append(p)
+    return paths
+
+
+@pytest.mark.gpu
+def test_scatter_search_writes_every_destination(tmp_path):
+    """hs_search_batch_device_scatter: the rows of a search land in slot `slot` of every destination
+    table and equal the rows of the plain device search."""
+    from hnsw_slim_b200 import capi
+    from hnsw_slim_b200.synth import make_dataset
+    n, nq, dim, k = 8000, 257, 64, 10
+    base, q = make_dataset(n, nq, dim, rank=8, seed=4)
+    g = str(tmp_path / "g.graph")
+    capi.build_slim_graph(base, g, M=16, ef_construction=100)
+    ix = capi.Index(g, dim)
+    ix.set_ef(50)
+    want_l, want_d = ix.search(q, k)
+    dq = torch.from_numpy(q).cuda()
+    slots = 3
+    tabs = [(torch.full((slots, nq, k), -7, dtype=torch.int32, device="cuda"),
+             torch.full((slots, nq, k), -7.0, dtype=torch.float32, device="cuda")) for _ in range(2)]
+    s = torch.cuda.current_stream().cuda_stream
+    capi.search_device_scatter(ix, dq.data_ptr(), nq, k, [t[0].data_ptr() for t in tabs],
+                               [t[1].data_ptr() for t in tabs], 1, s)
+    torch.cuda.synchronize()
+    for tl, td in tabs:
+        assert np.array_equal(tl[1].cpu().numpy().view(np.uint32), want_l)
+        assert np.array_equal(td[1].cpu().numpy().view(np.uint32), want_d.view(np.uint32))
+        assert (tl[0] == -7).all() and (tl[2] == -7).all() and (td[0] == -7).all()      # other slots untouched
+
+
+def _fused_worker(rank, world, paths, qfile, dim, k, ef, port, outdir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.cuda.set_device(0)
+    from hnsw_slim_b200 import sharding as sh
+    q = np.load(qfile)
+    nq = q.shape[0]
+    mine = sh.shards_of_rank(len(paths), rank, world)
+    ix = sh.ShardedIndex([paths[s] for s in mine], dim, device=0)
+    ix.set_ef(ef)
+    ix.connect_exchange(rank, world, len(paths), nq, k, 0)
+    dist.barrier()
+    res = []
+    for b in range(3):                                  # three batches: both buffer parities, reuse
+        dq = torch.from_numpy(np.ascontiguousarray(np.roll(q, b, axis=0))).cuda()
+        l, d = ix.search_fused(dq, nq, k)
+        torch.cuda.synchronize()
+        res.append((l.cpu().numpy().view(np.uint32), d.cpu().numpy()))
+    np.savez(os.path.join(outdir, f"r{rank}.npz"), **{f"l{b}": r[0] for b, r in enumerate(res)},
+             **{f"d{b}": r[1] for b, r in enumerate(res)})
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+def test_fused_exchange_two_ranks_one_gpu(tmp_path):
+    """The exchange fused into the traversal kernel, two PROCESSES (ranks) sharing cuda:0: each rank
+    owns 2 of 4 shards, its kernels store result rows into BOTH ranks' gather tables (the other
+    rank's through CUDA IPC), stream-ordered flags say when a batch is complete, every rank merges
+    locally.  Both ranks must end up with the (dist, label)-sorted union of the per-shard rows."""
+    from hnsw_slim_b200 import capi
+    from hnsw_slim_b200.synth import make_dataset
+    n, nq, dim, k, ef, S = 16000, 300, 64, 10, 60, 4
+    base, q = make_dataset(n, nq, dim, rank=8, seed=31)
+    paths = _build_shards(str(tmp_path), base, S)
+    qfile = str(tmp_path / "q.npy")
+    np.save(qfile, q)
+    want = []
+    for b in range(3):
+        qb = np.ascontiguousarray(np.roll(q, b, axis=0))
+        pl, pd = [], []
+        for p in paths:
+            one = capi.Index(p, dim)
+            one.set_ef(ef)
+            l, d = one.search(qb, k)
+            pl.append(l)
+            pd.append(d)
+        want.append(sharding.merge_numpy(np.stack(pl), np.stack(pd), k))
+    port = 29000 + os.getpid() % 2000
+    ctx = mp.get_context("spawn")
+    procs = [ctx.Process(target=_fused_worker, args=(r, 2, paths, qfile, dim, k, ef, port, str(tmp_path)))
+             for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=240)
+    alive = [p for p in procs if p.is_alive()]
+    for p in alive:
+        p.kill()
+    assert not alive, "fused-exchange ranks hung"
+    assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
+    for r in range(2):
+        z = np.load(tmp_path / f"r{r}.npz")
+        for b in range(3):
+            assert np.array_equal(z[f"l{b}"], want[b][0]), (r, b)
+            assert np.array_equal(z[f"d{b}"].view(np.uint32), want[b][1].view(np.uint32)), (r, b)
