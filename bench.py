@@ -529,8 +529,26 @@ def run_gpu_sharded(args, w):
     # measured SLOWER (2 GPUs, deep-sharded: 2.43 M vs 2.68 M QPS) — the NCCL kernels queue behind the
     # persistent traversal grid that already owns every SM slot.
     pipelined = args.pipeline_exchange
+    fused = args.exchange == "fused"
+    if fused:       # rows go straight into every rank's gather table (peer memory), flags instead of a collective
+        ok = 1
+        try:
+            ix.connect_exchange(rank, world, w["shards"], nq, k, local_rank)
+        except Exception as e:      # no peer access / IPC on this box: every rank falls back to the NCCL exchange
+            log(f"[bench] rank {rank}: fused exchange unavailable ({e}); using NCCL all-gather")
+            ok = 0
+        if world > 1:
+            t = torch.tensor([ok], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+            ok = int(t.item())
+        fused = bool(ok)
+        barrier()
+
+    def search_step(dq):
+        return ix.search_fused(dq, nq, k) if fused else ix.search(dq, nq, k, pipelined=pipelined)
+
     for i in range(args.warmup):
-        out = ix.search(d_q[i % n_batches], nq, k, pipelined=pipelined)
+        out = search_step(d_q[i % n_batches])
     ix.join()
     for s_ in ix.shards:
         s_.reset_stats()
@@ -539,7 +557,7 @@ def run_gpu_sharded(args, w):
     with ClockSampler(local_rank) as clocks:
         e0.record()
         for i in range(args.steps):
-            out = ix.search(d_q[(args.warmup + i) % n_batches], nq, k, pipelined=pipelined)
+            out = search_step(d_q[(args.warmup + i) % n_batches])
         ix.join()
         e1.record()
         torch.cuda.synchronize()
@@ -576,7 +594,9 @@ def run_gpu_sharded(args, w):
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": w["desc"], "k": k, "ef_search": w["ef"], "queries_per_step": nq,
                        "parallelism": f"{w['shards']} shards over {world} GPUs ({len(mine)} per GPU), "
-                                      "all_gather(nq*k*8 B per rank) + hs_topk_merge_device"
+                                      + ("rows stored into every rank's gather table by the traversal kernels (peer memory), "
+                                       "stream-ordered flags, hs_topk_merge_device" if fused else
+                                       "all_gather(nq*k*8 B per rank) + hs_topk_merge_device")
                                       + (", exchange of batch i overlapped with the searches of batch i+1" if pipelined else ""),
                        "recall_at_10": recall, "l2": "shards >> L2; a different query batch every step"},
             "roofline": {"bound": "hbm", "achieved": per_gpu, "peak": peaks["hbm_gbs"], "unit": "GB/s",
@@ -604,6 +624,8 @@ def main():
     ap.add_argument("--no-overlap", action="store_true",
                     help="do not let consecutive batches overlap on the stream (hs_set_overlap off)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exchange", default="fused", choices=["nccl", "fused"],
+                    help="sharded workloads: NCCL all-gather, or the exchange fused into the traversal kernels")
     ap.add_argument("--pipeline-exchange", action="store_true",
                     help="sharded workloads: run all-gather + merge of batch i on a side stream (see run_gpu_sharded)")
     args = ap.parse_args()
