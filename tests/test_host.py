@@ -33,6 +33,17 @@ def test_no_cpu_fallback_without_a_device():
     with pytest.raises(capi.HsError) as e:
         capi.bruteforce_knn(np.zeros((4, 4), np.float32), np.zeros((1, 4), np.float32), 1)
     assert e.value.code == -3
+    with pytest.raises(capi.HsError) as e:                     # the fused sharded exchange needs a device too
+        capi.Exchange(0, 2, 0, 4, 100, 10)
+    assert e.value.code == -3
+
+
+def test_exchange_argument_errors():
+    for bad in [(0, 0, 0, 4, 100, 10), (0, 2, 2, 4, 100, 10), (0, 17, 0, 4, 100, 10), (0, 2, 0, 0, 100, 10),
+                (0, 2, 0, 4, 0, 10), (0, 2, 0, 4, 100, 0)]:
+        with pytest.raises(capi.HsError) as e:
+            capi.Exchange(*bad)
+        assert e.value.code == -1, bad                          # HS_ERR_ARG before any CUDA call
 
 
 @pytest.mark.parametrize("name,metric", [("slim_l2_2k", 0), ("slim_ip_1k", 1)])
