@@ -40,9 +40,10 @@ WORKLOADS = {
                    desc="SIFT-shaped synthetic 1Mx128 L2, hnsw_slim M=16 efc=200 (rank-14 latent Gaussian, seed 1)"),
     # BASELINE.json configs[3] shape (DEEP 96-dim, 8 sub-graphs, NVLink top-k merge), scaled from
     # 100M to what the host can index inside a benchmark run: 8 shards x 500k rows.
-    "deep-sharded": dict(n=4_000_000, shards=8, dim=96, metric=0, M=16, efc=200, rank=12, nq=10_000, k=10, ef=100,
-                         desc="DEEP-shaped synthetic 4Mx96 L2 in 8 sub-graphs of 500k (100M config scaled down), "
-                              "hnsw_slim M=16 efc=200, all-gather + top-k merge"),
+    "deep-sharded": dict(n=8_000_000, shards=8, dim=96, metric=0, M=16, efc=200, rank=12, nq=10_000, k=10, ef=100,
+                         desc="DEEP-shaped synthetic {n}x96 L2 in 8 sub-graphs of {rows} rows (the 100M config scaled to "
+                              "what can be indexed inside a benchmark run), hnsw_slim M=16 efc=200, rows exchanged over "
+                              "NVLink + top-k merge"),
     # BASELINE.json configs[1]: GIST-shaped, ef_search sweep 50-400 (tools/perf_probe.py --efs ...)
     "gist1m": dict(n=1_000_000, dim=960, metric=0, M=32, efc=200, rank=24, nq=10_000, k=10, ef=100,
                    desc="GIST-shaped synthetic 1Mx960 L2, hnsw_slim M=32 efc=200 (rank-24 latent Gaussian, seed 1)"),
@@ -56,10 +57,10 @@ WORKLOADS = {
                              desc="MSTuring-shaped synthetic 1Mx96 L2, hnsw_slimq (16 clusters, 1-bit RaBitQ codes + exact "
                                   "rerank) M=16 efc=200 (rank-12 latent Gaussian, seed 1)"),
     # ... and sharded like configs[4]: 8 sub-graphs over 1/2/4/8 GPUs, scaled from 100M to 8 x 500k rows
-    "msturing-sharded-slimq": dict(n=4_000_000, shards=8, dim=96, metric=0, M=16, efc=200, rank=12, nq=10_000, k=10,
+    "msturing-sharded-slimq": dict(n=8_000_000, shards=8, dim=96, metric=0, M=16, efc=200, rank=12, nq=10_000, k=10,
                                    ef=100, kind="slimq",
-                                   desc="MSTuring-shaped synthetic 4Mx96 L2 in 8 hnsw_slimq sub-graphs of 500k (100M config "
-                                        "scaled down), M=16 efc=200, all-gather + top-k merge"),
+                                   desc="MSTuring-shaped synthetic {n}x96 L2 in 8 hnsw_slimq sub-graphs of {rows} rows (100M "
+                                        "config scaled down), M=16 efc=200, rows exchanged over NVLink + top-k merge"),
     # reduced-size variants for quick local runs (not contract lines)
     "sift200k": dict(n=200_000, dim=128, metric=0, M=16, efc=200, rank=14, nq=10_000, k=10, ef=100,
                      desc="SIFT-shaped synthetic 200kx128 L2 (dev size)"),
@@ -442,6 +443,23 @@ def run_gpu(args, w):
                              f"threads ({secs:.1f}s of search, rate of the median pass); serial 1-thread loop "
                              f"(hnsw_slim_strategy.h:112-114) on 2000 queries: {qps_1:.0f} queries/s"}
 
+    # ---- the sharded path of the same run (north_star (4), BASELINE.json configs[3] shape): the driver's
+    #      --gpus 1/2/4/8 runs thereby record its strong-scaling curve next to the replicated headline ----
+    sharded = None
+    if not args.no_sharded and args.workload == "sift1m":
+        del ix, d_q, h_q
+        torch.cuda.empty_cache()
+        ws = dict(WORKLOADS["deep-sharded"])
+        if args.shard_rows:
+            ws["n"] = args.shard_rows * ws["shards"]
+        sargs = argparse.Namespace(**vars(args))
+        sargs.ef = None
+        try:
+            sharded = measure_sharded(sargs, ws, rank, local_rank, world, dist if distributed else None)
+        except Exception as e:          # the headline stands on its own; say why the object is missing
+            log(f"[bench] rank {rank}: sharded measurement failed: {e!r}")
+            sharded = {"error": repr(e)} if rank == 0 else None
+
     if rank == 0:
         out = {
             "metric": "QPS at recall@10>=0.95", "value": value, "unit": "queries/s", "n_gpus": world,
@@ -456,7 +474,7 @@ def run_gpu(args, w):
                        "l2": "index (vectors+adjacency) %.0f MiB > 126 MB L2; a different query batch every step"
                              % (info["device_bytes"] / 2**20)},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": args.steps,
-            "clocks": clocks.summary(),
+            "clocks": clocks.summary(), "sharded": sharded,
         }
         print(json.dumps(out), flush=True)
     if distributed:
@@ -464,105 +482,165 @@ def run_gpu(args, w):
         dist.destroy_process_group()
 
 
+def shard_paths(w: dict):
+    fam = "hnsw_slimq" if w.get("kind") == "slimq" else "hnsw_slim"
+    return [os.path.join(CACHE, f"{fam}_shard{s}of{w['shards']}_n{w['n']}_d{w['dim']}_r{w['rank']}_M{w['M']}"
+                                f"_e{w['efc']}_b4_s1_v2.graph") for s in range(w["shards"])]
+
+
+def shard_rows(w: dict, s: int) -> np.ndarray:
+    """Rows of shard s of the sharded corpus (chunk-addressable generator: only this shard is drawn)."""
+    from hnsw_slim_b200 import sharding
+    from hnsw_slim_b200.synth import latent_gaussian_rows
+    lo, hi = sharding.shard_ranges(w["n"], w["shards"])[s]
+    return latent_gaussian_rows(lo, hi, w["dim"], rank=w["rank"], seed=1)
+
+
 def prepare_shards(w: dict, my_shards, threads: int):
     """Shard graphs with GLOBAL labels (label = row index in the full corpus), cached on disk."""
     from hnsw_slim_b200 import capi, sharding
-    from hnsw_slim_b200.synth import latent_gaussian
     os.makedirs(CACHE, exist_ok=True)
     ranges = sharding.shard_ranges(w["n"], w["shards"])
     slimq = w.get("kind") == "slimq"
-    fam = "hnsw_slimq" if slimq else "hnsw_slim"
-    paths = [os.path.join(CACHE, f"{fam}_shard{s}of{w['shards']}_n{w['n']}_d{w['dim']}_r{w['rank']}_M{w['M']}"
-                                 f"_e{w['efc']}_b4_s1.graph") for s in range(w["shards"])]
-    missing = [s for s in my_shards if not os.path.exists(paths[s])]
-    base = None
-    if missing or slimq:
-        base = latent_gaussian(w["n"], w["dim"], rank=w["rank"], seed=1)
-        for s in missing:
+    paths = shard_paths(w)
+    raws = []
+    for s in my_shards:
+        rows = None
+        if not os.path.exists(paths[s]):
             lo, hi = ranges[s]
             t0 = time.time()
+            rows = shard_rows(w, s)
             tmp = paths[s] + f".tmp{os.getpid()}"
             if slimq:
-                capi.build_slimq_graph(base[lo:hi], tmp, M=w["M"], ef_construction=w["efc"], branching="4",
+                capi.build_slimq_graph(rows, tmp, M=w["M"], ef_construction=w["efc"], branching="4",
                                        threads=threads, labels=np.arange(lo, hi, dtype=np.uint64))
             else:
-                capi.build_slim_graph(base[lo:hi], tmp, metric=w["metric"], M=w["M"], ef_construction=w["efc"],
+                capi.build_slim_graph(rows, tmp, metric=w["metric"], M=w["M"], ef_construction=w["efc"],
                                       branching="4", threads=threads, labels=np.arange(lo, hi, dtype=np.uint64))
             os.replace(tmp, paths[s])
             log(f"[bench] built shard {s} [{lo},{hi}) in {time.time()-t0:.1f}s with {threads} threads")
-    raws = [base[ranges[s][0]:ranges[s][1]] for s in my_shards] if slimq else None
-    return paths, raws
+        if slimq:
+            raws.append(rows if rows is not None else shard_rows(w, s))
+    return paths, (raws if slimq else None)
 
 
-def run_gpu_sharded(args, w):
-    """Sharded path: S sub-graphs over N ranks, every rank searches the whole batch on its shards,
-    all-gather (NCCL over NVLink) + top-k merge.  Total work is fixed => strong scaling."""
-    import torch
-    import torch.distributed as dist
+def sharded_queries(w: dict, n_batches: int):
+    from hnsw_slim_b200.synth import latent_gaussian_rows
+    return [latent_gaussian_rows(0, w["nq"], w["dim"], rank=w["rank"], seed=1, stream=1 + b) for b in range(n_batches)]
+
+
+def sharded_ground_truth(w: dict, q: np.ndarray, k: int, device: int):
+    """Exact top-k over the whole sharded corpus, shard by shard on the GPU (hs_bruteforce_knn), merged on the
+    host: the corpus never has to exist in one piece."""
     from hnsw_slim_b200 import capi, sharding
-    from hnsw_slim_b200.synth import latent_gaussian
-    rank, local_rank, world = env_rank()
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    ranges = sharding.shard_ranges(w["n"], w["shards"])
+    labs, dsts = [], []
+    for s, (lo, hi) in enumerate(ranges):
+        l, d = capi.bruteforce_knn(shard_rows(w, s), q, k, metric=w["metric"], device=device)
+        labs.append(l.astype(np.int64) + lo)
+        dsts.append(d)
+    lab, dst = np.concatenate(labs, 1), np.concatenate(dsts, 1)
+    order = np.argsort(dst, axis=1, kind="stable")[:, :k]       # shards are in label order: ties -> smaller label
+    return np.take_along_axis(lab, order, 1).astype(np.uint32)
+
+
+EF_LADDER = [10, 12, 16, 20, 24, 32, 48, 64, 100, 200]
+
+
+def measure_sharded(args, w, rank, local_rank, world, dist):
+    """The sharded path (north_star (4)): S sub-graphs over N ranks, every rank searches the whole batch on
+    its shards, rows are exchanged by the traversal kernels (hs_shardgroup) or one NCCL all-gather, top-k
+    merge.  Total work is fixed => strong scaling.  Returns the result dict (rank 0) or None."""
+    import torch
+    from hnsw_slim_b200 import capi, sharding
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    slimq = w.get("kind") == "slimq"
+    w = dict(w, desc=w["desc"].format(n=w["n"], rows=w["n"] // w["shards"]))
     mine = sharding.shards_of_rank(w["shards"], rank, world)
+    t_build = time.time()
     paths, raws = prepare_shards(w, mine, max(1, (os.cpu_count() or 1) // world))
     barrier()
-    slimq = w.get("kind") == "slimq"
+    t_build = time.time() - t_build
     ix = sharding.ShardedIndex([paths[s] for s in mine], w["dim"], metric=w["metric"], device=local_rank,
                                kind=capi.HS_KIND_SLIMQ if slimq else capi.HS_KIND_SLIM, raw_bases=raws)
-    ix.set_ef(w["ef"])
     nq, k = w["nq"], w["k"]
     n_batches = min(8, args.warmup + args.steps)
-    qb = [latent_gaussian(nq, w["dim"], rank=w["rank"], seed=1, stream=1 + b) for b in range(n_batches)]
+    qb = sharded_queries(w, n_batches)
     d_q = [torch.from_numpy(q).cuda() for q in qb]
-    torch.cuda.synchronize()
-    out = None
-    # --pipeline-exchange: the exchange step of batch i (all-gather + merge) runs on a side stream and overlaps
-    # the shard searches of batch i+1 (join() puts the last exchange inside the timed region).  Off by default:
-    # measured SLOWER (2 GPUs, deep-sharded: 2.43 M vs 2.68 M QPS) — the NCCL kernels queue behind the
-    # persistent traversal grid that already owns every SM slot.
-    pipelined = args.pipeline_exchange
+    depth = 4
     fused = args.exchange == "fused"
-    if fused:       # rows go straight into every rank's gather table (peer memory), flags instead of a collective
-        ok = 1
+    if fused:       # rows go straight into every rank's gather table (peer memory); flags instead of a collective
         try:
-            ix.connect_exchange(rank, world, w["shards"], nq, k, local_rank)
-        except Exception as e:      # no peer access / IPC on this box: every rank falls back to the NCCL exchange
+            ix.connect(rank, world, nq, k, depth=depth)
+        except Exception as e:      # raised on every rank (connect is collective): fall back to the NCCL exchange
             log(f"[bench] rank {rank}: fused exchange unavailable ({e}); using NCCL all-gather")
-            ok = 0
-        if world > 1:
-            t = torch.tensor([ok], device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MIN)
-            ok = int(t.item())
-        fused = bool(ok)
+            fused = False
         barrier()
+    ring = 2 * depth
+    outs = [(torch.empty((nq, k), dtype=torch.int32, device="cuda"), torch.empty((nq, k), device="cuda"))
+            for _ in range(ring)]
 
-    def search_step(dq):
-        return ix.search_fused(dq, nq, k) if fused else ix.search(dq, nq, k, pipelined=pipelined)
+    def step(i):
+        if fused:
+            ix.submit(d_q[i % n_batches].data_ptr(), nq, outs[i % ring][0].data_ptr(), outs[i % ring][1].data_ptr())
+            return outs[i % ring]
+        return ix.search(d_q[i % n_batches], nq, k, exchange="nccl")
+
+    # ---- per-shard ef: the smallest rung of the ladder whose recall@10 of the MERGED result is >= 0.95 ----
+    ns = min(1000, nq)
+    gt = sharded_ground_truth(w, qb[0][:ns], k, local_rank) if rank == 0 and not args.no_recall else None
+    ef, recall, ladder = w["ef"], None, []
+    if args.ef is None and not args.no_recall:
+        for ef in EF_LADDER:
+            ix.set_ef(ef)
+            out = step(0)
+            ix.join()
+            torch.cuda.synchronize()
+            ok = torch.zeros(1, device="cuda")
+            if rank == 0:
+                lab = out[0][:ns].cpu().numpy().view(np.uint32)
+                recall = float(np.mean([len(set(a) & set(b)) / k for a, b in zip(lab, gt)]))
+                ladder.append((ef, round(recall, 4)))
+                ok += float(recall >= 0.95)
+            if world > 1:
+                dist.broadcast(ok, 0)
+            if ok.item() > 0:
+                break
+    ix.set_ef(ef)
 
     for i in range(args.warmup):
-        out = search_step(d_q[i % n_batches])
+        out = step(i)
     ix.join()
     for s_ in ix.shards:
         s_.reset_stats()
     barrier()
+    if fused:
+        ss, ms_ = ix.group.streams()
+        s0, s1 = torch.cuda.ExternalStream(ss), torch.cuda.ExternalStream(ms_)
+    else:
+        s0 = s1 = torch.cuda.current_stream()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local_rank) as clocks:
-        e0.record()
+        e0.record(s0)
         for i in range(args.steps):
-            out = search_step(d_q[(args.warmup + i) % n_batches])
+            out = step(args.warmup + i)
+        if not fused:
+            ix.join()
+        e1.record(s1)               # the merge stream: behind the last batch's merge
         ix.join()
-        e1.record()
         torch.cuda.synchronize()
     barrier()
     ms = e0.elapsed_time(e1)
+    if rank == 0 and gt is not None:
+        b_last = (args.warmup + args.steps - 1) % n_batches
+        if b_last == 0:
+            lab = out[0][:ns].cpu().numpy().view(np.uint32)
+            recall = float(np.mean([len(set(a) & set(b)) / k for a, b in zip(lab, gt)]))
     stats = [s_.stats() for s_ in ix.shards]
     infos = [s_.info() for s_ in ix.shards]
     if slimq:
@@ -571,41 +649,116 @@ def run_gpu_sharded(args, w):
     else:
         alg = sum(st["n_dist"] * 4 * inf["dim_padded"] + st["n_hops"] * (8 + 4 * inf["sum_deg0"] / inf["n"])
                   for st, inf in zip(stats, infos)) / args.steps
+    evals = sum(st["n_dist"] for st in stats) / args.steps / nq
+
+    # ---- end to end: the batch starts in pinned host memory on every rank (the "broadcast" of north_star:
+    #      each rank's kernels read it in place) and the merged rows end in pinned host memory ----
+    e2e = None
+    if fused:
+        h_q = [torch.from_numpy(q).pin_memory() for q in qb]
+        h_out = [(torch.empty((nq, k), dtype=torch.int32).pin_memory(), torch.empty((nq, k)).pin_memory())
+                 for _ in range(ring)]
+        for i in range(args.warmup):
+            ix.submit(h_q[i % n_batches].data_ptr(), nq, h_out[i % ring][0].data_ptr(), h_out[i % ring][1].data_ptr())
+        ix.join()
+        barrier()
+        t0 = time.perf_counter()
+        checksum = 0
+        for i in range(args.steps):
+            if i >= depth:                       # keep `depth` batches in flight; consume the oldest on the host
+                ix.group.wait_oldest()
+                checksum += int(h_out[(i - depth) % ring][0][0, 0])
+            ix.submit(h_q[(args.warmup + i) % n_batches].data_ptr(), nq, h_out[i % ring][0].data_ptr(),
+                      h_out[i % ring][1].data_ptr())
+        ix.join()
+        e2e_s = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e_s = float(t.item())
+        e2e = {"value": nq * args.steps / e2e_s, "unit": "queries/s", "h2d_bytes_per_step": nq * w["dim"] * 4 * len(mine),
+               "d2h_bytes_per_step": nq * k * 8,
+               "timing": f"host wall clock, max over ranks; hs_shardgroup_submit / _wait_oldest with {depth} batches in "
+                         "flight; every rank's kernels read the pinned host batch in place (once per local shard) and "
+                         "its merge kernel writes the rows to pinned host memory"}
     if world > 1:
         t = torch.tensor([ms, alg], device="cuda", dtype=torch.float64)
         tmax = t.clone()
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         ms, alg_total = float(tmax[0]), float(t[1])
+        evals_t = torch.tensor([evals], device="cuda", dtype=torch.float64)
+        dist.all_reduce(evals_t, op=dist.ReduceOp.SUM)
+        evals = float(evals_t.item())
     else:
         alg_total = alg
-    recall = None
-    if rank == 0 and not args.no_recall:
-        base = latent_gaussian(w["n"], w["dim"], rank=w["rank"], seed=1)
-        gt, _ = capi.bruteforce_knn(base, qb[(args.warmup + args.steps - 1) % n_batches][:500], k, device=local_rank)
-        lab = out[0][:500].cpu().numpy().view(np.uint32)
-        recall = float(np.mean([len(set(a) & set(b)) / k for a, b in zip(lab, gt)]))
+
+    # ---- the reference's CPU search on ONE shard (rank 0, N=1 only; bounded sample) ----
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and not slimq:
+        cpu = cpu_sharded_baseline(w, paths, qb[0], ef, budget_s=8.0)
+    ix.close()
+    if rank != 0:
+        return None
+    peaks, peak_src = measured_peaks()
+    per_gpu = alg_total / world / (ms / args.steps * 1e-3) / 1e9
+    rows = w["n"] // w["shards"]
+    return {
+        "metric": "QPS at recall@10>=0.95", "value": nq * args.steps / (ms * 1e-3), "unit": "queries/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": w["desc"], "k": k, "ef_search_per_shard": ef, "queries_per_step": nq,
+                   "shards": w["shards"], "rows_per_shard": rows, "shards_per_gpu": len(mine),
+                   "exchange": ("fused: rows stored into every rank's gather table by the traversal kernels (peer memory "
+                                "over NVLink), flags raised by the last warp of a batch, merge kernel on a second stream; "
+                                f"up to {depth} batches in flight, no collective" if fused else
+                                "nccl: one all_gather(nq*k*8 B per rank) + hs_topk_merge_device per batch"),
+                   "recall_at_10": recall, "ef_ladder": ladder, "dist_evals_per_query_all_shards": evals,
+                   "graph_build_s": round(t_build, 1),
+                   "l2": "each shard (%.0f MB of rows) vs 126 MB L2; a different query batch every step"
+                         % (rows * w["dim"] * 4 / 1e6)},
+        "roofline": {"bound": "hbm", "achieved": per_gpu, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                     "frac": per_gpu / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_src,
+                     "kernel": ("hs::traverse_slimq_kernel" if slimq else "hs::traverse_kernel")
+                               + " (per GPU, algorithmic bytes of all local shard launches / whole step incl. merge)"},
+        "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": args.steps * (len(mine) + 1),
+        "clocks": clocks.summary(),
+    }
+
+
+def cpu_sharded_baseline(w, paths, queries, ef, budget_s):
+    """The reference's OpenMP search on shard 0 alone; a query of the sharded corpus visits all S shards, so the
+    whole-corpus rate of the same algorithm on this host is that rate / S."""
+    from oracle import refharness as rh
+    cores = os.cpu_count() or 1
+    rows = w["n"] // w["shards"]
+    if rh.ref_slim_path() is None:
+        return None
+    ix = rh.RefSlim(paths[0], w["dim"], rows, w["metric"])
+    qs = queries[:2000]
+    ix.search(qs, w["k"], ef, 0)
+    times = []
+    while sum(times) < budget_s and len(times) < 200:
+        _, sec, _ = ix.search(qs, w["k"], ef, 0)
+        times.append(sec)
+    shard_qps = len(qs) / float(np.median(times))
+    return {"value": shard_qps / w["shards"], "unit": "queries/s", "cores": cores, "kind": "reference",
+            "sample": f"{len(times)} passes x {len(qs)} queries on shard 0 of {w['shards']} ({rows} rows) at ef={ef}, omp dynamic "
+                      f"over queries, {cores} threads: {shard_qps:.0f} queries/s on one shard; every query visits all "
+                      f"{w['shards']} shards, so the corpus rate is 1/{w['shards']} of it"}
+
+
+def run_gpu_sharded(args, w):
+    import torch
+    import torch.distributed as dist
+    rank, local_rank, world = env_rank()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the engine has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    line = measure_sharded(args, w, rank, local_rank, world, dist)
     if rank == 0:
-        peaks, peak_src = measured_peaks()
-        per_gpu = alg_total / world / (ms / args.steps * 1e-3) / 1e9
-        line = {
-            "metric": "QPS at recall@10>=0.95", "value": nq * args.steps / (ms * 1e-3), "unit": "queries/s",
-            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
-            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": w["desc"], "k": k, "ef_search": w["ef"], "queries_per_step": nq,
-                       "parallelism": f"{w['shards']} shards over {world} GPUs ({len(mine)} per GPU), "
-                                      + ("rows stored into every rank's gather table by the traversal kernels (peer memory), "
-                                       "stream-ordered flags, hs_topk_merge_device" if fused else
-                                       "all_gather(nq*k*8 B per rank) + hs_topk_merge_device")
-                                      + (", exchange of batch i overlapped with the searches of batch i+1" if pipelined else ""),
-                       "recall_at_10": recall, "l2": "shards >> L2; a different query batch every step"},
-            "roofline": {"bound": "hbm", "achieved": per_gpu, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                         "frac": per_gpu / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_src,
-                         "kernel": ("hs::traverse_slimq_kernel" if slimq else "hs::traverse_kernel")
-                                   + " (per GPU, whole step incl. merge + all_gather)"},
-            "cpu_baseline": None, "e2e": None, "gpu_launches": args.steps * (len(mine) + 2),
-            "clocks": clocks.summary(),
-        }
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
@@ -624,15 +777,19 @@ def main():
     ap.add_argument("--no-overlap", action="store_true",
                     help="do not let consecutive batches overlap on the stream (hs_set_overlap off)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--shard-rows", type=int, default=None,
+                    help="sharded workloads: rows per shard (default: the workload's n / shards)")
     ap.add_argument("--exchange", default="fused", choices=["nccl", "fused"],
                     help="sharded workloads: NCCL all-gather, or the exchange fused into the traversal kernels")
-    ap.add_argument("--pipeline-exchange", action="store_true",
-                    help="sharded workloads: run all-gather + merge of batch i on a side stream (see run_gpu_sharded)")
+    ap.add_argument("--no-sharded", action="store_true",
+                    help="default workload: skip the embedded deep-sharded measurement (\"sharded\" object)")
     args = ap.parse_args()
     args.warmup = max(3, args.warmup) if args.impl == "ours" else max(1, args.warmup)
     w = dict(WORKLOADS[args.workload])
     if args.ef:
         w["ef"] = args.ef
+    if args.shard_rows and "shards" in w:
+        w["n"] = args.shard_rows * w["shards"]
     if args.impl == "reference":
         run_reference(args, w)
     elif "shards" in w:

@@ -26,6 +26,9 @@ EXPORTS = [
     "hs_slimq_default_tconst", "hs_debug_bf_tc_fallback", "hs_set_overlap",
     "hs_search_batch_device_scatter", "hs_exchange_create", "hs_exchange_handle", "hs_exchange_connect",
     "hs_exchange_search", "hs_exchange_signal_and_wait", "hs_exchange_tables", "hs_exchange_free",
+    "hs_shardgroup_create", "hs_shardgroup_handle", "hs_shardgroup_connect", "hs_shardgroup_connect_local",
+    "hs_shardgroup_submit", "hs_shardgroup_wait_oldest", "hs_shardgroup_wait", "hs_shardgroup_streams",
+    "hs_shardgroup_free",
 ]
 
 
@@ -117,11 +120,22 @@ def lib():
         L.hs_exchange_tables.argtypes = [vp, C.c_uint32, C.POINTER(vp), C.POINTER(vp)]
         L.hs_exchange_free.argtypes = [vp]
         L.hs_exchange_free.restype = None
+        L.hs_shardgroup_create.argtypes = [vp, sz, i32, i32, sz, sz, i32, C.POINTER(vp)]
+        L.hs_shardgroup_handle.argtypes = [vp, vp]
+        L.hs_shardgroup_connect.argtypes = [vp, vp]
+        L.hs_shardgroup_connect_local.argtypes = [vp, sz]
+        L.hs_shardgroup_submit.argtypes = [vp, vp, sz, vp, vp]
+        L.hs_shardgroup_wait_oldest.argtypes = [vp]
+        L.hs_shardgroup_wait.argtypes = [vp]
+        L.hs_shardgroup_streams.argtypes = [vp, C.POINTER(vp), C.POINTER(vp)]
+        L.hs_shardgroup_free.argtypes = [vp]
+        L.hs_shardgroup_free.restype = None
         L.hs_get_query_tconst.argtypes = [vp, C.POINTER(C.c_double)]
         L.hs_set_query_tconst.argtypes = [vp, C.c_double]
         L.hs_slimq_prepare.argtypes = [vp, vp, sz, vp, vp, vp, vp]
         for name in EXPORTS:
             if name not in ("hs_last_error", "hs_free", "hs_debug_free", "hs_build_params_default", "hs_exchange_free",
+                            "hs_shardgroup_free",
                             "hs_slimq_default_tconst", "hs_debug_bf_tc_fallback"):
                 getattr(L, name).restype = i32
         L.hs_slimq_default_tconst.restype = C.c_double
@@ -292,6 +306,57 @@ class Exchange:
     def close(self) -> None:
         if getattr(self, "_h", None):
             lib().hs_exchange_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class ShardGroup:
+    """hs_shardgroup: one rank's local shards + gather tables + streams of the pipelined sharded search."""
+
+    def __init__(self, shards, world: int, rank: int, nq_max: int, k: int, depth: int = 4):
+        self._h = C.c_void_p()
+        self._shards = list(shards)                       # keep the indices alive: the group borrows them
+        arr = (C.c_void_p * len(self._shards))(*[s.handle for s in self._shards])
+        _check(lib().hs_shardgroup_create(arr, len(self._shards), world, rank, nq_max, k, depth, C.byref(self._h)))
+        self.world, self.rank, self.k, self.nq_max, self.depth = world, rank, k, nq_max, depth
+
+    def handle(self) -> bytes:
+        buf = C.create_string_buffer(64)
+        _check(lib().hs_shardgroup_handle(self._h, buf))
+        return buf.raw
+
+    def connect(self, handles: bytes | None) -> None:
+        assert self.world == 1 or len(handles) == 64 * self.world
+        _check(lib().hs_shardgroup_connect(self._h, handles))
+
+    @staticmethod
+    def connect_local(groups) -> None:
+        """One process driving all GPUs: groups[r] = rank r."""
+        arr = (C.c_void_p * len(groups))(*[g._h for g in groups])
+        _check(lib().hs_shardgroup_connect_local(arr, len(groups)))
+
+    def submit(self, q_ptr: int, nq: int, lab_ptr: int, dist_ptr: int | None) -> None:
+        _check(lib().hs_shardgroup_submit(self._h, q_ptr, nq, lab_ptr, dist_ptr))
+
+    def wait_oldest(self) -> None:
+        _check(lib().hs_shardgroup_wait_oldest(self._h))
+
+    def wait(self) -> None:
+        _check(lib().hs_shardgroup_wait(self._h))
+
+    def streams(self):
+        a, b = C.c_void_p(), C.c_void_p()
+        _check(lib().hs_shardgroup_streams(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            lib().hs_shardgroup_free(self._h)
             self._h = None
 
     def __del__(self):

@@ -11,9 +11,7 @@
 #include <vector>
 
 #include "bruteforce.cuh"
-#include "hs_internal.h"
-#include "traverse_fp32.cuh"
-#include "traverse_slimq.cuh"
+#include "hs_index.h"
 
 namespace hs {
 static thread_local std::string g_error;
@@ -31,64 +29,42 @@ using namespace hs;
     }                                                                                 \
   } while (0)
 
-// Launches in flight at once are bounded by what fits on the GPU (a dozen small grids); a slot is
-// reused only kWorkRing launches later.
-constexpr unsigned int kWorkRing = 1024;
+namespace hs {
+int select_device(int device) {
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) {
+    set_error(std::string("no CUDA device available (") + cudaGetErrorString(e) +
+              "); hnswslim_b200 has no CPU fallback");
+    return HS_ERR_CUDA;
+  }
+  if (device < 0 || device >= count) {
+    set_error("device ordinal out of range");
+    return HS_ERR_ARG;
+  }
+  HS_CUDA(cudaSetDevice(device));
+  return HS_OK;
+}
 
-struct hs_index {
-  hs_index_info info{};
-  int device = 0;
-  int sm_count = 148;
-  // HBM-resident index
-  float *d_vec = nullptr;
-  uint32_t *d_adj0 = nullptr;
-  int32_t *d_upper_slot = nullptr;
-  uint32_t *d_upper_adj[kMaxLevels] = {};
-  uint32_t *d_labels = nullptr;
-  uint8_t *d_deleted = nullptr;
-  // hnsw_slimq payload
-  uint2 *d_qrec = nullptr;          // n x (words + 2) uint2: code words, (f_add, f_rescale), (cluster, 0)
-  float *d_centroids = nullptr;     // num_cluster x padded_dim (rotated)
-  uint8_t *d_flip = nullptr;        // 4 * padded_dim / 8
-  uint32_t words = 0, trunc_dim = 0;
-  uint32_t level_count[kMaxLevels] = {};
-  double t_const = 0.0;
-  // per-call scratch
-  unsigned long long *d_work = nullptr;    // ring of kWorkRing tagged work counters (traverse_common.cuh)
-  unsigned int launch_seq = 1;             // tags start at 1 (slots are initialised to 0xff..ff)
-  int overlap = 0;                         // hs_set_overlap
-  unsigned long long *d_stats = nullptr;   // [0] n_dist [1] n_hops [2] n_rerank
-  // staging for the host-buffer entry points
-  cudaStream_t stream = nullptr;
-  float *d_q = nullptr;
-  uint32_t *d_lab = nullptr;
-  float *d_dist = nullptr;
-  uint32_t *d_perq = nullptr;
-  size_t cap_q = 0, cap_out = 0, cap_perq = 0;
-  int hash_bits_override = 0;
-  int ghash_mode = -1;                     // HS_GHASH: -1 auto, 0 shared-memory visited tables, 1 global-memory
-  uint32_t *d_ghash = nullptr;             // two halves, alternated by consecutive (possibly overlapping) launches
-  size_t cap_ghash = 0;
-  uint32_t traverse_flags = 9;             // bit0: L2 row prefetch; bit1: speculative next-pop adjacency load (measured: a loss); bit3: evict_last adjacency prefetch
-  uint32_t slimq_flags = 0;
-  // the launch plan of the last fp32 traversal (occupancy queries are not free on the host)
-  bool plan_ok = false;
-  uint32_t plan_ef = 0;
-  size_t plan_nq = 0;
-  TraverseLaunch plan_l{};
-  TraverseParams plan_p{};
-  bool planq_ok = false;
-  uint32_t planq_ef = 0;
-  size_t planq_nq = 0, planq_k = 0;
-  TraverseQLaunch planq_l{};
-  TraverseQParams planq_p{};
-  // completion events of the batches handed to hs_search_batch_submit and not yet waited for (FIFO)
-  static constexpr int kEventRing = 16;
-  cudaEvent_t ev_ring[kEventRing] = {};
-  unsigned long long ev_head = 0, ev_tail = 0;      // [head, tail) are outstanding
-  bool zero_copy = true;                   // hs_search_batch reads/writes pinned+mapped host buffers in place
-  std::mutex mu;
-};
+// Device-visible alias of a host buffer when the whole range [p, p + bytes) is page-locked
+// (cudaHostAlloc / cudaHostRegister, e.g. torch pin_memory) and mapped into this device's address
+// space; nullptr otherwise (pageable memory, or pinned without mapping).
+void *mapped_alias(const void *p, size_t bytes) {
+  if (!p || bytes == 0) return nullptr;
+  cudaPointerAttributes a0{}, a1{};
+  if (cudaPointerGetAttributes(&a0, p) != cudaSuccess ||
+      cudaPointerGetAttributes(&a1, static_cast<const char *>(p) + bytes - 1) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  if (a0.type != cudaMemoryTypeHost || a1.type != cudaMemoryTypeHost || !a0.devicePointer || !a1.devicePointer)
+    return nullptr;
+  if (static_cast<char *>(a1.devicePointer) - static_cast<char *>(a0.devicePointer) != (ptrdiff_t)(bytes - 1))
+    return nullptr;
+  return a0.devicePointer;
+}
+
+}  // namespace hs
 
 namespace {
 
@@ -107,22 +83,6 @@ int upload(T **dst, const T *src, size_t count, size_t *bytes_total) {
     return HS_ERR_CUDA;
   }
   *bytes_total += count * sizeof(T);
-  return HS_OK;
-}
-
-int select_device(int device) {
-  int count = 0;
-  cudaError_t e = cudaGetDeviceCount(&count);
-  if (e != cudaSuccess || count == 0) {
-    set_error(std::string("no CUDA device available (") + cudaGetErrorString(e) +
-              "); hnswslim_b200 has no CPU fallback");
-    return HS_ERR_CUDA;
-  }
-  if (device < 0 || device >= count) {
-    set_error("device ordinal out of range");
-    return HS_ERR_ARG;
-  }
-  HS_CUDA(cudaSetDevice(device));
   return HS_OK;
 }
 
@@ -300,7 +260,7 @@ struct PrepDump {
 
 int search_device_slimq(hs_index *ix, const float *d_queries, size_t nq, size_t k, uint32_t *d_labels,
                         float *d_dists, uint32_t *d_perq, cudaStream_t stream, const PrepDump *dump,
-                        const ScatterDst *scatter = nullptr) {
+                        const ScatterDst *scatter = nullptr, uint32_t *plan_warps = nullptr) {
   TraverseQParams p{};
   p.qrec = ix->d_qrec;
   p.vec = reinterpret_cast<const float4 *>(ix->d_vec);
@@ -338,9 +298,6 @@ int search_device_slimq(hs_index *ix, const float *d_queries, size_t nq, size_t 
     p.prep_scal = dump->scal;
     p.prep_q2c = dump->q2c;
   }
-  const unsigned int seq = ix->launch_seq++;
-  p.work_counter = ix->d_work + (seq % kWorkRing);
-  p.launch_tag = seq;
   p.overlap = ix->overlap ? 1u : 0u;
   p.stats = ix->d_stats;
   p.per_query = d_perq;
@@ -363,22 +320,33 @@ int search_device_slimq(hs_index *ix, const float *d_queries, size_t nq, size_t 
     ix->planq_l = l;
     ix->planq_p = p;
   }
+  if (plan_warps) {
+    *plan_warps = (uint32_t)(l.grid * l.warps_per_cta);
+    return HS_OK;
+  }
+  const unsigned int seq = ix->launch_seq++;
+  p.work_counter = ix->d_work + (seq % kWorkRing);
+  p.launch_tag = seq;
   return launch_traverse_slimq(p, l, stream);
 }
 
-int search_device(hs_index *ix, const float *d_queries, size_t nq, size_t k, uint32_t *d_labels,
-                  float *d_dists, uint32_t *d_perq, cudaStream_t stream, const ScatterDst *scatter = nullptr) {
+}  // namespace
+
+int hs::search_device(hs_index *ix, const float *d_queries, size_t nq, size_t k, uint32_t *d_labels,
+                      float *d_dists, uint32_t *d_perq, cudaStream_t stream, const ScatterDst *scatter,
+                      uint32_t *plan_warps) {
   if (!ix || (!d_queries && nq) || (!d_labels && nq && !(scatter && scatter->n)) || k == 0) {
     set_error("null argument / k == 0");
     return HS_ERR_ARG;
   }
+  if (plan_warps) *plan_warps = 0;
   if (nq == 0 || ix->info.n == 0) return HS_OK;    // slim.h:2031-2032
   if (nq > 0x7fffffffu || k > 4096) {
     set_error("nq or k too large");
     return HS_ERR_ARG;
   }
   if (ix->info.kind == HS_KIND_SLIMQ)
-    return search_device_slimq(ix, d_queries, nq, k, d_labels, d_dists, d_perq, stream, nullptr, scatter);
+    return search_device_slimq(ix, d_queries, nq, k, d_labels, d_dists, d_perq, stream, nullptr, scatter, plan_warps);
   TraverseParams p{};
   p.vec = reinterpret_cast<const float4 *>(ix->d_vec);
   p.adj0 = ix->d_adj0;
@@ -403,9 +371,6 @@ int search_device(hs_index *ix, const float *d_queries, size_t nq, size_t k, uin
   p.out_labels = d_labels;
   p.out_dists = d_dists;
   if (scatter) p.scatter = *scatter;
-  const unsigned int seq = ix->launch_seq++;
-  p.work_counter = ix->d_work + (seq % kWorkRing);
-  p.launch_tag = seq;
   p.overlap = ix->overlap ? 1u : 0u;
   p.stats = ix->d_stats;
   p.per_query = d_perq;
@@ -428,6 +393,13 @@ int search_device(hs_index *ix, const float *d_queries, size_t nq, size_t k, uin
     ix->plan_l = l;
     ix->plan_p = p;
   }
+  if (plan_warps) {
+    *plan_warps = (uint32_t)(l.grid * l.warps_per_cta);
+    return HS_OK;
+  }
+  const unsigned int seq = ix->launch_seq++;
+  p.work_counter = ix->d_work + (seq % kWorkRing);
+  p.launch_tag = seq;
   if (l.ghash) {
     if ((rc = ensure((void **)&ix->d_ghash, &ix->cap_ghash, 2 * l.ghash_bytes)) != HS_OK) return rc;
     p.ghash = ix->d_ghash + (seq & 1u) * (l.ghash_bytes / 4);
@@ -436,23 +408,7 @@ int search_device(hs_index *ix, const float *d_queries, size_t nq, size_t k, uin
   return launch_traverse(p, ix->info.metric, l, stream);
 }
 
-// Device-visible alias of a host buffer when the whole range [p, p + bytes) is page-locked
-// (cudaHostAlloc / cudaHostRegister, e.g. torch pin_memory) and mapped into this device's address
-// space; nullptr otherwise (pageable memory, or pinned without mapping).
-void *mapped_alias(const void *p, size_t bytes) {
-  if (!p || bytes == 0) return nullptr;
-  cudaPointerAttributes a0{}, a1{};
-  if (cudaPointerGetAttributes(&a0, p) != cudaSuccess ||
-      cudaPointerGetAttributes(&a1, static_cast<const char *>(p) + bytes - 1) != cudaSuccess) {
-    cudaGetLastError();
-    return nullptr;
-  }
-  if (a0.type != cudaMemoryTypeHost || a1.type != cudaMemoryTypeHost || !a0.devicePointer || !a1.devicePointer)
-    return nullptr;
-  if (static_cast<char *>(a1.devicePointer) - static_cast<char *>(a0.devicePointer) != (ptrdiff_t)(bytes - 1))
-    return nullptr;
-  return a0.devicePointer;
-}
+namespace {
 
 int search_host(hs_index *ix, const float *queries, size_t nq, size_t k, uint32_t *labels_out,
                 float *dists_out, uint32_t *perq_out, bool sync = true) {

@@ -1,0 +1,88 @@
+// The index handle behind the C ABI (hs_index) and the internal entry points other translation
+// units of the library use (shard_group.cu, graph_gpu.cu).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <mutex>
+
+#include "hs_internal.h"
+#include "traverse_fp32.cuh"
+#include "traverse_slimq.cuh"
+
+// Launches in flight at once are bounded by what fits on the GPU (a dozen small grids); a slot is
+// reused only kWorkRing launches later.
+constexpr unsigned int kWorkRing = 1024;
+
+struct hs_index {
+  hs_index_info info{};
+  int device = 0;
+  int sm_count = 148;
+  // HBM-resident index
+  float *d_vec = nullptr;
+  uint32_t *d_adj0 = nullptr;
+  int32_t *d_upper_slot = nullptr;
+  uint32_t *d_upper_adj[hs::kMaxLevels] = {};
+  uint32_t *d_labels = nullptr;
+  uint8_t *d_deleted = nullptr;
+  // hnsw_slimq payload
+  uint2 *d_qrec = nullptr;          // n x (words + 2) uint2: code words, (f_add, f_rescale), (cluster, 0)
+  float *d_centroids = nullptr;     // num_cluster x padded_dim (rotated)
+  uint8_t *d_flip = nullptr;        // 4 * padded_dim / 8
+  uint32_t words = 0, trunc_dim = 0;
+  uint32_t level_count[hs::kMaxLevels] = {};
+  double t_const = 0.0;
+  // per-call scratch
+  unsigned long long *d_work = nullptr;    // ring of kWorkRing tagged work counters (traverse_common.cuh)
+  unsigned int launch_seq = 1;             // tags start at 1 (slots are initialised to 0xff..ff)
+  int overlap = 0;                         // hs_set_overlap
+  unsigned long long *d_stats = nullptr;   // [0] n_dist [1] n_hops [2] n_rerank
+  // staging for the host-buffer entry points
+  cudaStream_t stream = nullptr;
+  float *d_q = nullptr;
+  uint32_t *d_lab = nullptr;
+  float *d_dist = nullptr;
+  uint32_t *d_perq = nullptr;
+  size_t cap_q = 0, cap_out = 0, cap_perq = 0;
+  int hash_bits_override = 0;
+  int ghash_mode = -1;                     // HS_GHASH: -1 auto, 0 shared-memory visited tables, 1 global-memory
+  uint32_t *d_ghash = nullptr;             // two halves, alternated by consecutive (possibly overlapping) launches
+  size_t cap_ghash = 0;
+  uint32_t traverse_flags = 9;             // bit0: L2 row prefetch; bit1: speculative next-pop adjacency load (measured: a loss); bit3: evict_last adjacency prefetch
+  uint32_t slimq_flags = 0;
+  // the launch plan of the last fp32 traversal (occupancy queries are not free on the host)
+  bool plan_ok = false;
+  uint32_t plan_ef = 0;
+  size_t plan_nq = 0;
+  hs::TraverseLaunch plan_l{};
+  hs::TraverseParams plan_p{};
+  bool planq_ok = false;
+  uint32_t planq_ef = 0;
+  size_t planq_nq = 0, planq_k = 0;
+  hs::TraverseQLaunch planq_l{};
+  hs::TraverseQParams planq_p{};
+  // completion events of the batches handed to hs_search_batch_submit and not yet waited for (FIFO)
+  static constexpr int kEventRing = 16;
+  cudaEvent_t ev_ring[kEventRing] = {};
+  unsigned long long ev_head = 0, ev_tail = 0;      // [head, tail) are outstanding
+  bool zero_copy = true;                   // hs_search_batch reads/writes pinned+mapped host buffers in place
+  std::mutex mu;
+};
+
+namespace hs {
+
+// cudaSetDevice(device) with the error text the C ABI promises (no device => HS_ERR_CUDA, no fallback)
+int select_device(int device);
+
+// Device-visible alias of a host buffer when the whole range [p, p + bytes) is page-locked and mapped
+// into the current device's address space; nullptr otherwise.
+void *mapped_alias(const void *p, size_t bytes);
+
+// One traversal launch of `ix` over a device-visible query batch (the body of hs_search_batch_device).
+// plan_warps != nullptr: do not launch, only plan the launch shape (cached in the handle) and return
+// the number of warps the launch will have (grid x warps per CTA) — the shard group needs the total over
+// its local launches before the first one starts (ScatterDst::done_target).
+int search_device(hs_index *ix, const float *d_queries, size_t nq, size_t k, uint32_t *d_labels, float *d_dists,
+                  uint32_t *d_perq, cudaStream_t stream, const ScatterDst *scatter = nullptr,
+                  uint32_t *plan_warps = nullptr);
+
+}  // namespace hs

@@ -26,6 +26,20 @@ struct ScatterDst {
   unsigned long long row0 = 0;             // first row of this shard's slot in every destination table
   uint32_t *labels[kMaxScatter] = {};
   float *dists[kMaxScatter] = {};
+  // Completion protocol of a shard group (shard_group.cu), all optional (null / 0 = off).  The
+  // traversal launches of one batch count their finished warps in done_ctr; the warp that brings it to
+  // done_target resets it and writes `seq` into word [this rank] of every rank's flag array (release,
+  // system scope) — the "my rows of batch seq have landed" signal that used to be a stream memory
+  // operation between two launches and thereby cut the programmatic-launch chain.  Before its first
+  // row store a warp checks that every rank has merged batch seq - depth (acks[r] >= ack_need): the
+  // table slot it is about to overwrite is free.
+  unsigned int *done_ctr = nullptr;
+  uint32_t done_target = 0;
+  uint32_t seq = 0;
+  uint32_t n_flags = 0;
+  uint32_t *flags[kMaxScatter] = {};
+  const uint32_t *acks = nullptr;          // local array, one word per rank
+  uint32_t n_acks = 0, ack_need = 0;
 };
 
 // A .graph file flattened on the host, ready to upload (see DESIGN.md "HBM layout").

@@ -227,6 +227,40 @@ __device__ __forceinline__ uint32_t next_ticket(unsigned long long *ctr, uint32_
   return (uint32_t)old;
 }
 
+// ---- shard-group completion protocol (ScatterDst, hs_internal.h) ----
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t *p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(uint32_t *p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// Called by a whole warp before its first row store of a launch: the destination slot of every rank
+// must have been merged (ack words are written by the ranks' merge streams).  Sequence numbers are
+// compared as signed differences so that they may wrap.
+__device__ __forceinline__ void scatter_wait_acks(const ScatterDst &sc, int lane) {
+  if (sc.ack_need == 0) return;
+  if ((uint32_t)lane < sc.n_acks) {
+    while ((int32_t)(ld_acquire_sys(sc.acks + lane) - sc.ack_need) < 0) __nanosleep(256);
+  }
+  __syncwarp();
+}
+// Called by every warp of a launch exactly once, after its last row store.
+__device__ __forceinline__ void scatter_signal_done(const ScatterDst &sc, int lane) {
+  if (sc.done_ctr == nullptr) return;
+  __syncwarp();
+  if (lane == 0) {
+    __threadfence_system();                        // this warp's rows (local and peer memory) before the count
+    const unsigned int old = atomicAdd(sc.done_ctr, 1u);
+    if (old + 1u == sc.done_target) {
+      atomicExch(sc.done_ctr, 0u);                 // ready for the batch that reuses this counter
+      __threadfence_system();                      // every counted warp's rows before the flags
+      for (uint32_t t = 0; t < sc.n_flags; ++t) st_release_sys(sc.flags[t], sc.seq);
+    }
+  }
+}
+
 // lane holding the warp-wide smallest `key` ((dist,id) order; NONE = no entry); -1 if none
 __device__ __forceinline__ int warp_argmin_key(uint64_t key) {
   const uint32_t hi = (uint32_t)(key >> 32);

@@ -85,11 +85,16 @@ __global__ void __launch_bounds__(128, HS_TRAVERSE_MIN_CTAS) traverse_kernel(con
   constexpr int QN = CPL > 0 ? CPL : 1;
   const bool qvec = ((reinterpret_cast<uintptr_t>(p.queries) & 15u) == 0) && (p.dim & 3u) == 0;
 
+  bool acked = false;
   for (;;) {
     uint32_t qi = 0;
     if (lane == 0) qi = next_ticket(p.work_counter, p.launch_tag);
     qi = __shfl_sync(FULL, qi, 0);
     if (qi >= p.nq) break;
+    if (!acked) {              // shard group: the table slot this launch writes must have been merged everywhere
+      scatter_wait_acks(p.scatter, lane);
+      acked = true;
+    }
 
     // ---- query: lane t of each team owns chunks t, t+8, ... (zero-padded past dim).  Each
     //      chunk is read ONCE per warp (one 16-byte load per lane when the batch is 16-byte
@@ -344,6 +349,7 @@ __global__ void __launch_bounds__(128, HS_TRAVERSE_MIN_CTAS) traverse_kernel(con
     }
     __syncwarp();
   }
+  scatter_signal_done(p.scatter, lane);
 }
 
 template <int CPL, int METRIC, int SLOTS>

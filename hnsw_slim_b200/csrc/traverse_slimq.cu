@@ -213,11 +213,16 @@ traverse_slimq_kernel(const __grid_constant__ TraverseQParams p) {
   const uint32_t ef = p.ef;
   if (p.overlap) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // see traverse_fp32.cu
 
+  bool acked = false;
   for (;;) {
     uint32_t qi = 0;
     if (lane == 0) qi = next_ticket(p.work_counter, p.launch_tag);
     qi = __shfl_sync(FULL, qi, 0);
     if (qi >= p.nq) break;
+    if (!acked) {              // shard group: the table slot this launch writes must have been merged everywhere
+      scatter_wait_acks(p.scatter, lane);
+      acked = true;
+    }
     const float *qptr = p.queries + (size_t)qi * p.dim;
 
     Planes<WREG> pl;
@@ -391,6 +396,7 @@ traverse_slimq_kernel(const __grid_constant__ TraverseQParams p) {
     }
     __syncwarp();
   }
+  scatter_signal_done(p.scatter, lane);
 }
 
 inline int wreg_variant(uint32_t words) { return words == 2 ? 2 : 0; }

@@ -2,9 +2,10 @@
 
 The reference builds ONE graph even for its 100M datasets; here the base set is split into S
 contiguous label ranges, one HNSW-Slim sub-graph per range (labels stay global), the S shards are
-spread over the ranks (S/N per GPU), every rank searches the whole query batch on its shards, and
-one all-gather of nq x k x 8 bytes per rank plus the top-k merge kernel produce the global result
-on every rank.  1M-scale indices do not need any of this: they are replicated and the queries are
+spread over the ranks (S/N per GPU), every rank searches the whole query batch on its shards, the
+traversal kernels store their rows into the gather tables of every rank (hs_shardgroup; or one
+all-gather of nq x k x 8 bytes per rank) and a top-k merge kernel produces the global result on
+every rank.  1M-scale indices do not need any of this: they are replicated and the queries are
 split (bench.py --gpus N).
 
 The collective goes through torch.distributed (NCCL on GPUs; gloo in the CPU tests, which inject a
@@ -53,23 +54,26 @@ def merge_numpy(labels: np.ndarray, dists: np.ndarray, k: int):
 
 
 def gather_and_merge(local_labels, local_dists, k: int, *, group=None, merge: Callable | None = None):
-    """All-gather every rank's [nq, k] partial result and merge to the global top-k.
+    """All-gather every rank's [nq, k] partial result and merge to the global top-k (the NCCL form of
+    the exchange; the default on GPUs is the exchange fused into the traversal kernels, ShardedIndex).
 
     local_labels (int32/uint32 view) and local_dists (float32) are torch tensors on the device of
-    the process group's backend.  `merge(labels[parts,nq,k], dists[parts,nq,k], k)` defaults to the
-    CUDA merge kernel (hs_topk_merge_device)."""
+    the process group's backend; both travel in ONE all-gather (labels and the distances' bit
+    patterns stacked into a [2, nq, k] int32 block).  `merge(labels[parts,nq,k], dists[parts,nq,k], k)`
+    defaults to the CUDA merge kernel (hs_topk_merge_device)."""
     import torch
     import torch.distributed as dist
 
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     nq = local_labels.shape[0]
     if world > 1:
-        # concatenated along dim 0 (the layout gloo and NCCL both accept), viewed as [world, nq, k]
-        all_l = torch.empty((world * nq, k), dtype=local_labels.dtype, device=local_labels.device)
-        all_d = torch.empty((world * nq, k), dtype=local_dists.dtype, device=local_dists.device)
-        dist.all_gather_into_tensor(all_l, local_labels.contiguous(), group=group)
-        dist.all_gather_into_tensor(all_d, local_dists.contiguous(), group=group)
-        all_l, all_d = all_l.view(world, nq, k), all_d.view(world, nq, k)
+        both = torch.stack((local_labels.contiguous().view(torch.int32),
+                            local_dists.contiguous().view(torch.int32)))              # [2, nq, k]
+        gathered = torch.empty((world * 2, nq, k), dtype=torch.int32, device=both.device)
+        dist.all_gather_into_tensor(gathered, both, group=group)
+        gathered = gathered.view(world, 2, nq, k)
+        all_l = gathered[:, 0].contiguous().view(local_labels.dtype)
+        all_d = gathered[:, 1].contiguous().view(torch.float32)
     else:
         all_l, all_d = local_labels.unsqueeze(0), local_dists.unsqueeze(0)
     if merge is not None:
@@ -83,7 +87,13 @@ def gather_and_merge(local_labels, local_dists, k: int, *, group=None, merge: Ca
 
 
 class ShardedIndex:
-    """The shards one rank owns, resident on its GPU; search() returns the GLOBAL top-k."""
+    """The shards one rank owns, resident on its GPU.  search() returns the GLOBAL top-k.
+
+    Everything on the GPU goes through one hs_shardgroup (csrc/shard_group.cu): the traversal kernels
+    store their rows into every rank's gather table (peer memory), the last finishing warp of a
+    batch raises the flags, a merge kernel on a second stream produces the result — no collective and
+    nothing between two traversal launches, so a stream of batches is pipelined.  `exchange="nccl"`
+    keeps the all-gather form (local group of world size 1, then gather_and_merge)."""
 
     def __init__(self, graph_paths: Sequence[str], dim: int, *, metric: int = 0, device: int = 0,
                  kind: int = 0, raw_bases: Sequence | None = None):
@@ -97,13 +107,11 @@ class ShardedIndex:
                            for p, rb in zip(graph_paths, raw_bases)]
         else:
             self.shards = [capi.Index(p, dim, metric=metric, device=device) for p in graph_paths]
-        # the shard launches of one batch are independent (same queries, own outputs): let each one's
-        # tail overlap the next one's head on the stream (hs_set_overlap)
-        for s in self.shards:
-            s.set_overlap(True)
         self.dim = dim
-        self._side = None                    # stream of the pipelined exchange step (search(pipelined=True))
-        self._ex = None                      # fused exchange (connect_exchange / search_fused)
+        self.device = device
+        self.group = None                    # hs_shardgroup over all ranks (connect)
+        self._local = None                   # hs_shardgroup of world size 1 (NCCL form / single rank)
+        self._local_shape = None
 
     def set_ef(self, ef: int) -> None:
         for s in self.shards:
@@ -112,81 +120,91 @@ class ShardedIndex:
     def device_bytes(self) -> int:
         return sum(s.info()["device_bytes"] for s in self.shards)
 
-    def search_local(self, d_queries, nq: int, k: int):
-        """Every local shard on the whole batch, then the local top-k (device tensors)."""
-        import torch
-        stream = torch.cuda.current_stream().cuda_stream
-        n_loc = len(self.shards)
-        lab = torch.empty((n_loc, nq, k), dtype=torch.int32, device=d_queries.device)
-        dst = torch.empty((n_loc, nq, k), dtype=torch.float32, device=d_queries.device)
-        for i, s in enumerate(self.shards):
-            s.search_device(d_queries.data_ptr(), nq, k, lab[i].data_ptr(), dst[i].data_ptr(), stream)
-        if n_loc == 1:
-            return lab[0], dst[0]
-        out_l = torch.empty((nq, k), dtype=torch.int32, device=d_queries.device)
-        out_d = torch.empty((nq, k), dtype=torch.float32, device=d_queries.device)
-        self.capi.topk_merge_device(lab.data_ptr(), dst.data_ptr(), n_loc, nq, k, out_l.data_ptr(),
-                                    out_d.data_ptr(), stream)
-        return out_l, out_d
-
-    def search(self, d_queries, nq: int, k: int, group=None, pipelined: bool = False):
-        """Global top-k of one batch.  pipelined=True runs the exchange step (all-gather + merge) on
-        a side stream, so the NEXT batch's shard searches — enqueued on the caller's stream — do
-        not wait for it: a stream of batches then costs max(search, exchange) per batch instead of
-        their sum — in principle: measured on 2 B200s it is slower (2.43 M vs 2.68 M QPS), because the
-        NCCL kernels queue behind the persistent traversal grid that owns every SM slot, so it is off
-        by default.  The returned tensors are complete once join() (or a device synchronize) has
-        been called."""
-        l, d = self.search_local(d_queries, nq, k)
-        if not pipelined:
-            return gather_and_merge(l, d, k, group=group)
-        import torch
-        if self._side is None:
-            self._side = torch.cuda.Stream()
-        main = torch.cuda.current_stream()
-        self._side.wait_stream(main)
-        with torch.cuda.stream(self._side):
-            out = gather_and_merge(l, d, k, group=group)
-        l.record_stream(self._side)          # allocated on the caller's stream, consumed on the side stream
-        d.record_stream(self._side)
-        return out
-
-    # ---- exchange fused into the traversal kernel (no collective) ----
-    def connect_exchange(self, rank: int, world: int, n_shards_total: int, nq_max: int, k: int, device: int,
-                         group=None):
+    # ---- the pipelined group over all ranks ----
+    def connect(self, rank: int, world: int, nq_max: int, k: int, *, depth: int = 4, group=None):
         """Create this rank's gather tables and map every other rank's (CUDA IPC; the 64-byte handles
-        travel through torch.distributed).  Call once, collectively."""
-        import torch.distributed as dist
-        ex = self.capi.Exchange(device, world, rank, n_shards_total, nq_max, k)
+        travel through torch.distributed).  Collective.  Every rank reaches the all-gather even when
+        its own setup failed, so that a failure raises everywhere instead of hanging the others."""
+        err, g, h = None, None, None
+        try:
+            g = self.capi.ShardGroup(self.shards, world, rank, nq_max, k, depth)
+            h = g.handle() if world > 1 else None
+        except Exception as e:            # reported after the collective
+            err = e
         if world > 1:
+            import torch.distributed as dist
             handles = [None] * world
-            dist.all_gather_object(handles, ex.handle(), group=group)
-            ex.connect(b"".join(handles))
-        self._ex, self._ex_rank, self._ex_world, self._ex_slots, self._ex_seq = ex, rank, world, n_shards_total, 0
-        return ex
+            dist.all_gather_object(handles, h, group=group)
+            if err is None and any(x is None for x in handles):
+                err = RuntimeError("another rank could not create its shard group")
+            if err is None:
+                try:
+                    g.connect(b"".join(handles))
+                except Exception as e:
+                    err = e
+            oks = [None] * world
+            dist.all_gather_object(oks, err is None, group=group)
+            if err is None and not all(oks):
+                err = RuntimeError("another rank could not map the peer tables")
+        elif err is None:
+            g.connect(None)
+        if err is not None:
+            if g is not None:
+                g.close()
+            raise err
+        self.group = g
+        return g
 
-    def search_fused(self, d_queries, nq: int, k: int):
-        """Global top-k of one batch with the exchange fused into the traversal kernels: every local
-        shard's kernel stores its rows into slot (rank * shards_per_rank + i) of EVERY rank's gather
-        table (peer memory over NVLink), a stream-ordered flag exchange tells when all rows of the
-        batch have landed, and hs_topk_merge_device reads the local table.  No all-gather call."""
+    def submit(self, q_ptr: int, nq: int, lab_ptr: int, dist_ptr: int | None) -> None:
+        """hs_shardgroup_submit on raw pointers (device, or pinned + mapped host memory)."""
+        self.group.submit(q_ptr, nq, lab_ptr, dist_ptr)
+
+    def _local_group(self, nq: int, k: int):
+        if self._local is None or self._local_shape != (nq, k):
+            if self._local is not None:
+                self._local.wait()
+                self._local.close()
+            self._local = self.capi.ShardGroup(self.shards, 1, 0, nq, k, 4)
+            self._local.connect(None)
+            self._local_shape = (nq, k)
+        return self._local
+
+    def search_local(self, d_queries, nq: int, k: int):
+        """Every local shard on the whole batch, then the local top-k (device tensors, complete after
+        join()).  Single-rank form of the pipelined group."""
         import torch
-        ex = self._ex
-        self._ex_seq += 1
-        seq = self._ex_seq
-        stream = torch.cuda.current_stream().cuda_stream
-        n_loc = len(self.shards)
-        for i, s in enumerate(self.shards):
-            ex.search(s, d_queries.data_ptr(), nq, self._ex_rank * n_loc + i, seq, stream)
-        ex.signal_and_wait(seq, stream)
-        tl, td = ex.tables(seq)
+        g = self._local_group(nq, k)
         out_l = torch.empty((nq, k), dtype=torch.int32, device=d_queries.device)
         out_d = torch.empty((nq, k), dtype=torch.float32, device=d_queries.device)
-        self.capi.topk_merge_device(tl, td, self._ex_slots, nq, k, out_l.data_ptr(), out_d.data_ptr(), stream)
+        g.submit(d_queries.data_ptr(), nq, out_l.data_ptr(), out_d.data_ptr())
         return out_l, out_d
+
+    def search(self, d_queries, nq: int, k: int, group=None, exchange: str = "fused"):
+        """Global top-k of one batch (device tensors).  The call returns once the batch is enqueued; the
+        tensors are complete after join().  exchange="fused": the connected hs_shardgroup (or the local
+        one when this is the only rank); "nccl": local shards + one all-gather + hs_topk_merge_device."""
+        import torch
+        if exchange == "fused":
+            if self.group is None:
+                return self.search_local(d_queries, nq, k)
+            out_l = torch.empty((nq, k), dtype=torch.int32, device=d_queries.device)
+            out_d = torch.empty((nq, k), dtype=torch.float32, device=d_queries.device)
+            self.group.submit(d_queries.data_ptr(), nq, out_l.data_ptr(), out_d.data_ptr())
+            return out_l, out_d
+        l, d = self.search_local(d_queries, nq, k)
+        self._local.wait()                   # the all-gather reads the local result on torch's stream
+        return gather_and_merge(l, d, k, group=group)
 
     def join(self) -> None:
-        """Make the caller's stream wait for every pipelined exchange issued so far."""
-        import torch
-        if self._side is not None:
-            torch.cuda.current_stream().wait_stream(self._side)
+        """Block until every batch enqueued so far is complete."""
+        if self.group is not None:
+            self.group.wait()
+        if self._local is not None:
+            self._local.wait()
+
+    def close(self) -> None:
+        for g in (self.group, self._local):
+            if g is not None:
+                g.wait()
+                g.close()
+        self.group = self._local = None

@@ -35,6 +35,26 @@ def latent_gaussian(n: int, dim: int, *, rank: int = 16, noise: float = 0.1, see
     return out
 
 
+def latent_gaussian_rows(lo: int, hi: int, dim: int, *, rank: int = 16, noise: float = 0.1, seed: int = 1,
+                         normalize: bool = False, stream: int = 0, chunk: int = 1 << 16) -> np.ndarray:
+    """Rows [lo, hi) of a latent-model corpus whose rows are addressable: chunk c (rows c*chunk ..) has its
+    own generator, so a rank of a sharded run draws only its shard (the 100M-shaped corpora never exist in
+    one piece).  Same model as latent_gaussian, different stream of random numbers."""
+    A = np.random.default_rng(seed).standard_normal((rank, dim)).astype(np.float32)
+    out = np.empty((hi - lo, dim), dtype=np.float32)
+    for c in range(lo // chunk, (hi + chunk - 1) // chunk):
+        rng = np.random.default_rng([seed, stream, 0xC0DE, c])
+        z = rng.standard_normal((chunk, rank), dtype=np.float32)
+        eps = rng.standard_normal((chunk, dim), dtype=np.float32)
+        rows = z @ A
+        rows += noise * eps
+        a, b = max(lo, c * chunk), min(hi, (c + 1) * chunk)
+        out[a - lo: b - lo] = rows[a - c * chunk: b - c * chunk]
+    if normalize:
+        out /= np.linalg.norm(out, axis=1, keepdims=True)
+    return out
+
+
 def make_dataset(n: int, nq: int, dim: int, *, metric: int = 0, rank: int = 16, noise: float = 0.1,
                  seed: int = 1):
     """(base[n,dim], queries[nq,dim]) from the same distribution (same mixing matrix A, disjoint

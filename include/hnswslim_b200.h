@@ -205,6 +205,42 @@ int hs_exchange_signal_and_wait(hs_exchange *, unsigned int seq, void *stream);
 int hs_exchange_tables(hs_exchange *, unsigned int seq, uint32_t **d_labels, float **d_dists);
 void hs_exchange_free(hs_exchange *);
 
+/* ---- hs_shardgroup: one rank's part of a sharded corpus, pipelined ----------------------------------
+ * (no reference analogue; SURVEY.md §8(e): the reference builds ONE graph; here the base set is split into
+ * per-GPU sub-graphs with global labels and every shard answers every query with the searchKnn of
+ * slim.h:2030-2131 / slimq.h:1810-1924.)  A group owns the gather tables, flags and the two streams of ONE
+ * rank; its local shards are hs_index handles on one device, borrowed (free the group first).  With
+ * `world` ranks and n_local shards per rank the corpus has world * n_local shards; shard i of rank r is
+ * slot r * n_local + i.
+ *
+ * hs_shardgroup_submit enqueues one batch and returns: one traversal launch per local shard (chained by
+ * programmatic stream serialization — also across batches), whose kernels store every result row into
+ * the tables of ALL ranks (peer memory over NVLink) and whose last finishing warp raises this rank's flag
+ * on every rank; on a second, higher-priority stream a merge kernel waits for all ranks' flags of the
+ * batch (cuStreamWaitValue32), writes the global top-k (by (distance, label)) of every query to
+ * labels_out / dists_out and acknowledges the table slot to every rank.  No collective call, nothing
+ * between two traversal launches: in a stream of batches the exchange + merge of batch s overlap the
+ * searches of batch s + 1.  Up to `depth` batches may be in flight between ranks; all ranks must submit
+ * the same sequence of (nq, k) shapes.  queries / labels_out / dists_out are device pointers or
+ * page-locked + mapped host pointers (read / written in place); the query buffer must be complete when
+ * submit is called; outputs are valid after hs_shardgroup_wait (all batches) or the matching
+ * hs_shardgroup_wait_oldest.
+ *   create         n_local shards of this rank, `world` ranks, this rank's index, table shape nq_max x k
+ *   handle/connect one process per GPU: all-gather the 64-byte CUDA IPC handles (rank-major), then connect
+ *   connect_local  one process driving all GPUs: groups[r] = rank r; enables peer access
+ *   streams        the search / merge CUDA streams (to bracket a run with events) */
+typedef struct hs_shardgroup hs_shardgroup;
+int hs_shardgroup_create(hs_index *const *shards, size_t n_local, int world, int rank, size_t nq_max, size_t k,
+                         int depth, hs_shardgroup **out);
+int hs_shardgroup_handle(hs_shardgroup *, void *handle64);
+int hs_shardgroup_connect(hs_shardgroup *, const void *handles);
+int hs_shardgroup_connect_local(hs_shardgroup *const *groups, size_t world);
+int hs_shardgroup_submit(hs_shardgroup *, const float *queries, size_t nq, uint32_t *labels_out, float *dists_out);
+int hs_shardgroup_wait_oldest(hs_shardgroup *);
+int hs_shardgroup_wait(hs_shardgroup *);
+int hs_shardgroup_streams(hs_shardgroup *, void **search_stream, void **merge_stream);
+void hs_shardgroup_free(hs_shardgroup *);
+
 /* Counters accumulated since the last hs_reset_stats, with the meaning of
  * metric_distance_computations / metric_hops (slim.h:70-71,371-374,2064-2065):
  * n_dist = distances evaluated, n_hops = nodes expanded (upper + base layer).

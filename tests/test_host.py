@@ -46,6 +46,20 @@ def test_exchange_argument_errors():
         assert e.value.code == -1, bad                          # HS_ERR_ARG before any CUDA call
 
 
+def test_shardgroup_argument_errors():
+    import ctypes as C
+    L = capi.lib()
+    fake = (C.c_void_p * 1)(1)                     # never dereferenced: the shape checks come first
+    out = C.c_void_p()
+    for world, rank, nq_max, k, depth in [(0, 0, 100, 10, 4), (2, 2, 100, 10, 4), (17, 0, 100, 10, 4),
+                                          (2, 0, 0, 10, 4), (2, 0, 100, 0, 4), (2, 0, 100, 10, 1), (2, 0, 100, 10, 17)]:
+        assert L.hs_shardgroup_create(fake, 1, world, rank, nq_max, k, depth, C.byref(out)) == -1
+    assert L.hs_shardgroup_create(fake, 0, 1, 0, 100, 10, 4, C.byref(out)) == -1
+    assert L.hs_shardgroup_create(None, 1, 1, 0, 100, 10, 4, C.byref(out)) == -1
+    assert L.hs_shardgroup_submit(None, None, 1, None, None) == -1
+    assert L.hs_shardgroup_wait(None) == -1 and L.hs_shardgroup_wait_oldest(None) == -1
+
+
 @pytest.mark.parametrize("name,metric", [("slim_l2_2k", 0), ("slim_ip_1k", 1)])
 def test_flattened_graph_matches_reference_layout(name, metric):
     graph = os.path.join(GOLDEN, name + ".graph")

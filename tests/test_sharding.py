@@ -91,7 +91,7 @@ def test_sharded_index_local_shards_on_gpu(kind, tmp_path):
     ix.set_ef(ef)
     dq = torch.from_numpy(q).cuda()
     lab, dist = ix.search(dq, nq, k)
-    torch.cuda.synchronize()
+    ix.join()
     lab, dist = lab.cpu().numpy().view(np.uint32), dist.cpu().numpy()
     # per-shard results through the plain single-index API, merged on the host
     parts_l, parts_d = [], []
@@ -108,13 +108,108 @@ def test_sharded_index_local_shards_on_gpu(kind, tmp_path):
     gt, _ = capi.bruteforce_knn(base, q, k)
     rec = np.mean([len(set(a) & set(b)) / k for a, b in zip(lab, gt)])
     assert rec >= 0.97, rec
-    # a pipelined stream of batches (exchange step on a side stream): same rows after join()
-    outs = [ix.search(dq, nq, k, pipelined=True) for _ in range(4)]
+    # a stream of batches, more than the group's depth, enqueued without waiting: same rows after join()
+    outs = [ix.search(dq, nq, k) for _ in range(11)]
     ix.join()
-    torch.cuda.current_stream().synchronize()
     for pl, pd in outs:
         assert np.array_equal(pl.cpu().numpy().view(np.uint32), want_l)
         assert np.array_equal(pd.cpu().numpy().view(np.uint32), want_d.view(np.uint32))
+    # the all-gather form of the exchange (world size 1: no collective) gives the same rows
+    nl, nd = ix.search(dq, nq, k, exchange="nccl")
+    torch.cuda.synchronize()
+    assert np.array_equal(nl.cpu().numpy().view(np.uint32), want_l)
+    assert np.array_equal(nd.cpu().numpy().view(np.uint32), want_d.view(np.uint32))
+    ix.close()
+
+
+@pytest.mark.gpu
+def test_shard_group_skewed_shards_complete_before_merge(tmp_path):
+    """The launches of a batch overlap (programmatic stream serialization) and may FINISH in any order:
+    a large first shard followed by tiny ones must still be complete when the merge reads the table —
+    the batch is signalled by the last warp to finish over all launches, not by the last launch."""
+    import torch
+    from hnsw_slim_b200 import capi, sharding
+    from hnsw_slim_b200.synth import make_dataset
+    n, nq, dim, k = 60000, 2000, 128, 10
+    base, q = make_dataset(n, nq, dim, rank=10, seed=77)
+    cuts = [0, 56000, 58000, 59000, 60000]               # 56000 rows, then 2000 / 1000 / 1000
+    paths = []
+    for s in range(4):
+        lo, hi = cuts[s], cuts[s + 1]
+        p = str(tmp_path / f"sk{s}.graph")
+        capi.build_slim_graph(base[lo:hi], p, M=16, ef_construction=100, labels=np.arange(lo, hi, dtype=np.uint64))
+        paths.append(p)
+    ix = sharding.ShardedIndex(paths, dim, device=0)
+    ix.shards[0].set_ef(256)                              # the big shard is also the slow one
+    for s_ in ix.shards[1:]:
+        s_.set_ef(10)
+    parts_l, parts_d = [], []
+    for s_ in ix.shards:
+        l, d = s_.search(q, k)
+        parts_l.append(l)
+        parts_d.append(d)
+    want_l, want_d = sharding.merge_numpy(np.stack(parts_l), np.stack(parts_d), k)
+    dq = torch.from_numpy(q).cuda()
+    outs = [ix.search(dq, nq, k) for _ in range(6)]
+    ix.join()
+    for pl, pd in outs:
+        assert np.array_equal(pl.cpu().numpy().view(np.uint32), want_l)
+        assert np.array_equal(pd.cpu().numpy().view(np.uint32), want_d.view(np.uint32))
+    ix.close()
+
+
+@pytest.mark.gpu
+def test_shard_group_two_ranks_one_process(tmp_path):
+    """hs_shardgroup_connect_local: ONE process drives both ranks (here both on cuda:0; on a multi-GPU
+    box one per device with peer access — the C++ host CLI's mode).  Each rank owns 2 of 4 shards, its
+    kernels store rows into both ranks' tables; both ranks end with the merged union, batch after
+    batch, with more batches in flight than the group's depth; host (pinned) buffers work in place."""
+    import torch
+    from hnsw_slim_b200 import capi, sharding
+    from hnsw_slim_b200.synth import make_dataset
+    n, nq, dim, k, ef, S = 16000, 500, 96, 10, 40, 4
+    base, q = make_dataset(n, nq, dim, rank=8, seed=13)
+    paths = _build_shards(str(tmp_path), base, S)
+    shards = [capi.Index(p, dim) for p in paths]
+    for s_ in shards:
+        s_.set_ef(ef)
+    groups = [capi.ShardGroup(shards[2 * r: 2 * r + 2], 2, r, nq, k, depth=3) for r in range(2)]
+    capi.ShardGroup.connect_local(groups)
+    batches = [np.ascontiguousarray(np.roll(q, b, axis=0)) for b in range(8)]
+    want = []
+    for qb in batches:
+        pl, pd = zip(*[s_.search(qb, k) for s_ in shards])
+        want.append(sharding.merge_numpy(np.stack(pl), np.stack(pd), k))
+    dqs = [torch.from_numpy(b).cuda() for b in batches]
+    outs = [[(torch.empty((nq, k), dtype=torch.int32, device="cuda"), torch.empty((nq, k), device="cuda"))
+             for _ in batches] for _ in range(2)]
+    for b in range(len(batches)):
+        for r in range(2):
+            groups[r].submit(dqs[b].data_ptr(), nq, outs[r][b][0].data_ptr(), outs[r][b][1].data_ptr())
+    for g in groups:
+        g.wait()
+    for r in range(2):
+        for b in range(len(batches)):
+            assert np.array_equal(outs[r][b][0].cpu().numpy().view(np.uint32), want[b][0]), (r, b)
+            assert np.array_equal(outs[r][b][1].cpu().numpy().view(np.uint32), want[b][1].view(np.uint32)), (r, b)
+    # pinned + mapped host buffers in place (the end-to-end path of bench.py)
+    hq = torch.from_numpy(batches[1]).pin_memory()
+    hl = [torch.empty((nq, k), dtype=torch.int32).pin_memory() for _ in range(2)]
+    hd = [torch.empty((nq, k), dtype=torch.float32).pin_memory() for _ in range(2)]
+    for r in range(2):
+        groups[r].submit(hq.data_ptr(), nq, hl[r].data_ptr(), hd[r].data_ptr())
+    for g in groups:
+        g.wait()
+    for r in range(2):
+        assert np.array_equal(hl[r].numpy().view(np.uint32), want[1][0])
+        assert np.array_equal(hd[r].numpy().view(np.uint32), want[1][1].view(np.uint32))
+    # argument errors: pageable host memory, nq above the table shape
+    with pytest.raises(capi.HsError):
+        groups[0].submit(batches[0].ctypes.data, nq, hl[0].data_ptr(), hd[0].data_ptr())
+    with pytest.raises(capi.HsError):
+        groups[0].submit(dqs[0].data_ptr(), nq + 1, outs[0][0][0].data_ptr(), outs[0][0][1].data_ptr())
+    for g in groups:
+        g.close()
 
 
 def _build_shards(tmp, base, S, kind="slim"):
@@ -165,26 +260,26 @@ def _fused_worker(rank, world, paths, qfile, dim, k, ef, port, outdir):
     mine = sh.shards_of_rank(len(paths), rank, world)
     ix = sh.ShardedIndex([paths[s] for s in mine], dim, device=0)
     ix.set_ef(ef)
-    ix.connect_exchange(rank, world, len(paths), nq, k, 0)
+    ix.connect(rank, world, nq, k, depth=2)
     dist.barrier()
-    res = []
-    for b in range(3):                                  # three batches: both buffer parities, reuse
-        dq = torch.from_numpy(np.ascontiguousarray(np.roll(q, b, axis=0))).cuda()
-        l, d = ix.search_fused(dq, nq, k)
-        torch.cuda.synchronize()
-        res.append((l.cpu().numpy().view(np.uint32), d.cpu().numpy()))
+    dqs = [torch.from_numpy(np.ascontiguousarray(np.roll(q, b, axis=0))).cuda() for b in range(3)]
+    torch.cuda.synchronize()
+    outs = [ix.search(dq, nq, k) for dq in dqs]         # three batches in a row: table slots are reused
+    ix.join()
+    res = [(l.cpu().numpy().view(np.uint32), d.cpu().numpy()) for l, d in outs]
     np.savez(os.path.join(outdir, f"r{rank}.npz"), **{f"l{b}": r[0] for b, r in enumerate(res)},
              **{f"d{b}": r[1] for b, r in enumerate(res)})
     dist.barrier()
+    ix.close()
     dist.destroy_process_group()
 
 
 @pytest.mark.gpu
 def test_fused_exchange_two_ranks_one_gpu(tmp_path):
-    """The exchange fused into the traversal kernel, two PROCESSES (ranks) sharing cuda:0: each rank
-    owns 2 of 4 shards, its kernels store result rows into BOTH ranks' gather tables (the other
-    rank's through CUDA IPC), stream-ordered flags say when a batch is complete, every rank merges
-    locally.  Both ranks must end up with the (dist, label)-sorted union of the per-shard rows."""
+    """hs_shardgroup over two PROCESSES (ranks) sharing cuda:0: each rank owns 2 of 4 shards, its kernels
+    store result rows into BOTH ranks' gather tables (the other rank's through CUDA IPC), the last warp
+    of a batch raises the flags, every rank merges on its merge stream.  Both ranks must end up with
+    the (dist, label)-sorted union of the per-shard rows."""
     from hnsw_slim_b200 import capi
     from hnsw_slim_b200.synth import make_dataset
     n, nq, dim, k, ef, S = 16000, 300, 64, 10, 60, 4
