@@ -40,6 +40,8 @@ struct ScatterDst {
   uint32_t *flags[kMaxScatter] = {};
   const uint32_t *acks = nullptr;          // local array, one word per rank
   uint32_t n_acks = 0, ack_need = 0;
+  unsigned long long ack_timeout_ns = 0;   // give up on a peer's acknowledgement after this long ...
+  unsigned int *status = nullptr;          // ... and record it here (local word; 0 = healthy)
 };
 
 // A .graph file flattened on the host, ready to upload (see DESIGN.md "HBM layout").

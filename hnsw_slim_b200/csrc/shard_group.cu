@@ -63,6 +63,8 @@ struct hs_shardgroup {
   size_t off_flags() const { return off_ctrl(); }              // kMaxScatter words: flags[r] = last batch of rank r
   size_t off_acks() const { return off_ctrl() + 64; }          // kMaxScatter words: acks[r] = last batch rank r merged
   size_t off_done() const { return off_ctrl() + 128; }         // depth words: finished warps of the batch in flight
+  size_t off_status() const { return off_ctrl() + 192; }       // 1 word: a traversal warp gave up waiting for a peer
+  unsigned long long ack_timeout_ns = 20ull * 1000 * 1000 * 1000;
 };
 
 namespace hs {
@@ -310,6 +312,17 @@ int hs_shardgroup_submit(hs_shardgroup *g, const float *queries, size_t nq, uint
   }
   const unsigned int seq = ++g->seq;
   const unsigned d = seq % (unsigned)g->depth;
+  // Back-pressure on the host: batch `seq` reuses the table slot of batch seq - depth, and its warps wait
+  // in the kernel until every rank has merged that batch.  This rank's own merge must be complete BEFORE
+  // the launch: a grid of waiting warps holds every SM slot, including the ones that merge kernel needs.
+  // (Induction over the rank that has merged least shows that some rank can always proceed.)
+  if (seq > (unsigned)g->depth) {
+    const unsigned long long need = (unsigned long long)seq - (unsigned)g->depth;   // 1-based batch number
+    if (need > g->ev_head) {
+      SG_CUDA(cudaEventSynchronize(g->ev[(need - 1) % hs_shardgroup::kEvRing]));
+      g->ev_head = need;
+    }
+  }
   for (size_t i = 0; i < g->shards.size(); ++i) {
     ScatterDst sc;
     sc.n = (uint32_t)g->world;
@@ -326,6 +339,8 @@ int hs_shardgroup_submit(hs_shardgroup *g, const float *queries, size_t nq, uint
     sc.acks = reinterpret_cast<const uint32_t *>(g->base + g->off_acks());
     sc.n_acks = (uint32_t)g->world;
     sc.ack_need = seq > (unsigned)g->depth ? seq - (unsigned)g->depth : 0u;
+    sc.ack_timeout_ns = g->ack_timeout_ns;
+    sc.status = reinterpret_cast<unsigned int *>(g->base + g->off_status());
     if ((rc = search_device(g->shards[i], dq, nq, k, nullptr, nullptr, nullptr, g->s_search, &sc)) != HS_OK) return rc;
   }
   // merge stream: all ranks' rows of `seq` in place -> merge -> acknowledge -> completion event
@@ -398,6 +413,13 @@ int hs_shardgroup_wait(hs_shardgroup *g) {
   SG_CUDA(cudaStreamSynchronize(g->s_merge));
   SG_CUDA(cudaStreamSynchronize(g->s_search));
   g->ev_head = g->ev_tail;
+  unsigned int status = 0;
+  SG_CUDA(cudaMemcpy(&status, g->base + g->off_status(), 4, cudaMemcpyDeviceToHost));
+  if (status != 0) {
+    set_error("hs_shardgroup: a traversal warp gave up waiting for another rank's acknowledgement (peer dead or "
+              "not submitting the same batches); results since then are unreliable");
+    return HS_ERR_CUDA;
+  }
   return HS_OK;
 }
 

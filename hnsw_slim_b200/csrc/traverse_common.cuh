@@ -238,11 +238,29 @@ __device__ __forceinline__ void st_release_sys(uint32_t *p, uint32_t v) {
 }
 // Called by a whole warp before its first row store of a launch: the destination slot of every rank
 // must have been merged (ack words are written by the ranks' merge streams).  Sequence numbers are
-// compared as signed differences so that they may wrap.
+// compared as signed differences so that they may wrap.  The host never launches a batch before THIS
+// rank's merge of batch seq - depth has completed (hs_shardgroup_submit), so a warp only ever waits
+// here for OTHER ranks' merge streams — it cannot hold the SM slot its own merge kernel needs.  A wait
+// that exceeds sc.ack_timeout_ns (a dead or wedged peer) is recorded in *sc.status and abandoned: the
+// batch's rows are then unreliable, which hs_shardgroup_wait reports, but the GPU does not hang.
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 __device__ __forceinline__ void scatter_wait_acks(const ScatterDst &sc, int lane) {
   if (sc.ack_need == 0) return;
   if ((uint32_t)lane < sc.n_acks) {
-    while ((int32_t)(ld_acquire_sys(sc.acks + lane) - sc.ack_need) < 0) __nanosleep(256);
+    if ((int32_t)(ld_acquire_sys(sc.acks + lane) - sc.ack_need) < 0) {
+      const unsigned long long t0 = global_ns();
+      while ((int32_t)(ld_acquire_sys(sc.acks + lane) - sc.ack_need) < 0) {
+        __nanosleep(512);
+        if (global_ns() - t0 > sc.ack_timeout_ns) {
+          if (sc.status) atomicMax(sc.status, 1u);
+          break;
+        }
+      }
+    }
   }
   __syncwarp();
 }

@@ -249,6 +249,60 @@ def test_scatter_search_writes_every_destination(tmp_path):
         assert (tl[0] == -7).all() and (tl[2] == -7).all() and (td[0] == -7).all()      # other slots untouched
 
 
+@pytest.mark.gpu
+def test_shard_group_lagging_rank_does_not_deadlock(tmp_path):
+    """One rank runs far ahead of the other (its host thread submits 12 batches at once, the other rank
+    starts half a second later).  The table slot of batch s is reused by batch s + depth, whose warps wait
+    in the kernel for every rank's acknowledgement of batch s: the fast rank must not fill its SMs with
+    such waiting warps while its own merge of batch s still needs an SM slot (hs_shardgroup_submit holds
+    the HOST until the rank's own merge of batch s is complete).  Both ranks share cuda:0 here, which
+    makes the slot shortage worse than on separate GPUs."""
+    import threading
+    import time as _time
+    import torch
+    from hnsw_slim_b200 import capi, sharding
+    from hnsw_slim_b200.synth import make_dataset
+    n, nq, dim, k, ef, S = 12000, 8000, 96, 10, 30, 2
+    base, q = make_dataset(n, nq, dim, rank=8, seed=19)
+    paths = _build_shards(str(tmp_path), base, S)
+    shards = [capi.Index(p, dim) for p in paths]
+    for s_ in shards:
+        s_.set_ef(ef)
+    pl, pd = zip(*[s_.search(q, k) for s_ in shards])
+    want_l, want_d = sharding.merge_numpy(np.stack(pl), np.stack(pd), k)
+    groups = [capi.ShardGroup([shards[r]], 2, r, nq, k, depth=2) for r in range(2)]
+    capi.ShardGroup.connect_local(groups)
+    dq = torch.from_numpy(q).cuda()
+    nb = 12
+    outs = [[(torch.empty((nq, k), dtype=torch.int32, device="cuda"), torch.empty((nq, k), device="cuda"))
+             for _ in range(nb)] for _ in range(2)]
+    torch.cuda.synchronize()
+    errs = []
+
+    def run(r, delay):
+        try:
+            _time.sleep(delay)
+            for b in range(nb):
+                groups[r].submit(dq.data_ptr(), nq, outs[r][b][0].data_ptr(), outs[r][b][1].data_ptr())
+            groups[r].wait()
+        except Exception as e:      # pragma: no cover
+            errs.append(e)
+
+    th = [threading.Thread(target=run, args=(0, 0.0)), threading.Thread(target=run, args=(1, 0.5))]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join(timeout=120)
+    assert not any(t.is_alive() for t in th), "shard group deadlocked"
+    assert not errs, errs
+    for r in range(2):
+        for b in range(nb):
+            assert np.array_equal(outs[r][b][0].cpu().numpy().view(np.uint32), want_l), (r, b)
+            assert np.array_equal(outs[r][b][1].cpu().numpy().view(np.uint32), want_d.view(np.uint32)), (r, b)
+    for g in groups:
+        g.close()
+
+
 def _fused_worker(rank, world, paths, qfile, dim, k, ef, port, outdir):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
