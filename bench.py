@@ -111,8 +111,10 @@ def prepare_inputs(w: dict, n_query_batches: int, build_rank: bool):
 class ClockSampler:
     """Samples SM clock / throttle reasons through NVML during the timed region."""
 
-    def __init__(self, device_index: int):
+    def __init__(self, device_index: int, interval_s: float = 0.004):
         self.samples, self.reasons, self.max_mhz = [], set(), None
+        self.interval_s = interval_s
+        self.power_w = []
         self._stop = threading.Event()
         self._thr = None
         try:
@@ -141,12 +143,13 @@ class ClockSampler:
                 for bit, name in names.items():
                     if r & bit:
                         self.reasons.add(name)
+                self.power_w.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
             except Exception:
                 pass
-            self._stop.wait(0.004)
+            self._stop.wait(self.interval_s)
 
     def __enter__(self):
-        if self.nv:
+        if self.nv and not os.environ.get("HS_BENCH_NO_SAMPLER"):
             self._thr = threading.Thread(target=self._run, daemon=True)
             self._thr.start()
         return self
@@ -159,7 +162,7 @@ class ClockSampler:
     def summary(self):
         med = float(np.median(self.samples)) if self.samples else None
         return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
-                "samples": len(self.samples)}
+                "samples": len(self.samples), "power_w_max": max(self.power_w) if self.power_w else None}
 
 
 def measured_peaks():
@@ -330,7 +333,9 @@ def run_gpu(args, w):
     # only the two bracketing events sit on the stream: an event between two launches would split
     # the programmatic-serialization edge that lets consecutive batches overlap (hs_set_overlap)
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
-    with ClockSampler(local_rank) as clocks:
+    clocks = ClockSampler(local_rank)
+    barrier()
+    with clocks:
         ev[0].record(stream)
         for i in range(args.steps):
             step(args.warmup + i)
@@ -450,10 +455,16 @@ def run_gpu(args, w):
         del ix, d_q, h_q
         torch.cuda.empty_cache()
         ws = dict(WORKLOADS["deep-sharded"])
-        if args.shard_rows:
-            ws["n"] = args.shard_rows * ws["shards"]
+        if args.shard_rows or args.shards:
+            rows = args.shard_rows or ws["n"] // ws["shards"]
+            ws["shards"] = args.shards or ws["shards"]
+            ws["n"] = rows * ws["shards"]
+            ws["desc"] = ws["desc"].replace("in 8 ", f"in {ws['shards']} ")
         sargs = argparse.Namespace(**vars(args))
         sargs.ef = None
+        # a sharded step at 8 GPUs is ~0.3 ms and ranks depend on each other: K steps of it are dominated by
+        # the ranks' start-up skew, so the object times its own, larger number of steps (reported inside)
+        sargs.steps = max(args.steps, 200)
         try:
             sharded = measure_sharded(sargs, ws, rank, local_rank, world, dist if distributed else None)
         except Exception as e:          # the headline stands on its own; say why the object is missing
@@ -566,6 +577,9 @@ def measure_sharded(args, w, rank, local_rank, world, dist):
     paths, raws = prepare_shards(w, mine, max(1, (os.cpu_count() or 1) // world))
     barrier()
     t_build = time.time() - t_build
+    # a rank that stops submitting leaves the others waiting for its flags: bound every GPU phase
+    import faulthandler
+    faulthandler.dump_traceback_later(int(os.environ.get("HS_BENCH_WATCHDOG_S", "240")), exit=True)
     ix = sharding.ShardedIndex([paths[s] for s in mine], w["dim"], metric=w["metric"], device=local_rank,
                                kind=capi.HS_KIND_SLIMQ if slimq else capi.HS_KIND_SLIM, raw_bases=raws)
     nq, k = w["nq"], w["k"]
@@ -612,6 +626,8 @@ def measure_sharded(args, w, rank, local_rank, world, dist):
             if ok.item() > 0:
                 break
     ix.set_ef(ef)
+    if rank == 0:
+        log(f"[bench] sharded: {w['shards']} shards over {world} GPUs, per-shard ef {ef}, recall ladder {ladder}")
 
     for i in range(args.warmup):
         out = step(i)
@@ -625,7 +641,9 @@ def measure_sharded(args, w, rank, local_rank, world, dist):
     else:
         s0 = s1 = torch.cuda.current_stream()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local_rank) as clocks:
+    clocks = ClockSampler(local_rank)       # NVML start-up happens before the barrier, not inside the timed region
+    barrier()
+    with clocks:
         e0.record(s0)
         for i in range(args.steps):
             out = step(args.warmup + i)
@@ -636,6 +654,34 @@ def measure_sharded(args, w, rank, local_rank, world, dist):
         torch.cuda.synchronize()
     barrier()
     ms = e0.elapsed_time(e1)
+    if rank == 0:
+        log(f"[bench] sharded: {args.steps} steps in {ms:.2f} ms on rank 0")
+    # ---- sustained: the same step, back to back for about args.sustained seconds (its own clock record) ----
+    sustained = None
+    if args.sustained > 0:
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        if world > 1:               # every rank must submit the SAME number of batches
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        n_sus = max(args.steps, int(args.sustained * 1e3 / max(float(t.item()) / args.steps, 1e-3)))
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        clocks_s = ClockSampler(local_rank, 0.05)
+        barrier()
+        with clocks_s:
+            f0.record(s0)
+            for i in range(n_sus):
+                step(args.warmup + args.steps + i)
+            if not fused:
+                ix.join()
+            f1.record(s1)
+            ix.join()
+            torch.cuda.synchronize()
+        barrier()
+        t = torch.tensor([f0.elapsed_time(f1)], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        sustained = {"value": nq * n_sus / (float(t.item()) * 1e-3), "unit": "queries/s", "steps": n_sus,
+                     "ms_per_step": float(t.item()) / n_sus, "seconds": float(t.item()) * 1e-3,
+                     "clocks": clocks_s.summary()}
     if rank == 0 and gt is not None:
         b_last = (args.warmup + args.steps - 1) % n_batches
         if b_last == 0:
@@ -698,6 +744,7 @@ def measure_sharded(args, w, rank, local_rank, world, dist):
     if rank == 0 and world == 1 and not args.no_cpu_baseline and not slimq:
         cpu = cpu_sharded_baseline(w, paths, qb[0], ef, budget_s=8.0)
     ix.close()
+    faulthandler.cancel_dump_traceback_later()
     if rank != 0:
         return None
     peaks, peak_src = measured_peaks()
@@ -721,7 +768,7 @@ def measure_sharded(args, w, rank, local_rank, world, dist):
                      "frac": per_gpu / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_src,
                      "kernel": ("hs::traverse_slimq_kernel" if slimq else "hs::traverse_kernel")
                                + " (per GPU, algorithmic bytes of all local shard launches / whole step incl. merge)"},
-        "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": args.steps * (len(mine) + 1),
+        "cpu_baseline": cpu, "e2e": e2e, "sustained": sustained, "gpu_launches": args.steps * (len(mine) + 1),
         "clocks": clocks.summary(),
     }
 
@@ -777,6 +824,9 @@ def main():
     ap.add_argument("--no-overlap", action="store_true",
                     help="do not let consecutive batches overlap on the stream (hs_set_overlap off)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--shards", type=int, default=None, help="sharded workloads: number of sub-graphs (default 8)")
+    ap.add_argument("--sustained", type=float, default=2.0,
+                    help="seconds of the back-to-back stream reported as \"sustained\" (0: skip)")
     ap.add_argument("--shard-rows", type=int, default=None,
                     help="sharded workloads: rows per shard (default: the workload's n / shards)")
     ap.add_argument("--exchange", default="fused", choices=["nccl", "fused"],
@@ -788,8 +838,11 @@ def main():
     w = dict(WORKLOADS[args.workload])
     if args.ef:
         w["ef"] = args.ef
-    if args.shard_rows and "shards" in w:
-        w["n"] = args.shard_rows * w["shards"]
+    if "shards" in w and (args.shard_rows or args.shards):
+        rows = args.shard_rows or w["n"] // w["shards"]
+        w["shards"] = args.shards or w["shards"]
+        w["n"] = rows * w["shards"]
+        w["desc"] = w["desc"].replace("in 8 ", f"in {w['shards']} ")
     if args.impl == "reference":
         run_reference(args, w)
     elif "shards" in w:
