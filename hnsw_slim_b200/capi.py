@@ -28,7 +28,7 @@ EXPORTS = [
     "hs_exchange_search", "hs_exchange_signal_and_wait", "hs_exchange_tables", "hs_exchange_free",
     "hs_shardgroup_create", "hs_shardgroup_handle", "hs_shardgroup_connect", "hs_shardgroup_connect_local",
     "hs_shardgroup_submit", "hs_shardgroup_wait_oldest", "hs_shardgroup_wait", "hs_shardgroup_streams",
-    "hs_shardgroup_free",
+    "hs_shardgroup_free", "hs_build_slim_index_gpu", "hs_save_index",
 ]
 
 
@@ -120,6 +120,8 @@ def lib():
         L.hs_exchange_tables.argtypes = [vp, C.c_uint32, C.POINTER(vp), C.POINTER(vp)]
         L.hs_exchange_free.argtypes = [vp]
         L.hs_exchange_free.restype = None
+        L.hs_build_slim_index_gpu.argtypes = [vp, sz, sz, i32, C.POINTER(BuildParams), vp, i32, C.POINTER(vp)]
+        L.hs_save_index.argtypes = [vp, C.c_char_p]
         L.hs_shardgroup_create.argtypes = [vp, sz, i32, i32, sz, sz, i32, C.POINTER(vp)]
         L.hs_shardgroup_handle.argtypes = [vp, vp]
         L.hs_shardgroup_connect.argtypes = [vp, vp]
@@ -176,6 +178,35 @@ class Index:
                                     C.byref(self._h)))
         self.dim = dim
         return self
+
+    @classmethod
+    def build_gpu(cls, base, *, metric: int = HS_METRIC_L2, M: int = 16, ef_construction: int = 200,
+                  branching: str = "4", labels=None, seed: int = 100, device: int = 0, base_ptr: int | None = None,
+                  n: int | None = None, dim: int | None = None, **prune) -> "Index":
+        """hs_build_slim_index_gpu: HNSW build + HNSW-Slim conversion on the device.  `base` is a host array,
+        or pass base_ptr / n / dim for rows that already live in device memory."""
+        self = cls.__new__(cls)
+        self._h = C.c_void_p()
+        if base_ptr is None:
+            b = _f32(base)
+            base_ptr, n, dim = b.ctypes.data, b.shape[0], b.shape[1]
+        p = BuildParams()
+        lib().hs_build_params_default(C.byref(p))
+        p.M, p.ef_construction, p.branching_factor = M, ef_construction, branching.encode()
+        p.seed = seed
+        for k_, v in prune.items():
+            setattr(p, k_, v)
+        lab = None
+        if labels is not None:
+            labels = np.ascontiguousarray(labels, dtype=np.uint64)
+            lab = labels.ctypes.data
+        _check(lib().hs_build_slim_index_gpu(base_ptr, n, dim, metric, C.byref(p), lab, device, C.byref(self._h)))
+        self.dim = dim
+        return self
+
+    def save(self, path: str) -> None:
+        """hs_save_index: the reference's saveIndex format (slim.h:717-751)."""
+        _check(lib().hs_save_index(self._h, path.encode()))
 
     def close(self) -> None:
         if getattr(self, "_h", None):

@@ -86,20 +86,32 @@ int upload(T **dst, const T *src, size_t count, size_t *bytes_total) {
   return HS_OK;
 }
 
-int build_index(const HostGraph &g, int metric, int device, const float *raw_base, hs_index **out) {
-  int rc = select_device(device);
-  if (rc != HS_OK) return rc;
-  std::unique_ptr<hs_index> ix(new hs_index);
-  ix->device = device;
+// per-handle scratch, knobs and the handle's own stream (both construction paths end here)
+int init_scratch(hs_index *ix) {
   cudaDeviceProp prop;
-  HS_CUDA(cudaGetDeviceProperties(&prop, device));
+  HS_CUDA(cudaGetDeviceProperties(&prop, ix->device));
   ix->sm_count = prop.multiProcessorCount;
   if (const char *hb = std::getenv("HS_HASH_BITS")) ix->hash_bits_override = std::atoi(hb);
   if (const char *gh = std::getenv("HS_GHASH")) ix->ghash_mode = std::atoi(gh);
   if (const char *tf = std::getenv("HS_TRAVERSE_FLAGS")) ix->traverse_flags = (uint32_t)std::atoi(tf);
   if (const char *qf = std::getenv("HS_SLIMQ_FLAGS")) ix->slimq_flags = (uint32_t)std::atoi(qf);
   if (const char *zc = std::getenv("HS_ZERO_COPY")) ix->zero_copy = std::atoi(zc) != 0;
+  if (cudaMalloc(&ix->d_work, kWorkRing * sizeof(unsigned long long)) != cudaSuccess ||
+      cudaMemset(ix->d_work, 0xff, kWorkRing * sizeof(unsigned long long)) != cudaSuccess ||
+      cudaMalloc(&ix->d_stats, 4 * sizeof(unsigned long long)) != cudaSuccess ||
+      cudaMemset(ix->d_stats, 0, 4 * sizeof(unsigned long long)) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    set_error(std::string("scratch allocation: ") + cudaGetErrorString(cudaGetLastError()));
+    return HS_ERR_CUDA;
+  }
+  return HS_OK;
+}
 
+int build_index(const HostGraph &g, int metric, int device, const float *raw_base, hs_index **out) {
+  int rc = select_device(device);
+  if (rc != HS_OK) return rc;
+  std::unique_ptr<hs_index> ix(new hs_index);
+  ix->device = device;
   size_t bytes = 0;
   auto fail = [&](int code) {
     hs_free(ix.release());
@@ -143,14 +155,7 @@ int build_index(const HostGraph &g, int metric, int device, const float *raw_bas
   for (int l = 1; l <= g.maxlevel && l < kMaxLevels; ++l)
     if ((rc = upload(&ix->d_upper_adj[l], g.upper_adj[l].data(), g.upper_adj[l].size(), &bytes)) != HS_OK)
       return fail(rc);
-  if (cudaMalloc(&ix->d_work, kWorkRing * sizeof(unsigned long long)) != cudaSuccess ||
-      cudaMemset(ix->d_work, 0xff, kWorkRing * sizeof(unsigned long long)) != cudaSuccess ||
-      cudaMalloc(&ix->d_stats, 4 * sizeof(unsigned long long)) != cudaSuccess ||
-      cudaMemset(ix->d_stats, 0, 4 * sizeof(unsigned long long)) != cudaSuccess ||
-      cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking) != cudaSuccess) {
-    set_error(std::string("scratch allocation: ") + cudaGetErrorString(cudaGetLastError()));
-    return fail(HS_ERR_CUDA);
-  }
+  if ((rc = init_scratch(ix.get())) != HS_OK) return fail(rc);
 
   for (int l = 0; l <= g.maxlevel && l < kMaxLevels; ++l) ix->level_count[l] = g.level_count[l];
   hs_index_info &I = ix->info;
@@ -331,6 +336,59 @@ int search_device_slimq(hs_index *ix, const float *d_queries, size_t nq, size_t 
 }
 
 }  // namespace
+
+int hs::adopt_device_graph(DeviceGraph &dg, int device, hs_index **out) {
+  std::unique_ptr<hs_index> ix(new hs_index);
+  ix->device = device;
+  ix->d_vec = dg.d_vec;
+  ix->d_adj0 = dg.d_adj0;
+  ix->d_upper_slot = dg.d_upper_slot;
+  for (int l = 0; l < kMaxLevels; ++l) ix->d_upper_adj[l] = dg.d_upper_adj[l];
+  dg.d_vec = nullptr;                     // owned by the handle from here on (hs_free releases them)
+  dg.d_adj0 = nullptr;
+  dg.d_upper_slot = nullptr;
+  for (auto &p : dg.d_upper_adj) p = nullptr;
+  auto fail = [&](int code) {
+    hs_free(ix.release());
+    return code;
+  };
+  int rc = select_device(device);
+  if (rc != HS_OK) return fail(rc);
+  size_t bytes = dg.n * dg.dim_padded * 4 + dg.n * (size_t)dg.deg0_stride * 4 + dg.n * 4;
+  for (int l = 1; l <= dg.maxlevel && l < kMaxLevels; ++l) bytes += (size_t)dg.level_count[l] * dg.upper_stride * 4;
+  if ((rc = upload(&ix->d_labels, dg.h_labels, dg.n, &bytes)) != HS_OK) return fail(rc);
+  if (cudaMalloc(&ix->d_deleted, dg.n) != cudaSuccess || cudaMemset(ix->d_deleted, 0, dg.n) != cudaSuccess) {
+    set_error("cudaMalloc (deleted flags) failed");
+    cudaGetLastError();
+    return fail(HS_ERR_NOMEM);
+  }
+  bytes += dg.n;
+  if ((rc = init_scratch(ix.get())) != HS_OK) return fail(rc);
+  for (int l = 0; l <= dg.maxlevel && l < kMaxLevels; ++l) ix->level_count[l] = dg.level_count[l];
+  hs_index_info &I = ix->info;
+  I.n = dg.n;
+  I.dim = dg.dim;
+  I.dim_padded = dg.dim_padded;
+  I.M = dg.M;
+  I.maxM = dg.maxM;
+  I.maxM0 = dg.maxM0;
+  I.ef_construction = dg.ef_construction;
+  I.maxlevel = dg.maxlevel;
+  I.threshold_level = dg.threshold_level;
+  I.enterpoint = dg.enterpoint;
+  I.has_deleted = 0;
+  I.kind = dg.kind;
+  I.metric = dg.metric;
+  I.deg0_stride = dg.deg0_stride;
+  I.max_deg0 = dg.max_deg0;
+  I.upper_stride = dg.upper_stride;
+  I.n_upper = dg.n_upper;
+  I.sum_deg0 = dg.sum_deg0;
+  I.device_bytes = bytes;
+  I.ef = 10;
+  *out = ix.release();
+  return HS_OK;
+}
 
 int hs::search_device(hs_index *ix, const float *d_queries, size_t nq, size_t k, uint32_t *d_labels,
                       float *d_dists, uint32_t *d_perq, cudaStream_t stream, const ScatterDst *scatter,
@@ -1038,6 +1096,145 @@ int hs_build_hnsw_graph(const float *base, size_t n, size_t dim, int metric, con
   if (rc0 != HS_OK) return rc0;
   return build_hnsw_graph(base, n, dim, metric, p->M, p->ef_construction, bf, p->threads, p->seed, labels,
                           out_graph_path);
+}
+
+int hs_build_slim_index_gpu(const float *base, size_t n, size_t dim, int metric, const hs_build_params *p,
+                            const uint64_t *labels, int device, hs_index **out) {
+  if (!out) {
+    set_error("null argument");
+    return HS_ERR_ARG;
+  }
+  *out = nullptr;
+  if (metric != HS_METRIC_L2 && metric != HS_METRIC_IP) {
+    set_error("unknown metric");
+    return HS_ERR_ARG;
+  }
+  double bf;
+  int rc0 = parse_branching(p, &bf);
+  if (rc0 != HS_OK) return rc0;
+  try {
+    return gpu_build_slim_index(base, n, dim, metric, p, bf, labels, device, out);
+  } catch (const std::bad_alloc &) {
+    set_error("hs_build_slim_index_gpu: out of host memory");
+    return HS_ERR_NOMEM;
+  }
+}
+
+// saveIndex (slim.h:717-751) of an HBM-resident hnsw_slim index: header, element records
+// [int32 level][uint32 total][uint64 label][8 stale pointer bytes][float vec[dim]], then per node
+// uint32 blob size + [uint16 offsets[level]][uint32 ids[total]].
+int hs_save_index(hs_index *ix, const char *path) {
+  if (!ix || !path) {
+    set_error("null argument");
+    return HS_ERR_ARG;
+  }
+  if (ix->info.kind != HS_KIND_SLIM) {
+    set_error("hs_save_index: only hnsw_slim indices can be saved");
+    return HS_ERR_UNSUPPORTED;
+  }
+  try {
+    HS_CUDA(cudaSetDevice(ix->device));
+    HS_CUDA(cudaDeviceSynchronize());
+    const hs_index_info &I = ix->info;
+    const size_t n = I.n, dim = I.dim, dp = I.dim_padded;
+    std::vector<int32_t> slot(n);
+    std::vector<uint32_t> labels(n), adj0(n * (size_t)I.deg0_stride);
+    HS_CUDA(cudaMemcpy(slot.data(), ix->d_upper_slot, n * 4, cudaMemcpyDeviceToHost));
+    HS_CUDA(cudaMemcpy(labels.data(), ix->d_labels, n * 4, cudaMemcpyDeviceToHost));
+    HS_CUDA(cudaMemcpy(adj0.data(), ix->d_adj0, adj0.size() * 4, cudaMemcpyDeviceToHost));
+    std::vector<std::vector<uint32_t>> up(I.maxlevel + 1);
+    for (int l = 1; l <= I.maxlevel; ++l) {
+      up[l].resize((size_t)ix->level_count[l] * I.upper_stride);
+      if (!up[l].empty())
+        HS_CUDA(cudaMemcpy(up[l].data(), ix->d_upper_adj[l], up[l].size() * 4, cudaMemcpyDeviceToHost));
+    }
+    auto level_of = [&](size_t i) {
+      int lv = 0;
+      if (slot[i] >= 0)
+        while (lv < I.maxlevel && (uint32_t)slot[i] < ix->level_count[lv + 1]) ++lv;
+      return lv;
+    };
+    auto list = [&](size_t i, int l, const uint32_t **ids) {
+      const uint32_t *row = l == 0 ? &adj0[i * I.deg0_stride] : &up[l][(size_t)slot[i] * I.upper_stride];
+      const uint32_t stride = l == 0 ? I.deg0_stride : I.upper_stride;
+      uint32_t c = 0;
+      while (c < stride && row[c] != kInvalid) ++c;
+      *ids = row;
+      return c;
+    };
+    FILE *f = std::fopen(path, "wb");
+    if (!f) {
+      set_error(std::string("cannot open ") + path + " for writing");
+      return HS_ERR_IO;
+    }
+    auto put = [&](const void *p, size_t sz) { return std::fwrite(p, 1, sz, f) == sz; };
+    bool ok = true;
+    const uint64_t rec = 24 + 4 * dim;
+    const uint64_t hdr[6] = {n, rec, 8, 4, 24, 16};
+    ok &= put(hdr, sizeof hdr);
+    const int32_t ml = I.maxlevel, thr = I.threshold_level;
+    const uint32_t ep = I.enterpoint;
+    ok &= put(&ml, 4) && put(&thr, 4) && put(&ep, 4);
+    const uint64_t ms[4] = {I.maxM, I.maxM0, I.M, I.ef_construction};
+    ok &= put(ms, sizeof ms);
+    const uint8_t has_deleted = 0;
+    ok &= put(&has_deleted, 1);
+    // element records, the vectors streamed from the device in slabs
+    const size_t slab = std::max<size_t>(1, (64u << 20) / (dp * 4));
+    std::vector<float> rows(slab * dp);
+    std::vector<uint8_t> record(rec);
+    for (size_t i0 = 0; i0 < n && ok; i0 += slab) {
+      const size_t cnt = std::min(slab, n - i0);
+      HS_CUDA(cudaMemcpy(rows.data(), ix->d_vec + i0 * dp, cnt * dp * 4, cudaMemcpyDeviceToHost));
+      for (size_t j = 0; j < cnt && ok; ++j) {
+        const size_t i = i0 + j;
+        const int32_t lv = level_of(i);
+        uint32_t total = 0;
+        const uint32_t *ids;
+        for (int l = 0; l <= lv; ++l) total += list(i, l, &ids);
+        const uint64_t label = labels[i], stale_ptr = 0;
+        std::memcpy(&record[0], &lv, 4);
+        std::memcpy(&record[4], &total, 4);
+        std::memcpy(&record[8], &label, 8);
+        std::memcpy(&record[16], &stale_ptr, 8);
+        std::memcpy(&record[24], &rows[j * dp], 4 * dim);
+        ok &= put(record.data(), rec);
+      }
+    }
+    std::vector<uint8_t> blob;
+    for (size_t i = 0; i < n && ok; ++i) {
+      const int lv = level_of(i);
+      uint32_t total = 0;
+      const uint32_t *ids;
+      for (int l = 0; l <= lv; ++l) total += list(i, l, &ids);
+      const uint32_t bsz = (uint32_t)(2 * lv + 4 * total);
+      ok &= put(&bsz, 4);
+      if (bsz == 0 || total == 0) continue;          // slim.h:741-748
+      blob.resize(bsz);
+      uint32_t run = 0;
+      size_t w = 2 * (size_t)lv;
+      for (int l = 0; l <= lv; ++l) {
+        const uint32_t c = list(i, l, &ids);
+        std::memcpy(&blob[w], ids, 4 * (size_t)c);
+        w += 4 * (size_t)c;
+        run += c;
+        if (l < lv) {
+          const uint16_t o = (uint16_t)run;
+          std::memcpy(&blob[2 * l], &o, 2);
+        }
+      }
+      ok &= put(blob.data(), bsz);
+    }
+    ok &= std::fclose(f) == 0;
+    if (!ok) {
+      set_error(std::string("write error on ") + path);
+      return HS_ERR_IO;
+    }
+    return HS_OK;
+  } catch (const std::bad_alloc &) {
+    set_error("hs_save_index: out of host memory");
+    return HS_ERR_NOMEM;
+  }
 }
 
 // ---- host-only inspection of the flattened graph (used by the CPU test-suite; no CUDA) ----

@@ -85,4 +85,26 @@ int search_device(hs_index *ix, const float *d_queries, size_t nq, size_t k, uin
                   uint32_t *d_perq, cudaStream_t stream, const ScatterDst *scatter = nullptr,
                   uint32_t *plan_warps = nullptr);
 
+// A finished index whose arrays already live on the device (graph_gpu.cu); adopt_device_graph wraps it
+// into an hs_index that owns them (on failure the arrays are freed).
+struct DeviceGraph {
+  size_t n = 0, dim = 0, dim_padded = 0;
+  int metric = 0, kind = HS_KIND_SLIM;
+  uint64_t M = 0, maxM = 0, maxM0 = 0, ef_construction = 0;
+  int maxlevel = 0, threshold_level = 0;
+  uint32_t enterpoint = 0, deg0_stride = 32, max_deg0 = 0, upper_stride = 8, n_upper = 0;
+  uint64_t sum_deg0 = 0;
+  uint32_t level_count[kMaxLevels] = {};
+  float *d_vec = nullptr;
+  uint32_t *d_adj0 = nullptr;
+  int32_t *d_upper_slot = nullptr;
+  uint32_t *d_upper_adj[kMaxLevels] = {};
+  const uint32_t *h_labels = nullptr;      // host, n entries
+};
+int adopt_device_graph(DeviceGraph &dg, int device, hs_index **out);
+
+// graph_gpu.cu
+int gpu_build_slim_index(const float *base, size_t n, size_t dim, int metric, const hs_build_params *bp,
+                         double branching, const uint64_t *labels, int device, hs_index **out);
+
 }  // namespace hs

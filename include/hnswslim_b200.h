@@ -326,6 +326,21 @@ int hs_build_slimq_graph(const float *base, size_t n, size_t dim, const hs_build
                          const float *centroids, size_t num_cluster, const uint32_t *cluster_ids,
                          const uint64_t *labels, const char *out_graph_path);
 
+/* GPU-side index construction: the same two steps as hs_build_slim_graph — the
+ * HNSW build of hnsw_slim_strategy.h:60-82 (HierarchicalNSW::addPoint, hnsw.h:1248-1376) and
+ * convertFromHNSW (slim.h:867-1108: PruneByHeuristic per node and level, reverse-edge merge, re-prune,
+ * hierarchical pruning) — executed on `device` with the index staying in HBM: `base` (n x dim floats, host
+ * OR device memory) is copied once into the engine's 128-byte-aligned row store and the finished index is
+ * returned as an hs_index, ready for hs_search_batch*.  Points enter a layer in batches (one warp per
+ * point: ef_construction beam search + neighbour selection; reverse edges through one radix sort per
+ * batch), so the graph is not the one a sequential build gives; its recall/cost is measured against the
+ * host builder's in tests/test_gpu_build.py.  Needs 2 <= M <= 32, ef_construction <= 256.
+ * hs_save_index writes any HBM-resident hnsw_slim index in saveIndex's format (slim.h:717-751): the
+ * reference's loadIndex (and hs_load) read it. */
+int hs_build_slim_index_gpu(const float *base, size_t n, size_t dim, int metric, const hs_build_params *p,
+                            const uint64_t *labels, int device, hs_index **out);
+int hs_save_index(hs_index *, const char *out_graph_path);
+
 /* Host-only inspection of the flattened form of a .graph (no CUDA needed): what
  * hs_load uploads.  Used by the CPU test-suite to check the loader against the
  * reference's accessors (slim.h:620-661). */
