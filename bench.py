@@ -555,7 +555,71 @@ def sharded_ground_truth(w: dict, q: np.ndarray, k: int, device: int):
     return np.take_along_axis(lab, order, 1).astype(np.uint32)
 
 
-EF_LADDER = [10, 12, 16, 20, 24, 32, 48, 64, 100, 200]
+def shard_rows_device(w: dict, s: int, device: int):
+    """Rows of shard s generated ON the GPU (torch's Philox stream, one generator per 65536-row chunk, the
+    latent model of synth.py with the same mixing matrix): the 100M-shaped corpora never touch the host.
+    Deterministic in (row, dim, rank, seed) for this torch build, whatever the number of ranks."""
+    import torch
+    from hnsw_slim_b200 import sharding
+    lo, hi = sharding.shard_ranges(w["n"], w["shards"])[s]
+    chunk = 1 << 16
+    dev = torch.device("cuda", device)
+    A = torch.from_numpy(np.random.default_rng(1).standard_normal((w["rank"], w["dim"])).astype(np.float32)).to(dev)
+    out = torch.empty((hi - lo, w["dim"]), dtype=torch.float32, device=dev)
+    g = torch.Generator(device=dev)
+    for c in range(lo // chunk, (hi + chunk - 1) // chunk):
+        g.manual_seed(0x5EED0000 + c)
+        z = torch.randn((chunk, w["rank"]), generator=g, device=dev)
+        eps = torch.randn((chunk, w["dim"]), generator=g, device=dev)
+        rows = torch.addmm(eps * 0.1, z, A)
+        a, b = max(lo, c * chunk), min(hi, (c + 1) * chunk)
+        out[a - lo: b - lo] = rows[a - c * chunk: b - c * chunk]
+    return out
+
+
+def build_shards_gpu(w: dict, my_shards, device: int, gt_queries, k: int):
+    """This rank's shards built on its GPU (hs_build_slim_index_gpu) from device-generated rows, plus — while
+    the rows are at hand — the shard-local exact top-k of `gt_queries` for the recall of the merged result."""
+    import torch
+    from hnsw_slim_b200 import capi, sharding
+    ranges = sharding.shard_ranges(w["n"], w["shards"])
+    shards, gt_parts = [], []
+    d_gq = torch.from_numpy(gt_queries).cuda() if gt_queries is not None else None
+    for s in my_shards:
+        lo, hi = ranges[s]
+        t0 = time.time()
+        rows = shard_rows_device(w, s, device)
+        torch.cuda.synchronize()
+        t1 = time.time()
+        if d_gq is not None:
+            ns = d_gq.shape[0]
+            gl = torch.empty((ns, k), dtype=torch.int32, device="cuda")
+            gd = torch.empty((ns, k), dtype=torch.float32, device="cuda")
+            capi.bruteforce_knn_device(rows.data_ptr(), hi - lo, w["dim"], d_gq.data_ptr(), ns, k, gl.data_ptr(),
+                                       gd.data_ptr(), metric=w["metric"], stream=torch.cuda.current_stream().cuda_stream)
+            torch.cuda.synchronize()
+            gt_parts.append((gl.cpu().numpy().view(np.uint32).astype(np.int64) + lo, gd.cpu().numpy()))
+        t2 = time.time()
+        ix = capi.Index.build_gpu(None, base_ptr=rows.data_ptr(), n=hi - lo, dim=w["dim"], metric=w["metric"], M=w["M"],
+                                  ef_construction=w["efc"], branching="4", labels=np.arange(lo, hi, dtype=np.uint64),
+                                  device=device)
+        del rows
+        torch.cuda.empty_cache()
+        log(f"[bench] shard {s} [{lo},{hi}): rows generated on the GPU in {t1-t0:.1f}s, exact top-k {t2-t1:.1f}s, "
+            f"index built on the GPU in {time.time()-t2:.1f}s")
+        shards.append(ix)
+    return shards, gt_parts
+
+
+def merge_ground_truth(parts, k: int):
+    """[(labels[ns,k] int64 global, dists[ns,k])] over all shards -> exact global top-k labels."""
+    lab = np.concatenate([p[0] for p in parts], 1)
+    dst = np.concatenate([p[1] for p in parts], 1)
+    order = np.argsort(dst, axis=1, kind="stable")[:, :k]        # parts arrive in label order: ties -> smaller label
+    return np.take_along_axis(lab, order, 1).astype(np.uint32)
+
+
+EF_LADDER = [10, 12, 16, 20, 24, 28, 32, 40, 48, 64, 80, 100, 128, 200]
 
 
 def measure_sharded(args, w, rank, local_rank, world, dist):
@@ -573,18 +637,35 @@ def measure_sharded(args, w, rank, local_rank, world, dist):
     slimq = w.get("kind") == "slimq"
     w = dict(w, desc=w["desc"].format(n=w["n"], rows=w["n"] // w["shards"]))
     mine = sharding.shards_of_rank(w["shards"], rank, world)
-    t_build = time.time()
-    paths, raws = prepare_shards(w, mine, max(1, (os.cpu_count() or 1) // world))
-    barrier()
-    t_build = time.time() - t_build
-    # a rank that stops submitting leaves the others waiting for its flags: bound every GPU phase
-    import faulthandler
-    faulthandler.dump_traceback_later(int(os.environ.get("HS_BENCH_WATCHDOG_S", "240")), exit=True)
-    ix = sharding.ShardedIndex([paths[s] for s in mine], w["dim"], metric=w["metric"], device=local_rank,
-                               kind=capi.HS_KIND_SLIMQ if slimq else capi.HS_KIND_SLIM, raw_bases=raws)
     nq, k = w["nq"], w["k"]
     n_batches = min(8, args.warmup + args.steps)
     qb = sharded_queries(w, n_batches)
+    ns = min(1000, nq)
+    builder = "host" if slimq else args.builder
+    t_build = time.time()
+    paths, gt = None, None
+    if builder == "gpu":
+        shards, gt_parts = build_shards_gpu(w, mine, local_rank, None if args.no_recall else qb[0][:ns], k)
+        if not args.no_recall:
+            if world > 1:
+                allp = [None] * world
+                dist.all_gather_object(allp, gt_parts)
+                gt_parts = [p for rp in allp for p in rp]
+            gt = merge_ground_truth(gt_parts, k) if rank == 0 else None
+        barrier()
+        t_build = time.time() - t_build
+        ix = sharding.ShardedIndex.from_indices(shards, w["dim"], device=local_rank)
+    else:
+        paths, raws = prepare_shards(w, mine, max(1, (os.cpu_count() or 1) // world))
+        barrier()
+        t_build = time.time() - t_build
+        ix = sharding.ShardedIndex([paths[s] for s in mine], w["dim"], metric=w["metric"], device=local_rank,
+                                   kind=capi.HS_KIND_SLIMQ if slimq else capi.HS_KIND_SLIM, raw_bases=raws)
+        if rank == 0 and not args.no_recall:
+            gt = sharded_ground_truth(w, qb[0][:ns], k, local_rank)
+    # a rank that stops submitting leaves the others waiting for its flags: bound every GPU phase
+    import faulthandler
+    faulthandler.dump_traceback_later(int(os.environ.get("HS_BENCH_WATCHDOG_S", "240")), exit=True)
     d_q = [torch.from_numpy(q).cuda() for q in qb]
     depth = 4
     fused = args.exchange == "fused"
@@ -606,8 +687,6 @@ def measure_sharded(args, w, rank, local_rank, world, dist):
         return ix.search(d_q[i % n_batches], nq, k, exchange="nccl")
 
     # ---- per-shard ef: the smallest rung of the ladder whose recall@10 of the MERGED result is >= 0.95 ----
-    ns = min(1000, nq)
-    gt = sharded_ground_truth(w, qb[0][:ns], k, local_rank) if rank == 0 and not args.no_recall else None
     ef, recall, ladder = w["ef"], None, []
     if args.ef is None and not args.no_recall:
         for ef in EF_LADDER:
@@ -656,6 +735,8 @@ def measure_sharded(args, w, rank, local_rank, world, dist):
     ms = e0.elapsed_time(e1)
     if rank == 0:
         log(f"[bench] sharded: {args.steps} steps in {ms:.2f} ms on rank 0")
+    stats = [s_.stats() for s_ in ix.shards]          # counters of the K timed steps (before the sustained stream)
+    infos = [s_.info() for s_ in ix.shards]
     # ---- sustained: the same step, back to back for about args.sustained seconds (its own clock record) ----
     sustained = None
     if args.sustained > 0:
@@ -687,8 +768,6 @@ def measure_sharded(args, w, rank, local_rank, world, dist):
         if b_last == 0:
             lab = out[0][:ns].cpu().numpy().view(np.uint32)
             recall = float(np.mean([len(set(a) & set(b)) / k for a, b in zip(lab, gt)]))
-    stats = [s_.stats() for s_ in ix.shards]
-    infos = [s_.info() for s_ in ix.shards]
     if slimq:
         alg = sum(st["n_dist"] * (inf["padded_dim_q"] // 8 + 16) + st["n_rerank"] * 4 * inf["dim_padded"]
                   + st["n_hops"] * (8 + 4 * inf["sum_deg0"] / inf["n"]) for st, inf in zip(stats, infos)) / args.steps
@@ -742,7 +821,17 @@ def measure_sharded(args, w, rank, local_rank, world, dist):
     # ---- the reference's CPU search on ONE shard (rank 0, N=1 only; bounded sample) ----
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline and not slimq:
-        cpu = cpu_sharded_baseline(w, paths, qb[0], ef, budget_s=8.0)
+        try:
+            if paths is None:           # GPU-built shards live in HBM only: write shard 0 in saveIndex's format
+                os.makedirs(CACHE, exist_ok=True)
+                paths = [os.path.join(CACHE, f"gpu_built_shard0_{os.getpid()}.graph")]
+                ix.shards[0].save(paths[0])
+            cpu = cpu_sharded_baseline(w, paths, qb[0], ef, budget_s=8.0)
+        except Exception as e:
+            log(f"[bench] CPU baseline of the sharded workload failed: {e!r}")
+        finally:
+            if builder == "gpu" and paths and os.path.exists(paths[0]):
+                os.remove(paths[0])
     ix.close()
     faulthandler.cancel_dump_traceback_later()
     if rank != 0:
@@ -762,6 +851,9 @@ def measure_sharded(args, w, rank, local_rank, world, dist):
                                 "nccl: one all_gather(nq*k*8 B per rank) + hs_topk_merge_device per batch"),
                    "recall_at_10": recall, "ef_ladder": ladder, "dist_evals_per_query_all_shards": evals,
                    "graph_build_s": round(t_build, 1),
+                   "graph_builder": ("hs_build_slim_index_gpu: rows generated and indexed on each rank's GPU (HNSW build + "
+                                     "convertFromHNSW on the device)" if builder == "gpu" else
+                                     "host builder (hs_build_slim_graph / hs_build_slimq_graph), cached .graph files"),
                    "l2": "each shard (%.0f MB of rows) vs 126 MB L2; a different query batch every step"
                          % (rows * w["dim"] * 4 / 1e6)},
         "roofline": {"bound": "hbm", "achieved": per_gpu, "peak": peaks["hbm_gbs"], "unit": "GB/s",
@@ -824,6 +916,8 @@ def main():
     ap.add_argument("--no-overlap", action="store_true",
                     help="do not let consecutive batches overlap on the stream (hs_set_overlap off)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--builder", default="gpu", choices=["gpu", "host"],
+                    help="sharded workloads: build the shard graphs on the GPU (default) or with the host builder")
     ap.add_argument("--shards", type=int, default=None, help="sharded workloads: number of sub-graphs (default 8)")
     ap.add_argument("--sustained", type=float, default=2.0,
                     help="seconds of the back-to-back stream reported as \"sustained\" (0: skip)")

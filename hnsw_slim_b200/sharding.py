@@ -113,6 +113,17 @@ class ShardedIndex:
         self._local = None                   # hs_shardgroup of world size 1 (NCCL form / single rank)
         self._local_shape = None
 
+    @classmethod
+    def from_indices(cls, shards, dim: int, *, device: int = 0) -> "ShardedIndex":
+        """Shards that are already resident (e.g. built on the GPU, capi.Index.build_gpu)."""
+        from . import capi
+        self = cls.__new__(cls)
+        self.capi = capi
+        self.shards = list(shards)
+        self.dim, self.device = dim, device
+        self.group = self._local = self._local_shape = None
+        return self
+
     def set_ef(self, ef: int) -> None:
         for s in self.shards:
             s.set_ef(ef)
