@@ -260,6 +260,11 @@ int parse_graph(const uint8_t *bytes, size_t size, int kind, size_t dim, HostGra
     set_error("bad maxlevel / enterpoint in .graph header");
     return HS_ERR_IO;
   }
+  if (g->n == 0) g->maxlevel = std::max(0, std::min(g->maxlevel, kMaxLevels - 1));   // empty index: the header value is -1
+  if (g->maxM > 65535 || g->maxM0 > 65535) {
+    set_error("maxM / maxM0 above 65535 in .graph header");
+    return HS_ERR_IO;
+  }
 
   size_t payload_off = 24;
   if (kind == HS_KIND_SLIM) {
@@ -277,11 +282,15 @@ int parse_graph(const uint8_t *bytes, size_t size, int kind, size_t dim, HostGra
     uint64_t size_bin = r.get<uint64_t>(), size_ex = r.get<uint64_t>();
     g->ex_bits = r.get<uint64_t>();
     g->metric_type_q = r.get<uint8_t>();
-    (void)off_ex;
-    (void)size_ex;
-    if (!r.ok || qdim != dim || g->padded_dim_q % 64 != 0 || g->padded_dim_q < dim ||
-        off_cluster != 24 || off_bin != 28 || size_bin != g->padded_dim_q / 8 + 12) {
+    // slimq.h:1498-1505: size_data_per_element = offset_ex_data + size_ex_data, offset_ex_data = 28 + size_bin_data
+    if (!r.ok || qdim != dim || g->padded_dim_q % 64 != 0 || g->padded_dim_q < dim || g->padded_dim_q > (1u << 20) ||
+        off_cluster != 24 || off_bin != 28 || size_bin != g->padded_dim_q / 8 + 12 || off_ex != 28 + size_bin ||
+        size_ex > (1ull << 32) || g->size_data_per_element != 28 + size_bin + size_ex) {
       set_error("inconsistent RaBitQ metadata in hnsw_slimq .graph header");
+      return HS_ERR_IO;
+    }
+    if (g->num_cluster == 0 || g->num_cluster > (1u << 20)) {
+      set_error("cluster count out of range in hnsw_slimq .graph header");
       return HS_ERR_IO;
     }
     const uint8_t *c = r.take(g->num_cluster * g->padded_dim_q * sizeof(float));
@@ -299,7 +308,12 @@ int parse_graph(const uint8_t *bytes, size_t size, int kind, size_t dim, HostGra
   }
 
   const size_t n = g->n, rec = g->size_data_per_element;
-  const uint8_t *elements = r.take(n * rec);
+  size_t elements_bytes = 0;
+  if (__builtin_mul_overflow(n, rec, &elements_bytes)) {
+    set_error("element count x record size overflows in .graph header");
+    return HS_ERR_IO;
+  }
+  const uint8_t *elements = r.take(elements_bytes);
   if (!r.ok) {
     set_error("truncated element records in .graph");
     return HS_ERR_IO;
@@ -339,6 +353,10 @@ int parse_graph(const uint8_t *bytes, size_t size, int kind, size_t dim, HostGra
       // [uint32 cluster @24][bin @28: uint64 code[pd/64], float f_add, f_rescale, f_error]
       const size_t words = g->padded_dim_q / 64;
       std::memcpy(&g->cluster_id[i], e + 24, 4);
+      if (g->cluster_id[i] >= g->num_cluster) {       // the kernel indexes its centroid-distance table with it
+        set_error("cluster id out of range in hnsw_slimq .graph (node " + std::to_string(i) + ")");
+        return HS_ERR_IO;
+      }
       std::memcpy(&g->bin_code[i * words], e + 28, 8 * words);
       std::memcpy(&g->f_add[i], e + 28 + 8 * words, 4);
       std::memcpy(&g->f_rescale[i], e + 28 + 8 * words + 4, 4);
@@ -421,6 +439,10 @@ int parse_hnsw_graph(const uint8_t *bytes, size_t size, size_t dim, HostGraph *g
     set_error("truncated .graph header");
     return HS_ERR_IO;
   }
+  if (g->maxM > 65535 || g->maxM0 > 65535) {          // list lengths are uint16 (hnsw.h:170-172); also keeps 4 * maxM from wrapping
+    set_error("maxM / maxM0 above 65535 in .graph header");
+    return HS_ERR_IO;
+  }
   const uint64_t links0 = 4 + 4 * g->maxM0, links = 4 + 4 * g->maxM;
   if (offset_level0 != 0 || g->offset_data != links0 || g->label_offset != links0 + 4 * dim ||
       g->size_data_per_element != links0 + 4 * dim + 8 || g->maxM0 == 0 || g->maxM == 0) {
@@ -435,8 +457,14 @@ int parse_hnsw_graph(const uint8_t *bytes, size_t size, size_t dim, HostGraph *g
     set_error("bad maxlevel / enterpoint in .graph header");
     return HS_ERR_IO;
   }
+  if (g->n == 0) g->maxlevel = std::max(0, std::min(g->maxlevel, kMaxLevels - 1));   // empty index: maxlevel_ = -1
   const size_t n = g->n, rec = g->size_data_per_element;
-  const uint8_t *elements = r.take(n * rec);
+  size_t elements_bytes = 0;
+  if (__builtin_mul_overflow(n, rec, &elements_bytes)) {
+    set_error("element count x record size overflows in .graph header");
+    return HS_ERR_IO;
+  }
+  const uint8_t *elements = r.take(elements_bytes);
   if (!r.ok) {
     set_error("truncated level-0 records in .graph");
     return HS_ERR_IO;

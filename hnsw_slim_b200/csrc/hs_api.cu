@@ -7,6 +7,7 @@
 #include <cstring>
 #include <memory>
 #include <mutex>
+#include <stdexcept>
 #include <string>
 #include <vector>
 
@@ -28,6 +29,26 @@ using namespace hs;
       return HS_ERR_CUDA;                                                             \
     }                                                                                 \
   } while (0)
+
+namespace {
+// C++ exceptions must not unwind through the C ABI: file-derived sizes feed std::vector allocations
+// (a corrupt header, or a 100M-row shard on a small host, ends in bad_alloc / length_error)
+template <typename F>
+int guarded(const char *what, F &&body) {
+  try {
+    return body();
+  } catch (const std::bad_alloc &) {
+    set_error(std::string(what) + ": out of host memory");
+    return HS_ERR_NOMEM;
+  } catch (const std::length_error &) {
+    set_error(std::string(what) + ": size field out of range (corrupt header?)");
+    return HS_ERR_IO;
+  } catch (const std::exception &e) {
+    set_error(std::string(what) + ": " + e.what());
+    return HS_ERR_IO;
+  }
+}
+}  // namespace
 
 namespace hs {
 int select_device(int device) {
@@ -525,8 +546,10 @@ int hs_abi_version(void) { return HS_ABI_VERSION; }
 
 int hs_load_memory(const void *graph_bytes, size_t graph_size, int kind, int metric, size_t dim,
                    const float *raw_base, size_t n_raw, int device, hs_index **out) {
-  return load_common(static_cast<const uint8_t *>(graph_bytes), graph_size, kind, metric, dim, raw_base,
-                     n_raw, device, out);
+  return guarded("hs_load_memory", [&] {
+    return load_common(static_cast<const uint8_t *>(graph_bytes), graph_size, kind, metric, dim, raw_base, n_raw,
+                       device, out);
+  });
 }
 
 int hs_load(const char *graph_path, int kind, int metric, size_t dim, const float *raw_base, size_t n_raw,
@@ -536,10 +559,12 @@ int hs_load(const char *graph_path, int kind, int metric, size_t dim, const floa
     return HS_ERR_ARG;
   }
   *out = nullptr;
-  std::vector<uint8_t> bytes;
-  int rc = read_file(graph_path, &bytes);
-  if (rc != HS_OK) return rc;
-  return load_common(bytes.data(), bytes.size(), kind, metric, dim, raw_base, n_raw, device, out);
+  return guarded("hs_load", [&] {
+    std::vector<uint8_t> bytes;
+    int rc = read_file(graph_path, &bytes);
+    if (rc != HS_OK) return rc;
+    return load_common(bytes.data(), bytes.size(), kind, metric, dim, raw_base, n_raw, device, out);
+  });
 }
 
 void hs_free(hs_index *ix) {
@@ -815,7 +840,11 @@ int hs_exchange_create(int device, int world, int rank, size_t slots, size_t nq_
     set_error(std::string("hs_exchange_create: cudaMalloc: ") + cudaGetErrorString(e));
     return HS_ERR_NOMEM;
   }
-  HS_CUDA(cudaMemset(ex->base, 0, ex->bytes));
+  if (cudaMemset(ex->base, 0, ex->bytes) != cudaSuccess) {
+    set_error(std::string("hs_exchange_create: cudaMemset: ") + cudaGetErrorString(cudaGetLastError()));
+    cudaFree(ex->base);
+    return HS_ERR_CUDA;
+  }
   ex->peer.assign(world, nullptr);
   ex->peer[rank] = ex->base;
   *out = ex.release();
@@ -881,6 +910,12 @@ int hs_exchange_signal_and_wait(hs_exchange *ex, unsigned int seq, void *stream)
   if (!ex || seq == 0) {
     set_error("hs_exchange_signal_and_wait: sequence numbers start at 1");
     return HS_ERR_ARG;
+  }
+  for (int r = 0; r < ex->world; ++r) {
+    if (!ex->peer[r]) {
+      set_error("hs_exchange_signal_and_wait: exchange not connected");
+      return HS_ERR_ARG;
+    }
   }
   CUstream s = static_cast<CUstream>(stream);
   // stream-ordered: after this rank's shard searches of batch `seq`, tell every rank (flag word
@@ -1074,9 +1109,11 @@ int hs_build_slimq_graph(const float *base, size_t n, size_t dim, const hs_build
   double bf;
   int rc = parse_branching(p, &bf);
   if (rc != HS_OK) return rc;
-  return build_slimq_graph(base, n, dim, p->M, p->ef_construction, bf, p->threshold_level, p->top_degree_percent0,
-                           p->top_degree_percent, p->top_M0, p->low_m0, p->top_M, p->low_m, p->threads, p->seed,
-                           centroids, num_cluster, cluster_ids, labels, out_graph_path);
+  return guarded("hs_build_slimq_graph", [&] {
+    return build_slimq_graph(base, n, dim, p->M, p->ef_construction, bf, p->threshold_level, p->top_degree_percent0,
+                             p->top_degree_percent, p->top_M0, p->low_m0, p->top_M, p->low_m, p->threads, p->seed,
+                             centroids, num_cluster, cluster_ids, labels, out_graph_path);
+  });
 }
 
 int hs_build_slim_graph(const float *base, size_t n, size_t dim, int metric, const hs_build_params *p,
@@ -1084,9 +1121,11 @@ int hs_build_slim_graph(const float *base, size_t n, size_t dim, int metric, con
   double bf;
   int rc0 = parse_branching(p, &bf);
   if (rc0 != HS_OK) return rc0;
-  return build_slim_graph(base, n, dim, metric, p->M, p->ef_construction, bf, p->threshold_level,
-                          p->top_degree_percent0, p->top_degree_percent, p->top_M0, p->low_m0, p->top_M, p->low_m,
-                          p->threads, p->seed, labels, out_graph_path);
+  return guarded("hs_build_slim_graph", [&] {
+    return build_slim_graph(base, n, dim, metric, p->M, p->ef_construction, bf, p->threshold_level,
+                            p->top_degree_percent0, p->top_degree_percent, p->top_M0, p->low_m0, p->top_M, p->low_m,
+                            p->threads, p->seed, labels, out_graph_path);
+  });
 }
 
 int hs_build_hnsw_graph(const float *base, size_t n, size_t dim, int metric, const hs_build_params *p,
@@ -1094,8 +1133,10 @@ int hs_build_hnsw_graph(const float *base, size_t n, size_t dim, int metric, con
   double bf;
   int rc0 = parse_branching(p, &bf);
   if (rc0 != HS_OK) return rc0;
-  return build_hnsw_graph(base, n, dim, metric, p->M, p->ef_construction, bf, p->threads, p->seed, labels,
-                          out_graph_path);
+  return guarded("hs_build_hnsw_graph", [&] {
+    return build_hnsw_graph(base, n, dim, metric, p->M, p->ef_construction, bf, p->threads, p->seed, labels,
+                            out_graph_path);
+  });
 }
 
 int hs_build_slim_index_gpu(const float *base, size_t n, size_t dim, int metric, const hs_build_params *p,
@@ -1248,14 +1289,16 @@ int hs_debug_flatten(const char *graph_path, int kind, size_t dim, hs_host_graph
     return HS_ERR_ARG;
   }
   *out = nullptr;
-  std::vector<uint8_t> bytes;
-  int rc = read_file(graph_path, &bytes);
-  if (rc != HS_OK) return rc;
-  std::unique_ptr<hs_host_graph> h(new hs_host_graph);
-  rc = parse_graph(bytes.data(), bytes.size(), kind, dim, &h->g);
-  if (rc != HS_OK) return rc;
-  *out = h.release();
-  return HS_OK;
+  return guarded("hs_debug_flatten", [&] {
+    std::vector<uint8_t> bytes;
+    int rc = read_file(graph_path, &bytes);
+    if (rc != HS_OK) return rc;
+    std::unique_ptr<hs_host_graph> h(new hs_host_graph);
+    rc = parse_graph(bytes.data(), bytes.size(), kind, dim, &h->g);
+    if (rc != HS_OK) return rc;
+    *out = h.release();
+    return (int)HS_OK;
+  });
 }
 
 void hs_debug_free(hs_host_graph *h) { delete h; }

@@ -110,6 +110,70 @@ def test_loader_rejects_bad_files(tmp_path):
     assert e.value.code == -2 and "Cannot open" in str(e.value)
 
 
+def _patched(data: bytes, off: int, fmt: str, value) -> bytes:
+    import struct
+    b = bytearray(data)
+    struct.pack_into(fmt, b, off, value)
+    return bytes(b)
+
+
+def test_loader_rejects_corrupt_slimq_and_hnsw_headers(tmp_path):
+    """Crafted headers must end in HS_ERR_IO, never in an out-of-bounds read or an exception across the C ABI.
+    hnsw_slimq header (slimq.h:1161-1200): 93 bytes of the slim header, then num_cluster, dim, padded_dim,
+    offset_cluster_id, offset_bin_data, offset_ex_data, size_bin_data, size_ex_data, ex_bits (u64 each)."""
+    import struct
+    good = open(os.path.join(GOLDEN, "slimq_d96.graph"), "rb").read()
+    capi.HostGraph(os.path.join(GOLDEN, "slimq_d96.graph"), 96, capi.HS_KIND_SLIMQ).info()       # sanity: loads
+    n, rec = struct.unpack_from("<QQ", good, 0)
+    q0 = 93
+    num_cluster, qdim, pd, off_c, off_b, off_e, size_bin, size_ex, ex_bits = struct.unpack_from("<9Q", good, q0)
+    assert rec == 28 + size_bin + size_ex and off_e == 28 + size_bin
+    cases = {
+        "rec_too_small": _patched(good, 8, "<Q", 28 + 8),                    # record smaller than the code block
+        "rec_huge": _patched(good, 8, "<Q", 1 << 62),                         # n * rec overflows
+        "n_huge": _patched(good, 0, "<Q", (1 << 31) - 1),
+        "size_ex_mismatch": _patched(good, q0 + 7 * 8, "<Q", size_ex + 8),
+        "num_cluster_zero": _patched(good, q0, "<Q", 0),
+        "num_cluster_huge": _patched(good, q0, "<Q", 1 << 40),
+        "padded_dim_huge": _patched(good, q0 + 2 * 8, "<Q", 1 << 30),
+        "maxM_huge": _patched(good, 60, "<Q", 1 << 20),
+    }
+    # a node whose cluster id points past the centroid table (the kernel would index g2c[] with it)
+    elements_at = q0 + 9 * 8 + 1 + num_cluster * pd * 4 + 4 * pd // 8
+    cases["cluster_id_out_of_range"] = _patched(good, elements_at + 24, "<I", num_cluster)
+    for name, data in cases.items():
+        pth = tmp_path / f"q_{name}.graph"
+        pth.write_bytes(data)
+        with pytest.raises(capi.HsError) as e:
+            capi.HostGraph(str(pth), 96, capi.HS_KIND_SLIMQ)
+        assert e.value.code == -2, name
+    # plain HNSW files (hnsw.h:748-779): u64 offsetLevel0, max_elements, n, rec, label_offset, offsetData; i32 maxlevel;
+    # u32 enterpoint; u64 maxM, maxM0, M; f64 mult; u64 efc
+    hg = open(os.path.join(GOLDEN, "hnsw_l2_1k.graph"), "rb").read()
+    hdim = (struct.unpack_from("<Q", hg, 24)[0] - 8 - 4 - 4 * struct.unpack_from("<Q", hg, 64)[0]) // 4
+    capi.HostGraph(os.path.join(GOLDEN, "hnsw_l2_1k.graph"), hdim, capi.HS_KIND_HNSW).info()
+    hcases = {
+        "maxM0_wraps": _patched(hg, 64, "<Q", (1 << 62) + struct.unpack_from("<Q", hg, 64)[0]),   # 4 * maxM0 wraps to the same size
+        "maxM_wraps": _patched(hg, 56, "<Q", (1 << 62) + struct.unpack_from("<Q", hg, 56)[0]),
+        "rec_huge": _patched(hg, 24, "<Q", 1 << 62),
+        "truncated": hg[: len(hg) // 2],
+        "list_count_beyond_maxM0": _patched(hg, 100, "<H", 65535),
+    }
+    for name, data in hcases.items():
+        pth = tmp_path / f"h_{name}.graph"
+        pth.write_bytes(data)
+        with pytest.raises(capi.HsError) as e:
+            capi.HostGraph(str(pth), hdim, capi.HS_KIND_HNSW)
+        assert e.value.code == -2, name
+    # empty indices: maxlevel is -1 in the header and must not size anything
+    empty = bytearray(good[:93 + 9 * 8 + 1 + num_cluster * pd * 4 + 4 * pd // 8])
+    struct.pack_into("<Q", empty, 0, 0)
+    struct.pack_into("<i", empty, 48, -1)
+    pth = tmp_path / "q_empty.graph"
+    pth.write_bytes(bytes(empty))
+    assert capi.HostGraph(str(pth), 96, capi.HS_KIND_SLIMQ).info()["n"] == 0
+
+
 def test_vecs_io_roundtrip(tmp_path):
     a = np.random.default_rng(1).standard_normal((17, 5)).astype(np.float32)
     b = np.arange(34, dtype=np.uint32).reshape(17, 2)
