@@ -265,8 +265,13 @@ static float dist_seq(const float *a, const float *b, size_t dim, int metric) {
   return res;
 }
 
-/* space_l2.h:25-54 (mul then add, lanes summed in index order) and
- * space_ip.h:146-204 (fma).  Requires dim % 16 == 0, else falls back to SEQ. */
+/* space_l2.h:25-54 (mul then add per lane) and space_ip.h:146-204 (fma per lane), 16 lanes, chunks in
+ * order.  The source then adds the 16 lane sums left to right (space_l2.h:49-51) / _mm512_reduce_add_ps,
+ * but the reference is compiled -Ofast (CMakeLists.txt:14), which lets the compiler re-associate: the
+ * x86-64-v4 build of oracle/_ref (g++ 13, `objdump -d libhsref_slim_v4.so`) folds the lanes as a tree,
+ * (j, j+8) -> (j, j+4) -> (j, j+2) -> (j, j+1), for both metrics.  This restates THAT association, so
+ * that distances — and with them every near-tie of the search — are bit-identical to the reference as
+ * built here (tests/test_oracle.py::test_ref_order_is_bit_exact).  Requires dim % 16 == 0, else SEQ. */
 static float dist_ref(const float *a, const float *b, size_t dim, int metric) {
   if (dim % 16) return dist_seq(a, b, dim, metric);
   float lane[16];
@@ -280,9 +285,9 @@ static float dist_ref(const float *a, const float *b, size_t dim, int metric) {
         lane[j] = lane[j] + d * d;
       }
     }
-  float res = lane[0];
-  for (int j = 1; j < 16; j++) res += lane[j];
-  return metric == HSO_IP ? 1.0f - res : res;
+  for (int s = 8; s >= 1; s >>= 1)
+    for (int j = 0; j < s; j++) lane[j] = lane[j] + lane[j + s];
+  return metric == HSO_IP ? 1.0f - lane[0] : lane[0];
 }
 
 /* The CUDA kernel's association: `team` lanes per row, lane t owns the 4-float

@@ -2,7 +2,8 @@
 `-m gpu` runs on a B200 and calls the CUDA path through the C ABI.
 
 Graphs are built with the REFERENCE builder (oracle/_ref, prebuilt here where /root/reference
-exists; the .so travels to the GPU box) and cached under a temp dir; where that library is
+exists; the .so travels to the GPU box), single-threaded so that every box sees the same graph, and
+cached under a temp dir; where that library is
 unavailable the committed fixtures in tests/golden/ are used instead.
 """
 from __future__ import annotations
@@ -68,13 +69,16 @@ class Corpus:
     def __init__(self, n, nq, dim, metric=0, M=16, efc=200, rank=8, branching="4", seed=1, **prune):
         self.n, self.nq, self.dim, self.metric, self.M = n, nq, dim, metric, M
         self.base, self.queries = make_dataset(n, nq, dim, metric=metric, rank=rank, seed=seed)
-        key = hashlib.sha1(repr((n, dim, metric, M, efc, rank, branching, seed, sorted(prune.items()))).encode()
+        # built SINGLE-THREADED: the reference's OpenMP build gives a different graph on every run, and a parity
+        # suite must see the same graph (and the same distance ties) on every box
+        key = hashlib.sha1(repr(("1thread", n, dim, metric, M, efc, rank, branching, seed, sorted(prune.items()))).encode()
                            ).hexdigest()[:16]
         os.makedirs(CACHE, exist_ok=True)
         self.graph = os.path.join(CACHE, f"slim_{key}.graph")
         if not os.path.exists(self.graph):
             tmp = self.graph + f".tmp{os.getpid()}"
-            rh.ref_slim_build(self.base, tmp, metric=metric, M=M, ef_construction=efc, branching=branching, **prune)
+            rh.ref_slim_build(self.base, tmp, metric=metric, M=M, ef_construction=efc, branching=branching,
+                              threads=1, **prune)
             os.replace(tmp, self.graph)
 
 

@@ -33,20 +33,13 @@ def check_against_oracle(c, k, ef, *, min_exact=0.999):
     # bit-exact ids, distances and counters (ties aside)
     assert same_rows.mean() >= min_exact, f"only {same_rows.mean():.4f} of rows identical to the oracle"
     assert np.array_equal(dist[same_rows].view(np.uint32), odist[same_rows].view(np.uint32))
-    # counters: the same bar, ties aside.  An entry evicted from the result set whose distance EQUALS
-    # the new lowerBound is still expanded by the reference (`candidate_dist > lowerBound` is false)
-    # but is no longer in the pool here: one extra hop over visited neighbours, identical results.
-    # The graphs come from the reference's OpenMP builder (a different graph on every fresh box), so
-    # such a tie shows up on some boxes only: seen twice in ~15 cold runs, one query of 300 each.  A
-    # single such row is reported (with which side moved) and tolerated; more than that fails.
+    # counters: bit-exact as well.  (The test graphs are built single-threaded, hence identical on every box;
+    # the one known way the two sides can part — an entry evicted from the result set whose distance EQUALS
+    # the new lowerBound is still expanded by the reference but is gone from the pool here — needs an exact
+    # fp32 tie at the ef boundary and is exercised on purpose by test_exact_ties_at_the_ef_boundary.)
     bad = np.nonzero(same_rows & ((cnt[:, 0] != ond) | (cnt[:, 1] != onh)))[0]
-    if len(bad):
-        _, _, cnt2 = ix.search(c.queries, k, counts=True)
-        _, _, ond2, onh2 = rh.Oracle(c.graph, c.dim, c.metric).search(c.queries, k, ef, order=rh.ORDER_GPU, team=8)
-        msg = "; ".join(f"q{q}: gpu {cnt[q].tolist()} (again {cnt2[q].tolist()}) oracle [{ond[q]}, {onh[q]}] "
-                        f"(again [{ond2[q]}, {onh2[q]}])" for q in bad[:5])
-        print(f"\nCOUNTER MISMATCH ef={ef} on {len(bad)} of {len(cnt)} identical rows: {msg}")
-        assert len(bad) <= max(1, int((1 - min_exact) * len(cnt))), msg
+    msg = "; ".join(f"q{q}: gpu {cnt[q].tolist()} oracle [{ond[q]}, {onh[q]}]" for q in bad[:5])
+    assert len(bad) == 0, f"per-query counters differ on {len(bad)} of {len(cnt)} identical rows: {msg}"
     # rows that differ must be explainable by ties: same distance multiset within tolerance
     for i in np.nonzero(~same_rows)[0]:
         fin = np.isfinite(odist[i])
@@ -79,6 +72,47 @@ def test_small_l2_matches_reference(small_corpus, ef):
         for j in range(10):
             d = rh.ref_dist(c.queries[i], c.base[lab[i, j]], c.metric)
             assert abs(d - dist[i, j]) <= REL_TOL * max(abs(d), 1e-30)
+
+
+def test_exact_ties_at_the_ef_boundary(tmp_path):
+    """Constructed exact ties.  Every vector of the corpus exists THREE times, so every distance the search
+    sees exists three times bit for bit, also at the ef boundary.  The reference admits a neighbour iff
+    `top_size < ef || lowerBound > dist` (slim.h:403-404, strict) and stops when the closest candidate is
+    `> lowerBound` (slim.h:339-340, strict): a candidate whose distance EQUALS lowerBound is still expanded by
+    the reference even after it was trimmed from the result heap, while the engine's pool has dropped it.
+    Which of several equal-distance entries is trimmed / popped first is heap order in the reference and
+    (lane, slot) order here.  This pins what that is allowed to change: the k returned DISTANCES (as a sorted
+    multiset), never — only which of the identical copies carries a distance may differ, and with it the
+    counters."""
+    rng = np.random.default_rng(123)
+    distinct, copies, dim, nq, k = 2500, 3, 32, 400, 10
+    d0, q = make_dataset(distinct, nq, dim, rank=8, seed=41)
+    base = np.ascontiguousarray(np.repeat(d0, copies, axis=0)[rng.permutation(distinct * copies)])
+    graph = str(tmp_path / "ties.graph")
+    rh.ref_slim_build(base, graph, M=8, ef_construction=60, threads=1)
+    orc = rh.Oracle(graph, dim)
+    ix = capi.Index(graph, dim)
+    true_d = np.sort(((base[None, :, :] - q[:, None, :]) ** 2).sum(-1), axis=1)[:, :k]    # exact, tie-aware yardstick
+    for ef in (10, 12, 16, 24, 40):
+        ix.set_ef(ef)
+        lab, dist, cnt = ix.search(q, k, counts=True)
+        olab, odist, ond, onh = orc.search(q, k, ef, order=rh.ORDER_GPU, team=8)
+        assert (np.diff(dist, axis=1) >= 0).all()
+        # every returned distance is the distance of the returned row (bitwise, GPU association)
+        same_d = np.all(dist.view(np.uint32) == odist.view(np.uint32), axis=1)
+        same_ids = np.all(lab == olab, axis=1)
+        same_cnt = (cnt[:, 0] == ond) & (cnt[:, 1] == onh)
+        # tie-aware recall: a returned distance counts when it is within the true k-th distance
+        hit = lambda d: float(np.mean(d <= true_d[:, -1:] * (1 + 1e-6)))
+        print(f"\nties ef={ef}: identical distance rows {same_d.mean():.4f}, identical id rows {same_ids.mean():.4f}, "
+              f"identical counters {same_cnt.mean():.4f}, tie-aware recall gpu {hit(dist):.4f} oracle {hit(odist):.4f}")
+        # the bound: the divergence may move WHICH copy is reported and how many hops it took, and in rare
+        # cases reach one more / one fewer candidate — never more than 0.5 pp of recall, and at least 98 % of
+        # the rows carry bit-identical distances
+        assert same_d.mean() >= 0.98, (ef, same_d.mean())
+        assert abs(hit(dist) - hit(odist)) <= 0.005, (ef, hit(dist), hit(odist))
+        # where the ids agree, the distances agree bitwise
+        assert np.array_equal(dist[same_ids].view(np.uint32), odist[same_ids].view(np.uint32))
 
 
 @pytest.mark.parametrize("dim,rank", [(96, 12), (128, 14), (100, 12), (64, 8)])
