@@ -305,6 +305,49 @@ __device__ __forceinline__ int warp_argmax_key(uint64_t key) {
   return __ffs(b) - 1;
 }
 
+// ---- "ghost" candidates: exact distance ties at the ef boundary ----
+// The reference keeps candidates and results in two heaps.  An entry trimmed from the result heap stays in
+// the candidate heap, and the reference still EXPANDS it when it comes up unless its distance is strictly
+// beyond lowerBound (slim.h:237, :339-340: `>`).  A trimmed entry is the worst one, so that only happens
+// when another entry with the bit-identical distance stays behind as the new worst — an exact fp32 tie.
+// The pool drops a displaced entry, so the tie case is kept on the side: when the entry being displaced is
+// unexpanded and ties with another column's worst, it is appended to a small per-warp list in shared
+// memory (g[0] = count, then (distance word, id) pairs); when the pool runs out of unexpanded entries the
+// list is consulted: a ghost whose distance still equals the pool's worst is expanded like the reference
+// would, everything else in it is dead (lowerBound only shrinks).  Cost on the hot path: one AND and one
+// uniform branch per displacement.  Not caught: a tie whose two members sit in the SAME pool column and no
+// other (1 in 32 of an event that needs two bit-equal fp32 distances at the boundary).
+constexpr uint32_t kGhostCap = 7;            // pairs; the list occupies 16 words per warp
+__device__ __forceinline__ void ghost_append(uint32_t *g, uint32_t dword, uint32_t id) {
+  const uint32_t c = g[0];
+  if (c < kGhostCap) {
+    g[2 + 2 * c] = dword;
+    g[3 + 2 * c] = id;
+    g[0] = c + 1;
+  }
+}
+// the next ghost that the reference would still expand (distance word == worst of a FULL pool), or kInvalid
+__device__ __forceinline__ uint32_t ghost_take(uint32_t *g, uint32_t worst, bool full, int lane) {
+  const uint32_t cnt = g[0];
+  if (cnt == 0) return kInvalid;
+  uint32_t gd = 0, gi = kInvalid;
+  if ((uint32_t)lane < cnt) {
+    gd = g[2 + 2 * lane];
+    gi = g[3 + 2 * lane];
+  }
+  const unsigned alive = __ballot_sync(FULL, full && (uint32_t)lane < cnt && gd == worst);
+  __syncwarp();
+  if (alive == 0) {
+    if (lane == 0) g[0] = 0;
+    __syncwarp();
+    return kInvalid;
+  }
+  const int o = __ffs(alive) - 1;
+  if (lane == o) g[2 + 2 * o] = 0;          // taken (0 is no distance word of a used slot)
+  __syncwarp();
+  return __shfl_sync(FULL, gi, o);
+}
+
 // The candidate/result pool: at most ef keys, unsorted, column-distributed (entry e lives in
 // lane e % 32).  Two storages with one interface:
 //   RegPool<SLOTS>  ef <= 32*SLOTS: the column sits in registers; column min/max are a few
@@ -585,7 +628,7 @@ struct RegPool32 {
     for (int s = SLOTS - 2; s >= 0; --s) node = ku[s] == g ? id[s] : node;     // first matching slot wins
     return __shfl_sync(FULL, node, o);
   }
-  __device__ __forceinline__ unsigned admit(bool valid, uint64_t key) {
+  __device__ __forceinline__ unsigned admit(bool valid, uint64_t key, uint32_t *ghosts = nullptr) {
     const uint32_t d = (uint32_t)(key >> 32), cid = (uint32_t)key;
     unsigned entered = 0;
     const unsigned vmask = __ballot_sync(FULL, valid);
@@ -614,7 +657,23 @@ struct RegPool32 {
       const uint32_t cd = __shfl_sync(FULL, d, src);
       if (cd < worst) {
         const uint32_t ci = __shfl_sync(FULL, cid, src);
-        const int owner = __ffs(__ballot_sync(FULL, cm == worst)) - 1;
+        const unsigned wmask = __ballot_sync(FULL, cm == worst);
+        const int owner = __ffs(wmask) - 1;
+        if ((wmask & (wmask - 1)) && ghosts) {     // exact tie at the boundary (see ghost_append): rare
+          if (lane == owner) {
+            uint32_t gu = 0xffffffffu, gi = 0;
+            bool first = true;
+#pragma unroll
+            for (int s = 0; s < SLOTS; ++s) {
+              const bool h = first && kd[s] == worst;
+              gu = h ? ku[s] : gu;
+              gi = h ? id[s] : gi;
+              first = first && !h;
+            }
+            if (gu != 0xffffffffu) ghost_append(ghosts, worst, gi);     // still unexpanded: the reference keeps it
+          }
+          __syncwarp();
+        }
         bool open = lane == owner;
 #pragma unroll
         for (int s = 0; s < SLOTS; ++s) {
@@ -632,6 +691,10 @@ struct RegPool32 {
       }
     }
     return entered;
+  }
+  __device__ __forceinline__ uint32_t take_ghost(uint32_t *ghosts) {
+    if (ghosts[0] == 0) return kInvalid;
+    return ghost_take(ghosts, __reduce_max_sync(FULL, col_max()), size >= ef, lane);
   }
   // every entry becomes unexpanded again (a new layer of the layered beam, slim.h:228-233)
   __device__ __forceinline__ void clear_flags() {
@@ -776,7 +839,7 @@ struct SmemPool {
     }
     return node;
   }
-  __device__ __forceinline__ unsigned admit(bool valid, uint64_t key) {
+  __device__ __forceinline__ unsigned admit(bool valid, uint64_t key, uint32_t *ghosts = nullptr) {
     unsigned entered = 0;
     const unsigned vmask = __ballot_sync(FULL, valid);
     if (vmask == 0) return 0;
@@ -797,12 +860,19 @@ struct SmemPool {
     }
     int owner = warp_argmax_key(max_all);
     uint64_t worst = __shfl_sync(FULL, max_all, owner);
-    todo &= __ballot_sync(FULL, valid && key < worst);
+    // the reference's test is on the distance alone and strict (`lowerBound > dist`, slim.h:403-404)
+    todo &= __ballot_sync(FULL, valid && (uint32_t)(key >> 32) < (uint32_t)(worst >> 32));
     while (todo) {
       const int src = __ffs(todo) - 1;
       todo &= todo - 1;
       const uint64_t ck = __shfl_sync(FULL, key, src);
-      if (ck < worst) {
+      if ((uint32_t)(ck >> 32) < (uint32_t)(worst >> 32)) {
+        // exact tie at the boundary (see ghost_append): another column's worst carries the same distance
+        const unsigned tmask = __ballot_sync(FULL, (uint32_t)(max_all >> 32) == (uint32_t)(worst >> 32) && size > (uint32_t)lane);
+        if ((tmask & (tmask - 1)) && ghosts) {
+          if (lane == owner && !((uint32_t)pool[max_e] & FLAG)) ghost_append(ghosts, (uint32_t)(worst >> 32), (uint32_t)worst & ~FLAG);
+          __syncwarp();
+        }
         if (lane == owner) {
           const bool was_min = max_e == min_e && min_un != NONE;
           pool[max_e] = ck;
@@ -822,6 +892,12 @@ struct SmemPool {
       }
     }
     return entered;
+  }
+  __device__ __forceinline__ uint32_t take_ghost(uint32_t *ghosts) {
+    if (ghosts[0] == 0) return kInvalid;
+    const int o = warp_argmax_key(max_all);
+    const uint64_t worst = __shfl_sync(FULL, max_all, o);
+    return ghost_take(ghosts, (uint32_t)(worst >> 32), size >= ef, lane);
   }
   __device__ __forceinline__ void clear_flags() {
     __syncwarp();

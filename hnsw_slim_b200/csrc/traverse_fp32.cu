@@ -70,6 +70,7 @@ __global__ void __launch_bounds__(128, HS_TRAVERSE_MIN_CTAS) traverse_kernel(con
     hash = reinterpret_cast<uint32_t *>(wbase + p.off_hash);
   }
   uint32_t *stage_ids = reinterpret_cast<uint32_t *>(wbase + p.off_stage);
+  uint32_t *ghosts = stage_ids + 32;        // 16 words: exact-tie side list (traverse_common.cuh ghost_append)
   float4 *qs = reinterpret_cast<float4 *>(wbase + p.off_query);
 
   if (p.overlap) {
@@ -192,8 +193,11 @@ __global__ void __launch_bounds__(128, HS_TRAVERSE_MIN_CTAS) traverse_kernel(con
     //      pool", as on level 0: a candidate outside the pool implies a full pool. ----
     for (int layer = min(p.threshold_level, p.maxlevel); layer > 0; --layer) {
       const uint32_t *ladj = p.upper_adj[layer];
+      if (lane == 0) ghosts[0] = 0;         // the candidate set is re-made from the results on every layer
+      __syncwarp();
       for (;;) {
-        const uint32_t node = pool.pop_closest_unexpanded();
+        uint32_t node = pool.pop_closest_unexpanded();
+        if (node == kInvalid) node = pool.take_ghost(ghosts);
         if (node == kInvalid) break;
         const int slot = __ldg(p.upper_slot + node);
         // pool entries met on a lower layer may not exist on this one: the reference asserts
@@ -226,7 +230,7 @@ __global__ void __launch_bounds__(128, HS_TRAVERSE_MIN_CTAS) traverse_kernel(con
           __syncwarp();
           const float d = eval(cid, count);
           nd += (uint32_t)count;
-          pool.admit(lane < count, make_key(d, cid));
+          pool.admit(lane < count, make_key(d, cid), ghosts);
         }
         if (any) nh++;
       }
@@ -238,10 +242,14 @@ __global__ void __launch_bounds__(128, HS_TRAVERSE_MIN_CTAS) traverse_kernel(con
     // where the lines it pins compete with row lines that other queries would have hit: small dims only
     const bool opt_prefetch = p.flags & 1u, opt_spec = p.flags & 2u, opt_keep = (p.flags & 8u) && CPL > 0;
     uint32_t spec_node = kInvalid, spec_ids = kInvalid;
+    if (lane == 0) ghosts[0] = 0;
+    __syncwarp();
     for (;;) {
       if (p.flags & 4u) break;    // profiling aid (HS_TRAVERSE_FLAGS bit 2): time the descent alone
-      // closest unexpanded entry (the reference pops its candidate min-heap, slim.h:335-354)
-      const uint32_t node = pool.pop_closest_unexpanded();
+      // closest unexpanded entry (the reference pops its candidate min-heap, slim.h:335-354); once the pool
+      // has none left, an entry that was trimmed while tying with the worst one (ghost_append)
+      uint32_t node = pool.pop_closest_unexpanded();
+      if (node == kInvalid) node = pool.take_ghost(ghosts);
       if (node == kInvalid) break;
       const uint32_t *row = p.adj0 + (size_t)node * p.deg0_stride;
       uint32_t id = node == spec_node ? spec_ids : __ldg(row + lane);
@@ -298,7 +306,7 @@ __global__ void __launch_bounds__(128, HS_TRAVERSE_MIN_CTAS) traverse_kernel(con
         __syncwarp();
         const float d = eval(cid, count);
         nd += (uint32_t)count;
-        const unsigned entered = pool.admit(lane < count, make_key(d, cid));
+        const unsigned entered = pool.admit(lane < count, make_key(d, cid), ghosts);
         if ((entered >> lane) & 1u) {
           if (opt_keep) prefetch_l2_keep(p.adj0 + (size_t)cid * p.deg0_stride);
           else prefetch_l2(p.adj0 + (size_t)cid * p.deg0_stride);
@@ -459,7 +467,7 @@ int plan_traverse(TraverseParams &p, int metric, int hash_bits_override, int gha
   const int cplv = cpl_variant(p.row_chunks), slv = slots_variant(p.ef);
   const int met = metric == HS_METRIC_IP ? HS_METRIC_IP : HS_METRIC_L2;
   const uint32_t list_bytes = slv ? 0u : align_up(p.ef * 8u, 16);
-  const uint32_t stage_bytes = 32 * 4;
+  const uint32_t stage_bytes = 32 * 4 + 16 * 4;       // staging ids + the exact-tie side list
   const uint32_t query_bytes = cplv == 0 ? p.row_chunks * 16u : 0u;
 
   // Shared-memory tables first.  They bound the resident warps: 24 per SM (what the register file

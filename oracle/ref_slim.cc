@@ -21,6 +21,7 @@
 #include "hnswlib/hnswalg.h"
 #include "hnswlib/hnswalg_slim.h"
 #include "hnswlib/bruteforce.h"
+#include "strategy/solve_strategy.h"   // SolveStrategy::recall, executed as is (solve_strategy.h:67-103)
 
 #include <omp.h>
 
@@ -28,6 +29,8 @@
 #include <cstdint>
 #include <cstring>
 #include <memory>
+#include <iostream>
+#include <sstream>
 #include <string>
 
 namespace {
@@ -260,6 +263,40 @@ int ref_bruteforce(const float *base, size_t n, size_t dim, int metric,
   } catch (const std::exception &e) {
     g_err = e.what();
     return -1;
+  }
+}
+
+// SolveStrategy::recall (include/strategy/solve_strategy.h:67-103) EXECUTED, not restated: the strategy
+// object reads base / queries (.fvecs), the answers (.ivecs, read_knn :58-61) and the ground truth (.ivecs)
+// exactly as `main` would, and prints "Recall: x" — which is captured and returned.  k = the global K.
+double ref_strategy_recall(const char *source_fvecs, const char *query_fvecs, const char *knn_ivecs,
+                           const char *gt_ivecs, size_t k) {
+  struct RecallOnly : SolveStrategy {
+    using SolveStrategy::SolveStrategy;
+    void solve() override {}
+  };
+  try {
+    K = k;
+    std::ostringstream captured;
+    std::streambuf *old = std::cout.rdbuf(captured.rdbuf());
+    double value = -1.0;
+    {
+      RecallOnly s(source_fvecs, query_fvecs, "");
+      s.read_knn(knn_ivecs);
+      s.recall(gt_ivecs);
+    }
+    std::cout.rdbuf(old);
+    const std::string out = captured.str();
+    const size_t at = out.rfind("Recall: ");
+    if (at == std::string::npos) {
+      g_err = "SolveStrategy::recall printed no result";
+      return -1.0;
+    }
+    value = std::stod(out.substr(at + 8));
+    return value;
+  } catch (const std::exception &e) {
+    g_err = e.what();
+    return -1.0;
   }
 }
 

@@ -104,6 +104,9 @@ def slim_lib():
         L.ref_slim_counts.argtypes = [C.c_void_p, _f32p, C.c_size_t, C.c_size_t, C.c_size_t, _u32p, _u64p]
         L.ref_dist.restype = C.c_float
         L.ref_dist.argtypes = [_f32p, _f32p, C.c_size_t, C.c_int]
+        if hasattr(L, "ref_strategy_recall"):
+            L.ref_strategy_recall.restype = C.c_double
+            L.ref_strategy_recall.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_size_t]
         L.ref_bruteforce.restype = C.c_int
         L.ref_bruteforce.argtypes = [_f32p, C.c_size_t, C.c_size_t, C.c_int, _f32p, C.c_size_t, C.c_size_t,
                                      C.c_int, _u32p, C.c_void_p, C.POINTER(C.c_double)]
@@ -344,6 +347,23 @@ class RefSlim:
         per = np.zeros(q.shape[0], dtype=np.uint64)
         self.L.ref_slim_counts(self.h, q, q.shape[0], k, ef, out, per)
         return out, per
+
+
+def ref_strategy_recall(base, q, knn, gt, K: int) -> float:
+    """The reference's OWN SolveStrategy::recall (solve_strategy.h:67-103) executed on temp .fvecs/.ivecs files
+    (it prints with 6 significant digits)."""
+    import tempfile
+    from hnsw_slim_b200 import vecs_io
+    with tempfile.TemporaryDirectory() as td:
+        paths = [os.path.join(td, n) for n in ("base.fvecs", "query.fvecs", "knn.ivecs", "gt.ivecs")]
+        vecs_io.write_vecs(paths[0], np.ascontiguousarray(base, dtype=np.float32))
+        vecs_io.write_vecs(paths[1], np.ascontiguousarray(q, dtype=np.float32))
+        vecs_io.write_vecs(paths[2], np.ascontiguousarray(knn, dtype=np.uint32))
+        vecs_io.write_vecs(paths[3], np.ascontiguousarray(gt, dtype=np.uint32))
+        r = slim_lib().ref_strategy_recall(*[p.encode() for p in paths], K)
+    if r < 0:
+        raise RuntimeError(slim_lib().ref_last_error().decode())
+    return float(r)
 
 
 def ref_dist(a, b, metric=0) -> float:

@@ -111,3 +111,10 @@ def test_recall_matches_oracle():
         r = capi.recall(base, q, knn, arr, 10)
         assert abs(r - rh.oracle_recall(base, q, knn, arr, 10)) < 1e-12
     assert capi.recall(base, q, gt[:, :10].copy(), gt, 10) == 1.0
+    # ... and against the reference's own SolveStrategy::recall, executed (prints 6 significant digits)
+    if rh.ref_slim_path() is not None and hasattr(rh.slim_lib(), "ref_strategy_recall"):
+        knn2 = gt[:, :10].copy()
+        spoil = rng.random(knn2.shape) < 0.3
+        knn2[spoil] = (2900 + np.arange(10)[None, :].repeat(len(knn2), 0))[spoil]      # distinct wrong answers per row
+        want = rh.ref_strategy_recall(base, q, knn2, gt, 10)
+        assert abs(capi.recall(base, q, knn2, gt, 10) - want) <= 1e-5, want

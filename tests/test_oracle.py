@@ -97,6 +97,33 @@ def test_recall_definition():
 
 
 @needs_ref
+@pytest.mark.parametrize("K,gtk", [(10, 100), (3, 10), (10, 10)])
+def test_recall_pinned_to_the_executed_reference(K, gtk):
+    """hso_recall against the reference's OWN SolveStrategy::recall (solve_strategy.h:67-103), executed by
+    oracle/_ref on .fvecs/.ivecs files the way `main` runs it — not a restatement.  The reference prints the
+    value through operator<<(float) (6 significant digits), which bounds the comparison."""
+    rng = np.random.default_rng(K * 7 + gtk)
+    n, nq, dim = 4000, 120, 16
+    base = rng.standard_normal((n, dim)).astype(np.float32)
+    q = rng.standard_normal((nq, dim)).astype(np.float32)
+    d = ((base[None] - q[:, None]) ** 2).sum(-1)
+    gt = np.argsort(d, axis=1)[:, :gtk][:, ::-1].astype(np.uint32).copy()       # farthest first, as BruteForce writes it
+    knn = np.argsort(d, axis=1)[:, :K].astype(np.uint32)
+    wrong = rng.random((nq, K)) < 0.3                                            # spoil ~30 % of the answers
+    knn[wrong] = rng.integers(0, n, int(wrong.sum()))
+    for row in knn:                                                              # answers of a search are distinct
+        seen = set()
+        for j in range(K):
+            while int(row[j]) in seen:
+                row[j] = rng.integers(0, n)
+            seen.add(int(row[j]))
+    want = rh.ref_strategy_recall(base, q, knn, gt, K)
+    got = rh.oracle_recall(base, q, knn, gt, K)
+    assert 0.4 < want < 0.95
+    assert abs(got - want) <= 5e-6 * max(1.0, want) + 1e-6, (got, want)
+
+
+@needs_ref
 @pytest.mark.parametrize("metric,dim", [(0, 32), (1, 48)])
 def test_live_reference_search_and_counts(metric, dim):
     c = get_corpus(n=20000, nq=300, dim=dim, metric=metric, rank=8)
