@@ -79,8 +79,13 @@ def env_rank():
     return int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
 
 
-def prepare_inputs(w: dict, n_query_batches: int, build_rank: bool):
-    """Synthetic corpus + query batches + the .graph over the corpus (cached on disk)."""
+def prepare_inputs(w: dict, n_query_batches: int, build_rank: bool, reference_builder: bool = False):
+    """Synthetic corpus + query batches + the .graph over the corpus (cached on disk).  The reference arm
+    (reference_builder=True, `--impl reference`, which the driver runs first on a box) builds the hnsw_slim
+    graph with the REFERENCE's own builder (addPoint loop + convertFromHNSW through oracle/_ref), so that both
+    arms search the graph BASELINE.md specifies; the engine's arm never executes oracle/: it takes the cached
+    file, or builds one with its own host builder (profiles/r02_refgraph_probe.txt: same recall and QPS on
+    reference-built, host-built and GPU-built graphs)."""
     from hnsw_slim_b200 import capi
     from hnsw_slim_b200.synth import latent_gaussian
     os.makedirs(CACHE, exist_ok=True)
@@ -96,16 +101,34 @@ def prepare_inputs(w: dict, n_query_batches: int, build_rank: bool):
             base = latent_gaussian(w["n"], w["dim"], rank=w["rank"], seed=1, normalize=(w["metric"] == 1))
         t1 = time.time()
         tmp = graph + f".tmp{os.getpid()}"
+        who = "engine host builder"
         if slimq:
             capi.build_slimq_graph(base, tmp, M=w["M"], ef_construction=w["efc"], branching="4")
         else:
-            capi.build_slim_graph(base, tmp, metric=w["metric"], M=w["M"], ef_construction=w["efc"], branching="4")
+            built = False
+            if reference_builder:
+                from oracle import refharness as rh
+                if rh.ref_slim_path() is not None:
+                    rh.ref_slim_build(base, tmp, metric=w["metric"], M=w["M"], ef_construction=w["efc"], branching="4")
+                    built, who = True, "reference builder (oracle/_ref)"
+            if not built:
+                capi.build_slim_graph(base, tmp, metric=w["metric"], M=w["M"], ef_construction=w["efc"], branching="4")
         os.replace(tmp, graph)
-        log(f"[bench] generated corpus in {t1-t0:.1f}s, built {graph} in {time.time()-t1:.1f}s "
+        with open(graph + ".builder", "w") as f:
+            f.write(who)
+        log(f"[bench] generated corpus in {t1-t0:.1f}s, built {graph} with the {who} in {time.time()-t1:.1f}s "
             f"({os.cpu_count()} host threads)")
     queries = [latent_gaussian(w["nq"], w["dim"], rank=w["rank"], seed=1, normalize=(w["metric"] == 1),
                                stream=1 + b) for b in range(n_query_batches)]
     return graph, base, queries
+
+
+def graph_builder_of(graph: str) -> str:
+    try:
+        with open(graph + ".builder") as f:
+            return f.read().strip()
+    except OSError:
+        return "unknown (cached file)"
 
 
 class ClockSampler:
@@ -226,7 +249,7 @@ def run_reference(args, w):
     if rank != 0:
         return
     from oracle import refharness as rh
-    graph, base, qb = prepare_inputs(w, 1, True)
+    graph, base, qb = prepare_inputs(w, 1, True, reference_builder=True)
     q = qb[0]
     cores = os.cpu_count() or 1
     slimq = w.get("kind") == "slimq"
@@ -265,7 +288,8 @@ def run_reference(args, w):
         "impl": "reference", "metric": "QPS at recall@10>=0.95", "value": qps, "unit": "queries/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": w["desc"], "k": w["k"], "ef_search": w["ef"], "queries_per_step": len(q)},
+        "config": {"workload": w["desc"], "k": w["k"], "ef_search": w["ef"], "queries_per_step": len(q),
+                   "graph_built_by": graph_builder_of(graph)},
         "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -349,6 +373,28 @@ def run_gpu(args, w):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_total = float(t.item())
     value = world * nq * args.steps / (ms_total * 1e-3)
+
+    # ---- sustained: the same step back to back for about args.sustained seconds, with its own clock record
+    #      (the K timed steps above are a ~20 ms burst; a long stream may clock and cache differently) ----
+    sustained = None
+    if args.sustained > 0:
+        n_sus = max(args.steps, int(args.sustained * 1e3 / max(ms_total / args.steps, 1e-3)))
+        sev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        clocks_s = ClockSampler(local_rank, 0.05)
+        barrier()
+        with clocks_s:
+            sev[0].record(stream)
+            for i in range(n_sus):
+                step(args.warmup + args.steps + i)
+            sev[1].record(stream)
+            stream.synchronize()
+        barrier()
+        t = torch.tensor([sev[0].elapsed_time(sev[1])], device="cuda", dtype=torch.float64)
+        if distributed:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        sus_ms = float(t.item())
+        sustained = {"value": world * nq * n_sus / (sus_ms * 1e-3), "unit": "queries/s", "steps": n_sus,
+                     "ms_per_step": sus_ms / n_sus, "seconds": sus_ms * 1e-3, "clocks": clocks_s.summary()}
 
     # ---- roofline of the traversal kernel (the only kernel in the step) ----
     launch_ms = ev[0].elapsed_time(ev[-1]) / args.steps
@@ -478,13 +524,13 @@ def run_gpu(args, w):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": w["desc"], "k": k, "ef_search": w["ef"], "queries_per_step_per_gpu": nq,
                        "parallelism": f"replicated index x{world}, queries split, no collective",
-                       "recall_at_10": recall,
+                       "recall_at_10": recall, "graph_built_by": graph_builder_of(graph),
                        "batch_overlap": (not args.no_overlap) and "hs_set_overlap: the next step's grid is launched with "
                                         "programmatic stream serialization and fills SMs while this step's last queries "
                                         "drain; ms_per_step = timed region / steps",
                        "l2": "index (vectors+adjacency) %.0f MiB > 126 MB L2; a different query batch every step"
                              % (info["device_bytes"] / 2**20)},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": args.steps,
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "sustained": sustained, "gpu_launches": args.steps,
             "clocks": clocks.summary(), "sharded": sharded,
         }
         print(json.dumps(out), flush=True)

@@ -210,6 +210,85 @@ class HnswSlimQGpuStrategy : public SolveStrategy {
   std::string source_path_, centroid_path_, cluster_path_;
 };
 
+// hnsw_slim over a corpus that is SHARDED into per-GPU sub-graphs (no reference analogue: the reference
+// builds one graph; SURVEY.md §8(e), north_star (4)).  --shards S --gpus N: the base set is cut into S
+// contiguous ranges (labels stay global), rank r = GPU device_ + r holds S / N of them, every sub-graph is
+// built on its GPU (hs_build_slim_index_gpu), and ONE host thread drives all ranks: each query batch is
+// submitted to every rank's hs_shardgroup (peer memory between the GPUs, hs_shardgroup_connect_local), whose
+// traversal kernels exchange the rows and whose merge kernels write the global top-k; rank 0's rows are the
+// result.  ef_search is the PER-SHARD ef.
+class HnswSlimShardedGpuStrategy : public SolveStrategy {
+ public:
+  HnswSlimShardedGpuStrategy(std::string source_path, std::string query_path, std::string index_path, PruneParams pp,
+                             size_t shards, size_t gpus, size_t batch, int device = 0)
+      : SolveStrategy(source_path, query_path, index_path, device), pp_(pp), shards_(shards), gpus_(gpus), batch_(batch) {}
+
+  void solve() override {
+    if (shards_ == 0 || gpus_ == 0 || shards_ % gpus_ != 0)
+      throw std::runtime_error("--shards must be a positive multiple of --gpus");
+    const size_t per = shards_ / gpus_, nq = query_num_, k = K_, dim = data_dim_;
+    const size_t batch = std::max<size_t>(1, std::min(batch_, nq));
+    std::vector<hs_index *> ix(shards_, nullptr);
+    std::vector<hs_shardgroup *> groups(gpus_, nullptr);
+    std::vector<std::vector<uint32_t>> side(gpus_);            // result rows of the ranks other than 0
+    auto cleanup = [&]() {
+      for (auto *g : groups) hs_shardgroup_free(g);
+      for (auto *i : ix) hs_free(i);
+      for (auto &v : side)
+        if (!v.empty()) hs_unpin_host(v.data());
+    };
+    try {
+      auto s_build = std::chrono::system_clock::now();
+      hs_build_params bp = make_build_params(M_, ef_construction_, branching_factor_, pp_);
+      size_t bytes = 0;
+      for (size_t s = 0; s < shards_; ++s) {                   // contiguous label ranges, sizes differing by <= 1
+        const size_t lo = data_num_ * s / shards_, hi = data_num_ * (s + 1) / shards_;
+        std::vector<uint64_t> labels(hi - lo);
+        for (size_t i = lo; i < hi; ++i) labels[i - lo] = i;
+        check(hs_build_slim_index_gpu(data_set_.data() + lo * dim, hi - lo, dim, HS_METRIC_L2, &bp, labels.data(),
+                                      device_ + (int)(s / per), &ix[s]));
+        check(hs_set_ef(ix[s], ef_search_));
+        hs_index_info info;
+        hs_get_info(ix[s], &info);
+        bytes += info.device_bytes;
+      }
+      auto e_build = std::chrono::system_clock::now();
+      std::cout << "build cost: " << time_cost(s_build, e_build) << " (ms) for " << shards_ << " shards on " << gpus_
+                << " GPUs\n";
+      std::cout << "hnsw_slim index size: " << bytes << " bytes\n";
+      for (size_t r = 0; r < gpus_; ++r)
+        check(hs_shardgroup_create(&ix[r * per], per, (int)gpus_, (int)r, batch, k, 4, &groups[r]));
+      check(hs_shardgroup_connect_local(groups.data(), gpus_));
+      for (size_t r = 1; r < gpus_; ++r) {
+        side[r].resize(nq * k);
+        check(hs_pin_host(side[r].data(), side[r].size() * sizeof(uint32_t)));
+      }
+      auto s_solve = std::chrono::system_clock::now();
+      for (size_t q0 = 0; q0 < nq; q0 += batch) {              // every rank gets every batch, in the same order
+        const size_t n = std::min(batch, nq - q0);
+        for (size_t r = 0; r < gpus_; ++r) {
+          uint32_t *out = (r == 0 ? knn_results_.data() : side[r].data()) + q0 * k;
+          check(hs_shardgroup_submit(groups[r], query_set_.data() + q0 * dim, n, out, nullptr));
+        }
+      }
+      for (auto *g : groups) check(hs_shardgroup_wait(g));
+      auto e_solve = std::chrono::system_clock::now();
+      std::cout << "solve cost: " << time_cost(s_solve, e_solve) << " (ms)\n";
+      std::cout << "query cost: " << std::chrono::duration<double>(e_solve - s_solve).count() << "\n";
+      for (size_t r = 1; r < gpus_; ++r)                        // every rank merged the same rows
+        if (side[r] != knn_results_) throw std::runtime_error("ranks disagree on the merged result");
+    } catch (...) {
+      cleanup();
+      throw;
+    }
+    cleanup();
+  }
+
+ private:
+  PruneParams pp_;
+  size_t shards_, gpus_, batch_;
+};
+
 // brute_force_strategy.h:15-45: exact k-NN of every query, rows written FARTHEST first to gt_path
 class BruteForceGpu : public SolveStrategy {
  public:

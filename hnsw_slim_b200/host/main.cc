@@ -1,7 +1,9 @@
 // Command line of the reference (main.cc:10-139) in front of the B200 engine: same flag names,
 // same derived pruning parameters, same index-file naming, same console output.
 //   hs_main --dataset=sift --solve_strategy=hnsw_slim --k=10 --m=16 --ef_construction=200 --ef_search=100
-// Extra flags: --data_dir (default ../data), --index_dir (default ../statistics/index), --device.
+// Extra flags: --data_dir (default ../data), --index_dir (default ../statistics/index), --device, and for
+// corpora sharded over the GPUs of one box: --shards S --gpus N [--batch B] with --solve_strategy=hnsw_slim
+// (S sub-graphs built on the GPUs, queries in batches of B through one hs_shardgroup per GPU).
 #include <cmath>
 #include <cstring>
 #include <map>
@@ -38,7 +40,7 @@ int main(int argc, char **argv) {
   static const char *known[] = {"dataset", "solve_strategy", "k", "m", "m0", "ef_construction", "ef_search",
                                 "branching_factor", "threshold_level", "top_degree_percent0", "top_degree_percent",
                                 "top_M0", "low_m0", "top_M", "low_m", "level_ratio", "Mm_ratio", "min_indegree0",
-                                "min_indegree", "data_dir", "index_dir", "device"};
+                                "min_indegree", "data_dir", "index_dir", "device", "shards", "gpus", "batch"};
   for (auto &kv : flags) {
     bool ok = false;
     for (const char *k : known) ok |= kv.first == k;
@@ -104,7 +106,10 @@ int main(int argc, char **argv) {
 
   try {
     SolveStrategy *strategy = nullptr;
-    if (solve_strategy == "hnsw_slim") {
+    const size_t shards = (size_t)i64("shards", 0), gpus = (size_t)i64("gpus", 1), batch = (size_t)i64("batch", 10000);
+    if (solve_strategy == "hnsw_slim" && shards > 0) {
+      strategy = new HnswSlimShardedGpuStrategy(source_path, query_path, index_path, pp, shards, gpus, batch, device);
+    } else if (solve_strategy == "hnsw_slim") {
       strategy = new HnswSlimGpuStrategy(source_path, query_path, index_path, pp, device);
     } else if (solve_strategy == "hnsw_slimq") {
       strategy = new HnswSlimQGpuStrategy(source_path, query_path, index_path, pp, device);

@@ -240,12 +240,13 @@ def test_reference_loads_and_searches_our_graph(tmp_path):
     path = str(tmp_path / "mine.graph")
     capi.build_slim_graph(c.base, path, M=16, ef_construction=200)
     gt, _ = rh.ref_bruteforce(c.base, c.queries, 10)
-    recalls = {}
-    for name, g in (("ours", path), ("reference", c.graph)):
-        ref = rh.RefSlim(g, c.dim, c.n)
-        lab, _, _ = ref.search(c.queries, 10, 64)
-        recalls[name] = np.mean([len(set(a) & set(b)) / 10 for a, b in zip(lab, gt)])
-    assert abs(recalls["ours"] - recalls["reference"]) < 0.02, recalls
+    for ef in (32, 64):           # 0.5 pp, north_star's recall bar (measured spread over builder seeds: <= 0.3 pp)
+        recalls = {}
+        for name, g in (("ours", path), ("reference", c.graph)):
+            ref = rh.RefSlim(g, c.dim, c.n)
+            lab, _, _ = ref.search(c.queries, 10, ef)
+            recalls[name] = np.mean([len(set(a) & set(b)) / 10 for a, b in zip(lab, gt)])
+        assert abs(recalls["ours"] - recalls["reference"]) <= 0.005, (ef, recalls)
     hi, ri = capi.HostGraph(path, c.dim).info(), capi.HostGraph(c.graph, c.dim).info()
     assert abs(hi["sum_deg0"] - ri["sum_deg0"]) / ri["sum_deg0"] < 0.05
 
