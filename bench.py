@@ -45,12 +45,13 @@ WORKLOADS = {
                               "what can be indexed inside a benchmark run), hnsw_slim M=16 efc=200, rows exchanged over "
                               "NVLink + top-k merge"),
     # BASELINE.json configs[1]: GIST-shaped, ef_search sweep 50-400 (tools/perf_probe.py --efs ...)
-    "gist1m": dict(n=1_000_000, dim=960, metric=0, M=32, efc=200, rank=24, nq=10_000, k=10, ef=100,
+    "gist1m": dict(n=1_000_000, dim=960, metric=0, M=32, efc=200, rank=24, nq=10_000, k=10, ef=100, curve=True,
                    desc="GIST-shaped synthetic 1Mx960 L2, hnsw_slim M=32 efc=200 (rank-24 latent Gaussian, seed 1)"),
     # BASELINE.json configs[2]: COHERE-shaped, inner product on unit vectors
-    "cohere1m": dict(n=1_000_000, dim=768, metric=1, M=32, efc=200, rank=24, nq=10_000, k=10, ef=100,
+    # (rank 16: with rank 24 the pruned graph stays below recall 0.95 up to ef=400, profiles/r01_probe_gist_cohere_final.txt)
+    "cohere1m": dict(n=1_000_000, dim=768, metric=1, M=32, efc=200, rank=16, nq=10_000, k=10, ef=100, curve=True,
                      desc="COHERE-shaped synthetic 1Mx768 inner product (unit rows), hnsw_slim M=32 efc=200 "
-                          "(rank-24 latent Gaussian, seed 1)"),
+                          "(rank-16 latent Gaussian, seed 1)"),
     # BASELINE.json configs[4] shape (MSTuring 96-dim, hnsw-slimq = RaBitQ codes + exact rerank) on one GPU
     "msturing1m-slimq": dict(n=1_000_000, dim=96, metric=0, M=16, efc=200, rank=12, nq=10_000, k=10, ef=100,
                              kind="slimq",
@@ -64,7 +65,7 @@ WORKLOADS = {
     # reduced-size variants for quick local runs (not contract lines)
     "sift200k": dict(n=200_000, dim=128, metric=0, M=16, efc=200, rank=14, nq=10_000, k=10, ef=100,
                      desc="SIFT-shaped synthetic 200kx128 L2 (dev size)"),
-    "gist200k": dict(n=200_000, dim=960, metric=0, M=32, efc=200, rank=24, nq=10_000, k=10, ef=100,
+    "gist200k": dict(n=200_000, dim=960, metric=0, M=32, efc=200, rank=24, nq=10_000, k=10, ef=100, curve=True,
                      desc="GIST-shaped synthetic 200kx960 L2 (dev size; 768 MB of vectors, still >> L2)"),
     "msturing200k-slimq": dict(n=200_000, dim=96, metric=0, M=16, efc=200, rank=12, nq=10_000, k=10, ef=100,
                                kind="slimq", desc="MSTuring-shaped synthetic 200kx96 hnsw_slimq (dev size)"),
@@ -539,6 +540,154 @@ def run_gpu(args, w):
         dist.destroy_process_group()
 
 
+def device_rows(n: int, dim: int, rank: int, normalize: bool, device: int):
+    """n x dim rows of the latent model generated on the GPU (see shard_rows_device)."""
+    w = {"n": n, "shards": 1, "dim": dim, "rank": rank}
+    rows = shard_rows_device(w, 0, device)
+    if normalize:
+        rows /= rows.norm(dim=1, keepdim=True)
+    return rows
+
+
+def run_gpu_curve(args, w):
+    """BASELINE.json configs[1] / [2] (GIST-shaped ef sweep, COHERE-shaped recall-QPS curve) on ONE GPU: rows
+    generated on the GPU, index built on the GPU (hs_build_slim_index_gpu), an ef_search sweep with recall@10
+    against exact kNN, and the headline fields for the smallest ef of the sweep that reaches recall >= 0.95;
+    the reference's OpenMP search on the same graph (saved in saveIndex's format) beside it."""
+    import torch
+    from hnsw_slim_b200 import capi
+    from hnsw_slim_b200.synth import latent_gaussian
+    rank, local_rank, world = env_rank()
+    if world != 1:
+        raise SystemExit("bench.py: the curve workloads are single-GPU measurements (--gpus 1)")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the engine has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    n, dim, k, nq, metric = w["n"], w["dim"], w["k"], w["nq"], w["metric"]
+    t0 = time.time()
+    rows = device_rows(n, dim, w["rank"], metric == 1, local_rank)
+    torch.cuda.synchronize()
+    t1 = time.time()
+    ix = capi.Index.build_gpu(None, base_ptr=rows.data_ptr(), n=n, dim=dim, metric=metric, M=w["M"],
+                              ef_construction=w["efc"], branching="4", device=local_rank)
+    t_build = time.time() - t1
+    info = ix.info()
+    log(f"[bench] {n}x{dim} rows generated on the GPU in {t1-t0:.1f}s, index built on the GPU in {t_build:.1f}s "
+        f"({info['device_bytes']/2**20:.0f} MiB HBM, avg deg0 {info['sum_deg0']/n:.2f}, maxlevel {info['maxlevel']})")
+    n_batches = min(8, args.warmup + args.steps)
+    qb = [latent_gaussian(nq, dim, rank=w["rank"], seed=1, normalize=(metric == 1), stream=1 + b) for b in range(n_batches)]
+    d_q = [torch.from_numpy(q).cuda() for q in qb]
+    ns = min(1000, nq)
+    gl = torch.empty((ns, k), dtype=torch.int32, device="cuda")
+    capi.bruteforce_knn_device(rows.data_ptr(), n, dim, d_q[0].data_ptr(), ns, k, gl.data_ptr(), None, metric=metric,
+                               stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    gt = gl.cpu().numpy().view(np.uint32)
+    del rows
+    torch.cuda.empty_cache()
+    ix.set_overlap(not args.no_overlap)
+    stream = torch.cuda.Stream()
+    d_lab = torch.empty((nq, k), dtype=torch.int32, device="cuda")
+    d_dist = torch.empty((nq, k), dtype=torch.float32, device="cuda")
+    peaks, peak_src = measured_peaks()
+    avg_deg0 = info["sum_deg0"] / n
+
+    def measure(ef, steps):
+        ix.set_ef(ef)
+        lab, _ = ix.search(qb[0][:ns], k)
+        rec = float(np.mean([len(set(a) & set(b)) / k for a, b in zip(lab, gt)]))
+        for i in range(args.warmup):
+            ix.search_device(d_q[i % n_batches].data_ptr(), nq, k, d_lab.data_ptr(), d_dist.data_ptr(), stream.cuda_stream)
+        stream.synchronize()
+        ix.reset_stats()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        clocks = ClockSampler(local_rank)
+        torch.cuda.synchronize()
+        with clocks:
+            e0.record(stream)
+            for i in range(steps):
+                ix.search_device(d_q[(args.warmup + i) % n_batches].data_ptr(), nq, k, d_lab.data_ptr(), d_dist.data_ptr(),
+                                 stream.cuda_stream)
+            e1.record(stream)
+            stream.synchronize()
+        ms = e0.elapsed_time(e1)
+        st = ix.stats()
+        alg = (st["n_dist"] * 4 * info["dim_padded"] + st["n_hops"] * (8 + 4 * avg_deg0)) / steps
+        gbs = alg / (ms / steps * 1e-3) / 1e9
+        return {"ef_search": ef, "recall_at_10": rec, "qps": nq * steps / (ms * 1e-3), "ms_per_step": ms / steps,
+                "hbm_gbs_algorithmic": gbs, "frac": gbs / peaks["hbm_gbs"], "dist_evals_per_query": st["n_dist"] / steps / nq,
+                "alg_bytes": alg, "clocks": clocks.summary()}
+
+    efs = [args.ef] if args.ef else [50, 100, 200, 400]
+    curve = [measure(ef, args.steps) for ef in efs]
+    for c in curve:
+        log(f"[bench] ef={c['ef_search']}: recall {c['recall_at_10']:.4f}, {c['qps']/1e6:.3f} M QPS, "
+            f"{c['hbm_gbs_algorithmic']:.0f} GB/s algorithmic ({c['frac']:.2f} of peak)")
+    ok = [c for c in curve if c["recall_at_10"] >= 0.95]
+    head = min(ok, key=lambda c: c["ef_search"]) if ok else max(curve, key=lambda c: c["recall_at_10"])
+    ef = head["ef_search"]
+
+    # end to end: pinned host batches in, pinned host rows out, three batches in flight (as the headline workload)
+    ix.set_ef(ef)
+    h_q = [torch.from_numpy(q).pin_memory() for q in qb]
+    depth = 3
+    h_lab = [torch.empty((nq, k), dtype=torch.int32).pin_memory() for _ in range(depth)]
+    h_dist = [torch.empty((nq, k), dtype=torch.float32).pin_memory() for _ in range(depth)]
+    for i in range(args.warmup):
+        ix.search_ptr(h_q[i % n_batches].data_ptr(), nq, k, h_lab[0].data_ptr(), h_dist[0].data_ptr())
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        if i >= depth:
+            ix.wait_oldest()
+        ix.submit_ptr(h_q[(args.warmup + i) % n_batches].data_ptr(), nq, k, h_lab[i % depth].data_ptr(),
+                      h_dist[i % depth].data_ptr())
+    ix.wait()
+    e2e_s = time.perf_counter() - t0
+    e2e = {"value": nq * args.steps / e2e_s, "unit": "queries/s", "h2d_bytes_per_step": nq * dim * 4,
+           "d2h_bytes_per_step": nq * k * 8,
+           "timing": "host wall clock; hs_search_batch_submit / _wait_oldest, three batches in flight, pinned host buffers"}
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        try:
+            from oracle import refharness as rh
+            if rh.ref_slim_path() is not None:
+                os.makedirs(CACHE, exist_ok=True)
+                path = os.path.join(CACHE, f"gpu_built_{args.workload}_{os.getpid()}.graph")
+                ix.save(path)
+                ref = rh.RefSlim(path, dim, n, metric)
+                qs = qb[0][:2000]
+                ref.search(qs[:500], k, ef, 0)
+                times = []
+                while sum(times) < 10.0 and len(times) < 100:
+                    _, sec, _ = ref.search(qs, k, ef, 0)
+                    times.append(sec)
+                ref.close()
+                os.remove(path)
+                cores = os.cpu_count() or 1
+                cpu = {"value": len(qs) / float(np.median(times)), "unit": "queries/s", "cores": cores, "kind": "reference",
+                       "sample": f"{len(times)} passes x {len(qs)} queries at ef={ef} on the same graph (saved by "
+                                 f"hs_save_index, loaded by the reference's loadIndex), omp dynamic over queries, {cores} threads"}
+        except Exception as e:
+            log(f"[bench] CPU baseline failed: {e!r}")
+    out = {
+        "metric": "QPS at recall@10>=0.95", "value": head["qps"], "unit": "queries/s", "n_gpus": 1, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": w["desc"], "k": k, "ef_search": ef, "queries_per_step": nq,
+                   "recall_at_10": head["recall_at_10"], "reached_0.95": bool(ok),
+                   "curve": [{kk: c[kk] for kk in ("ef_search", "recall_at_10", "qps", "hbm_gbs_algorithmic", "frac",
+                                                    "dist_evals_per_query")} for c in curve],
+                   "graph_built_by": f"hs_build_slim_index_gpu in {t_build:.1f}s (rows generated on the GPU)",
+                   "l2": "index %.0f MiB >> 126 MB L2; a different query batch every step" % (info["device_bytes"] / 2**20)},
+        "roofline": {"bound": "hbm", "achieved": head["hbm_gbs_algorithmic"], "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                     "frac": head["frac"], "traffic": None, "peak_source": peak_src, "kernel": "hs::traverse_kernel",
+                     "algorithmic_bytes_per_launch": head["alg_bytes"]},
+        "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": args.steps, "clocks": head["clocks"],
+    }
+    print(json.dumps(out), flush=True)
+
+
 def shard_paths(w: dict):
     fam = "hnsw_slimq" if w.get("kind") == "slimq" else "hnsw_slim"
     return [os.path.join(CACHE, f"{fam}_shard{s}of{w['shards']}_n{w['n']}_d{w['dim']}_r{w['rank']}_M{w['M']}"
@@ -623,7 +772,7 @@ def shard_rows_device(w: dict, s: int, device: int):
     return out
 
 
-def build_shards_gpu(w: dict, my_shards, device: int, gt_queries, k: int):
+def build_shards_gpu(w: dict, my_shards, device: int, gt_queries, k: int, slimq: bool = False):
     """This rank's shards built on its GPU (hs_build_slim_index_gpu) from device-generated rows, plus — while
     the rows are at hand — the shard-local exact top-k of `gt_queries` for the recall of the merged result."""
     import torch
@@ -648,7 +797,7 @@ def build_shards_gpu(w: dict, my_shards, device: int, gt_queries, k: int):
         t2 = time.time()
         ix = capi.Index.build_gpu(None, base_ptr=rows.data_ptr(), n=hi - lo, dim=w["dim"], metric=w["metric"], M=w["M"],
                                   ef_construction=w["efc"], branching="4", labels=np.arange(lo, hi, dtype=np.uint64),
-                                  device=device)
+                                  device=device, kind=capi.HS_KIND_SLIMQ if slimq else capi.HS_KIND_SLIM)
         del rows
         torch.cuda.empty_cache()
         log(f"[bench] shard {s} [{lo},{hi}): rows generated on the GPU in {t1-t0:.1f}s, exact top-k {t2-t1:.1f}s, "
@@ -687,11 +836,11 @@ def measure_sharded(args, w, rank, local_rank, world, dist):
     n_batches = min(8, args.warmup + args.steps)
     qb = sharded_queries(w, n_batches)
     ns = min(1000, nq)
-    builder = "host" if slimq else args.builder
+    builder = args.builder
     t_build = time.time()
     paths, gt = None, None
     if builder == "gpu":
-        shards, gt_parts = build_shards_gpu(w, mine, local_rank, None if args.no_recall else qb[0][:ns], k)
+        shards, gt_parts = build_shards_gpu(w, mine, local_rank, None if args.no_recall else qb[0][:ns], k, slimq)
         if not args.no_recall:
             if world > 1:
                 allp = [None] * world
@@ -897,8 +1046,9 @@ def measure_sharded(args, w, rank, local_rank, world, dist):
                                 "nccl: one all_gather(nq*k*8 B per rank) + hs_topk_merge_device per batch"),
                    "recall_at_10": recall, "ef_ladder": ladder, "dist_evals_per_query_all_shards": evals,
                    "graph_build_s": round(t_build, 1),
-                   "graph_builder": ("hs_build_slim_index_gpu: rows generated and indexed on each rank's GPU (HNSW build + "
-                                     "convertFromHNSW on the device)" if builder == "gpu" else
+                   "graph_builder": (("hs_build_slimq_index_gpu" if slimq else "hs_build_slim_index_gpu") +
+                                     ": rows generated and indexed on each rank's GPU (HNSW build + convertFromHNSW"
+                                     + (" + RaBitQ codes" if slimq else "") + " on the device)" if builder == "gpu" else
                                      "host builder (hs_build_slim_graph / hs_build_slimq_graph), cached .graph files"),
                    "l2": "each shard (%.0f MB of rows) vs 126 MB L2; a different query batch every step"
                          % (rows * w["dim"] * 4 / 1e6)},
@@ -987,6 +1137,8 @@ def main():
         run_reference(args, w)
     elif "shards" in w:
         run_gpu_sharded(args, w)
+    elif w.get("curve") and args.builder == "gpu":
+        run_gpu_curve(args, w)
     else:
         run_gpu(args, w)
 

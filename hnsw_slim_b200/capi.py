@@ -28,7 +28,7 @@ EXPORTS = [
     "hs_exchange_search", "hs_exchange_signal_and_wait", "hs_exchange_tables", "hs_exchange_free",
     "hs_shardgroup_create", "hs_shardgroup_handle", "hs_shardgroup_connect", "hs_shardgroup_connect_local",
     "hs_shardgroup_submit", "hs_shardgroup_wait_oldest", "hs_shardgroup_wait", "hs_shardgroup_streams",
-    "hs_shardgroup_free", "hs_build_slim_index_gpu", "hs_save_index",
+    "hs_shardgroup_free", "hs_build_slim_index_gpu", "hs_save_index", "hs_build_slimq_index_gpu",
 ]
 
 
@@ -122,6 +122,7 @@ def lib():
         L.hs_exchange_free.restype = None
         L.hs_build_slim_index_gpu.argtypes = [vp, sz, sz, i32, C.POINTER(BuildParams), vp, i32, C.POINTER(vp)]
         L.hs_save_index.argtypes = [vp, C.c_char_p]
+        L.hs_build_slimq_index_gpu.argtypes = [vp, sz, sz, C.POINTER(BuildParams), vp, sz, vp, i32, C.POINTER(vp)]
         L.hs_shardgroup_create.argtypes = [vp, sz, i32, i32, sz, sz, i32, C.POINTER(vp)]
         L.hs_shardgroup_handle.argtypes = [vp, vp]
         L.hs_shardgroup_connect.argtypes = [vp, vp]
@@ -182,9 +183,11 @@ class Index:
     @classmethod
     def build_gpu(cls, base, *, metric: int = HS_METRIC_L2, M: int = 16, ef_construction: int = 200,
                   branching: str = "4", labels=None, seed: int = 100, device: int = 0, base_ptr: int | None = None,
-                  n: int | None = None, dim: int | None = None, **prune) -> "Index":
-        """hs_build_slim_index_gpu: HNSW build + HNSW-Slim conversion on the device.  `base` is a host array,
-        or pass base_ptr / n / dim for rows that already live in device memory."""
+                  n: int | None = None, dim: int | None = None, kind: int = HS_KIND_SLIM, centroids=None,
+                  num_cluster: int = 16, **prune) -> "Index":
+        """hs_build_slim_index_gpu / hs_build_slimq_index_gpu (kind = HS_KIND_SLIMQ): HNSW build + HNSW-Slim
+        conversion (+ RaBitQ codes) on the device.  `base` is a host array, or pass base_ptr / n / dim for rows
+        that already live in device memory."""
         self = cls.__new__(cls)
         self._h = C.c_void_p()
         if base_ptr is None:
@@ -200,7 +203,15 @@ class Index:
         if labels is not None:
             labels = np.ascontiguousarray(labels, dtype=np.uint64)
             lab = labels.ctypes.data
-        _check(lib().hs_build_slim_index_gpu(base_ptr, n, dim, metric, C.byref(p), lab, device, C.byref(self._h)))
+        if kind == HS_KIND_SLIMQ:
+            cen = None
+            if centroids is not None:
+                centroids = _f32(centroids)
+                num_cluster, cen = centroids.shape[0], centroids.ctypes.data
+            _check(lib().hs_build_slimq_index_gpu(base_ptr, n, dim, C.byref(p), cen, num_cluster, lab, device,
+                                                  C.byref(self._h)))
+        else:
+            _check(lib().hs_build_slim_index_gpu(base_ptr, n, dim, metric, C.byref(p), lab, device, C.byref(self._h)))
         self.dim = dim
         return self
 

@@ -599,7 +599,6 @@ int build_hnsw_graph(const float *base, size_t n, size_t dim, int metric, size_t
 // 1-bit RaBitQ codes + factors, written in HierarchicalNSWSlimQ::saveIndex's format
 // (slimq.h:1161-1216) so both hs_load and the reference's loadIndex read it.
 namespace {
-
 void host_fwht(float *buf, size_t len) {          // natural order, butterfly distance 1, 2, 4, ...
   for (size_t h = 1; h < len; h *= 2)
     for (size_t j = 0; j < len; j += 2 * h)
@@ -609,6 +608,8 @@ void host_fwht(float *buf, size_t len) {          // natural order, butterfly di
         buf[j + k + h] = u - v;
       }
 }
+
+}  // namespace
 
 // FhtKacRotator::rotate (rabitqlib/utils/rotator.hpp:370-423)
 void host_rotate(const float *x, size_t dim, size_t pd, size_t td, const uint8_t *flip, float *out) {
@@ -639,6 +640,7 @@ void host_rotate(const float *x, size_t dim, size_t pd, size_t td, const uint8_t
 // *_clusterids_16.ivecs that no code in it produces, hnsw_slimq_strategy.h:42-45)
 void host_kmeans(const float *base, size_t n, size_t dim, size_t k, int iters, uint64_t seed, int threads,
                  std::vector<float> &cent, std::vector<uint32_t> &ids) {
+  if (threads <= 0) threads = (int)std::max(1u, std::thread::hardware_concurrency());
   cent.assign(k * dim, 0.f);
   ids.assign(n, 0);
   for (size_t c = 0; c < k; ++c) {
@@ -680,8 +682,6 @@ void host_kmeans(const float *base, size_t n, size_t dim, size_t k, int iters, u
   }
   parallel_for(0, n, threads, [&](size_t i, int) { ids[i] = assign(i); });
 }
-
-}  // namespace
 
 int build_slimq_graph(const float *base, size_t n, size_t dim, size_t M, size_t ef_construction, double branching,
                       int threshold_level, float top_pct0, float top_pct, size_t top_M0, size_t low_m0,

@@ -604,6 +604,122 @@ __global__ void pad_rows_kernel(const float *__restrict__ src, uint32_t dim, flo
 }
 
 // ---------------------------------------------------------------------------------------------
+// hnsw_slimq payload: cluster assignment, FHT-Kac rotation, 1-bit RaBitQ code + factors per node
+// (the host builder's loop, graph_build.cpp build_slimq_graph; one_bit_code_with_factor,
+// rabitqlib/quantization/rabitq_impl.hpp:76-135; rotator.hpp:370-423; pack_binary, space.hpp:272-286)
+// ---------------------------------------------------------------------------------------------
+struct PayloadParams {
+  const float *vec;               // n x dim_padded raw rows
+  uint32_t n, dim, dim_padded, pd, td, words, num_cluster;
+  const float *cent;              // num_cluster x dim   raw centroids (cluster assignment)
+  const float *rcent;             // num_cluster x pd    rotated centroids
+  const uint8_t *flip;            // 4 * pd / 8
+  float fac;                      // 1 / sqrt(td)
+  uint2 *qrec;                    // n x (words + 2)
+};
+
+__global__ void __launch_bounds__(128) slimq_payload_kernel(const __grid_constant__ PayloadParams p) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  float *buf = reinterpret_cast<float *>(smem) + (size_t)wid * p.pd;
+  const uint32_t i = blockIdx.x * (blockDim.x >> 5) + wid;
+  if (i >= p.n) return;
+  const float *row = p.vec + (size_t)i * p.dim_padded;
+  for (uint32_t d = lane; d < p.pd; d += 32) buf[d] = d < p.dim ? row[d] : 0.f;
+  __syncwarp();
+  // nearest raw centroid, first minimum (host_kmeans assign)
+  uint32_t cluster = 0;
+  {
+    float best = 3.402823466e+38f;
+    for (uint32_t c0 = 0; c0 < p.num_cluster; c0 += 32) {
+      const uint32_t c = c0 + lane;
+      float d = 3.402823466e+38f;
+      if (c < p.num_cluster) {
+        const float *cv = p.cent + (size_t)c * p.dim;
+        float acc = 0.f;
+        for (uint32_t k = 0; k < p.dim; ++k) {
+          const float t = buf[k] - cv[k];
+          acc = fmaf(t, t, acc);
+        }
+        d = acc;
+      }
+      uint64_t key = ((uint64_t)f2ord(d) << 32) | c;
+      key = warp_min_u64(key);
+      const float bd = ord2f((uint32_t)(key >> 32));
+      if (bd < best) {
+        best = bd;
+        cluster = (uint32_t)key;
+      }
+    }
+  }
+  // FhtKacRotator::rotate, operation for operation as host_rotate (graph_build.cpp)
+  const bool pow2 = p.td == p.pd;
+  const uint32_t start = p.pd - p.td;
+  for (int r = 0; r < 4; ++r) {
+    const uint8_t *fl = p.flip + (size_t)r * p.pd / 8;
+    for (uint32_t d = lane; d < p.pd; d += 32)
+      if ((fl[d >> 3] >> (d & 7)) & 1u) buf[d] = -buf[d];
+    __syncwarp();
+    float *seg = (!pow2 && (r & 1)) ? buf + start : buf;
+    for (uint32_t h = 1; h < p.td; h *= 2) {
+      for (uint32_t idx = lane; idx < p.td / 2; idx += 32) {
+        const uint32_t j = (idx / h) * 2 * h + (idx % h);
+        const float u = seg[j], v = seg[j + h];
+        seg[j] = u + v;
+        seg[j + h] = u - v;
+      }
+      __syncwarp();
+    }
+    for (uint32_t d = lane; d < p.td; d += 32) seg[d] *= p.fac;
+    __syncwarp();
+    if (!pow2) {
+      for (uint32_t d = lane; d < p.pd / 2; d += 32) {
+        const float a = buf[d], b = buf[d + p.pd / 2];
+        buf[d] = a + b;
+        buf[d + p.pd / 2] = a - b;
+      }
+      __syncwarp();
+    }
+  }
+  if (!pow2) {
+    for (uint32_t d = lane; d < p.pd; d += 32) buf[d] *= 0.25f;
+    __syncwarp();
+  }
+  // residual against the rotated centroid: sign bits + the three sums of one_bit_code_with_factor, in double
+  const float *cen = p.rcent + (size_t)cluster * p.pd;
+  uint2 *rec = p.qrec + (size_t)i * (p.words + 2);
+  double l2 = 0, ip_resi = 0, ip_cent = 0;
+  for (uint32_t w = 0; w < p.words; ++w) {
+    uint32_t half[2];
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+      const uint32_t d = 64 * w + 32 * hh + lane;
+      const float rr = buf[d] - cen[d];
+      const bool bit = rr > 0.f;
+      const double xu = bit ? 0.5 : -0.5;
+      l2 += (double)rr * rr;
+      ip_resi += (double)rr * xu;
+      ip_cent += (double)cen[d] * xu;
+      half[hh] = __brev(__ballot_sync(FULL, bit));      // dimension 64w + j  <->  bit 63 - j (MSB first)
+    }
+    if (lane == 0) rec[w] = make_uint2(half[1], half[0]);   // (low 32 bits, high 32 bits) of the code word
+  }
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    l2 += __shfl_xor_sync(FULL, l2, off);
+    ip_resi += __shfl_xor_sync(FULL, ip_resi, off);
+    ip_cent += __shfl_xor_sync(FULL, ip_cent, off);
+  }
+  if (lane == 0) {
+    if (ip_resi == 0) ip_resi = __longlong_as_double(0x7ff0000000000000ll);
+    const float f_add = (float)(l2 + 2 * l2 * ip_cent / ip_resi);
+    const float f_rescale = (float)(-2 * l2 / ip_resi);
+    rec[p.words] = make_uint2(__float_as_uint(f_add), __float_as_uint(f_rescale));
+    rec[p.words + 1] = make_uint2(cluster, 0u);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
 struct DevBuf {                       // frees on scope exit unless released
@@ -1020,22 +1136,14 @@ int convert_gpu(const float4 *d_vec, uint32_t row_chunks, int metric, const GpuH
 }  // namespace
 
 // ---- entry points used by hs_api.cu ----
-int gpu_build_slim_index(const float *base, size_t n, size_t dim, int metric, const hs_build_params *bp,
-                         double branching, const uint64_t *labels, int device, hs_index **out_ix) {
-  if (!base || n == 0 || dim == 0 || n >= (1ull << 31) || !bp || !out_ix) {
-    set_error("hs_build_slim_index_gpu: bad argument");
-    return HS_ERR_ARG;
-  }
-  int rc = select_device(device);
-  if (rc != HS_OK) return rc;
+namespace {
+
+// rows -> HNSW -> HNSW-Slim lists, all on the device; fills `dg` (ownership of the arrays moves to it)
+int build_slim_device_graph(const float *base, size_t n, size_t dim, int metric, const hs_build_params *bp,
+                            double branching, int device, cudaStream_t st, DeviceGraph *dg) {
   const size_t dim_padded = (dim + kRowAlignFloats - 1) / kRowAlignFloats * kRowAlignFloats;
   const uint32_t row_chunks = (uint32_t)(dim_padded / 4);
-  cudaStream_t st = nullptr;
-  GB_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-  struct StreamGuard {
-    cudaStream_t s;
-    ~StreamGuard() { cudaStreamDestroy(s); }
-  } guard{st};
+  int rc;
   // the vector store: 128-byte rows, zero padded (DESIGN.md "HBM layout")
   DevBuf vec;
   if ((rc = vec.alloc(n * dim_padded * 4)) != HS_OK) return rc;
@@ -1065,34 +1173,162 @@ int gpu_build_slim_index(const float *base, size_t n, size_t dim, int metric, co
   for (int l = 1; l <= g.maxlevel; ++l) hup[l] = g.up[l].as<uint32_t>();
   rc = convert_gpu(vec.as<float4>(), row_chunks, metric, g, g.adj0.as<uint32_t>(), g.stride0, hup, g.ustride, cp, st, &s);
   if (rc != HS_OK) return rc;
-  // free the HNSW lists before the index takes its final shape
-  g.adj0.alloc(0);
-  for (int l = 1; l <= g.maxlevel; ++l) g.up[l].alloc(0);
+  dg->n = n;
+  dg->dim = dim;
+  dg->dim_padded = dim_padded;
+  dg->metric = metric;
+  dg->M = g.M;
+  dg->maxM = g.maxM;
+  dg->maxM0 = g.maxM0;
+  dg->ef_construction = g.efc;
+  dg->maxlevel = g.maxlevel;
+  dg->threshold_level = bp->threshold_level;
+  dg->enterpoint = g.ep;
+  dg->deg0_stride = s.deg0_stride;
+  dg->max_deg0 = s.max_deg0;
+  dg->upper_stride = s.upper_stride;
+  dg->n_upper = g.n_upper;
+  dg->sum_deg0 = s.sum_deg0;
+  for (int l = 0; l <= g.maxlevel; ++l) dg->level_count[l] = g.level_count[l];
+  dg->d_vec = static_cast<float *>(vec.release());
+  dg->d_adj0 = static_cast<uint32_t *>(s.adj0.release());
+  dg->d_upper_slot = static_cast<int32_t *>(g.slot.release());
+  for (int l = 1; l <= g.maxlevel; ++l) dg->d_upper_adj[l] = static_cast<uint32_t *>(s.up[l].release());
+  return HS_OK;
+}
 
+void free_device_graph(DeviceGraph &dg) {
+  cudaFree(dg.d_vec);
+  cudaFree(dg.d_adj0);
+  cudaFree(dg.d_upper_slot);
+  for (auto *p : dg.d_upper_adj) cudaFree(p);
+  cudaFree(dg.d_qrec);
+  cudaFree(dg.d_centroids);
+  cudaFree(dg.d_flip);
+  dg = DeviceGraph();
+}
+
+struct StreamGuard {
+  cudaStream_t s;
+  ~StreamGuard() { cudaStreamDestroy(s); }
+};
+
+}  // namespace
+
+int gpu_build_slim_index(const float *base, size_t n, size_t dim, int metric, const hs_build_params *bp,
+                         double branching, const uint64_t *labels, int device, hs_index **out_ix) {
+  if (!base || n == 0 || dim == 0 || n >= (1ull << 31) || !bp || !out_ix) {
+    set_error("hs_build_slim_index_gpu: bad argument");
+    return HS_ERR_ARG;
+  }
+  int rc = select_device(device);
+  if (rc != HS_OK) return rc;
+  cudaStream_t st = nullptr;
+  GB_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  StreamGuard guard{st};
+  DeviceGraph dg;
+  if ((rc = build_slim_device_graph(base, n, dim, metric, bp, branching, device, st, &dg)) != HS_OK) {
+    free_device_graph(dg);
+    return rc;
+  }
   std::vector<uint32_t> lab(n);
   for (size_t i = 0; i < n; ++i) lab[i] = labels ? (uint32_t)labels[i] : (uint32_t)i;     // truncated as slim.h:2129
+  dg.h_labels = lab.data();
+  return adopt_device_graph(dg, device, out_ix);
+}
+
+// hnsw_slimq on the device: the hnsw_slim graph over the raw rows (as the host builder, graph_build.cpp), the
+// centroids from Lloyd iterations on a host-side sample of the rows (the reference reads them from files no
+// code of it produces, hnsw_slimq_strategy.h:42-45) or as given, and one kernel for every node's cluster id,
+// rotation, 1-bit code and factors, written straight into the engine's 8-byte-word records.
+int gpu_build_slimq_index(const float *base, size_t n, size_t dim, const hs_build_params *bp, double branching,
+                          const float *centroids, size_t num_cluster, const uint64_t *labels, int device,
+                          hs_index **out_ix) {
+  if (!base || n == 0 || dim == 0 || n >= (1ull << 31) || !bp || !out_ix || num_cluster == 0 || num_cluster > 4096) {
+    set_error("hs_build_slimq_index_gpu: bad argument");
+    return HS_ERR_ARG;
+  }
+  const size_t pd = (dim + 63) / 64 * 64, words = pd / 64;     // rabitqlib/index/hnsw/hnsw.hpp:424-427
+  size_t td = 1;
+  while (td * 2 <= dim) td *= 2;                                // rotator.hpp:233-235
+  if (td < 64 || pd > 2048) {
+    set_error("hs_build_slimq_index_gpu: dim must be in [64, 2048] (FhtKacRotator, rotator.hpp:237-258)");
+    return HS_ERR_UNSUPPORTED;
+  }
+  int rc = select_device(device);
+  if (rc != HS_OK) return rc;
+  cudaStream_t st = nullptr;
+  GB_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  StreamGuard guard{st};
   DeviceGraph dg;
-  dg.n = n;
-  dg.dim = dim;
-  dg.dim_padded = dim_padded;
-  dg.metric = metric;
-  dg.M = g.M;
-  dg.maxM = g.maxM;
-  dg.maxM0 = g.maxM0;
-  dg.ef_construction = g.efc;
-  dg.maxlevel = g.maxlevel;
-  dg.threshold_level = bp->threshold_level;
-  dg.enterpoint = g.ep;
-  dg.deg0_stride = s.deg0_stride;
-  dg.max_deg0 = s.max_deg0;
-  dg.upper_stride = s.upper_stride;
-  dg.n_upper = g.n_upper;
-  dg.sum_deg0 = s.sum_deg0;
-  for (int l = 0; l <= g.maxlevel; ++l) dg.level_count[l] = g.level_count[l];
-  dg.d_vec = static_cast<float *>(vec.release());
-  dg.d_adj0 = static_cast<uint32_t *>(s.adj0.release());
-  dg.d_upper_slot = static_cast<int32_t *>(g.slot.release());
-  for (int l = 1; l <= g.maxlevel; ++l) dg.d_upper_adj[l] = static_cast<uint32_t *>(s.up[l].release());
+  if ((rc = build_slim_device_graph(base, n, dim, HS_METRIC_L2, bp, branching, device, st, &dg)) != HS_OK) {
+    free_device_graph(dg);
+    return rc;
+  }
+  auto fail = [&](int code) {
+    free_device_graph(dg);
+    return code;
+  };
+  // centroids: given, or k-means over an evenly spaced sample of at most 200k rows
+  std::vector<float> cent(num_cluster * dim);
+  if (centroids) {
+    std::memcpy(cent.data(), centroids, cent.size() * 4);
+  } else {
+    const size_t sample = std::min<size_t>(n, 200000), stride = n / sample;
+    std::vector<float> rows(sample * dim);
+    if (cudaMemcpy2D(rows.data(), dim * 4, dg.d_vec, dg.dim_padded * 4 * stride, dim * 4, sample, cudaMemcpyDeviceToHost) !=
+        cudaSuccess) {
+      set_error(std::string("hs_build_slimq_index_gpu: sample download: ") + cudaGetErrorString(cudaGetLastError()));
+      return fail(HS_ERR_CUDA);
+    }
+    std::vector<uint32_t> ids;
+    host_kmeans(rows.data(), sample, dim, num_cluster, 8, bp->seed, 0, cent, ids);
+  }
+  std::vector<uint8_t> flip(4 * pd / 8);          // the host builder's sign bits (graph_build.cpp)
+  for (size_t i = 0; i < flip.size(); ++i) flip[i] = (uint8_t)(mix64(bp->seed * 0xD1B54A32D192ED03ull + i) >> 56);
+  std::vector<float> rcent(num_cluster * pd);
+  for (size_t c = 0; c < num_cluster; ++c) host_rotate(&cent[c * dim], dim, pd, td, flip.data(), &rcent[c * pd]);
+  DevBuf d_cent, d_rcent, d_flip, d_qrec;
+  if ((rc = d_cent.alloc(cent.size() * 4)) != HS_OK || (rc = d_rcent.alloc(rcent.size() * 4)) != HS_OK ||
+      (rc = d_flip.alloc(flip.size())) != HS_OK || (rc = d_qrec.alloc(n * (words + 2) * 8)) != HS_OK)
+    return fail(rc);
+  if (cudaMemcpyAsync(d_cent.p, cent.data(), cent.size() * 4, cudaMemcpyHostToDevice, st) != cudaSuccess ||
+      cudaMemcpyAsync(d_rcent.p, rcent.data(), rcent.size() * 4, cudaMemcpyHostToDevice, st) != cudaSuccess ||
+      cudaMemcpyAsync(d_flip.p, flip.data(), flip.size(), cudaMemcpyHostToDevice, st) != cudaSuccess) {
+    set_error(std::string("hs_build_slimq_index_gpu: upload: ") + cudaGetErrorString(cudaGetLastError()));
+    return fail(HS_ERR_CUDA);
+  }
+  PayloadParams pp{};
+  pp.vec = dg.d_vec;
+  pp.n = (uint32_t)n;
+  pp.dim = (uint32_t)dim;
+  pp.dim_padded = (uint32_t)dg.dim_padded;
+  pp.pd = (uint32_t)pd;
+  pp.td = (uint32_t)td;
+  pp.words = (uint32_t)words;
+  pp.num_cluster = (uint32_t)num_cluster;
+  pp.cent = d_cent.as<float>();
+  pp.rcent = d_rcent.as<float>();
+  pp.flip = d_flip.as<uint8_t>();
+  pp.fac = 1.0f / std::sqrt((float)td);
+  pp.qrec = d_qrec.as<uint2>();
+  const size_t smem = 4 * pd * 4;
+  if (cudaFuncSetAttribute(slimq_payload_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+    return fail(HS_ERR_CUDA);
+  slimq_payload_kernel<<<(unsigned)((n + 3) / 4), 128, smem, st>>>(pp);
+  if (cudaStreamSynchronize(st) != cudaSuccess || cudaGetLastError() != cudaSuccess) {
+    set_error(std::string("slimq_payload_kernel: ") + cudaGetErrorString(cudaGetLastError()));
+    return fail(HS_ERR_CUDA);
+  }
+  dg.kind = HS_KIND_SLIMQ;
+  dg.padded_dim_q = pd;
+  dg.num_cluster = num_cluster;
+  dg.trunc_dim = (uint32_t)td;
+  dg.d_qrec = static_cast<uint2 *>(d_qrec.release());
+  dg.d_centroids = static_cast<float *>(d_rcent.release());
+  dg.d_flip = static_cast<uint8_t *>(d_flip.release());
+  std::vector<uint32_t> lab(n);
+  for (size_t i = 0; i < n; ++i) lab[i] = labels ? (uint32_t)labels[i] : (uint32_t)i;
   dg.h_labels = lab.data();
   return adopt_device_graph(dg, device, out_ix);
 }

@@ -365,6 +365,12 @@ int hs::adopt_device_graph(DeviceGraph &dg, int device, hs_index **out) {
   ix->d_adj0 = dg.d_adj0;
   ix->d_upper_slot = dg.d_upper_slot;
   for (int l = 0; l < kMaxLevels; ++l) ix->d_upper_adj[l] = dg.d_upper_adj[l];
+  ix->d_qrec = dg.d_qrec;
+  ix->d_centroids = dg.d_centroids;
+  ix->d_flip = dg.d_flip;
+  dg.d_qrec = nullptr;
+  dg.d_centroids = nullptr;
+  dg.d_flip = nullptr;
   dg.d_vec = nullptr;                     // owned by the handle from here on (hs_free releases them)
   dg.d_adj0 = nullptr;
   dg.d_upper_slot = nullptr;
@@ -405,6 +411,14 @@ int hs::adopt_device_graph(DeviceGraph &dg, int device, hs_index **out) {
   I.upper_stride = dg.upper_stride;
   I.n_upper = dg.n_upper;
   I.sum_deg0 = dg.sum_deg0;
+  if (dg.kind == HS_KIND_SLIMQ) {
+    ix->words = (uint32_t)(dg.padded_dim_q / 64);
+    ix->trunc_dim = dg.trunc_dim;
+    ix->t_const = slimq_default_tconst(dg.padded_dim_q, 3);
+    I.padded_dim_q = dg.padded_dim_q;
+    I.num_cluster = dg.num_cluster;
+    bytes += dg.n * (dg.padded_dim_q / 64 + 2) * 8 + dg.num_cluster * dg.padded_dim_q * 4 + 4 * dg.padded_dim_q / 8;
+  }
   I.device_bytes = bytes;
   I.ef = 10;
   *out = ix.release();
@@ -1159,6 +1173,21 @@ int hs_build_slim_index_gpu(const float *base, size_t n, size_t dim, int metric,
     set_error("hs_build_slim_index_gpu: out of host memory");
     return HS_ERR_NOMEM;
   }
+}
+
+int hs_build_slimq_index_gpu(const float *base, size_t n, size_t dim, const hs_build_params *p, const float *centroids,
+                             size_t num_cluster, const uint64_t *labels, int device, hs_index **out) {
+  if (!out) {
+    set_error("null argument");
+    return HS_ERR_ARG;
+  }
+  *out = nullptr;
+  double bf;
+  int rc0 = parse_branching(p, &bf);
+  if (rc0 != HS_OK) return rc0;
+  return guarded("hs_build_slimq_index_gpu", [&] {
+    return gpu_build_slimq_index(base, n, dim, p, bf, centroids, num_cluster, labels, device, out);
+  });
 }
 
 // saveIndex (slim.h:717-751) of an HBM-resident hnsw_slim index: header, element records

@@ -100,11 +100,20 @@ struct DeviceGraph {
   int32_t *d_upper_slot = nullptr;
   uint32_t *d_upper_adj[kMaxLevels] = {};
   const uint32_t *h_labels = nullptr;      // host, n entries
+  // hnsw_slimq payload (kind == HS_KIND_SLIMQ)
+  uint2 *d_qrec = nullptr;
+  float *d_centroids = nullptr;            // rotated, num_cluster x padded_dim_q
+  uint8_t *d_flip = nullptr;
+  uint64_t padded_dim_q = 0, num_cluster = 0;
+  uint32_t trunc_dim = 0;
 };
 int adopt_device_graph(DeviceGraph &dg, int device, hs_index **out);
 
 // graph_gpu.cu
 int gpu_build_slim_index(const float *base, size_t n, size_t dim, int metric, const hs_build_params *bp,
                          double branching, const uint64_t *labels, int device, hs_index **out);
+int gpu_build_slimq_index(const float *base, size_t n, size_t dim, const hs_build_params *bp, double branching,
+                          const float *centroids, size_t num_cluster, const uint64_t *labels, int device,
+                          hs_index **out);
 
 }  // namespace hs

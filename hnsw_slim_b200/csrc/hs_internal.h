@@ -97,4 +97,9 @@ int build_slimq_graph(const float *base, size_t n, size_t dim, size_t M, size_t 
                       size_t num_cluster, const uint32_t *cluster_ids, const uint64_t *labels,
                       const char *out_path);
 
+// pieces of the hnsw_slimq builder shared with the device builder (graph_gpu.cu)
+void host_rotate(const float *x, size_t dim, size_t pd, size_t td, const uint8_t *flip, float *out);
+void host_kmeans(const float *base, size_t n, size_t dim, size_t k, int iters, uint64_t seed, int threads,
+                 std::vector<float> &cent, std::vector<uint32_t> &ids);
+
 }  // namespace hs

@@ -341,6 +341,15 @@ int hs_build_slim_index_gpu(const float *base, size_t n, size_t dim, int metric,
                             const uint64_t *labels, int device, hs_index **out);
 int hs_save_index(hs_index *, const char *out_graph_path);
 
+/* The same for hnsw_slimq (HnswSlimQStrategy's build branch, hnsw_slimq_strategy.h:100-142 + convertFromHNSW,
+ * slimq.h:1471-1762): the hnsw_slim graph over the raw rows is built on the device as above, then one kernel
+ * gives every node its cluster id, FHT-Kac rotation (rotator.hpp:370-423), 1-bit RaBitQ code and factors
+ * (one_bit_code_with_factor, rabitq_impl.hpp:76-135) — the payload of hs_build_slimq_graph, computed where the
+ * rows already are.  centroids (num_cluster x dim, host) may be NULL: Lloyd iterations over a host-side sample
+ * of at most 200k rows then pick them.  The raw rows stay in the index for the exact rerank (setDataset). */
+int hs_build_slimq_index_gpu(const float *base, size_t n, size_t dim, const hs_build_params *p, const float *centroids,
+                             size_t num_cluster, const uint64_t *labels, int device, hs_index **out);
+
 /* Host-only inspection of the flattened form of a .graph (no CUDA needed): what
  * hs_load uploads.  Used by the CPU test-suite to check the loader against the
  * reference's accessors (slim.h:620-661). */

@@ -106,3 +106,41 @@ def test_gpu_builder_rows_already_on_the_device_and_argument_errors():
         capi.Index.build_gpu(base, M=64)                   # beyond the device builder's list capacity
     with pytest.raises(capi.HsError):
         capi.Index.build_gpu(base, M=16, ef_construction=400)
+
+
+@pytest.mark.parametrize("dim", [96, 128])
+def test_gpu_built_slimq_index_matches_host_built_quality(dim, tmp_path):
+    """hs_build_slimq_index_gpu (graph + cluster ids + rotation + 1-bit codes + factors, all on the device)
+    against hs_build_slimq_graph with the SAME centroids and seed: the per-node payload is a function of
+    (row, centroids, rotator bits), so the two indices differ only in their graphs — recall and estimate
+    counts must agree like the hnsw_slim builders do."""
+    n, nq, k = 30000, 1000, 10
+    base, q = make_dataset(n, nq, dim, rank=12, seed=6)
+    gt, _ = capi.bruteforce_knn(base, q, k)
+    rng = np.random.default_rng(1)
+    centroids = base[rng.choice(n, 16, replace=False)].copy()
+    cluster_ids = np.argmin(((base[:, None, :] - centroids[None]) ** 2).sum(-1), axis=1).astype(np.uint32)
+    host_path = str(tmp_path / "hq.graph")
+    capi.build_slimq_graph(base, host_path, M=16, ef_construction=200, centroids=centroids, cluster_ids=cluster_ids)
+    host = capi.Index(host_path, dim, kind=capi.HS_KIND_SLIMQ, raw_base=base)
+    gpu = capi.Index.build_gpu(base, kind=capi.HS_KIND_SLIMQ, M=16, ef_construction=200, centroids=centroids)
+    gi = gpu.info()
+    assert gi["kind"] == capi.HS_KIND_SLIMQ and gi["padded_dim_q"] == 128 and gi["num_cluster"] == 16
+    for ef in (30, 60, 120):
+        rec, est = {}, {}
+        for name, ix in (("gpu", gpu), ("host", host)):
+            ix.set_ef(ef)
+            ix.reset_stats()
+            lab, dist = ix.search(q, k)
+            rec[name] = _recall(lab, gt, k)
+            est[name] = ix.stats()["n_dist"] / nq
+            assert (np.diff(dist, axis=1) >= 0).all()
+        assert rec["gpu"] >= rec["host"] - 0.015, (ef, rec, est)
+        assert est["gpu"] <= est["host"] * 1.15, (ef, rec, est)
+    # centroids picked by the builder itself (k-means over a host-side sample)
+    auto = capi.Index.build_gpu(base, kind=capi.HS_KIND_SLIMQ, M=16, ef_construction=200)
+    auto.set_ef(60)
+    host.set_ef(60)
+    la, _ = auto.search(q, k)
+    lh, _ = host.search(q, k)
+    assert _recall(la, gt, k) >= _recall(lh, gt, k) - 0.02

@@ -135,3 +135,24 @@ def test_cli_hnsw_and_slimzero(tmp_path):
         rc, out, err = run_cli("--solve_strategy=hnsw-slimzero", *common)
         assert rc == 0, err
         assert float(re.search(r"Recall: ([0-9.]+)", out).group(1)) >= 0.9
+
+
+@pytest.mark.gpu
+def test_cli_sharded_mode_one_process(tmp_path):
+    """hs_main --shards S --gpus N: the C++ host path of the sharded corpus (no Python, no torch.distributed): the
+    sub-graphs are built on the GPU(s), one host thread drives one hs_shardgroup per GPU over peer memory, batches
+    of --batch queries stream through.  On a one-GPU box N = 1 (all shards local); with more devices N = 2."""
+    import torch
+    base, q, data_dir, index_dir = make_files(tmp_path, n=24000, nq=300, dim=96)
+    common = ["--dataset=toy", "--data_dir", data_dir, "--index_dir", index_dir, "--m=16", "--ef_construction=100",
+              "--k=10"]
+    rc, out, err = run_cli("--solve_strategy=bruteforce", *common)
+    assert rc == 0, err
+    gpus = 2 if torch.cuda.device_count() >= 2 else 1
+    rc, out, err = run_cli("--solve_strategy=hnsw_slim", "--shards=4", f"--gpus={gpus}", "--batch=64", "--ef_search=40",
+                           *common)
+    assert rc == 0, err
+    assert f"for 4 shards on {gpus} GPUs" in out
+    assert float(re.search(r"Recall: ([0-9.]+)", out).group(1)) >= 0.97
+    rc, out, err = run_cli("--solve_strategy=hnsw_slim", "--shards=3", "--gpus=2", *common)
+    assert rc != 0 and "multiple of --gpus" in err
