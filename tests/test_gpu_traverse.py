@@ -115,6 +115,43 @@ def test_exact_ties_at_the_ef_boundary(tmp_path):
         assert np.array_equal(dist[same_ids].view(np.uint32), odist[same_ids].view(np.uint32))
 
 
+@needs_ref
+def test_c1_graph_against_live_reference(tmp_path):
+    """The north-star bar on the REAL configuration (BASELINE.json configs[0]): SIFT-shaped 1M x 128, M=16,
+    efc=200, graph built by the reference itself (omp addPoint + convertFromHNSW), ef_search=100, k=10, 2000
+    queries — the engine's recall@10 within 0.5 pp of the live reference's searchKnn on the same graph, the
+    neighbour sets themselves equal for >= 99 % of the queries, returned distances within 1e-5 relative of the
+    reference's DISTFUNC, and bit-exact ids / distances / counters against the oracle."""
+    from hnsw_slim_b200.synth import latent_gaussian
+    n, dim, nq, k, ef = 1_000_000, 128, 2000, 10, 100
+    base = latent_gaussian(n, dim, rank=14, seed=1)
+    q = latent_gaussian(nq, dim, rank=14, seed=1, stream=1)
+    graph = str(tmp_path / "c1.graph")
+    rh.ref_slim_build(base, graph, M=16, ef_construction=200, branching="4")
+    ix = capi.Index(graph, dim)
+    ix.set_ef(ef)
+    lab, dist, cnt = ix.search(q, k, counts=True)
+    ref = rh.RefSlim(graph, dim, n)
+    rlab, _, _ = ref.search(q, k, ef, 0)
+    gt, _ = capi.bruteforce_knn(base, q, k)
+    gts = [set(r) for r in gt]
+    r_gpu, r_ref = _recall(lab, gts), _recall(rlab, gts)
+    print(f"\nC1 1M x 128 ef=100: recall@10 engine {r_gpu:.4f}, live reference {r_ref:.4f}")
+    assert r_gpu >= 0.95 and abs(r_gpu - r_ref) <= 0.005, (r_gpu, r_ref)
+    same = np.mean([set(a) == set(b) for a, b in zip(lab, rlab)])
+    assert same >= 0.99, same
+    for i in range(0, nq, 40):
+        for j in range(k):
+            d = rh.ref_dist(q[i], base[lab[i, j]], 0)
+            assert abs(d - dist[i, j]) <= REL_TOL * max(abs(d), 1e-30)
+    orc = rh.Oracle(graph, dim)
+    olab, odist, ond, onh = orc.search(q, k, ef, order=rh.ORDER_GPU, team=8)
+    same_rows = np.all(lab == olab, axis=1)
+    assert same_rows.mean() >= 0.999, same_rows.mean()
+    assert np.array_equal(dist[same_rows].view(np.uint32), odist[same_rows].view(np.uint32))
+    assert np.array_equal(cnt[same_rows, 0], ond[same_rows]) and np.array_equal(cnt[same_rows, 1], onh[same_rows])
+
+
 @pytest.mark.parametrize("dim,rank", [(96, 12), (128, 14), (100, 12), (64, 8)])
 def test_dims_l2(dim, rank):
     c = get_corpus(n=20000, nq=200, dim=dim, rank=rank)
