@@ -20,13 +20,22 @@ ap.add_argument("--iters", type=int, default=10)
 ap.add_argument("--check", type=int, default=0)
 ap.add_argument("--nq", type=int, default=0)
 ap.add_argument("--overlap", type=int, default=0)
+ap.add_argument("--gpu-build", type=int, default=0, help="build the index on the GPU instead of loading a host-built .graph")
 a = ap.parse_args()
 w = dict(bench.WORKLOADS[a.workload])
 if a.nq:
     w["nq"] = a.nq
-graph, base, qb = bench.prepare_inputs(w, 4, True)
 slimq = w.get("kind") == "slimq"
-if slimq:
+if a.gpu_build:
+    base = latent_gaussian(w["n"], w["dim"], rank=w["rank"], seed=1, normalize=(w["metric"] == 1))
+    qb = [latent_gaussian(w["nq"], w["dim"], rank=w["rank"], seed=1, normalize=(w["metric"] == 1), stream=1 + b) for b in range(4)]
+    ix = capi.Index.build_gpu(base, metric=w["metric"], M=w["M"], ef_construction=w["efc"],
+                              kind=capi.HS_KIND_SLIMQ if slimq else capi.HS_KIND_SLIM)
+else:
+    graph, base, qb = bench.prepare_inputs(w, 4, True)
+if a.gpu_build:
+    pass
+elif slimq:
     ix = capi.Index(graph, w["dim"], kind=capi.HS_KIND_SLIMQ, raw_base=base)
 else:
     ix = capi.Index(graph, w["dim"], metric=w["metric"])
