@@ -259,9 +259,10 @@ def run_reference(args, w):
     if slimq:
         from hnsw_slim_b200 import capi
         if rh.ref_slimq_path():
-            ix, orc, kind, cores = rh.RefSlimQ(graph, base), None, "reference", 1
-            how = ("serial loop of hnsw_slimq_strategy.h:157-159, 1 thread (the reference's hnsw_slimq search is not "
-                   "re-entrant: member search_pool_, slimq.h:220,1814)")
+            ix, orc, kind = "copies", None, "reference"
+            how = (f"{cores} OpenMP threads, each searching its own copy of the index over one shared raw dataset "
+                   "(one index copy per thread, BASELINE.md §2: the reference's hnsw_slimq search is not re-entrant, "
+                   "member search_pool_, slimq.h:220,1814); copies are loaded once per step, outside the timed loop")
         else:
             pd = (w["dim"] + 63) // 64 * 64
             ix, orc, kind = None, rh.OracleQ(graph, base, t_const=capi.slimq_default_tconst(pd)), "port"
@@ -272,7 +273,7 @@ def run_reference(args, w):
 
     def step():
         if ix is not None and slimq:
-            return ix.search(q, w["k"], w["ef"])[1]
+            return rh.ref_slimq_search_copies(graph, base, q, w["k"], w["ef"], threads=cores, passes=1)[1]
         if ix is not None:
             _, sec, _ = ix.search(q, w["k"], w["ef"], 0)         # omp dynamic, all cores
             return sec
@@ -477,16 +478,20 @@ def run_gpu(args, w):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         if slimq:
-            qps_ref, kind, secs, _ = cpu_reference_qps_slimq(graph, base, w, qbatches[0][:5000], 1, 1)
-            qps_port, secs_p = cpu_port_qps_slimq(graph, base, w, qbatches[0], ix.query_tconst, cores)
-            if qps_ref is None:
+            from oracle import refharness as rh
+            if rh.ref_slimq_path() is not None and hasattr(rh.slimq_lib(), "refq_search_copies"):
+                # all cores: one index copy per thread (the reference's slimq search is not re-entrant)
+                _, sec, thr = rh.ref_slimq_search_copies(graph, base, qbatches[0], w["k"], w["ef"], threads=cores, passes=3)
+                qps_1, _, secs1, _ = cpu_reference_qps_slimq(graph, base, w, qbatches[0][:2000], 1, 1)
+                cpu = {"value": nq / sec, "unit": "queries/s", "cores": thr, "kind": "reference",
+                       "sample": f"3 passes x {nq} queries of the same workload (median), {thr} OpenMP threads each searching "
+                                 f"its OWN copy of the index over one shared raw dataset (the reference's hnsw_slimq "
+                                 f"searchKnn is not re-entrant: member search_pool_, slimq.h:220,1814); its serial loop "
+                                 f"(hnsw_slimq_strategy.h:157-159) on 2000 queries: {qps_1:.0f} queries/s"}
+            else:
+                qps_port, secs_p = cpu_port_qps_slimq(graph, base, w, qbatches[0], ix.query_tconst, cores)
                 cpu = {"value": qps_port, "unit": "queries/s", "cores": cores, "kind": "port",
                        "sample": f"{nq} queries of the same workload, plain-C restatement, omp over queries ({secs_p:.1f}s)"}
-            else:
-                cpu = {"value": qps_ref, "unit": "queries/s", "cores": 1, "kind": kind,
-                       "sample": f"5000 queries of the same workload, serial loop of hnsw_slimq_strategy.h:157-159 "
-                                 f"({secs:.1f}s; the reference's hnsw_slimq search is not re-entrant); the plain-C "
-                                 f"restatement on {cores} threads: {qps_port:.0f} queries/s"}
         else:
             qps_all, kind, secs, np_all = cpu_reference_qps(graph, w, qbatches[0], 0, 4, budget_s=10.0)
             qps_1, _, secs1, _ = cpu_reference_qps(graph, w, qbatches[0][:2000], 1, 1)

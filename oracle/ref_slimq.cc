@@ -23,6 +23,9 @@
 #include "hnswlib/hnswalg.h"
 #include "hnswlib/hnswalg_slimq.h"
 
+#include <omp.h>
+
+#include <algorithm>
 #include <chrono>
 #include <cstdint>
 #include <cstring>
@@ -241,6 +244,59 @@ int refq_node(void *hp, uint32_t node, uint32_t *cluster, uint64_t *code,
   int m = (int)size < cap ? (int)size : cap;
   for (int j = 0; j < m; ++j) nbr_out[j] = data[j];
   return (int)size;
+}
+
+// All-core baseline for hnsw_slimq ("one index copy per thread — state which").  The
+// reference's slimq searchKnn is not re-entrant (member search_pool_, slimq.h:220,1814), so `copies` =
+// `threads` independent HierarchicalNSWSlimQ objects are loaded from the same file (loadIndex, slimq.h:1218)
+// over ONE shared raw dataset (setDataset only borrows it, slimq.h:303-305), and every OpenMP thread runs
+// the serial loop of hnsw_slimq_strategy.h:157-159 on its own copy over its share of the queries
+// (schedule(dynamic), as hnsw_slim_client_update_patch.cc:223-226 does for hnsw_slim).  passes > 1 repeats the
+// batch; *seconds = median pass.  t_const > 0 fixes every copy's query-quantiser constant.
+int refq_search_copies(const char *graph, size_t dim, size_t n, const float *base, int threads,
+                       const float *queries, size_t nq, size_t k, size_t ef, double t_const, int passes,
+                       uint32_t *out_labels, double *seconds) {
+  try {
+    if (threads <= 0) threads = omp_get_num_procs();
+    K = k;
+    std::vector<std::vector<float>> dataset(n);
+    for (size_t i = 0; i < n; ++i) dataset[i].assign(base + i * dim, base + (i + 1) * dim);
+    hnswlib::L2Space space(dim);
+    std::vector<std::unique_ptr<hnswlib::HierarchicalNSWSlimQ<float>>> copies(threads);
+    std::string err;
+#pragma omp parallel for num_threads(threads) schedule(static, 1)
+    for (int t = 0; t < threads; ++t) {
+      try {
+        copies[t].reset(new hnswlib::HierarchicalNSWSlimQ<float>(&space, n));
+        copies[t]->loadIndex(graph, &space, n);
+        copies[t]->setDataset(&dataset);
+        copies[t]->setEf(ef);
+        if (t_const > 0) copies[t]->query_config_.t_const = t_const;
+      } catch (const std::exception &e) {
+#pragma omp critical
+        err = e.what();
+      }
+    }
+    if (!err.empty()) {
+      g_err = err;
+      return -1;
+    }
+    std::vector<double> times;
+    for (int pass = 0; pass < std::max(1, passes); ++pass) {
+      auto t0 = std::chrono::steady_clock::now();
+#pragma omp parallel for num_threads(threads) schedule(dynamic)
+      for (size_t i = 0; i < nq; ++i)
+        copies[omp_get_thread_num()]->searchKnn(queries + i * dim, k, out_labels + i * k);
+      auto t1 = std::chrono::steady_clock::now();
+      times.push_back(std::chrono::duration<double>(t1 - t0).count());
+    }
+    std::sort(times.begin(), times.end());
+    if (seconds) *seconds = times[times.size() / 2];
+    return 0;
+  } catch (const std::exception &e) {
+    g_err = e.what();
+    return -1;
+  }
 }
 
 }  // extern "C"

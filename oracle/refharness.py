@@ -481,6 +481,27 @@ def ref_slimq_build(base, centroids, cluster_ids, path: str, *, M: int = 32, ef_
     return bs.value, cs.value
 
 
+def ref_slimq_search_copies(path: str, base, q, k: int, ef: int, threads: int = 0, t_const: float = 0.0,
+                            passes: int = 1):
+    """All-core hnsw_slimq baseline: one index copy per OpenMP thread over one shared dataset (the reference's
+    slimq search is not re-entrant).  -> labels[nq,k], seconds of the median pass, threads used."""
+    L = slimq_lib()
+    if not hasattr(L, "refq_search_copies"):
+        raise RuntimeError("oracle/_ref/libhsref_slimq was built before refq_search_copies existed")
+    L.refq_search_copies.restype = C.c_int
+    L.refq_search_copies.argtypes = [C.c_char_p, C.c_size_t, C.c_size_t, _f32p, C.c_int, _f32p, C.c_size_t, C.c_size_t,
+                                     C.c_size_t, C.c_double, C.c_int, _u32p, C.POINTER(C.c_double)]
+    base = np.ascontiguousarray(base, dtype=np.float32)
+    q = np.ascontiguousarray(q, dtype=np.float32)
+    threads = threads or (os.cpu_count() or 1)
+    out = np.zeros((q.shape[0], k), dtype=np.uint32)
+    sec = C.c_double(0)
+    if L.refq_search_copies(path.encode(), base.shape[1], base.shape[0], base, threads, q, q.shape[0], k, ef,
+                            float(t_const), passes, out, C.byref(sec)) != 0:
+        raise RuntimeError(L.refq_last_error().decode())
+    return out, sec.value, threads
+
+
 class RefSlimQ:
     """The reference's HierarchicalNSWSlimQ<float> loaded from a .graph file + setDataset(base)."""
 
