@@ -29,7 +29,9 @@ EXPORTS = [
     "hs_shardgroup_create", "hs_shardgroup_handle", "hs_shardgroup_connect", "hs_shardgroup_connect_local",
     "hs_shardgroup_submit", "hs_shardgroup_wait_oldest", "hs_shardgroup_wait", "hs_shardgroup_streams",
     "hs_shardgroup_free", "hs_build_slim_index_gpu", "hs_save_index", "hs_build_slimq_index_gpu",
+    "hs_load_reserve", "hs_patch_apply", "hs_debug_patch",
 ]
+HS_PATCH_INLINE_ROWS = 1
 
 
 class HsError(RuntimeError):
@@ -49,6 +51,27 @@ class IndexInfo(C.Structure):
 
     def as_dict(self) -> dict:
         return {f: getattr(self, f) for f, _ in self._fields_}
+
+
+class PatchInfo(C.Structure):
+    _fields_ = [("n_before", C.c_uint64), ("n_after", C.c_uint64), ("changed_old", C.c_uint64),
+                ("changed_new", C.c_uint64), ("bytes_consumed", C.c_uint64), ("rows_written", C.c_uint64),
+                ("upper_rebuilt", C.c_uint64)]
+
+    def as_dict(self) -> dict:
+        return {f: int(getattr(self, f)) for f, _ in self._fields_}
+
+
+def _patch_args(stream: bytes, rows, row_labels, inline: bool):
+    buf = np.frombuffer(stream, dtype=np.uint8)
+    r = _f32(rows) if rows is not None else None
+    rl = np.ascontiguousarray(row_labels, dtype=np.uint64) if row_labels is not None else None
+    if rl is not None:
+        assert r is not None and rl.shape[0] == r.shape[0]
+    keep = (buf, r, rl)
+    return keep, (buf.ctypes.data, buf.size, HS_PATCH_INLINE_ROWS if inline else 0,
+                  r.ctypes.data if r is not None else None, rl.ctypes.data if rl is not None else None,
+                  r.shape[0] if r is not None else 0)
 
 
 class BuildParams(C.Structure):
@@ -133,6 +156,9 @@ def lib():
         L.hs_shardgroup_streams.argtypes = [vp, C.POINTER(vp), C.POINTER(vp)]
         L.hs_shardgroup_free.argtypes = [vp]
         L.hs_shardgroup_free.restype = None
+        L.hs_load_reserve.argtypes = [C.c_char_p, i32, i32, sz, sz, i32, C.POINTER(vp)]
+        L.hs_patch_apply.argtypes = [vp, vp, sz, C.c_uint, vp, vp, sz, C.POINTER(PatchInfo)]
+        L.hs_debug_patch.argtypes = [vp, vp, sz, C.c_uint, vp, vp, sz, C.POINTER(PatchInfo)]
         L.hs_get_query_tconst.argtypes = [vp, C.POINTER(C.c_double)]
         L.hs_set_query_tconst.argtypes = [vp, C.c_double]
         L.hs_slimq_prepare.argtypes = [vp, vp, sz, vp, vp, vp, vp]
@@ -168,6 +194,26 @@ class Index:
                              raw.ctypes.data if raw is not None else None,
                              raw.shape[0] if raw is not None else 0, device, C.byref(self._h)))
         self.dim = dim
+
+    @classmethod
+    def load_reserve(cls, graph_path: str, dim: int, max_elements: int, *, metric: int = HS_METRIC_L2,
+                     device: int = 0) -> "Index":
+        """hs_load_reserve: loadIndex(path, space, max_elements) with room for delta patches (slim.h:753-761)."""
+        self = cls.__new__(cls)
+        self._h = C.c_void_p()
+        _check(lib().hs_load_reserve(graph_path.encode(), HS_KIND_SLIM, metric, dim, max_elements, device,
+                                     C.byref(self._h)))
+        self.dim = dim
+        return self
+
+    def patch(self, stream: bytes, *, rows=None, row_labels=None, inline: bool = False) -> dict:
+        """hs_patch_apply: patchFromStream (slim.h:2206-2388) on the HBM-resident index.  rows[label] (or, with
+        row_labels, the row whose label matches) supply the vectors of new nodes unless they are inline."""
+        keep, args = _patch_args(stream, rows, row_labels, inline)
+        info = PatchInfo()
+        _check(lib().hs_patch_apply(self._h, *args, C.byref(info)))
+        del keep
+        return info.as_dict()
 
     @classmethod
     def from_bytes(cls, image: bytes, dim: int, *, kind: int = HS_KIND_SLIM, metric: int = HS_METRIC_L2,
@@ -499,6 +545,14 @@ class HostGraph:
         s = IndexInfo()
         _check(lib().hs_debug_info(self._h, C.byref(s)))
         return s.as_dict()
+
+    def patch(self, stream: bytes, *, rows=None, row_labels=None, inline: bool = False) -> dict:
+        """hs_debug_patch: hs_patch_apply on the host image (same parser, validation and re-slotting)."""
+        keep, args = _patch_args(stream, rows, row_labels, inline)
+        info = PatchInfo()
+        _check(lib().hs_debug_patch(self._h, *args, C.byref(info)))
+        del keep
+        return info.as_dict()
 
     def row(self, node: int, level: int) -> np.ndarray:
         """Valid ids of the node's level-`level` row (padding stripped; checks it is a suffix)."""

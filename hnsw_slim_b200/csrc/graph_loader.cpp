@@ -184,10 +184,18 @@ int flatten_lists(HostGraph *g, ListFn &&list) {
   g->sum_deg0 = sum_deg0;
   g->deg0_stride = std::max<uint32_t>(32, round_up(max_deg0, 32));
   g->upper_stride = std::max<uint32_t>(8, round_up(max_deg_up, 8));
+  if (g->reserve_strides) {      // room for the longest lists later patches may bring (re-prune limits, slim.h:1036-1058)
+    g->deg0_stride = std::max(g->deg0_stride, round_up((uint32_t)g->maxM0, 32));
+    g->upper_stride = std::max(g->upper_stride, round_up((uint32_t)g->maxM, 8));
+  }
 
   // upper-level slots: nodes sorted by level descending, so the rows of level l are the dense
   // slot prefix [0, level_count[l])
-  g->level_count.assign(g->maxlevel + 2, 0);
+  // (a client index that received delta patches may hold nodes above the header's maxlevel: patchFromStream,
+  // slim.h:2206-2388, leaves maxlevel_ alone — the search never looks at those levels, the rows are kept anyway)
+  int top = g->maxlevel;
+  for (size_t i = 0; i < n; ++i) top = std::max(top, (int)g->levels[i]);
+  g->level_count.assign(top + 2, 0);
   std::vector<uint32_t> upper_nodes;
   for (size_t i = 0; i < n; ++i) {
     for (int l = 0; l <= g->levels[i]; ++l) g->level_count[l]++;
@@ -200,8 +208,8 @@ int flatten_lists(HostGraph *g, ListFn &&list) {
   for (uint32_t s = 0; s < upper_nodes.size(); ++s) g->upper_slot[upper_nodes[s]] = (int32_t)s;
 
   g->adj0.assign(n * (size_t)g->deg0_stride, kInvalid);
-  g->upper_adj.assign(g->maxlevel + 1, {});
-  for (int l = 1; l <= g->maxlevel; ++l)
+  g->upper_adj.assign(top + 1, {});
+  for (int l = 1; l <= top; ++l)
     g->upper_adj[l].assign((size_t)g->level_count[l] * g->upper_stride, kInvalid);
   for (size_t i = 0; i < n; ++i) {
     for (int l = 0; l <= g->levels[i]; ++l) {
@@ -340,7 +348,7 @@ int parse_graph(const uint8_t *bytes, size_t size, int kind, size_t dim, HostGra
     std::memcpy(&lvl, e, 4);
     std::memcpy(&total[i], e + 4, 4);
     std::memcpy(&label, e + 8, 8);
-    if (lvl < 0 || lvl > g->maxlevel) {
+    if (lvl < 0 || lvl >= kMaxLevels) {
       set_error("node level out of range in .graph");
       return HS_ERR_IO;
     }

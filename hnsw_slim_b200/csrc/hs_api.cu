@@ -107,6 +107,27 @@ int upload(T **dst, const T *src, size_t count, size_t *bytes_total) {
   return HS_OK;
 }
 
+// upload into an allocation of cap_count (>= count) elements whose tail is filled with `fill` bytes
+template <typename T>
+int upload_cap(T **dst, const T *src, size_t count, size_t cap_count, int fill, size_t *bytes_total) {
+  *dst = nullptr;
+  if (cap_count < count) cap_count = count;
+  if (cap_count == 0) return HS_OK;
+  cudaError_t e = cudaMalloc(reinterpret_cast<void **>(dst), cap_count * sizeof(T));
+  if (e != cudaSuccess) {
+    set_error(std::string("cudaMalloc(") + std::to_string(cap_count * sizeof(T)) + "): " + cudaGetErrorString(e));
+    return e == cudaErrorMemoryAllocation ? HS_ERR_NOMEM : HS_ERR_CUDA;
+  }
+  if (count) e = cudaMemcpy(*dst, src, count * sizeof(T), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess && cap_count > count) e = cudaMemset(*dst + count, fill, (cap_count - count) * sizeof(T));
+  if (e != cudaSuccess) {
+    set_error(std::string("cudaMemcpy H2D: ") + cudaGetErrorString(e));
+    return HS_ERR_CUDA;
+  }
+  *bytes_total += cap_count * sizeof(T);
+  return HS_OK;
+}
+
 // per-handle scratch, knobs and the handle's own stream (both construction paths end here)
 int init_scratch(hs_index *ix) {
   cudaDeviceProp prop;
@@ -128,11 +149,14 @@ int init_scratch(hs_index *ix) {
   return HS_OK;
 }
 
-int build_index(const HostGraph &g, int metric, int device, const float *raw_base, hs_index **out) {
+// capacity > 0: room for `capacity` nodes (hs_load_reserve); rows past n read as "no neighbours" / zero vectors
+int build_index(const HostGraph &g, int metric, int device, const float *raw_base, hs_index **out, size_t capacity = 0) {
   int rc = select_device(device);
   if (rc != HS_OK) return rc;
   std::unique_ptr<hs_index> ix(new hs_index);
   ix->device = device;
+  const size_t cap = std::max<size_t>(capacity, g.n);
+  ix->capacity = cap;
   size_t bytes = 0;
   auto fail = [&](int code) {
     hs_free(ix.release());
@@ -167,18 +191,20 @@ int build_index(const HostGraph &g, int metric, int device, const float *raw_bas
     ix->trunc_dim = td;
     ix->t_const = slimq_default_tconst(g.padded_dim_q, 3);   // kNumBits = 4 (query.hpp:126)
   } else {
-    if ((rc = upload(&ix->d_vec, g.vec.data(), g.vec.size(), &bytes)) != HS_OK) return fail(rc);
+    if ((rc = upload_cap(&ix->d_vec, g.vec.data(), g.vec.size(), cap * g.dim_padded, 0, &bytes)) != HS_OK) return fail(rc);
   }
-  if ((rc = upload(&ix->d_adj0, g.adj0.data(), g.adj0.size(), &bytes)) != HS_OK) return fail(rc);
-  if ((rc = upload(&ix->d_upper_slot, g.upper_slot.data(), g.upper_slot.size(), &bytes)) != HS_OK) return fail(rc);
-  if ((rc = upload(&ix->d_labels, g.labels.data(), g.labels.size(), &bytes)) != HS_OK) return fail(rc);
-  if ((rc = upload(&ix->d_deleted, g.deleted.data(), g.deleted.size(), &bytes)) != HS_OK) return fail(rc);
-  for (int l = 1; l <= g.maxlevel && l < kMaxLevels; ++l)
+  if ((rc = upload_cap(&ix->d_adj0, g.adj0.data(), g.adj0.size(), cap * g.deg0_stride, 0xff, &bytes)) != HS_OK) return fail(rc);
+  if ((rc = upload_cap(&ix->d_upper_slot, g.upper_slot.data(), g.upper_slot.size(), cap, 0xff, &bytes)) != HS_OK) return fail(rc);
+  if ((rc = upload_cap(&ix->d_labels, g.labels.data(), g.labels.size(), cap, 0, &bytes)) != HS_OK) return fail(rc);
+  if ((rc = upload_cap(&ix->d_deleted, g.deleted.data(), g.deleted.size(), cap, 0, &bytes)) != HS_OK) return fail(rc);
+  for (int l = 1; l < (int)g.upper_adj.size() && l < kMaxLevels; ++l) {
     if ((rc = upload(&ix->d_upper_adj[l], g.upper_adj[l].data(), g.upper_adj[l].size(), &bytes)) != HS_OK)
       return fail(rc);
+    ix->cap_upper_words[l] = g.upper_adj[l].size();
+  }
   if ((rc = init_scratch(ix.get())) != HS_OK) return fail(rc);
 
-  for (int l = 0; l <= g.maxlevel && l < kMaxLevels; ++l) ix->level_count[l] = g.level_count[l];
+  for (int l = 0; l < (int)g.level_count.size() && l < kMaxLevels; ++l) ix->level_count[l] = g.level_count[l];
   hs_index_info &I = ix->info;
   I.n = g.n;
   I.dim = g.dim;
@@ -207,7 +233,7 @@ int build_index(const HostGraph &g, int metric, int device, const float *raw_bas
 }
 
 int load_common(const uint8_t *bytes, size_t size, int kind, int metric, size_t dim, const float *raw_base,
-                size_t n_raw, int device, hs_index **out) {
+                size_t n_raw, int device, hs_index **out, size_t capacity = 0) {
   if (!out || !bytes) {
     set_error("null argument");
     return HS_ERR_ARG;
@@ -227,8 +253,19 @@ int load_common(const uint8_t *bytes, size_t size, int kind, int metric, size_t 
     return HS_ERR_UNSUPPORTED;
   }
   HostGraph g;
+  g.reserve_strides = capacity > 0;
   int rc = parse_graph(bytes, size, kind, dim, &g);
   if (rc != HS_OK) return rc;
+  if (capacity > 0) {
+    if (capacity < g.n) {
+      set_error("max_elements is below the element count of the .graph");     // loadIndex, slim.h:759-761
+      return HS_ERR_ARG;
+    }
+    if (capacity >= (1ull << 31)) {
+      set_error("max_elements >= 2^31");
+      return HS_ERR_UNSUPPORTED;
+    }
+  }
   if (kind == HS_KIND_SLIMQ) {
     if (!raw_base || n_raw < g.n) {
       set_error("hnsw_slimq needs raw_base with at least n rows for the exact rerank (setDataset, slimq.h:303-305)");
@@ -261,7 +298,15 @@ int load_common(const uint8_t *bytes, size_t size, int kind, int metric, size_t 
       return HS_ERR_UNSUPPORTED;
     }
   }
-  return build_index(g, metric, device, raw_base, out);
+  rc = build_index(g, metric, device, raw_base, out, capacity);
+  if (rc == HS_OK && capacity > 0) {
+    // the mirror of a patchable index: everything but the arrays that only the device needs
+    g.mirror_only = true;
+    std::vector<float>().swap(g.vec);
+    std::vector<uint32_t>().swap(g.adj0);
+    (*out)->mirror.reset(new HostGraph(std::move(g)));
+  }
+  return rc;
 }
 
 int ensure(void **p, size_t *cap, size_t need) {
@@ -578,6 +623,57 @@ int hs_load(const char *graph_path, int kind, int metric, size_t dim, const floa
     int rc = read_file(graph_path, &bytes);
     if (rc != HS_OK) return rc;
     return load_common(bytes.data(), bytes.size(), kind, metric, dim, raw_base, n_raw, device, out);
+  });
+}
+
+int hs_load_reserve(const char *graph_path, int kind, int metric, size_t dim, size_t max_elements, int device,
+                    hs_index **out) {
+  if (!graph_path || !out) {
+    set_error("null argument");
+    return HS_ERR_ARG;
+  }
+  *out = nullptr;
+  if (kind != HS_KIND_SLIM) {
+    set_error("hs_load_reserve: delta patches exist for hnsw_slim indices only (patchFromStream, slim.h:2206-2388)");
+    return HS_ERR_UNSUPPORTED;
+  }
+  if (max_elements == 0) {
+    set_error("hs_load_reserve: max_elements must be > 0");
+    return HS_ERR_ARG;
+  }
+  return guarded("hs_load_reserve", [&] {
+    std::vector<uint8_t> bytes;
+    int rc = read_file(graph_path, &bytes);
+    if (rc != HS_OK) return rc;
+    return load_common(bytes.data(), bytes.size(), kind, metric, dim, nullptr, 0, device, out, max_elements);
+  });
+}
+
+int hs_patch_apply(hs_index *ix, const void *patch, size_t patch_bytes, unsigned flags, const float *rows,
+                   const uint64_t *row_labels, size_t n_rows, hs_patch_info *info_out) {
+  if (!ix || !patch) {
+    set_error("null argument");
+    return HS_ERR_ARG;
+  }
+  if (!ix->mirror) {
+    set_error("hs_patch_apply: the index was not loaded with hs_load_reserve");
+    return HS_ERR_UNSUPPORTED;
+  }
+  return guarded("hs_patch_apply", [&]() -> int {
+    std::lock_guard<std::mutex> lock(ix->mu);
+    HS_CUDA(cudaSetDevice(ix->device));
+    HS_CUDA(cudaStreamSynchronize(ix->stream));        // batches handed to hs_search_batch_submit
+    PatchSet ps;
+    int rc = parse_patch(static_cast<const uint8_t *>(patch), patch_bytes, ix->info.dim, (flags & HS_PATCH_INLINE_ROWS) != 0,
+                         ix->info.n, ix->capacity, &ps);
+    if (rc != HS_OK) return rc;
+    PatchRows pr;
+    pr.rows = rows;
+    pr.row_labels = row_labels;
+    pr.n_rows = n_rows;
+    pr.dim = ix->info.dim;
+    pr.prepare();
+    return apply_patch_device(ix, ps, pr, info_out);
   });
 }
 
@@ -1212,8 +1308,11 @@ int hs_save_index(hs_index *ix, const char *path) {
     HS_CUDA(cudaMemcpy(slot.data(), ix->d_upper_slot, n * 4, cudaMemcpyDeviceToHost));
     HS_CUDA(cudaMemcpy(labels.data(), ix->d_labels, n * 4, cudaMemcpyDeviceToHost));
     HS_CUDA(cudaMemcpy(adj0.data(), ix->d_adj0, adj0.size() * 4, cudaMemcpyDeviceToHost));
-    std::vector<std::vector<uint32_t>> up(I.maxlevel + 1);
-    for (int l = 1; l <= I.maxlevel; ++l) {
+    // a patched index may hold nodes above the header's maxlevel (patchFromStream leaves maxlevel_ alone)
+    int top = I.maxlevel;
+    while (top + 1 < kMaxLevels && ix->level_count[top + 1] > 0 && ix->d_upper_adj[top + 1]) ++top;
+    std::vector<std::vector<uint32_t>> up(top + 1);
+    for (int l = 1; l <= top; ++l) {
       up[l].resize((size_t)ix->level_count[l] * I.upper_stride);
       if (!up[l].empty())
         HS_CUDA(cudaMemcpy(up[l].data(), ix->d_upper_adj[l], up[l].size() * 4, cudaMemcpyDeviceToHost));
@@ -1221,7 +1320,7 @@ int hs_save_index(hs_index *ix, const char *path) {
     auto level_of = [&](size_t i) {
       int lv = 0;
       if (slot[i] >= 0)
-        while (lv < I.maxlevel && (uint32_t)slot[i] < ix->level_count[lv + 1]) ++lv;
+        while (lv < top && (uint32_t)slot[i] < ix->level_count[lv + 1]) ++lv;
       return lv;
     };
     auto list = [&](size_t i, int l, const uint32_t **ids) {
@@ -1369,7 +1468,8 @@ int hs_debug_row(const hs_host_graph *h, uint32_t node, int level, uint32_t *out
     row = &g.adj0[(size_t)node * g.deg0_stride];
     stride = (int)g.deg0_stride;
   } else {
-    if (level > g.maxlevel || g.upper_slot[node] < 0 || (uint32_t)g.upper_slot[node] >= g.level_count[level])
+    if ((size_t)level >= g.upper_adj.size() || (size_t)level >= g.level_count.size() || g.upper_slot[node] < 0 ||
+        (uint32_t)g.upper_slot[node] >= g.level_count[level])
       return 0;
     row = &g.upper_adj[level][(size_t)g.upper_slot[node] * g.upper_stride];
     stride = (int)g.upper_stride;
@@ -1385,6 +1485,42 @@ int hs_debug_node(const hs_host_graph *h, uint32_t node, int *level, uint32_t *l
   if (label) *label = g.labels[node];
   if (vec_out && !g.vec.empty()) std::memcpy(vec_out, &g.vec[(size_t)node * g.dim_padded], g.dim_padded * 4);
   return HS_OK;
+}
+
+int hs_debug_patch(hs_host_graph *h, const void *patch, size_t patch_bytes, unsigned flags, const float *rows,
+                   const uint64_t *row_labels, size_t n_rows, hs_patch_info *info_out) {
+  if (!h || !patch) {
+    set_error("null argument");
+    return HS_ERR_ARG;
+  }
+  return guarded("hs_debug_patch", [&]() -> int {
+    HostGraph &g = h->g;
+    PatchSet ps;
+    // the host image grows as needed: no capacity limit
+    int rc = parse_patch(static_cast<const uint8_t *>(patch), patch_bytes, g.dim, (flags & HS_PATCH_INLINE_ROWS) != 0, g.n,
+                         (1ull << 31) - 1, &ps);
+    if (rc != HS_OK) return rc;
+    PatchRows pr;
+    pr.rows = rows;
+    pr.row_labels = row_labels;
+    pr.n_rows = n_rows;
+    pr.dim = g.dim;
+    pr.prepare();
+    const uint64_t n_before = g.n;
+    bool upper = false;
+    rc = apply_patch_host(&g, ps, pr, &upper);
+    if (rc != HS_OK) return rc;
+    if (info_out) {
+      info_out->n_before = n_before;
+      info_out->n_after = g.n;
+      info_out->changed_old = ps.n_old;
+      info_out->changed_new = ps.n_new;
+      info_out->bytes_consumed = ps.consumed;
+      info_out->rows_written = 0;
+      info_out->upper_rebuilt = upper ? 1 : 0;
+    }
+    return (int)HS_OK;
+  });
 }
 
 int hs_stats(hs_index *ix, uint64_t *n_dist, uint64_t *n_hops, uint64_t *n_rerank) {

@@ -3,6 +3,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <memory>
 #include <mutex>
 
 #include "hs_internal.h"
@@ -30,6 +31,11 @@ struct hs_index {
   uint8_t *d_flip = nullptr;        // 4 * padded_dim / 8
   uint32_t words = 0, trunc_dim = 0;
   uint32_t level_count[hs::kMaxLevels] = {};
+  // delta patches (patch.cu): an index loaded with hs_load_reserve has rows for `capacity` nodes and keeps the
+  // small host-side arrays (levels, upper-level slots and rows, labels) as a mirror; null / n otherwise
+  size_t capacity = 0;
+  size_t cap_upper_words[hs::kMaxLevels] = {};
+  std::unique_ptr<hs::HostGraph> mirror;
   double t_const = 0.0;
   // per-call scratch
   unsigned long long *d_work = nullptr;    // ring of kWorkRing tagged work counters (traverse_common.cuh)
@@ -108,6 +114,9 @@ struct DeviceGraph {
   uint32_t trunc_dim = 0;
 };
 int adopt_device_graph(DeviceGraph &dg, int device, hs_index **out);
+
+// patch.cu: the device side of patchFromStream (slim.h:2206-2388); the caller holds ix->mu
+int apply_patch_device(hs_index *ix, const PatchSet &ps, const PatchRows &rows, hs_patch_info *info);
 
 // graph_gpu.cu
 int gpu_build_slim_index(const float *base, size_t n, size_t dim, int metric, const hs_build_params *bp,

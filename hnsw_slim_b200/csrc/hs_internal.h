@@ -3,6 +3,7 @@
 #include <cstddef>
 #include <cstdint>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/hnswslim_b200.h"
@@ -55,7 +56,10 @@ struct HostGraph {
   int kind = HS_KIND_SLIM;
   size_t dim = 0, dim_padded = 0;
 
-  // flattened graph
+  // flattened graph.  reserve_strides: rows wide enough for ANY list the header allows (maxM0 / maxM ids) instead
+  // of the longest list found — an index that will receive delta patches (patch.cu) must not need re-striding
+  bool reserve_strides = false;
+  bool mirror_only = false;     // adj0 / vec / payload arrays were dropped after the upload: the small arrays mirror a device index
   uint32_t deg0_stride = 32, max_deg0 = 0, upper_stride = 16, max_deg_upper = 0, n_upper = 0;
   uint64_t sum_deg0 = 0;
   std::vector<float> vec;             // n x dim_padded (hnsw_slim); empty for slimq
@@ -79,6 +83,42 @@ struct HostGraph {
 
 // Parses a reference .graph image.  Returns HS_OK or a negative hs_status (message via set_error).
 int parse_graph(const uint8_t *bytes, size_t size, int kind, size_t dim, HostGraph *out);
+
+// ---- delta patches: the stream HierarchicalNSWSlim::patchFromStream consumes (slim.h:2206-2388), patch.cu ----
+struct PatchNode {
+  uint32_t id = 0;
+  int32_t level = 0;
+  uint32_t total = 0;
+  bool is_new = false;                 // "changed_new" record: carries the label and brings a vector
+  uint64_t label = 0;
+  const uint8_t *blob = nullptr;       // [uint16 offsets[level]][uint32 ids[total]] inside the stream (unaligned), or null
+  const uint8_t *row = nullptr;        // inline vector (dim floats, unaligned) or null
+  // level-l slice (slim.h:245-260): ids[(l ? offsets[l-1] : 0) .. (l == level ? total : offsets[l]))
+  uint32_t slice(int l, const uint8_t **ids) const;
+};
+struct PatchSet {
+  uint64_t n_after = 0, n_old = 0, n_new = 0;
+  size_t consumed = 0;
+  std::vector<PatchNode> nodes;        // stream order; a later record of the same id supersedes an earlier one
+};
+// Parses and validates a patch stream against an index of `n_before` nodes and room for `capacity`.
+int parse_patch(const uint8_t *bytes, size_t size, size_t dim, bool inline_rows, uint64_t n_before, uint64_t capacity,
+                PatchSet *out);
+// The vector a "changed_new" record brings: inline, or looked up by label in the caller's rows
+// (rows[label] when row_labels == nullptr — patchFromStream(in, data_set), slim.h:2225 — else the row whose
+// row_labels entry equals the label — patchFromStream(in, new_data), slim.h:2360).  nullptr if absent.
+struct PatchRows {
+  const float *rows = nullptr;
+  const uint64_t *row_labels = nullptr;
+  size_t n_rows = 0, dim = 0;
+  std::vector<std::pair<uint64_t, size_t>> sorted;   // (label, row) when row_labels is given
+  void prepare();
+  const uint8_t *find(const PatchNode &nd) const;
+};
+// Applies a parsed patch to the host image: levels, labels, upper-level slots and rows are always maintained;
+// adj0 / vec only when they are present (host-only inspection, hs_debug_patch) — a device-resident index keeps
+// just the small arrays as its mirror.  *upper_changed: the upper-level arrays were rebuilt.
+int apply_patch_host(HostGraph *g, const PatchSet &ps, const PatchRows &rows, bool *upper_changed);
 int read_file(const char *path, std::vector<uint8_t> *out);
 double slimq_default_tconst(size_t padded_dim, size_t ex_bits);
 

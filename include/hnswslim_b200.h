@@ -83,6 +83,41 @@ int hs_load(const char *graph_path, int kind, int metric, size_t dim, const floa
 int hs_load_memory(const void *graph_bytes, size_t graph_size, int kind, int metric, size_t dim,
                    const float *raw_base, size_t n_raw, int device, hs_index **out);
 
+/* ---- Delta patches ---------------------------------------------------------
+ * The reference's serving pair keeps a client index current without re-sending it: the server re-prunes its
+ * full HNSW after every /updateIndex (convertFromHNSWWithDiff, slim.h:1110-1424; genPatch, slim.h:1427-1476;
+ * hnsw_slim_server_patch.cc:186-279) and answers with the records that changed; the client applies the stream
+ * with HierarchicalNSWSlim::patchFromStream (slim.h:2206-2388; hnsw_slim_client_update_patch.cc:41,73,179) and
+ * goes on searching.
+ *
+ * hs_load_reserve = loadIndex(path, space, max_elements) with room to grow (slim.h:753-761,784; the client opens
+ * its partial index with the final row count, hnsw_slim_client_update_patch.cc:113): hs_load for an hnsw_slim
+ * .graph whose HBM arrays hold max_elements (>= n) nodes and whose adjacency rows are wide enough for any list
+ * the header's maxM0 / maxM allow.  Only such an index accepts patches.
+ *
+ * hs_patch_apply = patchFromStream on the HBM-resident index: the changed level-0 rows (and the vectors and labels
+ * of new nodes) are staged once and scattered into place by one kernel each; the upper-level rows (a small
+ * fraction of the index) are re-derived on the host mirror and re-uploaded when a patched node has level > 0.
+ * Like the reference it leaves the entry point and maxlevel alone.  Vectors of "changed_new" records:
+ *   flags & HS_PATCH_INLINE_ROWS   they travel inside the stream        patchFromStream(in, true), slim.h:2292-2340
+ *   rows, row_labels == NULL       rows[label * dim], label < n_rows    patchFromStream(in, data_set), slim.h:2206-2253
+ *   rows, row_labels               the row i with row_labels[i] == label   patchFromStream(in, new_data), slim.h:2343-2388
+ * Synchronous.  The call waits for the batches submitted through this handle (hs_search_batch_submit); launches
+ * the caller made on its own streams (hs_search_batch_device) must have completed — patchFromStream is not
+ * synchronised with searchKnn in the reference either.  On error the index is unchanged.  hnsw_slim only. */
+#define HS_PATCH_INLINE_ROWS 1u
+typedef struct {
+  uint64_t n_before, n_after;        /* cur_element_count_ before / after                         */
+  uint64_t changed_old, changed_new; /* record counts of the stream                               */
+  uint64_t bytes_consumed;           /* stream bytes read (a caller may concatenate patches)      */
+  uint64_t rows_written;             /* level-0 rows scattered on the device                      */
+  uint64_t upper_rebuilt;            /* 1: the upper-level arrays were re-derived and re-uploaded */
+} hs_patch_info;
+int hs_load_reserve(const char *graph_path, int kind, int metric, size_t dim, size_t max_elements, int device,
+                    hs_index **out);
+int hs_patch_apply(hs_index *, const void *patch, size_t patch_bytes, unsigned flags, const float *rows,
+                   const uint64_t *row_labels, size_t n_rows, hs_patch_info *info_out);
+
 /* ~HierarchicalNSWSlim / clear() (slim.h:147-167) */
 void hs_free(hs_index *);
 
@@ -359,6 +394,10 @@ void hs_debug_free(hs_host_graph *);
 int hs_debug_info(const hs_host_graph *, hs_index_info *out);
 int hs_debug_row(const hs_host_graph *, uint32_t node, int level, uint32_t *out, int cap);
 int hs_debug_node(const hs_host_graph *, uint32_t node, int *level, uint32_t *label, float *vec_out);
+/* hs_patch_apply on the host image (no CUDA needed): the parser, the validation and the upper-level re-slotting
+ * are the code the device path runs; the level-0 rows and vectors are written to the host arrays instead. */
+int hs_debug_patch(hs_host_graph *, const void *patch, size_t patch_bytes, unsigned flags, const float *rows,
+                   const uint64_t *row_labels, size_t n_rows, hs_patch_info *info_out);
 
 const char *hs_last_error(void);
 int hs_abi_version(void);

@@ -202,6 +202,90 @@ void hso_free(hso_index *ix) {
   free(ix);
 }
 
+/* patchFromStream: slim.h:2206-2253 (rows by label, mode HSO_PATCH_ROWS), :2292-2340 (rows inline,
+ * HSO_PATCH_INLINE), :2343-2388 (rows by label from a map — the same lookup as far as this restatement goes).
+ * Stream: size_t cur_element_count, changed_old_cnt, changed_new_cnt; then per record uint32 id, the first
+ * label_offset (old: level + total) or offsetNeighbor (new: + label) bytes of the element record, uint32
+ * blob size, the blob, and for new records of the inline form the vector.  The element array grows to the new
+ * count (the reference allocated max_elements up front, slim.h:784); enterpoint and maxlevel stay as they are. */
+int hso_patch(hso_index *ix, const void *bytes, size_t len, int mode, const float *rows, size_t n_rows) {
+  const unsigned char *p = (const unsigned char *)bytes;
+  size_t pos = 0;
+#define HSO_NEED(nb)                                                   \
+  do {                                                                 \
+    if ((size_t)(nb) > len - pos) {                                    \
+      snprintf(g_err, sizeof g_err, "truncated patch stream");         \
+      return -1;                                                       \
+    }                                                                  \
+  } while (0)
+  uint64_t cur = 0, n_old = 0, n_new = 0;
+  HSO_NEED(24);
+  memcpy(&cur, p, 8);
+  memcpy(&n_old, p + 8, 8);
+  memcpy(&n_new, p + 16, 8);
+  pos = 24;
+  if (cur < ix->n) {
+    snprintf(g_err, sizeof g_err, "patch shrinks the index");
+    return -1;
+  }
+  if (cur > ix->n) {
+    char *e = (char *)realloc(ix->elements, cur * ix->size_data_per_element + 1);
+    char **b = (char **)realloc(ix->blobs, (cur + 1) * sizeof(char *));
+    if (!e || !b) {
+      snprintf(g_err, sizeof g_err, "out of memory");
+      return -1;
+    }
+    memset(e + ix->n * ix->size_data_per_element, 0, (cur - ix->n) * ix->size_data_per_element);
+    for (uint64_t i = ix->n; i <= cur; i++) b[i] = NULL;
+    ix->elements = e;
+    ix->blobs = b;
+    ix->n = cur;                                   /* slim.h:2209, :2294, :2346 */
+  }
+  for (uint64_t i = 0; i < n_old + n_new; i++) {
+    uint32_t id, bsz;
+    HSO_NEED(4);
+    memcpy(&id, p + pos, 4);
+    pos += 4;
+    if (id >= ix->n) {
+      snprintf(g_err, sizeof g_err, "patch: node id out of range");
+      return -1;
+    }
+    char *e = ix->elements + (size_t)id * ix->size_data_per_element;
+    const size_t head = i < n_old ? ix->label_offset : ix->offset_nbr;     /* slim.h:2223-2226 */
+    HSO_NEED(head);
+    memcpy(e, p + pos, head);
+    pos += head;
+    HSO_NEED(4);
+    memcpy(&bsz, p + pos, 4);
+    pos += 4;
+    free(ix->blobs[id]);
+    ix->blobs[id] = NULL;
+    if (bsz) {                                                              /* slim.h:2238-2247 */
+      HSO_NEED(bsz);
+      ix->blobs[id] = (char *)malloc(bsz);
+      memcpy(ix->blobs[id], p + pos, bsz);
+      pos += bsz;
+    }
+    if (i >= n_old) {
+      if (mode == HSO_PATCH_INLINE) {                                       /* slim.h:2332-2334 */
+        HSO_NEED(4 * ix->dim);
+        memcpy(e + ix->offset_data, p + pos, 4 * ix->dim);
+        pos += 4 * ix->dim;
+      } else {                                                              /* slim.h:2227-2229, :2362-2364 */
+        uint64_t label;
+        memcpy(&label, e + ix->label_offset, 8);
+        if (!rows || label >= n_rows) {
+          snprintf(g_err, sizeof g_err, "patch: no row for label %llu", (unsigned long long)label);
+          return -1;
+        }
+        memcpy(e + ix->offset_data, rows + label * ix->dim, 4 * ix->dim);
+      }
+    }
+  }
+#undef HSO_NEED
+  return 0;
+}
+
 void hso_get_info(const hso_index *ix, hso_info *o) {
   o->n = ix->n;
   o->size_data_per_element = ix->size_data_per_element;

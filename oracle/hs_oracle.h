@@ -45,6 +45,10 @@ hso_index *hso_load(const char *graph_path, size_t dim, int metric);
 /* hnsw.h:781-893 (file written by hnsw.h:748-779): the `hnsw` strategy's un-pruned index */
 hso_index *hso_load_hnsw(const char *graph_path, size_t dim, int metric);
 void hso_free(hso_index *);
+/* patchFromStream, slim.h:2206-2388: rows[label * dim] supply the vectors of new nodes (HSO_PATCH_ROWS) or they
+ * sit inline in the stream (HSO_PATCH_INLINE).  0 on success. */
+enum { HSO_PATCH_ROWS = 0, HSO_PATCH_INLINE = 2 };
+int hso_patch(hso_index *, const void *bytes, size_t len, int mode, const float *rows, size_t n_rows);
 void hso_get_info(const hso_index *, hso_info *out);
 const char *hso_last_error(void);
 

@@ -28,10 +28,13 @@
 #include <chrono>
 #include <cstdint>
 #include <cstring>
+#include <fstream>
 #include <memory>
 #include <iostream>
 #include <sstream>
 #include <string>
+#include <unordered_map>
+#include <vector>
 
 namespace {
 
@@ -126,6 +129,14 @@ void *ref_slim_open(const char *graph, size_t dim, int metric,
     h->space.reset(new Space(dim, metric, counting != 0));
     h->index.reset(new hnswlib::HierarchicalNSWSlim<float>(h->space.get()));
     h->index->loadIndex(graph, h->space.get(), max_elements);
+    // patchFromStream's vector<vector> and to_add overloads free() the neighbour pointer of NEW nodes too
+    // (slim.h:2221-2236, :2303-2319), i.e. they rely on the unused tail of elements_ (a plain malloc,
+    // slim.h:785) reading as zero — true for the client's fresh multi-hundred-MB mapping, not for a
+    // small block recycled inside a test process.  Give the tail the state it has there.
+    auto &ix = *h->index;
+    if (ix.max_elements_ > ix.cur_element_count_)
+      std::memset(ix.elements_ + ix.cur_element_count_ * ix.size_data_per_element_, 0,
+                  (ix.max_elements_ - ix.cur_element_count_) * ix.size_data_per_element_);
     return h;
   } catch (const std::exception &e) {
     g_err = e.what();
@@ -259,6 +270,125 @@ int ref_bruteforce(const float *base, size_t n, size_t dim, int metric,
     }
     auto t1 = std::chrono::steady_clock::now();
     if (seconds) *seconds = std::chrono::duration<double>(t1 - t0).count();
+    return 0;
+  } catch (const std::exception &e) {
+    g_err = e.what();
+    return -1;
+  }
+}
+
+// ---- delta patches ----
+// SERVER side of the protocol, hnsw_slim_server_patch.cc:186-228 (/updateIndex) and :232-279
+// (/getLastBatch): the full HNSW receives new rows with addPoint, convertFromHNSWWithDiff re-prunes it
+// and writes what changed (slim.h:1110-1424) — the response body a client feeds to patchFromStream.
+// Here: rows [0, n0) make the partial index (saved to out_partial_graph); rows [n0, n) arrive in
+// `rounds` equal updates, round r's stream goes to "<patch_prefix><r>.bin".  inline_last != 0: the last
+// round is produced the /getLastBatch way instead — convertFromHNSWWithDiff(hnsw, old_cnt, new_cnt) +
+// genPatch(..., to_add = true) (slim.h:1427-1476, :1478-1751), new rows INLINE in the stream; the file
+// holds what the client hands to patchFromStream(in, true) (i.e. without the leading `finished` word).
+// The server's own index after the last round is saved to out_final_graph (may be empty).
+int ref_slim_make_patches(const float *base, size_t n, size_t dim, int metric, size_t M, size_t ef_construction,
+                          const char *branching, int threshold_level, float top_degree_percent0,
+                          float top_degree_percent, size_t top_M0, size_t low_m0, size_t top_M, size_t low_m,
+                          int threads, size_t n0, size_t rounds, int inline_last, const char *out_partial_graph,
+                          const char *patch_prefix, const char *out_final_graph) {
+  try {
+    if (n0 == 0 || n0 >= n || rounds == 0) {
+      g_err = "ref_slim_make_patches: need 0 < n0 < n and rounds > 0";
+      return -1;
+    }
+    Space space(dim, metric, false);
+    hnswlib::HierarchicalNSW<float> hnsw(&space, n, M, ef_construction, std::string(branching));
+    if (threads <= 0) threads = omp_get_num_procs();
+#pragma omp parallel for schedule(dynamic) num_threads(threads)
+    for (size_t i = 0; i < n0; ++i) hnsw.addPoint(base + i * dim, i);
+    hnswlib::HierarchicalNSWSlim<float> slim(&space, n, M, ef_construction, threshold_level, top_degree_percent0,
+                                             top_degree_percent, top_M0, low_m0, top_M, low_m);
+    std::ostringstream quiet;
+    std::streambuf *old = std::cout.rdbuf(quiet.rdbuf());       // "lookup", "changed nodes count: ..." chatter
+    slim.convertFromHNSW(&hnsw);
+    slim.saveIndex(out_partial_graph);
+    // convertFromHNSWWithDiff reads the previous neighbour pointer of EVERY node below the new count, new
+    // ones included (slim.h:1251-1254, :1360-1375), i.e. it relies on the unused tail of elements_ (a plain
+    // malloc of max_elements records, slim.h:827-828) reading as zero — true for the server's fresh
+    // multi-hundred-MB mapping, not for a small recycled block.  Give the tail the state it has there.
+    std::memset(slim.elements_ + slim.cur_element_count_ * slim.size_data_per_element_, 0,
+                (slim.max_elements_ - slim.cur_element_count_) * slim.size_data_per_element_);
+    for (size_t r = 0; r < rounds; ++r) {
+      const size_t lo = n0 + (n - n0) * r / rounds, hi = n0 + (n - n0) * (r + 1) / rounds;
+#pragma omp parallel for schedule(dynamic) num_threads(threads)
+      for (size_t i = lo; i < hi; ++i) hnsw.addPoint(base + i * dim, i, false);
+      std::ostringstream oss(std::ios::binary);
+      if (inline_last && r + 1 == rounds) {
+        size_t changed_old = 0, changed_new = 0;
+        slim.convertFromHNSWWithDiff(&hnsw, changed_old, changed_new);
+        std::ostringstream body(std::ios::binary);
+        size_t old_written = 0, new_written = 0;
+        const uint32_t finished = slim.genPatch(body, old_written, new_written, (size_t)1 << 62, true);
+        if (finished != 1) {
+          std::cout.rdbuf(old);
+          g_err = "genPatch did not finish in one batch";
+          return -1;
+        }
+        const size_t cur = slim.cur_element_count_;
+        hnswlib::writeBinaryPOD(oss, cur);
+        hnswlib::writeBinaryPOD(oss, old_written);
+        hnswlib::writeBinaryPOD(oss, new_written);
+        oss << body.str();
+      } else {
+        slim.convertFromHNSWWithDiff(&hnsw, oss);
+      }
+      const std::string bytes = oss.str();
+      const std::string path = std::string(patch_prefix) + std::to_string(r) + ".bin";
+      std::ofstream f(path, std::ios::binary);
+      f.write(bytes.data(), (std::streamsize)bytes.size());
+      if (!f) {
+        std::cout.rdbuf(old);
+        g_err = "cannot write " + path;
+        return -1;
+      }
+    }
+    if (out_final_graph && out_final_graph[0]) slim.saveIndex(out_final_graph);
+    std::cout.rdbuf(old);
+    return 0;
+  } catch (const std::exception &e) {
+    g_err = e.what();
+    return -1;
+  }
+}
+
+// CLIENT side: patchFromStream on an index opened with max_elements >= the patched count
+// (hnsw_slim_client_update_patch.cc:113, :56-81).  mode 0: the unordered_map overload the client uses
+// (slim.h:2343-2388; rows = the new vectors by LABEL: rows[label * dim] for label < n_rows);
+// mode 1: the vector<vector<float>> overload (slim.h:2206-2253); mode 2: rows inline, patchFromStream(in, true)
+// (slim.h:2292-2340, the /getLastBatch path).
+int ref_slim_patch(void *hv, const void *bytes, size_t len, int mode, const float *rows, size_t n_rows) {
+  auto *h = static_cast<SlimHandle *>(hv);
+  try {
+    std::istringstream in(std::string(static_cast<const char *>(bytes), len), std::ios::binary);
+    if (mode == 2) {
+      h->index->patchFromStream(in, true);
+    } else if (mode == 1) {
+      std::vector<std::vector<float>> data(n_rows);
+      for (size_t i = 0; i < n_rows; ++i) data[i].assign(rows + i * h->dim, rows + (i + 1) * h->dim);
+      h->index->patchFromStream(in, data);
+    } else {
+      std::unordered_map<uint32_t, std::vector<float>> data;
+      data.reserve(n_rows);
+      for (size_t i = 0; i < n_rows; ++i) data[(uint32_t)i].assign(rows + i * h->dim, rows + (i + 1) * h->dim);
+      h->index->patchFromStream(in, data);
+    }
+    return 0;
+  } catch (const std::exception &e) {
+    g_err = e.what();
+    return -1;
+  }
+}
+
+int ref_slim_save(void *hv, const char *path) {
+  auto *h = static_cast<SlimHandle *>(hv);
+  try {
+    h->index->saveIndex(path);
     return 0;
   } catch (const std::exception &e) {
     g_err = e.what();

@@ -110,6 +110,16 @@ def slim_lib():
         L.ref_bruteforce.restype = C.c_int
         L.ref_bruteforce.argtypes = [_f32p, C.c_size_t, C.c_size_t, C.c_int, _f32p, C.c_size_t, C.c_size_t,
                                      C.c_int, _u32p, C.c_void_p, C.POINTER(C.c_double)]
+        if hasattr(L, "ref_slim_make_patches"):
+            L.ref_slim_make_patches.restype = C.c_int
+            L.ref_slim_make_patches.argtypes = [_f32p, C.c_size_t, C.c_size_t, C.c_int, C.c_size_t, C.c_size_t,
+                                                C.c_char_p, C.c_int, C.c_float, C.c_float, C.c_size_t, C.c_size_t,
+                                                C.c_size_t, C.c_size_t, C.c_int, C.c_size_t, C.c_size_t, C.c_int,
+                                                C.c_char_p, C.c_char_p, C.c_char_p]
+            L.ref_slim_patch.restype = C.c_int
+            L.ref_slim_patch.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t, C.c_int, C.c_void_p, C.c_size_t]
+            L.ref_slim_save.restype = C.c_int
+            L.ref_slim_save.argtypes = [C.c_void_p, C.c_char_p]
         _slim_lib = L
     return _slim_lib
 
@@ -299,6 +309,38 @@ def ref_slim_build(base: np.ndarray, path: str, *, metric: int = 0, M: int = 16,
     return bs.value, cs.value
 
 
+PATCH_MAP, PATCH_VECTORS, PATCH_INLINE = 0, 1, 2   # the three patchFromStream overloads (ref_slim_patch)
+
+
+def ref_slim_make_patches(base: np.ndarray, n0: int, rounds: int, partial_path: str, patch_prefix: str, *,
+                          final_path: str = "", inline_last: bool = False, metric: int = 0, M: int = 16,
+                          ef_construction: int = 200, branching: str = "4", threads: int = 1,
+                          isolate: bool = True, **prune) -> list[str]:
+    """The reference's SERVER side of the delta-patch protocol (hnsw_slim_server_patch.cc:186-279): the index
+    over rows [0, n0) -> partial_path, then `rounds` updates (addPoint + convertFromHNSWWithDiff), one patch
+    stream per round -> patch_prefix + "<r>.bin".  Returns the patch file names."""
+    names = [f"{patch_prefix}{r}.bin" for r in range(rounds)]
+    if isolate:
+        _run_isolated("--make-patches", base, dict(n0=n0, rounds=rounds, partial_path=partial_path,
+                                                   patch_prefix=patch_prefix, final_path=final_path,
+                                                   inline_last=inline_last, metric=metric, M=M,
+                                                   ef_construction=ef_construction, branching=branching,
+                                                   threads=threads, prune=prune))
+        return names
+    L = slim_lib()
+    p = dict(PRUNE_DEFAULTS)
+    p.update(prune)
+    base = np.ascontiguousarray(base, dtype=np.float32)
+    n, dim = base.shape
+    rc = L.ref_slim_make_patches(base, n, dim, metric, M, ef_construction, branching.encode(), p["threshold_level"],
+                                 p["top_degree_percent0"], p["top_degree_percent"], p["top_M0"], p["low_m0"],
+                                 p["top_M"], p["low_m"], threads, n0, rounds, int(inline_last),
+                                 partial_path.encode(), patch_prefix.encode(), final_path.encode())
+    if rc != 0:
+        raise RuntimeError(L.ref_last_error().decode())
+    return names
+
+
 class RefSlim:
     """The reference's HierarchicalNSWSlim<float> loaded from a .graph file."""
 
@@ -347,6 +389,19 @@ class RefSlim:
         per = np.zeros(q.shape[0], dtype=np.uint64)
         self.L.ref_slim_counts(self.h, q, q.shape[0], k, ef, out, per)
         return out, per
+
+    def patch(self, stream: bytes, mode: int = PATCH_MAP, rows: np.ndarray | None = None) -> None:
+        """patchFromStream (slim.h:2206-2388); rows[label] = the vector of external label `label` (modes 0, 1)."""
+        ptr, n_rows = None, 0
+        if rows is not None:
+            rows = np.ascontiguousarray(rows, dtype=np.float32)
+            ptr, n_rows = rows.ctypes.data_as(C.c_void_p), rows.shape[0]
+        if self.L.ref_slim_patch(self.h, stream, len(stream), mode, ptr, n_rows) != 0:
+            raise RuntimeError(self.L.ref_last_error().decode())
+
+    def save(self, path: str) -> None:
+        if self.L.ref_slim_save(self.h, path.encode()) != 0:
+            raise RuntimeError(self.L.ref_last_error().decode())
 
 
 def ref_strategy_recall(base, q, knn, gt, K: int) -> float:
@@ -613,6 +668,8 @@ def oracle_lib():
         L.hso_load_hnsw.restype = C.c_void_p
         L.hso_load_hnsw.argtypes = [C.c_char_p, C.c_size_t, C.c_int]
         L.hso_free.argtypes = [C.c_void_p]
+        L.hso_patch.restype = C.c_int
+        L.hso_patch.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t, C.c_int, C.c_void_p, C.c_size_t]
         L.hso_get_info.argtypes = [C.c_void_p, C.POINTER(_HsoInfo)]
         L.hso_node_level.restype = C.c_int
         L.hso_node_level.argtypes = [C.c_void_p, C.c_uint32]
@@ -671,6 +728,15 @@ class Oracle:
 
     def __del__(self):
         self.close()
+
+    def patch(self, stream: bytes, rows: np.ndarray | None = None, inline: bool = False) -> None:
+        """hso_patch: the restatement of patchFromStream (slim.h:2206-2388); rows[label] = vectors of new nodes."""
+        ptr, n_rows = None, 0
+        if rows is not None:
+            rows = np.ascontiguousarray(rows, dtype=np.float32)
+            ptr, n_rows = rows.ctypes.data_as(C.c_void_p), rows.shape[0]
+        if self.L.hso_patch(self.h, stream, len(stream), 2 if inline else 0, ptr, n_rows) != 0:
+            raise RuntimeError(self.L.hso_last_error().decode())
 
     def info(self) -> dict:
         s = _HsoInfo()
@@ -829,6 +895,15 @@ if __name__ == "__main__":
                              ef_construction=a["ef_construction"], branching=a["branching"], threads=a["threads"],
                              labels=labels, hnsw_path=a["hnsw_path"], isolate=False, **a["prune"])
         print(json.dumps(out))
+    if len(sys.argv) == 3 and sys.argv[1] == "--make-patches":
+        td = sys.argv[2]
+        with open(os.path.join(td, "args.json")) as f:
+            a = json.load(f)
+        ref_slim_make_patches(np.ascontiguousarray(np.load(os.path.join(td, "base.npy"))), a["n0"], a["rounds"],
+                              a["partial_path"], a["patch_prefix"], final_path=a["final_path"],
+                              inline_last=a["inline_last"], metric=a["metric"], M=a["M"],
+                              ef_construction=a["ef_construction"], branching=a["branching"], threads=a["threads"],
+                              isolate=False, **a["prune"])
     if len(sys.argv) == 3 and sys.argv[1] == "--build-slimq":
         td = sys.argv[2]
         with open(os.path.join(td, "args.json")) as f:
