@@ -30,6 +30,8 @@ EXPORTS = [
     "hs_shardgroup_submit", "hs_shardgroup_wait_oldest", "hs_shardgroup_wait", "hs_shardgroup_streams",
     "hs_shardgroup_free", "hs_build_slim_index_gpu", "hs_save_index", "hs_build_slimq_index_gpu",
     "hs_load_reserve", "hs_patch_apply", "hs_debug_patch",
+    "hs_service_create", "hs_service_query", "hs_service_set_ef", "hs_service_patch", "hs_service_get_stats",
+    "hs_service_free", "hs_debug_service_create",
 ]
 HS_PATCH_INLINE_ROWS = 1
 
@@ -60,6 +62,14 @@ class PatchInfo(C.Structure):
 
     def as_dict(self) -> dict:
         return {f: int(getattr(self, f)) for f, _ in self._fields_}
+
+
+class ServiceStats(C.Structure):
+    _fields_ = [("batches", C.c_uint64), ("queries", C.c_uint64), ("max_batch", C.c_uint64), ("patches", C.c_uint64),
+                ("busy_seconds", C.c_double)]
+
+
+SERVICE_BACKEND = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_void_p)
 
 
 def _patch_args(stream: bytes, rows, row_labels, inline: bool):
@@ -159,12 +169,20 @@ def lib():
         L.hs_load_reserve.argtypes = [C.c_char_p, i32, i32, sz, sz, i32, C.POINTER(vp)]
         L.hs_patch_apply.argtypes = [vp, vp, sz, C.c_uint, vp, vp, sz, C.POINTER(PatchInfo)]
         L.hs_debug_patch.argtypes = [vp, vp, sz, C.c_uint, vp, vp, sz, C.POINTER(PatchInfo)]
+        L.hs_service_create.argtypes = [vp, sz, C.c_uint, sz, C.POINTER(vp)]
+        L.hs_debug_service_create.argtypes = [SERVICE_BACKEND, vp, sz, sz, C.c_uint, sz, C.POINTER(vp)]
+        L.hs_service_query.argtypes = [vp, vp, sz, vp, vp]
+        L.hs_service_set_ef.argtypes = [vp, sz]
+        L.hs_service_patch.argtypes = [vp, vp, sz, C.c_uint, vp, vp, sz, C.POINTER(PatchInfo)]
+        L.hs_service_get_stats.argtypes = [vp, C.POINTER(ServiceStats)]
+        L.hs_service_free.argtypes = [vp]
+        L.hs_service_free.restype = None
         L.hs_get_query_tconst.argtypes = [vp, C.POINTER(C.c_double)]
         L.hs_set_query_tconst.argtypes = [vp, C.c_double]
         L.hs_slimq_prepare.argtypes = [vp, vp, sz, vp, vp, vp, vp]
         for name in EXPORTS:
             if name not in ("hs_last_error", "hs_free", "hs_debug_free", "hs_build_params_default", "hs_exchange_free",
-                            "hs_shardgroup_free",
+                            "hs_shardgroup_free", "hs_service_free",
                             "hs_slimq_default_tconst", "hs_debug_bf_tc_fallback"):
                 getattr(L, name).restype = i32
         L.hs_slimq_default_tconst.restype = C.c_double
@@ -521,6 +539,70 @@ def build_slimq_graph(base, path: str, *, M: int = 16, ef_construction: int = 20
 
 def slimq_default_tconst(padded_dim: int) -> float:
     return float(lib().hs_slimq_default_tconst(padded_dim))
+
+
+class Service:
+    """hs_service: single-query serving in front of the batched search (the /query, /setEf and update handlers of
+    hnsw_slim_server.cc:69-142).  `backend` is an Index, or — CPU tests — a python function
+    f(queries[nq, dim], k) -> (labels[nq, k], dists[nq, k]) standing in for hs_search_batch."""
+
+    def __init__(self, backend, *, max_batch: int = 4096, max_wait_us: int = 0, k_max: int = 100, dim: int | None = None):
+        self._h = C.c_void_p()
+        self._cb = None
+        if isinstance(backend, Index):
+            self.dim = backend.dim
+            self._index = backend                      # keep it alive: the service borrows the handle
+            _check(lib().hs_service_create(backend.handle, max_batch, max_wait_us, k_max, C.byref(self._h)))
+        else:
+            assert dim is not None
+            self.dim = dim
+
+            def trampoline(_ctx, qp, nq, k, lp, dp):
+                try:
+                    q = np.ctypeslib.as_array(C.cast(qp, C.POINTER(C.c_float)), shape=(nq, dim))
+                    lab, dist = backend(q.copy(), k)
+                    np.ctypeslib.as_array(C.cast(lp, C.POINTER(C.c_uint32)), shape=(nq, k))[:] = lab
+                    np.ctypeslib.as_array(C.cast(dp, C.POINTER(C.c_float)), shape=(nq, k))[:] = dist
+                    return 0
+                except Exception:                      # noqa: BLE001 — reported through the C status code
+                    return -2
+
+            self._cb = SERVICE_BACKEND(trampoline)
+            _check(lib().hs_debug_service_create(self._cb, None, dim, max_batch, max_wait_us, k_max, C.byref(self._h)))
+
+    def query(self, vec, k: int, want_dists: bool = False):
+        v = _f32(vec)
+        assert v.shape == (self.dim,)
+        lab = np.empty(k, dtype=np.uint32)
+        dist = np.empty(k, dtype=np.float32) if want_dists else None
+        _check(lib().hs_service_query(self._h, v.ctypes.data, k, lab.ctypes.data, dist.ctypes.data if want_dists else None))
+        return (lab, dist) if want_dists else lab
+
+    def set_ef(self, ef: int) -> None:
+        _check(lib().hs_service_set_ef(self._h, ef))
+
+    def patch(self, stream: bytes, *, rows=None, row_labels=None, inline: bool = False) -> dict:
+        keep, args = _patch_args(stream, rows, row_labels, inline)
+        info = PatchInfo()
+        _check(lib().hs_service_patch(self._h, *args, C.byref(info)))
+        del keep
+        return info.as_dict()
+
+    def stats(self) -> dict:
+        s = ServiceStats()
+        _check(lib().hs_service_get_stats(self._h, C.byref(s)))
+        return {f: getattr(s, f) for f, _ in s._fields_}
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            lib().hs_service_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class HostGraph:

@@ -3,11 +3,15 @@
 //   hs_main --dataset=sift --solve_strategy=hnsw_slim --k=10 --m=16 --ef_construction=200 --ef_search=100
 // Extra flags: --data_dir (default ../data), --index_dir (default ../statistics/index), --device, and for
 // corpora sharded over the GPUs of one box: --shards S --gpus N [--batch B] with --solve_strategy=hnsw_slim
-// (S sub-graphs built on the GPUs, queries in batches of B through one hs_shardgroup per GPU).
+// (S sub-graphs built on the GPUs, queries in batches of B through one hs_shardgroup per GPU);
+// --solve_strategy=hnsw_slim_serve [--threads T --max_batch B --max_wait_us U --patches a.bin,b.bin
+// --patch_inline_last --index_path P]: the query set as single queries from T concurrent callers through hs_service
+// (the server's /query handler), after applying the reference server's delta patches (gpu_service.h).
 #include <cmath>
 #include <cstring>
 #include <map>
 
+#include "gpu_service.h"
 #include "gpu_strategies.h"
 
 static std::map<std::string, std::string> parse_flags(int argc, char **argv) {   // gflags syntax: --name=value | --name value
@@ -40,7 +44,8 @@ int main(int argc, char **argv) {
   static const char *known[] = {"dataset", "solve_strategy", "k", "m", "m0", "ef_construction", "ef_search",
                                 "branching_factor", "threshold_level", "top_degree_percent0", "top_degree_percent",
                                 "top_M0", "low_m0", "top_M", "low_m", "level_ratio", "Mm_ratio", "min_indegree0",
-                                "min_indegree", "data_dir", "index_dir", "device", "shards", "gpus", "batch"};
+                                "min_indegree", "data_dir", "index_dir", "device", "shards", "gpus", "batch", "index_path",
+                                "threads", "max_batch", "max_wait_us", "patches", "patch_inline_last"};
   for (auto &kv : flags) {
     bool ok = false;
     for (const char *k : known) ok |= kv.first == k;
@@ -96,7 +101,7 @@ int main(int argc, char **argv) {
   const std::string source_path = data_dir + "/" + dataset + "/" + dataset + "_base.fvecs";
   const std::string query_path = data_dir + "/" + dataset + "/" + dataset + "_query.fvecs";
   const std::string gt_path = data_dir + "/" + dataset + "/" + dataset + "_groundtruth.ivecs";
-  const std::string index_path = index_dir + "/" + dataset + "/" + suffix;
+  const std::string index_path = str("index_path", index_dir + "/" + dataset + "/" + suffix);
 
   std::cout << "Index path: " << index_path << std::endl;
   std::cout << "gt path: " << gt_path << std::endl;
@@ -109,6 +114,10 @@ int main(int argc, char **argv) {
     const size_t shards = (size_t)i64("shards", 0), gpus = (size_t)i64("gpus", 1), batch = (size_t)i64("batch", 10000);
     if (solve_strategy == "hnsw_slim" && shards > 0) {
       strategy = new HnswSlimShardedGpuStrategy(source_path, query_path, index_path, pp, shards, gpus, batch, device);
+    } else if (solve_strategy == "hnsw_slim_serve") {      // the server's /query handler under concurrent callers + client-side patches
+      strategy = new HnswSlimServeGpuStrategy(source_path, query_path, index_path, (size_t)i64("threads", 32),
+                                              (size_t)i64("max_batch", 4096), (unsigned)i64("max_wait_us", 0),
+                                              str("patches", ""), str("patch_inline_last", "false") == "true", device);
     } else if (solve_strategy == "hnsw_slim") {
       strategy = new HnswSlimGpuStrategy(source_path, query_path, index_path, pp, device);
     } else if (solve_strategy == "hnsw_slimq") {

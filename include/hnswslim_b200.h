@@ -118,6 +118,42 @@ int hs_load_reserve(const char *graph_path, int kind, int metric, size_t dim, si
 int hs_patch_apply(hs_index *, const void *patch, size_t patch_bytes, unsigned flags, const float *rows,
                    const uint64_t *row_labels, size_t n_rows, hs_patch_info *info_out);
 
+/* ---- hs_service: single-query serving in front of the batched search -------------------------------------
+ * The reference's server answers ONE query per request: each /query handler thread calls
+ * hnsw_slim.searchKnn(vec, k, out) itself (hnsw_slim_server.cc:69-98, hnsw_slim_server_patch.cc:133-160), /setEf
+ * calls setEf (:100-115).  hs_service_query is that handler body for the GPU engine: thread-safe and blocking, it
+ * puts the query into the batch that is currently collecting and returns when the batch has been searched.  A
+ * dispatcher thread hands a batch to hs_search_batch as soon as the previous one has completed (while one batch
+ * is on the GPU the next one fills: the batch size follows the load), when it holds max_batch queries, or — if
+ * max_wait_us > 0 — once its first query has waited that long.  Batches live in page-locked mapped memory and are
+ * searched in place.  A batch holds requests of ONE k (ef = max(ef_, k), slim.h:2080); a request with another k
+ * goes to the next batch.  labels_out: k labels, nearest first; dists_out may be NULL.
+ *   set_ef   setEf for the batches launched from now on
+ *   patch    hs_patch_apply between two batches: requests that have joined a batch are answered on the old
+ *            index, later ones wait and see the patched one (the reference's patchFromStream is not synchronised
+ *            with its searches at all)
+ * The index is borrowed: free the service first. */
+typedef struct hs_service hs_service;
+typedef struct {
+  uint64_t batches, queries;       /* launches, and the queries they carried */
+  uint64_t max_batch;              /* largest batch launched                 */
+  uint64_t patches;
+  double busy_seconds;             /* time spent inside hs_search_batch      */
+} hs_service_stats;
+int hs_service_create(hs_index *, size_t max_batch, unsigned max_wait_us, size_t k_max, hs_service **out);
+int hs_service_query(hs_service *, const float *vec, size_t k, uint32_t *labels_out, float *dists_out);
+int hs_service_set_ef(hs_service *, size_t ef);
+int hs_service_patch(hs_service *, const void *patch, size_t patch_bytes, unsigned flags, const float *rows,
+                     const uint64_t *row_labels, size_t n_rows, hs_patch_info *info_out);
+int hs_service_get_stats(hs_service *, hs_service_stats *out);
+void hs_service_free(hs_service *);
+/* The same batching front over a caller-supplied search function with hs_search_batch's meaning (host buffers,
+ * synchronous, 0 = ok).  No CUDA needed: the CPU test-suite drives the batching logic through it. */
+typedef int (*hs_service_backend_fn)(void *ctx, const float *queries, size_t nq, size_t k, uint32_t *labels_out,
+                                     float *dists_out);
+int hs_debug_service_create(hs_service_backend_fn fn, void *ctx, size_t dim, size_t max_batch, unsigned max_wait_us,
+                            size_t k_max, hs_service **out);
+
 /* ~HierarchicalNSWSlim / clear() (slim.h:147-167) */
 void hs_free(hs_index *);
 

@@ -156,3 +156,45 @@ def test_cli_sharded_mode_one_process(tmp_path):
     assert float(re.search(r"Recall: ([0-9.]+)", out).group(1)) >= 0.97
     rc, out, err = run_cli("--solve_strategy=hnsw_slim", "--shards=3", "--gpus=2", *common)
     assert rc != 0 and "multiple of --gpus" in err
+
+
+@pytest.mark.skipif(HAVE_GPU, reason="checks the no-GPU behaviour")
+def test_serve_strategy_without_a_gpu_fails_loudly(tmp_path):
+    base, q, data_dir, index_dir = make_files(tmp_path, n=1200, nq=10, dim=16)
+    graph = os.path.join(os.path.dirname(__file__), "golden", "patch_l2_1k.graph")
+    rc, out, err = run_cli("--solve_strategy=hnsw_slim_serve", "--dataset=toy", "--data_dir", data_dir, "--index_path", graph,
+                           "--k=5", "--threads=4")
+    assert rc != 0 and "no CUDA device" in err and "no CPU fallback" in err
+
+
+@pytest.mark.gpu
+def test_cli_serve_with_patches(tmp_path):
+    """hs_main --solve_strategy=hnsw_slim_serve: the reference client's flow (partial index opened with room for
+    the whole base set, the server's patch streams applied, hnsw_slim_client_update_patch.cc:113,147-179) with the
+    query set going through the serving front one query per call from 16 threads."""
+    from conftest import HAVE_REF
+    from oracle import refharness as rh
+    if not HAVE_REF:
+        pytest.skip("oracle/_ref (compiled reference) not available on this host")
+    base, q, data_dir, index_dir = make_files(tmp_path, n=12000, nq=300, dim=64)
+    part = str(tmp_path / "part.graph")
+    names = rh.ref_slim_make_patches(base, 9000, 2, part, str(tmp_path / "p"), inline_last=True, M=16,
+                                     ef_construction=100, threads=1)
+    common = ["--dataset=toy", "--data_dir", data_dir, "--index_dir", index_dir, "--k=10", "--ef_search=64"]
+    rc, out, err = run_cli("--solve_strategy=bruteforce", *common)
+    assert rc == 0, err
+    rc, out, err = run_cli("--solve_strategy=hnsw_slim_serve", *common, "--index_path", part, "--patches",
+                           ",".join(names), "--patch_inline_last", "--threads=16", "--max_batch=64")
+    assert rc == 0, err
+    assert "9000 -> 10500 elements" in out and "10500 -> 12000 elements" in out
+    m = re.search(r"served (\d+) queries from 16 threads in (\d+) batches \(largest (\d+)\)", out)
+    assert m and int(m.group(1)) == 300 and int(m.group(2)) < 300 and 1 < int(m.group(3)) <= 64
+    got = float(re.search(r"Recall: ([0-9.]+)", out).group(1))
+    ix = capi.Index.load_reserve(part, 64, 12000)
+    ix.patch(open(names[0], "rb").read(), rows=base)
+    ix.patch(open(names[1], "rb").read(), inline=True)
+    ix.set_ef(64)
+    lab, _ = ix.search(q, 10)
+    gt, _ = capi.bruteforce_knn(base, q, 10)
+    want = float(np.mean([len(set(a) & set(b)) / 10 for a, b in zip(lab, gt)]))
+    assert abs(got - want) < 1e-6 and got > 0.9
