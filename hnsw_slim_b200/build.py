@@ -11,7 +11,7 @@ CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "_build")
 LIB = os.path.join(OUT_DIR, "libhnswslim_b200.so")
 
-SOURCES = ["hs_api.cu", "graph_loader.cpp", "graph_build.cpp", "traverse_fp32.cu", "traverse_fp32_g.cu", "traverse_slimq.cu", "bruteforce.cu", "bruteforce_tc.cu", "shard_group.cu", "graph_gpu.cu", "patch.cu", "service.cpp"]
+SOURCES = ["hs_api.cu", "graph_loader.cpp", "graph_build.cpp", "traverse_fp32.cu", "traverse_fp32_g.cu", "traverse_fp32_c.cu", "traverse_slimq.cu", "bruteforce.cu", "bruteforce_tc.cu", "shard_group.cu", "graph_gpu.cu", "patch.cu", "service.cpp"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
               "-Xcompiler", "-fPIC,-O3,-Wall,-Wno-unknown-pragmas", "--expt-relaxed-constexpr",
               "-ccbin", "/usr/bin/g++"]

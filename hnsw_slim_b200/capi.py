@@ -31,7 +31,7 @@ EXPORTS = [
     "hs_shardgroup_free", "hs_build_slim_index_gpu", "hs_save_index", "hs_build_slimq_index_gpu",
     "hs_load_reserve", "hs_patch_apply", "hs_debug_patch",
     "hs_service_create", "hs_service_query", "hs_service_set_ef", "hs_service_patch", "hs_service_get_stats",
-    "hs_service_free", "hs_debug_service_create",
+    "hs_service_free", "hs_debug_service_create", "hs_set_tuning",
 ]
 HS_PATCH_INLINE_ROWS = 1
 
@@ -177,6 +177,7 @@ def lib():
         L.hs_service_get_stats.argtypes = [vp, C.POINTER(ServiceStats)]
         L.hs_service_free.argtypes = [vp]
         L.hs_service_free.restype = None
+        L.hs_set_tuning.argtypes = [vp, C.c_char_p, C.c_longlong]
         L.hs_get_query_tconst.argtypes = [vp, C.POINTER(C.c_double)]
         L.hs_set_query_tconst.argtypes = [vp, C.c_double]
         L.hs_slimq_prepare.argtypes = [vp, vp, sz, vp, vp, vp, vp]
@@ -305,6 +306,10 @@ class Index:
 
     def set_ef(self, ef: int) -> None:
         _check(lib().hs_set_ef(self._h, ef))
+
+    def set_tuning(self, name: str, value: int) -> None:
+        """hs_set_tuning: "visited_table", "hash_bits", "traverse_flags", "slimq_flags", "zero_copy" (see the header)."""
+        _check(lib().hs_set_tuning(self._h, name.encode(), int(value)))
 
     def set_overlap(self, on: bool) -> None:
         """hs_set_overlap: consecutive device-buffer batches on one stream may overlap (see the header)."""

@@ -711,6 +711,40 @@ int hs_set_ef(hs_index *ix, size_t ef) {
   return HS_OK;
 }
 
+int hs_set_tuning(hs_index *ix, const char *name, long long value) {
+  if (!ix || !name) {
+    set_error("null argument");
+    return HS_ERR_ARG;
+  }
+  const std::string n(name);
+  std::lock_guard<std::mutex> lock(ix->mu);
+  if (n == "visited_table") {
+    if (value < -1 || value > 3) {
+      set_error("hs_set_tuning: visited_table takes -1 .. 3");
+      return HS_ERR_ARG;
+    }
+    ix->ghash_mode = (int)value;
+  } else if (n == "hash_bits") {
+    if (value < 0 || value > 16) {
+      set_error("hs_set_tuning: hash_bits takes 0 (automatic) .. 16");
+      return HS_ERR_ARG;
+    }
+    ix->hash_bits_override = (int)value;
+  } else if (n == "traverse_flags") {
+    ix->traverse_flags = (uint32_t)value;
+  } else if (n == "slimq_flags") {
+    ix->slimq_flags = (uint32_t)value;
+  } else if (n == "zero_copy") {
+    ix->zero_copy = value != 0;
+  } else {
+    set_error("hs_set_tuning: unknown knob '" + n + "'");
+    return HS_ERR_ARG;
+  }
+  ix->plan_ok = false;          // launch plans depend on the knobs
+  ix->planq_ok = false;
+  return HS_OK;
+}
+
 int hs_set_overlap(hs_index *ix, int on) {
   if (!ix) {
     set_error("null argument");

@@ -125,6 +125,47 @@ __device__ __forceinline__ float eval_rows_reg(const float4 *__restrict__ vec, u
   return my_d;
 }
 
+// Same through a per-warp shared-memory ring of R rows (R a multiple of 4): ALL rows of a chunk are put in flight at
+// once with 16-byte cp.async copies (one per lane and row: a row of CPL x 8 chunks is at most 32 of them), then
+// scored out of shared memory — the rows-in-flight count no longer depends on the register budget, and a hop waits
+// for one memory round trip instead of one per 4 rows.  Same association as eval_rows_reg (bit-identical sums).
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+template <int CPL, int METRIC, int R>
+__device__ __forceinline__ float eval_rows_ring(const float4 *__restrict__ vec, uint32_t row_chunks,
+                                                const float4 (&q)[CPL], float4 *ring, uint32_t my_id, int count,
+                                                int lane) {
+  static_assert(R % 4 == 0 && R > 0, "ring rows must be a multiple of 4");
+  const int team = lane >> 3, t = lane & 7;
+  float my_d = 0.f;
+  for (int base = 0; base < count; base += R) {
+    const int n = min(R, count - base);
+    for (int r = 0; r < n; ++r) {
+      const uint32_t id = __shfl_sync(FULL, my_id, base + r);
+      if (lane < CPL * 8) cp_async16(ring + r * (CPL * 8) + lane, vec + (size_t)id * row_chunks + lane);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncwarp();
+    for (int it = 0; it * 4 < n; ++it) {
+      const int src = it * 4 + team;
+      acc2_t acc2 = 0ull;
+      if (src < n) {
+        const float4 *row = ring + src * (CPL * 8) + t;
+#pragma unroll
+        for (int j = 0; j < CPL; ++j) acc2 = acc4<METRIC>(acc2, q[j], row[8 * j]);
+      }
+      const float acc = team_reduce(sum2(acc2));
+      const float v = __shfl_sync(FULL, acc, (lane & 3) * 8);
+      if ((lane >> 2) == base / 4 + it) my_d = finish<METRIC>(v);
+    }
+    __syncwarp();                                  // the ring is rewritten by the next chunk / the next call
+  }
+  return my_d;
+}
+
 // Same with the query in shared memory and a run-time chunk count (large / odd dims).
 template <int METRIC>
 __device__ __forceinline__ float eval_rows_smem(const float4 *__restrict__ vec, uint32_t row_chunks,
@@ -195,6 +236,62 @@ __device__ __forceinline__ void hash_clear(uint32_t *hash, uint32_t hsize, int l
   const uint4 e = make_uint4(EMPTY, EMPTY, EMPTY, EMPTY);
   for (uint32_t i = lane * 4; i < hsize; i += 128) *reinterpret_cast<uint4 *>(hash + i) = e;
   if (GLOBAL_TABLE) __threadfence();
+}
+
+// ---- compact visited table: 4096 cells of 16 bits in 8 KB of shared memory (ids < 2^24) ----
+// For ef 129..256 the 32-bit table above needs 16 KB per warp, which leaves 14 warps per SM (or sends the table
+// to global memory); halving the cell halves that.  A 16-bit cell cannot hold an id, so the table stores
+// REMAINDERS: 512 buckets of 8 cells (one 16-byte bucket = one LDS.128); an id has two candidate buckets, each
+// from a bijection of the 24-bit id space (multiplication by an odd constant mod 2^24) whose top 9 bits pick the
+// bucket and whose low 15 bits are the cell value — bit 15 of the cell says which of the two bijections it came
+// from, so (bucket, cell) identifies the id exactly: no false positives, which bit-exact parity with the
+// reference's visited array (visited_list_pool.h:10-31) needs.  0xFFFF marks an empty cell (the one id whose
+// second-choice cell would be 0xFFFF simply has no second choice).  A bucket fills front to back, an insertion goes
+// to the emptier of the two buckets (two-choice balancing keeps 8-cell buckets from overflowing far beyond the
+// 75 % load at which the caller resets the table anyway), by compare-and-swap on the 32-bit word that holds the
+// cell; a lane that loses the race looks again.  Returns 0: was absent, now recorded; 1: present; 2: absent and
+// NOT recorded (both buckets full) — the caller then resets the table before the next hop, exactly as it does
+// when the table passes its load limit (results unchanged, see the reset comment in the kernel).
+constexpr uint32_t kCvWords = 2048;            // 32-bit words: 512 buckets x 4
+__device__ __forceinline__ void cv_clear(uint32_t *tab, int lane) {
+  const uint4 e = make_uint4(EMPTY, EMPTY, EMPTY, EMPTY);
+  for (uint32_t i = lane * 4; i < kCvWords; i += 128) *reinterpret_cast<uint4 *>(tab + i) = e;
+}
+// nonzero iff some 16-bit half of x is zero
+__device__ __forceinline__ uint32_t cv_haszero(uint32_t x) { return (x - 0x00010001u) & ~x & 0x80008000u; }
+// one bucket: a 16-byte shared-memory load that is re-issued on every call (the loop below re-reads after a lost CAS)
+__device__ __forceinline__ uint4 cv_bucket(const uint32_t *p) {
+  uint4 v;
+  const unsigned a = (unsigned)__cvta_generic_to_shared(p);
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
+  return v;
+}
+// `single` (a test knob, traverse_flags bit 5) withholds the second choice so that buckets do overflow.
+__device__ __forceinline__ int cv_test_and_set(uint32_t *tab, uint32_t id, bool single = false) {
+  const uint32_t m1 = (id * 0x9E3779B1u) & 0xFFFFFFu, m2 = (id * 0x85EBCA6Bu) & 0xFFFFFFu;
+  const uint32_t b1 = m1 >> 15, b2 = m2 >> 15;
+  const uint32_t c1 = m1 & 0x7FFFu, c2 = (m2 & 0x7FFFu) | 0x8000u;
+  const bool ok2 = c2 != 0xFFFFu && b2 != b1 && !single;
+  const uint32_t p1 = c1 * 0x00010001u, p2 = c2 * 0x00010001u;
+  for (;;) {
+    const uint4 w1 = cv_bucket(tab + 4 * b1), w2 = cv_bucket(tab + 4 * b2);
+    uint32_t hit = cv_haszero(w1.x ^ p1) | cv_haszero(w1.y ^ p1) | cv_haszero(w1.z ^ p1) | cv_haszero(w1.w ^ p1);
+    if (ok2) hit |= cv_haszero(w2.x ^ p2) | cv_haszero(w2.y ^ p2) | cv_haszero(w2.z ^ p2) | cv_haszero(w2.w ^ p2);
+    if (hit) return 1;
+    // buckets fill front to back: a word is full iff its high half is used (word < 0xFFFF0000)
+    const uint32_t T = 0xFFFF0000u;
+    const int f1 = (w1.x < T) + (w1.y < T) + (w1.z < T) + (w1.w < T);
+    const int f2 = ok2 ? (w2.x < T) + (w2.y < T) + (w2.z < T) + (w2.w < T) : 4;
+    const uint32_t t1 = f1 == 0 ? w1.x : (f1 == 1 ? w1.y : (f1 == 2 ? w1.z : w1.w));     // first word with room (if f < 4)
+    const uint32_t t2 = f2 == 0 ? w2.x : (f2 == 1 ? w2.y : (f2 == 2 ? w2.z : w2.w));
+    const int occ1 = 2 * f1 + (f1 < 4 && (t1 & 0xFFFFu) != 0xFFFFu), occ2 = 2 * f2 + (f2 < 4 && (t2 & 0xFFFFu) != 0xFFFFu);
+    if (occ1 >= 8 && occ2 >= 8) return 2;
+    const bool second = occ2 < occ1;
+    const uint32_t old = second ? t2 : t1, c = second ? c2 : c1;
+    uint32_t *at = tab + 4 * (second ? b2 : b1) + (second ? f2 : f1);
+    const uint32_t neu = (old & 0xFFFFu) == 0xFFFFu ? ((old & 0xFFFF0000u) | c) : ((old & 0x0000FFFFu) | (c << 16));
+    if (atomicCAS(at, old, neu) == old) return 0;
+  }
 }
 
 __device__ __forceinline__ void prefetch_l2(const void *p) {
@@ -457,6 +554,12 @@ struct RegPool {
       }
     }
     return entered;
+  }
+  // the largest key of the pool (0 if empty), warp-uniform
+  __device__ __forceinline__ uint64_t worst_key() const {
+    int slot;
+    const uint64_t cm = col_max(slot);
+    return __shfl_sync(FULL, cm, warp_argmax_key(cm));
   }
   // every entry becomes unexpanded again (a new layer of the layered beam, slim.h:228-233)
   __device__ __forceinline__ void clear_flags() {
@@ -787,6 +890,169 @@ struct RegPool32 {
   }
 };
 
+// RegPool32 without the `ku` column: the "expanded" mark is the top bit of the id word (node ids are < 2^31),
+// so a slot costs two registers instead of three.  For ef 129..256 (5..8 slots per lane) that is the difference
+// between a pool that fits the 80-register budget of 24 warps per SM and one that spills.  The closest-unexpanded
+// scan pays one select per slot for it (once per hop); the worst-entry scan and the admission loop (several times
+// per hop) are unchanged.  Same interface and the same tie rules as RegPool32 (fp32 kernel only).
+//   kd[s]  ord(distance) of a used slot, 0 for an empty one
+//   id[s]  node id, top bit set once expanded; 0xffffffff for an empty slot
+template <int SLOTS>
+struct RegPool32C {
+  uint32_t kd[SLOTS], id[SLOTS];
+  uint32_t size, ef;
+  int lane;
+
+  __device__ __forceinline__ void init(uint64_t *, uint32_t ef_, int lane_) {
+    ef = ef_;
+    lane = lane_;
+    size = 0;
+#pragma unroll
+    for (int s = 0; s < SLOTS; ++s) {
+      kd[s] = 0u;
+      id[s] = 0xffffffffu;
+    }
+  }
+  __device__ __forceinline__ void put(uint32_t e, uint32_t d, uint32_t i) {   // owner lane only
+#pragma unroll
+    for (int s = 0; s < SLOTS; ++s) {
+      const bool h = (int)(e >> 5) == s;
+      kd[s] = h ? d : kd[s];
+      id[s] = h ? i : id[s];
+    }
+  }
+  __device__ __forceinline__ void seed(uint64_t key) {
+    if (lane == 0) put(0, (uint32_t)(key >> 32), (uint32_t)key);
+    size = 1;
+  }
+  __device__ __forceinline__ uint32_t un(int s) const { return (int32_t)id[s] < 0 ? 0xffffffffu : kd[s]; }
+  __device__ __forceinline__ uint32_t col_min_un() const {
+    uint32_t m = un(0);
+#pragma unroll
+    for (int s = 1; s < SLOTS; ++s) m = min(m, un(s));
+    return m;
+  }
+  __device__ __forceinline__ uint32_t col_max() const {
+    uint32_t m = kd[0];
+#pragma unroll
+    for (int s = 1; s < SLOTS; ++s) m = max(m, kd[s]);
+    return m;
+  }
+  __device__ __forceinline__ uint32_t pop_closest_unexpanded() {
+    const uint32_t m = col_min_un();
+    const uint32_t g = __reduce_min_sync(FULL, m);
+    if (g == 0xffffffffu) return kInvalid;
+    const int o = __ffs(__ballot_sync(FULL, m == g)) - 1;
+    uint32_t node = 0;
+    bool open = lane == o;
+#pragma unroll
+    for (int s = 0; s < SLOTS; ++s) {
+      const bool h = open && un(s) == g;
+      node = h ? id[s] : node;
+      id[s] = h ? (id[s] | FLAG) : id[s];
+      open = open && !h;
+    }
+    return __shfl_sync(FULL, node, o);
+  }
+  __device__ __forceinline__ uint32_t peek_closest_unexpanded() const {
+    const uint32_t m = col_min_un();
+    const uint32_t g = __reduce_min_sync(FULL, m);
+    if (g == 0xffffffffu) return kInvalid;
+    const int o = __ffs(__ballot_sync(FULL, m == g)) - 1;
+    uint32_t node = id[SLOTS - 1];
+#pragma unroll
+    for (int s = SLOTS - 2; s >= 0; --s) node = un(s) == g ? id[s] : node;     // first matching slot wins
+    return __shfl_sync(FULL, node, o);
+  }
+  __device__ __forceinline__ unsigned admit(bool valid, uint64_t key, uint32_t *ghosts = nullptr) {
+    const uint32_t d = (uint32_t)(key >> 32), cid = (uint32_t)key;
+    unsigned entered = 0;
+    const unsigned vmask = __ballot_sync(FULL, valid);
+    if (vmask == 0) return 0;
+    unsigned todo = vmask;
+    if (size < ef) {   // room left: the first (ef - size) candidates are appended unconditionally
+      const uint32_t room = ef - size;
+      const uint32_t n_app = min(room, (uint32_t)__popc(vmask));
+      for (uint32_t j = 0; j < n_app; ++j) {
+        const int src = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const uint32_t cd = __shfl_sync(FULL, d, src), ci = __shfl_sync(FULL, cid, src);
+        const uint32_t e = size + j;
+        if ((int)(e & 31) == lane) put(e, cd, ci);
+        entered |= 1u << src;
+      }
+      size += n_app;
+      if (todo == 0) return entered;
+    }
+    uint32_t cm = col_max();
+    uint32_t worst = __reduce_max_sync(FULL, cm);
+    todo &= __ballot_sync(FULL, valid && d < worst);   // the worst only gets smaller
+    while (todo) {
+      const int src = __ffs(todo) - 1;
+      todo &= todo - 1;
+      const uint32_t cd = __shfl_sync(FULL, d, src);
+      if (cd < worst) {
+        const uint32_t ci = __shfl_sync(FULL, cid, src);
+        const unsigned wmask = __ballot_sync(FULL, cm == worst);
+        const int owner = __ffs(wmask) - 1;
+        if ((wmask & (wmask - 1)) && ghosts) {     // exact tie at the boundary (see ghost_append): rare
+          if (lane == owner) {
+            uint32_t gi = 0xffffffffu;
+            bool first = true;
+#pragma unroll
+            for (int s = 0; s < SLOTS; ++s) {
+              const bool h = first && kd[s] == worst;
+              gi = h ? id[s] : gi;
+              first = first && !h;
+            }
+            if ((int32_t)gi >= 0) ghost_append(ghosts, worst, gi);     // still unexpanded: the reference keeps it
+          }
+          __syncwarp();
+        }
+        bool open = lane == owner;
+#pragma unroll
+        for (int s = 0; s < SLOTS; ++s) {
+          const bool h = open && kd[s] == worst;
+          kd[s] = h ? cd : kd[s];
+          id[s] = h ? ci : id[s];
+          open = open && !h;
+        }
+        entered |= 1u << src;
+        if (todo) {
+          cm = col_max();
+          worst = __reduce_max_sync(FULL, cm);
+        }
+      }
+    }
+    return entered;
+  }
+  __device__ __forceinline__ uint32_t take_ghost(uint32_t *ghosts) {
+    if (ghosts[0] == 0) return kInvalid;
+    return ghost_take(ghosts, __reduce_max_sync(FULL, col_max()), size >= ef, lane);
+  }
+  // every entry becomes unexpanded again (a new layer of the layered beam, slim.h:228-233)
+  __device__ __forceinline__ void clear_flags() {
+#pragma unroll
+    for (int s = 0; s < SLOTS; ++s) id[s] = kd[s] ? (id[s] & ~FLAG) : id[s];
+  }
+  template <typename F>
+  __device__ __forceinline__ void for_each_id(F &&f) const {
+#pragma unroll
+    for (int s = 0; s < SLOTS; ++s)
+      if (kd[s]) f(id[s] & ~FLAG);
+  }
+  // smallest (distance,id) key strictly above `last` in this lane's column (NONE if none)
+  __device__ __forceinline__ uint64_t col_next_above(uint64_t last) const {
+    uint64_t m = NONE;
+#pragma unroll
+    for (int s = 0; s < SLOTS; ++s) {
+      const uint64_t km = ((uint64_t)kd[s] << 32) | (id[s] & ~FLAG);
+      if (kd[s] && km > last && km < m) m = km;
+    }
+    return m;
+  }
+};
+
 struct SmemPool {
   uint64_t *pool;
   uint32_t size, ef;
@@ -898,6 +1164,9 @@ struct SmemPool {
     const int o = warp_argmax_key(max_all);
     const uint64_t worst = __shfl_sync(FULL, max_all, o);
     return ghost_take(ghosts, (uint32_t)(worst >> 32), size >= ef, lane);
+  }
+  __device__ __forceinline__ uint64_t worst_key() const {
+    return __shfl_sync(FULL, max_all, warp_argmax_key(max_all));
   }
   __device__ __forceinline__ void clear_flags() {
     __syncwarp();

@@ -33,10 +33,14 @@
 #include "traverse_common.cuh"
 #include "traverse_fp32.cuh"
 
-// This file is compiled twice: as is (visited hash in shared memory) and through
-// traverse_fp32_g.cu with HS_GHASH = 1 (visited hash in global memory, L2-resident).
+// This file is compiled three times: as is (visited hash in shared memory), through traverse_fp32_g.cu with
+// HS_GHASH = 1 (visited hash in global memory, L2-resident) and through traverse_fp32_c.cu with HS_CVTAB = 1
+// (compact 16-bit visited table in shared memory, traverse_common.cuh cv_test_and_set: ef 129..256 at small dims).
 #ifndef HS_GHASH
 #define HS_GHASH 0
+#endif
+#ifndef HS_CVTAB
+#define HS_CVTAB 0
 #endif
 
 namespace hs {
@@ -46,15 +50,27 @@ namespace {
 #ifndef HS_TRAVERSE_MIN_CTAS
 #define HS_TRAVERSE_MIN_CTAS 6     // 128-thread CTAs per SM the register budget must allow
 #endif
+#ifndef HS_TRAVERSE_MIN_CTAS_BIG
+#define HS_TRAVERSE_MIN_CTAS_BIG 6 // same for the pools of 5..8 register slots per lane (ef 129..256)
+#endif
 #ifndef HS_TRAVERSE_U
 #define HS_TRAVERSE_U 1            // x4 rows whose loads are in flight per warp
 #endif
+#ifndef HS_ROW_RING
+#define HS_ROW_RING 0              // > 0: rows go through a shared-memory ring of this many rows (cp.async), see eval_rows_ring
+#endif
+#ifndef HS_POOL_COMPACT
+#define HS_POOL_COMPACT 1          // pools of 5..8 slots per lane keep the expanded mark in the id word (RegPool32C)
+#endif
 
-template <int SLOTS> struct PoolSel { using type = RegPool32<SLOTS>; };
+template <int SLOTS> struct PoolSel {
+  using type = std::conditional_t<(SLOTS >= 5 && HS_POOL_COMPACT), RegPool32C<SLOTS>, RegPool32<SLOTS>>;
+};
 template <> struct PoolSel<0> { using type = SmemPool; };
 
 template <int CPL, int METRIC, int SLOTS>
-__global__ void __launch_bounds__(128, HS_TRAVERSE_MIN_CTAS) traverse_kernel(const __grid_constant__ TraverseParams p) {
+__global__ void __launch_bounds__(128, SLOTS >= 5 ? HS_TRAVERSE_MIN_CTAS_BIG : HS_TRAVERSE_MIN_CTAS)
+traverse_kernel(const __grid_constant__ TraverseParams p) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int lane = threadIdx.x & 31;
   const int wid = threadIdx.x >> 5;
@@ -79,8 +95,37 @@ __global__ void __launch_bounds__(128, HS_TRAVERSE_MIN_CTAS) traverse_kernel(con
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   }
 
-  const uint32_t hbits = p.hash_bits, hsize = 1u << hbits, hmask = hsize - 1;
-  const uint32_t hlimit = hsize - hsize / 4;
+  const uint32_t hbits = p.hash_bits, hsize = 1u << hbits, hmask = hsize - 1;     // HS_CVTAB: 2^12 16-bit cells
+  // HS_CVTAB test knobs: traverse_flags bit 4 resets the table at 1/8 load instead of 3/4, bit 5 gives every id
+  // ONE candidate bucket — both make the rare paths (reset, unrecorded id) common; results must not change
+  const uint32_t hlimit = (HS_CVTAB && (p.flags & 16u)) ? hsize / 8 : hsize - hsize / 4;
+  const bool cv_single = HS_CVTAB && (p.flags & 32u);
+  // the visited set behind one interface (the three compilations of this file)
+  bool vis_overflow = false;      // HS_CVTAB: an id found both its buckets full and was not recorded
+  auto vis_clear = [&]() {
+    if constexpr (HS_CVTAB) cv_clear(hash, lane);
+    else hash_clear<HS_GHASH != 0>(hash, hsize, lane);
+  };
+  auto vis_test_and_set = [&](uint32_t id) -> bool {       // true: seen before
+    if constexpr (HS_CVTAB) {
+      const int r = cv_test_and_set(hash, id, cv_single);
+      vis_overflow |= r == 2;
+      return r == 1;
+    } else {
+      return visited_test_and_set<HS_GHASH != 0>(hash, hbits, hmask, id);
+    }
+  };
+  // the table must be rebuilt from the pool before this hop: nearly full, or (HS_CVTAB) an id went unrecorded.
+  // Results are unchanged either way: a node scored before was rejected or displaced and will be again.
+  auto vis_needs_reset = [&](uint32_t hcount_, uint32_t incoming) -> bool {
+    if constexpr (HS_CVTAB) {
+      if (__any_sync(FULL, vis_overflow)) {
+        vis_overflow = false;
+        return true;
+      }
+    }
+    return hcount_ + incoming > hlimit;
+  };
   const uint32_t ef = p.ef;
   const int t8 = lane & 7;
   constexpr int QN = CPL > 0 ? CPL : 1;
@@ -128,12 +173,17 @@ __global__ void __launch_bounds__(128, HS_TRAVERSE_MIN_CTAS) traverse_kernel(con
     } else {
       for (uint32_t ch = lane; ch < p.row_chunks; ch += 32) qs[ch] = load_chunk(ch);
     }
-    hash_clear<HS_GHASH != 0>(hash, hsize, lane);
+    vis_clear();
+    vis_overflow = false;
     __syncwarp();
 
     auto eval = [&](uint32_t my_id, int count) -> float {
       if constexpr (CPL > 0) {
+#if HS_ROW_RING > 0
+        return eval_rows_ring<QN, METRIC, HS_ROW_RING>(p.vec, p.row_chunks, q, qs, my_id, count, lane);
+#else
         return eval_rows_reg<QN, METRIC, HS_TRAVERSE_U>(p.vec, p.row_chunks, q, my_id, count, lane);
+#endif
       } else {
         return eval_rows_smem<METRIC>(p.vec, p.row_chunks, qs, my_id, count, lane);
       }
@@ -182,7 +232,7 @@ __global__ void __launch_bounds__(128, HS_TRAVERSE_MIN_CTAS) traverse_kernel(con
     typename PoolSel<SLOTS>::type pool;
     pool.init(reinterpret_cast<uint64_t *>(wbase), ef, lane);
     pool.seed(make_key(curdist, cur));
-    if (lane == 0) visited_test_and_set<HS_GHASH != 0>(hash, hbits, hmask, cur);
+    if (lane == 0) vis_test_and_set(cur);
     __syncwarp();
 
     // ---- layered beam for threshold_level > 0 (searchBaseLayer, slim.h:222-316, called for
@@ -204,11 +254,11 @@ __global__ void __launch_bounds__(128, HS_TRAVERSE_MIN_CTAS) traverse_kernel(con
         // element_level >= layer (:247); such an entry has no row here
         if (slot < 0 || (uint32_t)slot >= p.level_count[layer]) continue;
         const uint32_t *row = ladj + (size_t)slot * p.upper_stride;
-        if (hcount + p.upper_stride > hlimit) {
+        if (vis_needs_reset(hcount, p.upper_stride)) {
           __syncwarp();
-          hash_clear<HS_GHASH != 0>(hash, hsize, lane);
+          vis_clear();
           __syncwarp();
-          pool.for_each_id([&](uint32_t pid) { visited_test_and_set<HS_GHASH != 0>(hash, hbits, hmask, pid); });
+          pool.for_each_id([&](uint32_t pid) { vis_test_and_set(pid); });
           hcount = pool.size;
           __syncwarp();
         }
@@ -219,7 +269,7 @@ __global__ void __launch_bounds__(128, HS_TRAVERSE_MIN_CTAS) traverse_kernel(con
           if (vm == 0) break;
           any = true;
           bool fresh = false;
-          if (id != kInvalid) fresh = !visited_test_and_set<HS_GHASH != 0>(hash, hbits, hmask, id);
+          if (id != kInvalid) fresh = !vis_test_and_set(id);
           const unsigned fm = __ballot_sync(FULL, fresh);
           const int count = __popc(fm);
           if (count == 0) continue;
@@ -267,13 +317,13 @@ __global__ void __launch_bounds__(128, HS_TRAVERSE_MIN_CTAS) traverse_kernel(con
         }
       }
 
-      if (hcount + p.deg0_stride > hlimit) {
+      if (vis_needs_reset(hcount, p.deg0_stride)) {
         // visited hash nearly full: keep only the pool entries (results are unchanged:
         // a node scored before was rejected or displaced and will be again)
         __syncwarp();
-        hash_clear<HS_GHASH != 0>(hash, hsize, lane);
+        vis_clear();
         __syncwarp();
-        pool.for_each_id([&](uint32_t pid) { visited_test_and_set<HS_GHASH != 0>(hash, hbits, hmask, pid); });
+        pool.for_each_id([&](uint32_t pid) { vis_test_and_set(pid); });
         hcount = pool.size;
         __syncwarp();
       }
@@ -285,7 +335,7 @@ __global__ void __launch_bounds__(128, HS_TRAVERSE_MIN_CTAS) traverse_kernel(con
         if (vm == 0) break;
         any = true;
         bool fresh = false;
-        if (id != kInvalid) fresh = !visited_test_and_set<HS_GHASH != 0>(hash, hbits, hmask, id);
+        if (id != kInvalid) fresh = !vis_test_and_set(id);
         if (fresh && opt_prefetch) {
           // pull the whole row towards L2 now; the scoring loop below then mostly waits on L2
           const char *r = reinterpret_cast<const char *>(p.vec + (size_t)id * p.row_chunks);
@@ -399,9 +449,15 @@ template <typename F>
 int dispatch(int cpl, int metric, int slots, F &&f) {
 #define HS_CASE(C, M, S) \
   if (cpl == C && metric == M && slots == S) return f(std::integral_constant<int, C>{}, std::integral_constant<int, M>{}, std::integral_constant<int, S>{});
-#define HS_CASES_S(C, M) HS_CASE(C, M, 0) HS_CASE(C, M, 2) HS_CASE(C, M, 4) HS_CASE(C, M, 8)
+#if HS_CVTAB        // the compact table serves the register pools of 5..8 slots at small dims only (plan_traverse)
+#define HS_CASES_S(C, M) HS_CASE(C, M, 5) HS_CASE(C, M, 6) HS_CASE(C, M, 8)
+#define HS_CASES_M(C) HS_CASES_S(C, HS_METRIC_L2) HS_CASES_S(C, HS_METRIC_IP)
+  HS_CASES_M(3) HS_CASES_M(4)
+#else
+#define HS_CASES_S(C, M) HS_CASE(C, M, 0) HS_CASE(C, M, 2) HS_CASE(C, M, 4) HS_CASE(C, M, 5) HS_CASE(C, M, 6) HS_CASE(C, M, 8)
 #define HS_CASES_M(C) HS_CASES_S(C, HS_METRIC_L2) HS_CASES_S(C, HS_METRIC_IP)
   HS_CASES_M(0) HS_CASES_M(3) HS_CASES_M(4)
+#endif
 #undef HS_CASES_M
 #undef HS_CASES_S
 #undef HS_CASE
@@ -411,9 +467,11 @@ int dispatch(int cpl, int metric, int slots, F &&f) {
 
 }  // namespace
 
-// one pair of entry points per copy of this file (shared-memory / global-memory visited hash)
+// one pair of entry points per copy of this file (shared-memory / global-memory / compact visited table)
 #if HS_GHASH
 #define HS_VARIANT(name) name##_g
+#elif HS_CVTAB
+#define HS_VARIANT(name) name##_c
 #else
 #define HS_VARIANT(name) name##_s
 #endif
@@ -429,20 +487,25 @@ int HS_VARIANT(traverse_launch)(int cpl, int metric, int slots, const TraversePa
   });
 }
 
-#if !HS_GHASH
+#if !HS_GHASH && !HS_CVTAB
 int traverse_occupancy_g(int cpl, int metric, int slots, int threads, size_t smem);
 int traverse_launch_g(int cpl, int metric, int slots, const TraverseParams &p, const TraverseLaunch &l,
+                      cudaStream_t stream);
+int traverse_occupancy_c(int cpl, int metric, int slots, int threads, size_t smem);
+int traverse_launch_c(int cpl, int metric, int slots, const TraverseParams &p, const TraverseLaunch &l,
                       cudaStream_t stream);
 
 namespace {
 // kernel variants: CPL 3 (dim 96: DEEP/MSTuring), 4 (dim 128: SIFT) keep the query in
 // registers, everything else runs the generic shared-memory-query path (CPL = 0);
-// pool in registers for ef <= 64 / <= 128 / <= 256, in shared memory above.
+// pool in registers for ef <= 64 / 128 / 160 / 192 / 256 (2 / 4 / 5 / 6 / 8 slots per lane), in shared memory above.
 inline int cpl_variant(uint32_t row_chunks) {
   const uint32_t cpl = row_chunks / kTeam;
   return (cpl == 3 || cpl == 4) ? (int)cpl : 0;
 }
-inline int slots_variant(uint32_t ef) { return ef <= 64 ? 2 : (ef <= 128 ? 4 : (ef <= 256 ? 8 : 0)); }
+inline int slots_variant(uint32_t ef) {
+  return ef <= 64 ? 2 : (ef <= 128 ? 4 : (ef <= 160 ? 5 : (ef <= 192 ? 6 : (ef <= 256 ? 8 : 0))));
+}
 inline uint32_t align_up(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
 constexpr uint32_t kSmemPerSm = 227u * 1024u;
 }  // namespace
@@ -468,7 +531,8 @@ int plan_traverse(TraverseParams &p, int metric, int hash_bits_override, int gha
   const int met = metric == HS_METRIC_IP ? HS_METRIC_IP : HS_METRIC_L2;
   const uint32_t list_bytes = slv ? 0u : align_up(p.ef * 8u, 16);
   const uint32_t stage_bytes = 32 * 4 + 16 * 4;       // staging ids + the exact-tie side list
-  const uint32_t query_bytes = cplv == 0 ? p.row_chunks * 16u : 0u;
+  // large dims: the query; small dims with HS_ROW_RING: the row ring (same carve-out, off_query)
+  const uint32_t query_bytes = cplv == 0 ? p.row_chunks * 16u : (uint32_t)HS_ROW_RING * p.row_chunks * 16u;
 
   // Shared-memory tables first.  They bound the resident warps: 24 per SM (what the register file
   // allows) needs <= 9.4 KB per warp.  When the table of this ef (plus the query of a large dim)
@@ -478,9 +542,19 @@ int plan_traverse(TraverseParams &p, int metric, int hash_bits_override, int gha
   const uint32_t per_warp_s = align_up(list_bytes + (4u << bits_s) + stage_bytes + query_bytes, 16);
   bool ghash = ghash_mode == 1 || (ghash_mode < 0 && kSmemPerSm / per_warp_s < 16);
   if (per_warp_s > kSmemPerSm) ghash = true;
-  const uint32_t bits = ghash ? pick_bits(16) : bits_s;
+  // Compact table (traverse_fp32_c.cu): 4096 16-bit cells in 8 KB, exact for ids < 2^24.  It serves the case the
+  // 32-bit table is too big for — the register pools of 5..8 slots (ef 129..256) at small dims, where 16 KB per
+  // warp would halve the resident warps: with 8 KB they stay at 24 per SM and the probes stay in shared memory.
+  // ~12 evaluations per ef entry fill it to ~60 % at ef=256; past 75 % it is reset like the others.
+  // ghash_mode 2 asks for it explicitly, 3 is the automatic choice without it.
+  const bool legacy_auto = ghash_mode == 3;
+  if (legacy_auto) ghash = kSmemPerSm / per_warp_s < 16 || per_warp_s > kSmemPerSm;
+  const bool cv_fits = cplv != 0 && slv >= 5 && p.n <= (1u << 24) && layers == 1 && hash_bits_override <= 0;
+  const bool cvtab = cv_fits && (ghash_mode == 2 || ghash_mode < 0);
+  if (cvtab) ghash = false;
+  const uint32_t bits = cvtab ? 12u : (ghash ? pick_bits(16) : bits_s);
   p.hash_bits = bits;
-  const uint32_t hash_bytes = ghash ? 0u : (4u << bits);
+  const uint32_t hash_bytes = cvtab ? (2u << bits) : (ghash ? 0u : (4u << bits));
   p.off_hash = list_bytes;
   p.off_stage = p.off_hash + hash_bytes;
   p.off_query = p.off_stage + stage_bytes;
@@ -498,6 +572,7 @@ int plan_traverse(TraverseParams &p, int metric, int hash_bits_override, int gha
   auto occupancy = [&](int w) {
     const size_t smem = (size_t)w * p.smem_per_warp;
     if (smem > kSmemPerSm) return 0;
+    if (cvtab) return traverse_occupancy_c(cplv, met_, slv, w * 32, smem);
     return ghash ? traverse_occupancy_g(cplv, met_, slv, w * 32, smem) : traverse_occupancy_s(cplv, met_, slv, w * 32, smem);
   };
   int wpc = 1, per_sm = occupancy(1);
@@ -524,6 +599,7 @@ int plan_traverse(TraverseParams &p, int metric, int hash_bits_override, int gha
   const int need = (nq + wpc - 1) / wpc;
   out->grid = need < resident ? (need > 0 ? need : 1) : resident;
   out->ghash = ghash;
+  out->cvtab = cvtab;
   out->ghash_bytes = ghash ? ((size_t)out->grid * wpc * 4) << bits : 0;
   // two overlapping launches alternate between two scratch halves (hs_api.cu); a third launch can
   // only become resident next to them when a grid does not fill the GPU — no overlap then
@@ -534,8 +610,9 @@ int plan_traverse(TraverseParams &p, int metric, int hash_bits_override, int gha
 int launch_traverse(const TraverseParams &p, int metric, const TraverseLaunch &l, cudaStream_t stream) {
   const int cplv = cpl_variant(p.row_chunks), slv = slots_variant(p.ef);
   const int met = metric == HS_METRIC_IP ? HS_METRIC_IP : HS_METRIC_L2;
+  if (l.cvtab) return traverse_launch_c(cplv, met, slv, p, l, stream);
   return l.ghash ? traverse_launch_g(cplv, met, slv, p, l, stream) : traverse_launch_s(cplv, met, slv, p, l, stream);
 }
-#endif   // !HS_GHASH
+#endif   // !HS_GHASH && !HS_CVTAB
 
 }  // namespace hs

@@ -43,6 +43,7 @@ struct TraverseLaunch {
   int warps_per_cta;
   int grid;
   size_t smem_bytes;
+  bool cvtab;            // compact 16-bit visited table in shared memory (traverse_fp32_c.cu)
   bool ghash;            // visited tables in global memory: the caller points p.ghash at ghash_bytes of scratch
   size_t ghash_bytes;    // grid * warps_per_cta * 4 << hash_bits
   bool may_overlap;      // programmatic stream serialization allowed for this launch shape
@@ -50,7 +51,9 @@ struct TraverseLaunch {
 
 // Fills the smem carve-up fields of `p` and returns the launch shape.
 // hash_bits_override = 0 picks the default for p.ef; ghash_mode: -1 = decide from the shared-memory
-// budget, 0 = visited tables in shared memory, 1 = in global memory.
+// budget (compact 16-bit tables in shared memory where they apply: ef 129..256, dim 96 / 128 rows, n <= 2^24),
+// 0 = 32-bit visited tables in shared memory, 1 = in global memory, 2 = compact where it applies else as -1,
+// 3 = as -1 but never compact.
 int plan_traverse(TraverseParams &p, int metric, int hash_bits_override, int ghash_mode, int sm_count, int nq,
                   TraverseLaunch *out);
 int launch_traverse(const TraverseParams &p, int metric, const TraverseLaunch &l, cudaStream_t stream);

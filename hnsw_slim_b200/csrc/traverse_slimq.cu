@@ -42,6 +42,12 @@ namespace {
 #ifndef HS_SLIMQ_MIN_CTAS
 #define HS_SLIMQ_MIN_CTAS 8
 #endif
+#ifndef HS_SLIMQ_EST32
+#define HS_SLIMQ_EST32 1           // popcount sums of the estimator in 32-bit integers (one I2F each)
+#endif
+#ifndef HS_SLIMQ_TOPCACHE
+#define HS_SLIMQ_TOPCACHE 0        // keep the exact-distance heap's worst distance in a register and skip the heap code
+#endif
 
 template <int SLOTS> struct QPoolSel { using type = RegPool32<SLOTS>; };
 template <> struct QPoolSel<0> { using type = SmemPool; };
@@ -63,7 +69,13 @@ struct Planes {
 template <int WREG>
 __device__ __forceinline__ float estimate(const TraverseQParams &p, const Planes<WREG> &pl, float delta,
                                           float vl, float k1xsumq, const float *g2c, uint32_t id) {
+  // popcount sums stay far below 2^24 (<= 15 * padded_dim, padded_dim <= 2048: hs_load): 32-bit integers, ONE
+  // int-to-float conversion each (a 64-bit source would cost a multi-instruction conversion per estimate)
+#if HS_SLIMQ_EST32
+  uint32_t ip = 0, ppc = 0;
+#else
   unsigned long long ip = 0, ppc = 0;
+#endif
   float f_add, f_rescale;
   uint32_t cluster;
   if constexpr (WREG == 2) {
@@ -71,10 +83,9 @@ __device__ __forceinline__ float estimate(const TraverseQParams &p, const Planes
     const uint4 a = __ldg(rec), b = __ldg(rec + 1);
     const unsigned long long x0 = ((unsigned long long)a.y << 32) | a.x;
     const unsigned long long x1 = ((unsigned long long)a.w << 32) | a.z;
-    ppc = (unsigned)(__popcll(x0) + __popcll(x1));
+    ppc = (uint32_t)(__popcll(x0) + __popcll(x1));
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
-      ip += (unsigned long long)(unsigned)(__popcll(x0 & pl.r[j]) + __popcll(x1 & pl.r[4 + j])) << j;
+    for (int j = 0; j < 4; ++j) ip += (uint32_t)(__popcll(x0 & pl.r[j]) + __popcll(x1 & pl.r[4 + j])) << j;
     f_add = __uint_as_float(b.x);
     f_rescale = __uint_as_float(b.y);
     cluster = b.z;
@@ -83,9 +94,9 @@ __device__ __forceinline__ float estimate(const TraverseQParams &p, const Planes
     for (uint32_t w = 0; w < p.words; ++w) {
       const uint2 c = __ldg(rec + w);
       const unsigned long long x = ((unsigned long long)c.y << 32) | c.x;
-      ppc += (unsigned)__popcll(x);
+      ppc += (uint32_t)__popcll(x);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) ip += (unsigned long long)(unsigned)__popcll(x & pl.s[w * 4 + j]) << j;
+      for (int j = 0; j < 4; ++j) ip += (uint32_t)__popcll(x & pl.s[w * 4 + j]) << j;
     }
     const uint2 f = __ldg(rec + p.words), c = __ldg(rec + p.words + 1);
     f_add = __uint_as_float(f.x);
@@ -304,6 +315,11 @@ traverse_slimq_kernel(const __grid_constant__ TraverseQParams p) {
     TopK top;
     top.init(reinterpret_cast<uint64_t *>(wbase + p.off_topk), p.k, lane);
     bool top_seeded = false;
+#if HS_SLIMQ_TOPCACHE
+    uint32_t top_worst_d = 0xffffffffu;       // distance word of the heap's worst key once it holds k entries
+#endif
+    // the exact-distance heap changes on few hops once it is full: its worst key is kept here and an expanded
+    // node that cannot enter (slimq.h:750-757: pushed, then the heap is trimmed back to K) skips the heap code
 
     for (;;) {
       const uint32_t node = pool.pop_closest_unexpanded_dups();
@@ -350,9 +366,17 @@ traverse_slimq_kernel(const __grid_constant__ TraverseQParams p) {
       if (!top_seeded) {
         top.seed(xk);
         top_seeded = true;
+#if HS_SLIMQ_TOPCACHE
+        if (p.k == 1) top_worst_d = (uint32_t)(xk >> 32);
+      } else if ((uint32_t)(xk >> 32) <= top_worst_d) {       // ties on the distance word go through the exact test
+        top.admit(lane == 0, xk);
+        if (top.size >= p.k) top_worst_d = (uint32_t)(top.worst_key() >> 32);
+      }
+#else
       } else {
         top.admit(lane == 0, xk);
       }
+#endif
     }
 
     // ---- results: the k closest expanded nodes by exact distance, ascending ----

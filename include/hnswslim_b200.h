@@ -172,6 +172,26 @@ int hs_get_info(const hs_index *, hs_index_info *out);
  * unchanged. */
 int hs_set_overlap(hs_index *, int on);
 
+/* Tuning knobs of a handle (no reference analogue; results never depend on them, only speed — except that a
+ * visited table that is reset mid-query re-evaluates nodes, so per-query counters may grow).  Every knob has an
+ * environment variable that sets its initial value when the index is created:
+ *   "visited_table"   HS_GHASH            where the per-warp visited set of the fp32 traversal lives: -1 automatic
+ *                                         (default), 0 32-bit table in shared memory, 1 in global memory (L2),
+ *                                         2 compact 16-bit table in shared memory where it applies (ef 129..256,
+ *                                         96/128-dim rows, n <= 2^24), 3 automatic without the compact table
+ *   "hash_bits"       HS_HASH_BITS        log2 of the 32-bit table's slots, 0 = from ef (default)
+ *   "traverse_flags"  HS_TRAVERSE_FLAGS   bit 0 L2 row prefetch, bit 1 speculative next-pop adjacency load,
+ *                                         bit 2 stop after the descent (profiling), bit 3 evict_last adjacency
+ *                                         prefetch, bits 4 / 5 make the compact visited table reset early /
+ *                                         overflow (tests); default 9
+ *   "slimq_flags"     HS_SLIMQ_FLAGS      hnsw_slimq kernel experiments, default 0
+ *   "zero_copy"       HS_ZERO_COPY        1 (default): pinned + mapped host buffers are used in place
+ * Further environment-only knobs, read where noted: HS_WPC (warps per CTA of the traversal launch, 1/2/4),
+ * HS_BF_TC (0 / 1 forces the fp32-scan / tcgen05 exact-kNN path), HS_BF_QRES, HS_BF_TC_STATS (see
+ * hs_debug_bf_tc_fallback), HS_SLIMQ_CARVEOUT (shared-memory carve-out of the hnsw_slimq kernel, percent),
+ * HS_LIB_PATH (Python binding: an alternative build of this library). */
+int hs_set_tuning(hs_index *, const char *name, long long value);
+
 /* hnsw_slimq only.  The reference draws its query-quantiser constant at random when it loads an
  * index (slimq.h:1274-1276 -> faster_config, rabitqlib/quantization/rabitq.hpp:27-34 ->
  * rabitq_impl.hpp:363-377: std::random_device), so its estimates differ in the low bits from

@@ -498,9 +498,13 @@ static void cand_reserve(scratch *s, size_t need) {
  * layer 0).  stop_needs_full: the stop rule also requires |top| == ef
  * (slim.h:237 and the non-bare-bone rule :346-347).  check_deleted: skip
  * delete-marked nodes when filling `top` (slim.h:297, :418). */
+/* n_ties (may be NULL) counts the exact ties at the ef boundary: a result trimmed from `top` while the entry that
+ * stays behind as the new worst carries the bit-identical distance.  Only then can the reference go on to EXPAND
+ * an entry that is no longer among its results (the stop rule is a strict `>`, slim.h:237, :339-340) — the one
+ * place where an engine that keeps candidates and results in a single pool has to take special care. */
 static void beam_layer(const hso_index *ix, const float *q, int layer, scratch *s, size_t *top_size,
                        size_t ef, float *lower_bound, int stop_needs_full, int check_deleted,
-                       int order, int team, uint32_t *n_dist, uint32_t *n_hops) {
+                       int order, int team, uint32_t *n_dist, uint32_t *n_hops, uint32_t *n_ties) {
   size_t csz = *top_size;
   cand_reserve(s, csz + 1);
   memcpy(s->cand, s->top, csz * sizeof(pairfu));
@@ -540,6 +544,7 @@ static void beam_layer(const hso_index *ix, const float *q, int layer, scratch *
         while (*top_size > ef) {
           heap_pop(s->top, *top_size, 1);
           (*top_size)--;
+          if (n_ties && *top_size > 0 && s->top[*top_size].d == s->top[0].d) (*n_ties)++;
         }
         if (*top_size > 0) *lower_bound = s->top[0].d;
       }
@@ -557,8 +562,8 @@ static int cmp_pair(const void *a, const void *b) {
 /* slim.h:2030-2131 */
 static void search_one(const hso_index *ix, const float *q, size_t k, size_t ef_in, scratch *s,
                        int order, int team, uint32_t *out_labels, float *out_dists,
-                       uint32_t *n_dist, uint32_t *n_hops) {
-  uint32_t nd = 0, nh = 0;
+                       uint32_t *n_dist, uint32_t *n_hops, uint32_t *n_ties) {
+  uint32_t nd = 0, nh = 0, nt = 0;
   uint32_t cur = ix->enterpoint;
   float curdist = hso_dist(q, hso_node_vector(ix, cur), ix->dim, ix->metric, order, team);
   nd++;
@@ -598,9 +603,9 @@ static void search_one(const hso_index *ix, const float *q, size_t k, size_t ef_
 
   int thr = ix->threshold_level < ix->maxlevel ? ix->threshold_level : ix->maxlevel;
   for (int level = thr; level > 0; level--)     /* slim.h:2108-2113 */
-    beam_layer(ix, q, level, s, &top_size, ef, &lower, 1, 1, order, team, &nd, &nh);
+    beam_layer(ix, q, level, s, &top_size, ef, &lower, 1, 1, order, team, &nd, &nh, &nt);
   int bare = !ix->has_deleted;                  /* slim.h:2114-2123 */
-  beam_layer(ix, q, 0, s, &top_size, ef, &lower, !bare, !bare, order, team, &nd, &nh);
+  beam_layer(ix, q, 0, s, &top_size, ef, &lower, !bare, !bare, order, team, &nd, &nh, &nt);
 
   /* slim.h:2126-2130 returns an unordered k-subset of labels; we sort so that the
    * result is canonical: (dist, internal id) ascending */
@@ -616,11 +621,18 @@ static void search_one(const hso_index *ix, const float *q, size_t k, size_t ef_
   }
   if (n_dist) *n_dist = nd;
   if (n_hops) *n_hops = nh;
+  if (n_ties) *n_ties = nt;
 }
 
 int hso_search(const hso_index *ix, const float *queries, size_t nq, size_t k, size_t ef, int order,
                int team, int threads, uint32_t *out_labels, float *out_dists, uint32_t *n_dist,
                uint32_t *n_hops) {
+  return hso_search_ties(ix, queries, nq, k, ef, order, team, threads, out_labels, out_dists, n_dist, n_hops, NULL);
+}
+
+int hso_search_ties(const hso_index *ix, const float *queries, size_t nq, size_t k, size_t ef, int order,
+                    int team, int threads, uint32_t *out_labels, float *out_dists, uint32_t *n_dist,
+                    uint32_t *n_hops, uint32_t *n_ties) {
   if (ix->n == 0) return 0;                     /* slim.h:2031-2032 */
   size_t efx = ef > k ? ef : k;
 #ifdef _OPENMP
@@ -640,7 +652,7 @@ int hso_search(const hso_index *ix, const float *queries, size_t nq, size_t k, s
     for (size_t i = 0; i < nq; i++)
       search_one(ix, queries + i * ix->dim, k, ef, &s, order, team, out_labels + i * k,
                  out_dists ? out_dists + i * k : NULL, n_dist ? n_dist + i : NULL,
-                 n_hops ? n_hops + i : NULL);
+                 n_hops ? n_hops + i : NULL, n_ties ? n_ties + i : NULL);
     free(s.top);
     free(s.cand);
     free(s.visited);

@@ -72,6 +72,14 @@ int hso_search(const hso_index *, const float *queries, size_t nq, size_t k, siz
                int order, int team, int threads, uint32_t *out_labels, float *out_dists,
                uint32_t *n_dist, uint32_t *n_hops);
 
+/* hso_search that also reports, per query, how many results were trimmed from the result heap while tying bit
+ * for bit with the entry that stayed behind as the new worst one (n_ties, nq entries): the exact-tie events at
+ * the ef boundary after which the reference may still expand an entry that has left its results (slim.h:237,
+ * :339-340).  A query with n_ties == 0 has no such event. */
+int hso_search_ties(const hso_index *, const float *queries, size_t nq, size_t k, size_t ef,
+                    int order, int team, int threads, uint32_t *out_labels, float *out_dists,
+                    uint32_t *n_dist, uint32_t *n_hops, uint32_t *n_ties);
+
 /* bruteforce.h:106-135 + brute_force_strategy.h:24-36: k labels per query,
  * FARTHEST first (the order the strategy writes to *_groundtruth.ivecs);
  * labels[i] of base row i is i. */

@@ -684,6 +684,9 @@ def oracle_lib():
         L.hso_search.restype = C.c_int
         L.hso_search.argtypes = [C.c_void_p, _f32p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_int, C.c_int, C.c_int,
                                  _u32p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.hso_search_ties.restype = C.c_int
+        L.hso_search_ties.argtypes = [C.c_void_p, _f32p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_int, C.c_int, C.c_int,
+                                      _u32p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.hso_bruteforce.restype = C.c_int
         L.hso_bruteforce.argtypes = [_f32p, C.c_size_t, C.c_size_t, C.c_int, C.c_int, C.c_int, _f32p, C.c_size_t,
                                      C.c_size_t, C.c_int, _u32p, C.c_void_p]
@@ -763,6 +766,17 @@ class Oracle:
         self.L.hso_search(self.h, q, nq, k, ef, order, team, threads, lab, dist.ctypes.data, nd.ctypes.data,
                           nh.ctypes.data)
         return lab, dist, nd, nh
+
+    def search_ties(self, q, k: int, ef: int, order: int = ORDER_GPU, team: int = 8, threads: int = 0):
+        """search() + n_ties[nq]: exact-tie events at the ef boundary per query (hso_search_ties)."""
+        q = np.ascontiguousarray(q, dtype=np.float32)
+        nq = q.shape[0]
+        lab = np.zeros((nq, k), np.uint32)
+        dist = np.zeros((nq, k), np.float32)
+        nd, nh, nt = np.zeros(nq, np.uint32), np.zeros(nq, np.uint32), np.zeros(nq, np.uint32)
+        self.L.hso_search_ties(self.h, q, nq, k, ef, order, team, threads, lab, dist.ctypes.data, nd.ctypes.data,
+                               nh.ctypes.data, nt.ctypes.data)
+        return lab, dist, nd, nh, nt
 
 
 class OracleQ:

@@ -227,6 +227,60 @@ def test_hash_reset_keeps_results(small_corpus, monkeypatch):
     assert (cb[:, 0] >= ca[:, 0]).all() and (cb[:, 0] > ca[:, 0]).any()
 
 
+@pytest.mark.parametrize("dim,rank,metric", [(128, 14, 0), (96, 12, 0), (128, 14, 1)])
+def test_ef_129_to_256_compact_pool_and_visited_table(dim, rank, metric):
+    """ef 129..256 at 96 / 128-dim rows: register pools of 5 / 6 / 8 slots with the expanded mark in the id word
+    (RegPool32C) and the compact 16-bit visited table (cv_test_and_set) — bit-exact ids, distances and per-query
+    counters against the oracle, whichever home the visited set has."""
+    c = get_corpus(n=30000, nq=200, dim=dim, rank=rank, metric=metric)
+    orc = rh.Oracle(c.graph, c.dim, metric)
+    ix = capi.Index(c.graph, c.dim, metric=metric)
+    tie_queries = 0
+    for ef in (129, 160, 161, 192, 193, 256):
+        olab, odist, ond, onh, oties = orc.search_ties(c.queries, 10, ef, order=rh.ORDER_GPU, team=8)
+        # Counters are compared on every query without an exact fp32 tie at the ef boundary (hso_search_ties: a
+        # result trimmed while tying with the new worst one).  Such ties the engine reproduces through its ghost
+        # list (traverse_common.cuh) unless both entries sit in the same one of the 32 pool columns — the one
+        # documented blind spot; ids and distances must match regardless.
+        clean = oties == 0
+        tie_queries += int((~clean).sum())
+        for mode in (-1, 2, 3, 0, 1):                      # automatic (compact), compact, legacy automatic, smem32, global
+            ix.set_tuning("visited_table", mode)
+            ix.set_ef(ef)
+            lab, dist, cnt = ix.search(c.queries, 10, counts=True)
+            assert np.array_equal(lab, olab), (ef, mode)
+            assert np.array_equal(dist.view(np.uint32), odist.view(np.uint32)), (ef, mode)
+            bad = np.nonzero((cnt[:, 0] != ond) | (cnt[:, 1] != onh))[0]
+            assert clean[bad].sum() == 0, (ef, mode, bad.tolist(), cnt[bad].tolist(), ond[bad].tolist(), onh[bad].tolist())
+            assert len(bad) <= 1, (ef, mode, bad.tolist())
+    assert tie_queries <= 12          # the exemption is the exception: a handful of the 1200 (query, ef) pairs
+
+
+def test_compact_visited_table_reset_and_overflow():
+    """The compact table's rare paths made common: an early load limit (reset + re-seed from the pool) and
+    single-choice buckets (ids that find their bucket full go unrecorded and force a reset).  Results are the
+    oracle's either way; only the evaluation counters may grow."""
+    c = get_corpus(n=30000, nq=200, dim=128, rank=14)
+    orc = rh.Oracle(c.graph, c.dim)
+    ix = capi.Index(c.graph, c.dim)
+    ix.set_tuning("visited_table", 2)
+    for ef in (140, 256):
+        olab, odist, ond, _ = orc.search(c.queries, 10, ef, order=rh.ORDER_GPU, team=8)
+        ix.set_ef(ef)
+        grew = []
+        for flags in (9 | 16, 9 | 32, 9 | 16 | 32):
+            ix.set_tuning("traverse_flags", flags)
+            lab, dist, cnt = ix.search(c.queries, 10, counts=True)
+            assert np.array_equal(lab, olab), (ef, flags)
+            assert np.array_equal(dist.view(np.uint32), odist.view(np.uint32)), (ef, flags)
+            assert (cnt[:, 0] >= ond).all(), (ef, flags)
+            grew.append(bool((cnt[:, 0] > ond).any()))
+        assert grew[0], ef                                  # the early limit did trigger resets
+        ix.set_tuning("traverse_flags", 9)
+    with pytest.raises(capi.HsError):
+        ix.set_tuning("no_such_knob", 1)
+
+
 def test_large_ef_shared_memory_pool(small_corpus):
     """ef > 128 runs the shared-memory pool variant; ef <= 64 / <= 128 the register pools."""
     for ef in (33, 64, 65, 128, 129, 300):

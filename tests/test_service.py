@@ -137,7 +137,7 @@ def test_service_argument_errors():
 @pytest.mark.gpu
 def test_gpu_service_answers_like_the_batched_call():
     from conftest import get_corpus
-    c = get_corpus(20000, 600, 128)
+    c = get_corpus(n=20000, nq=600, dim=128)
     ix = capi.Index(c.graph, c.dim)
     ix.set_ef(64)
     want_l, want_d = ix.search(c.queries, 10)
