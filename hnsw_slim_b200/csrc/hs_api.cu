@@ -865,11 +865,20 @@ int hs_search_batch_wait_oldest(hs_index *ix) {
     set_error("null argument");
     return HS_ERR_ARG;
   }
-  std::lock_guard<std::mutex> lock(ix->mu);
-  if (ix->ev_head == ix->ev_tail) return HS_OK;                    // nothing outstanding
+  cudaEvent_t ev;
+  unsigned long long head;
+  {
+    std::lock_guard<std::mutex> lock(ix->mu);
+    if (ix->ev_head == ix->ev_tail) return HS_OK;                  // nothing outstanding
+    head = ix->ev_head;
+    ev = ix->ev_ring[head % hs_index::kEventRing];
+  }
+  // the wait itself runs WITHOUT the handle's lock: another thread may go on submitting batches meanwhile
+  // (hs_service: one thread submits, one waits).  The event cannot be re-used before ev_head moves past it.
   HS_CUDA(cudaSetDevice(ix->device));
-  HS_CUDA(cudaEventSynchronize(ix->ev_ring[ix->ev_head % hs_index::kEventRing]));
-  ix->ev_head++;
+  HS_CUDA(cudaEventSynchronize(ev));
+  std::lock_guard<std::mutex> lock(ix->mu);
+  if (ix->ev_head == head) ix->ev_head++;
   return HS_OK;
 }
 
@@ -910,6 +919,14 @@ int hs_search_batch_counts(hs_index *ix, const float *queries, size_t nq, size_t
 
 int hs_search_batch_device(hs_index *ix, const float *d_queries, size_t nq, size_t k, uint32_t *d_labels,
                            float *d_dists, void *stream) {
+  if (!ix) {
+    set_error("null argument");
+    return HS_ERR_ARG;
+  }
+  // enqueueing mutates the handle (launch sequence number, plan cache, scratch growth): one caller at a time;
+  // the launch itself is asynchronous, so this serialises microseconds of host work, not the searches
+  std::lock_guard<std::mutex> lock(ix->mu);
+  HS_CUDA(cudaSetDevice(ix->device));
   return search_device(ix, d_queries, nq, k, d_labels, d_dists, nullptr, static_cast<cudaStream_t>(stream));
 }
 
@@ -931,6 +948,12 @@ int hs_search_batch_device_scatter(hs_index *ix, const float *d_queries, size_t 
     sc.labels[i] = d_labels_dsts[i];
     sc.dists[i] = d_dists_dsts[i];
   }
+  if (!ix) {
+    set_error("null argument");
+    return HS_ERR_ARG;
+  }
+  std::lock_guard<std::mutex> lock(ix->mu);
+  HS_CUDA(cudaSetDevice(ix->device));
   return search_device(ix, d_queries, nq, k, nullptr, nullptr, nullptr, static_cast<cudaStream_t>(stream), &sc);
 }
 

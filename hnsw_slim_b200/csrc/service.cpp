@@ -4,19 +4,26 @@
 // hnsw_slim.searchKnn(vec, k, out) on its own (hnsw_slim_server.cc:69-98, hnsw_slim_server_patch.cc:133-160),
 // /setEf calls setEf (:100-115) and the update path swaps neighbour lists under the searches' feet
 // (patchFromStream, slim.h:2206-2388).  A GPU answers a BATCH per launch, so the handler's one call becomes:
-// copy the query into the batch that is currently filling, sleep, wake up with the answer.  A dispatcher
-// thread launches the filling batch as soon as the previous one has completed (or when it is full / has waited
-// max_wait_us): while batch A runs on the GPU the requests that arrive collect in batch B — the batch size
-// adapts to the load by itself, an idle server answers a lone query at once and a busy one fills its batches.
-// The two batches live in page-locked, mapped host memory: hs_search_batch reads the queries and writes the
-// result rows in place (no staging copies).
+// copy the query into the batch that is currently filling, sleep, wake up with the answer.
+//
+// Batches live in a small ring of page-locked, mapped host buffers (hs_search_batch_submit reads the queries
+// and writes the result rows in place, no staging copies).  Two threads drive the ring:
+//   dispatcher  hands the filling batch to hs_search_batch_submit as soon as it holds a query (or, with
+//               max_wait_us > 0, once it is full / its first query has waited that long) and moves the fill
+//               point to the next free buffer.  Launches go to the handle's stream with batch overlap on
+//               (hs_set_overlap), so the small batches of a lightly loaded server run side by side instead of
+//               queueing behind each other: a request's latency is its own batch's.
+//   completer   waits for the batches in submission order (hs_search_batch_wait_oldest) and wakes their callers.
+// When every buffer of the ring is in flight, arrivals wait for the next free one and then share it: the batch
+// size follows the load by itself — a lone query is answered at once, a busy server fills its batches.
 //
 // Same-k batching: a launch has one k, and ef = max(ef_, k) (slim.h:2080) depends on it, so a batch only takes
-// requests with the k of its first request; a request with another k waits for the next batch.
-// hs_service_set_ef takes effect with the next batch; hs_service_patch drains both batches, applies the patch
+// requests with the k of its first request; a request with another k goes to the next buffer.
+// hs_service_set_ef takes effect with the next launch; hs_service_patch lets the ring drain, applies the patch
 // (hs_patch_apply) and lets the requests continue — what the reference does NOT guarantee (its patchFromStream
 // runs unsynchronised with searchKnn) is guaranteed here: a query sees the index before or after a patch, never
-// in between.
+// in between.  The service owns the handle's submit queue: no other caller may use hs_search_batch_submit /
+// _wait* on the index while the service exists.
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -24,8 +31,10 @@
 #include <condition_variable>
 #include <cstdlib>
 #include <cstring>
+#include <deque>
 #include <mutex>
 #include <thread>
+#include <vector>
 
 #include "hs_index.h"
 
@@ -49,6 +58,8 @@ struct Batch {
   Clock::time_point t0;
 };
 
+constexpr int kDepth = 8;              // ring buffers; at most kDepth batches between "filling" and "answered"
+
 }  // namespace
 
 struct hs_service {
@@ -61,21 +72,50 @@ struct hs_service {
   bool pinned = false;
 
   std::mutex mu;
-  std::condition_variable cv_join, cv_work, cv_done, cv_idle;
-  Batch b[2];
+  std::condition_variable cv_join, cv_work, cv_flight, cv_done, cv_idle;
+  std::vector<Batch> b;
   int fill = 0;
-  bool closing = false, paused = false;
+  std::deque<int> inflight;            // submitted, not yet completed — in submission order
+  bool closing = false, closing_completer = false, paused = false;
   size_t pending_ef = 0;
-  std::thread dispatcher;
+  std::thread dispatcher, completer;
   hs_service_stats st{};
 
-  void run();
-  bool idle() const { return b[0].state == State::Filling && b[1].state == State::Filling && b[0].count == 0 && b[1].count == 0; }
+  void dispatch_loop();
+  void complete_loop();
+  bool ready() const { return b[fill].state == State::Filling && b[fill].count > 0; }
+  bool idle() const {
+    if (!inflight.empty()) return false;
+    for (const Batch &x : b)
+      if (x.state != State::Filling || x.count != 0) return false;
+    return true;
+  }
+  // the fill point moves to a free buffer, if there is one (else arrivals wait for the next to free up)
+  void advance_fill() {
+    for (int i = 1; i <= (int)b.size(); ++i) {
+      const int c = (fill + i) % (int)b.size();
+      if (b[c].state == State::Filling && b[c].count == 0) {
+        fill = c;
+        return;
+      }
+    }
+  }
+  void finish(int me, int rc, const std::string &err, double seconds) {     // mu held
+    Batch &done = b[me];
+    done.rc = rc;
+    done.err = err;
+    done.state = State::Draining;
+    done.readers = done.count;
+    st.batches++;
+    st.queries += done.count;
+    st.max_batch = std::max<uint64_t>(st.max_batch, done.count);
+    st.busy_seconds += seconds;
+    cv_done.notify_all();
+  }
 };
 
-void hs_service::run() {
+void hs_service::dispatch_loop() {
   std::unique_lock<std::mutex> lk(mu);
-  auto ready = [&] { return b[fill].state == State::Filling && b[fill].count > 0; };
   for (;;) {
     cv_work.wait(lk, [&] { return closing || ready(); });
     if (!ready()) {
@@ -83,43 +123,61 @@ void hs_service::run() {
       continue;
     }
     Batch &cur = b[fill];
-    // the previous batch has completed (this thread ran it synchronously): launch at once unless the caller asked
-    // for a minimum collection window and the batch is neither full nor held up by a patch
-    if (max_wait_us > 0) {
+    if (max_wait_us > 0) {             // the caller asked for a collection window
       const auto deadline = cur.t0 + std::chrono::microseconds(max_wait_us);
       cv_work.wait_until(lk, deadline, [&] { return closing || paused || cur.count >= max_batch; });
     }
     const int me = fill;
     cur.state = State::Running;
     cur.ticket++;
-    fill ^= 1;                          // requests now collect in the other batch (once its readers are done)
+    advance_fill();                     // requests now collect in another buffer
     cv_join.notify_all();
     const size_t count = cur.count, k = cur.k, ef = pending_ef;
     pending_ef = 0;
-    lk.unlock();
     int rc = HS_OK;
+    std::string err;
+    if (ix) {
+      lk.unlock();
+      if (ef) rc = hs_set_ef(ix, ef);
+      if (rc == HS_OK) rc = hs_search_batch_submit(ix, cur.q, count, k, cur.lab, cur.dist);     // asynchronous
+      if (rc != HS_OK) err = hs_last_error();
+      lk.lock();
+    }
+    if (rc != HS_OK) {
+      finish(me, rc, err, 0.0);         // nothing was enqueued: the callers get the error
+    } else {
+      inflight.push_back(me);           // only now: the completer must not wait for a batch that is not enqueued yet
+      cv_flight.notify_one();
+    }
+  }
+}
+
+void hs_service::complete_loop() {
+  std::unique_lock<std::mutex> lk(mu);
+  for (;;) {
+    cv_flight.wait(lk, [&] { return closing_completer || !inflight.empty(); });
+    if (inflight.empty()) {
+      if (closing_completer) return;
+      continue;
+    }
+    const int me = inflight.front();
+    Batch &cur = b[me];
+    const size_t count = cur.count, k = cur.k;
+    lk.unlock();
+    int rc;
     std::string err;
     const auto t0 = Clock::now();
     if (ix) {
-      if (ef) rc = hs_set_ef(ix, ef);
-      if (rc == HS_OK) rc = hs_search_batch(ix, cur.q, count, k, cur.lab, cur.dist);
+      rc = hs_search_batch_wait_oldest(ix);        // batches complete in submission order
       if (rc != HS_OK) err = hs_last_error();
     } else {
       rc = fn(fn_ctx, cur.q, count, k, cur.lab, cur.dist);
       if (rc != HS_OK) err = "backend callback failed";
     }
-    const double busy = std::chrono::duration<double>(Clock::now() - t0).count();
+    const double seconds = std::chrono::duration<double>(Clock::now() - t0).count();
     lk.lock();
-    Batch &done = b[me];
-    done.rc = rc;
-    done.err = err;
-    done.state = State::Draining;
-    done.readers = count;
-    st.batches++;
-    st.queries += count;
-    st.max_batch = std::max<uint64_t>(st.max_batch, count);
-    st.busy_seconds += busy;
-    cv_done.notify_all();
+    inflight.pop_front();
+    finish(me, rc, err, seconds);
   }
 }
 
@@ -135,7 +193,9 @@ static int service_create(hs_index *ix, hs_service_backend_fn fn, void *ctx, siz
   hs_service *s = nullptr;
   try {
     s = new hs_service;
+    s->b.resize(kDepth);
   } catch (const std::bad_alloc &) {
+    delete s;
     set_error("hs_service_create: out of host memory");
     return HS_ERR_NOMEM;
   }
@@ -149,19 +209,18 @@ static int service_create(hs_index *ix, hs_service_backend_fn fn, void *ctx, siz
   const size_t qb = max_batch * dim * sizeof(float), rb = max_batch * k_max * 4;
   bool ok = true;
   if (ix) {
-    // page-locked + mapped: hs_search_batch uses the buffers in place
+    // page-locked + mapped: hs_search_batch_submit uses the buffers in place
     ok = cudaSetDevice(ix->device) == cudaSuccess;
-    for (int i = 0; i < 2 && ok; ++i) {
+    s->pinned = true;
+    for (size_t i = 0; i < s->b.size() && ok; ++i) {
       ok = cudaHostAlloc(reinterpret_cast<void **>(&s->b[i].q), qb, cudaHostAllocMapped | cudaHostAllocPortable) == cudaSuccess &&
            cudaHostAlloc(reinterpret_cast<void **>(&s->b[i].lab), rb, cudaHostAllocMapped | cudaHostAllocPortable) == cudaSuccess &&
            cudaHostAlloc(reinterpret_cast<void **>(&s->b[i].dist), rb, cudaHostAllocMapped | cudaHostAllocPortable) == cudaSuccess;
     }
-    s->pinned = true;
-    if (!ok) {
-      set_error(std::string("hs_service_create: cudaHostAlloc: ") + cudaGetErrorString(cudaGetLastError()));
-    }
+    if (!ok) set_error(std::string("hs_service_create: cudaHostAlloc: ") + cudaGetErrorString(cudaGetLastError()));
+    if (ok) hs_set_overlap(ix, 1);        // consecutive small launches run side by side (see the header comment)
   } else {
-    for (int i = 0; i < 2 && ok; ++i) {
+    for (size_t i = 0; i < s->b.size() && ok; ++i) {
       s->b[i].q = static_cast<float *>(std::malloc(qb));
       s->b[i].lab = static_cast<uint32_t *>(std::malloc(rb));
       s->b[i].dist = static_cast<float *>(std::malloc(rb));
@@ -174,9 +233,10 @@ static int service_create(hs_index *ix, hs_service_backend_fn fn, void *ctx, siz
     return ix ? HS_ERR_CUDA : HS_ERR_NOMEM;
   }
   try {
-    s->dispatcher = std::thread([s] { s->run(); });
+    s->dispatcher = std::thread([s] { s->dispatch_loop(); });
+    s->completer = std::thread([s] { s->complete_loop(); });
   } catch (const std::exception &e) {
-    set_error(std::string("hs_service_create: cannot start the dispatcher thread: ") + e.what());
+    set_error(std::string("hs_service_create: cannot start the service threads: ") + e.what());
     hs_service_free(s);
     return HS_ERR_NOMEM;
   }
@@ -230,9 +290,10 @@ int hs_service_query(hs_service *s, const float *vec, size_t k, uint32_t *labels
   } else {
     set_error(bt->err);
   }
-  if (--bt->readers == 0) {             // last reader: the batch may fill again
+  if (--bt->readers == 0) {             // last reader: the buffer may fill again
     bt->count = 0;
     bt->state = State::Filling;
+    if (s->b[s->fill].state != State::Filling) s->fill = (int)(bt - s->b.data());     // arrivals were waiting for a buffer
     s->cv_join.notify_all();
     s->cv_work.notify_one();
     if (s->idle()) s->cv_idle.notify_all();
@@ -296,6 +357,12 @@ void hs_service_free(hs_service *s) {
     s->cv_join.notify_all();
   }
   if (s->dispatcher.joinable()) s->dispatcher.join();
+  {
+    std::lock_guard<std::mutex> lk(s->mu);
+    s->closing_completer = true;        // after the dispatcher: what it submitted is still waited for
+    s->cv_flight.notify_all();
+  }
+  if (s->completer.joinable()) s->completer.join();
   for (auto &bt : s->b) {
     if (s->pinned) {
       cudaFreeHost(bt.q);

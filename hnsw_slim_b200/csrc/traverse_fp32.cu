@@ -450,11 +450,11 @@ int dispatch(int cpl, int metric, int slots, F &&f) {
 #define HS_CASE(C, M, S) \
   if (cpl == C && metric == M && slots == S) return f(std::integral_constant<int, C>{}, std::integral_constant<int, M>{}, std::integral_constant<int, S>{});
 #if HS_CVTAB        // the compact table serves the register pools of 5..8 slots at small dims only (plan_traverse)
-#define HS_CASES_S(C, M) HS_CASE(C, M, 5) HS_CASE(C, M, 6) HS_CASE(C, M, 8)
+#define HS_CASES_S(C, M) HS_CASE(C, M, 5) HS_CASE(C, M, 6) HS_CASE(C, M, 7) HS_CASE(C, M, 8)
 #define HS_CASES_M(C) HS_CASES_S(C, HS_METRIC_L2) HS_CASES_S(C, HS_METRIC_IP)
   HS_CASES_M(3) HS_CASES_M(4)
 #else
-#define HS_CASES_S(C, M) HS_CASE(C, M, 0) HS_CASE(C, M, 2) HS_CASE(C, M, 4) HS_CASE(C, M, 5) HS_CASE(C, M, 6) HS_CASE(C, M, 8)
+#define HS_CASES_S(C, M) HS_CASE(C, M, 0) HS_CASE(C, M, 2) HS_CASE(C, M, 4) HS_CASE(C, M, 5) HS_CASE(C, M, 6) HS_CASE(C, M, 7) HS_CASE(C, M, 8)
 #define HS_CASES_M(C) HS_CASES_S(C, HS_METRIC_L2) HS_CASES_S(C, HS_METRIC_IP)
   HS_CASES_M(0) HS_CASES_M(3) HS_CASES_M(4)
 #endif
@@ -498,13 +498,13 @@ int traverse_launch_c(int cpl, int metric, int slots, const TraverseParams &p, c
 namespace {
 // kernel variants: CPL 3 (dim 96: DEEP/MSTuring), 4 (dim 128: SIFT) keep the query in
 // registers, everything else runs the generic shared-memory-query path (CPL = 0);
-// pool in registers for ef <= 64 / 128 / 160 / 192 / 256 (2 / 4 / 5 / 6 / 8 slots per lane), in shared memory above.
+// pool in registers for ef <= 64 / 128 / 160 / 192 / 224 / 256 (2 / 4 / 5 / 6 / 7 / 8 slots per lane), in shared memory above.
 inline int cpl_variant(uint32_t row_chunks) {
   const uint32_t cpl = row_chunks / kTeam;
   return (cpl == 3 || cpl == 4) ? (int)cpl : 0;
 }
 inline int slots_variant(uint32_t ef) {
-  return ef <= 64 ? 2 : (ef <= 128 ? 4 : (ef <= 160 ? 5 : (ef <= 192 ? 6 : (ef <= 256 ? 8 : 0))));
+  return ef <= 64 ? 2 : (ef <= 128 ? 4 : (ef <= 160 ? 5 : (ef <= 192 ? 6 : (ef <= 224 ? 7 : (ef <= 256 ? 8 : 0)))));
 }
 inline uint32_t align_up(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
 constexpr uint32_t kSmemPerSm = 227u * 1024u;

@@ -123,11 +123,15 @@ int hs_patch_apply(hs_index *, const void *patch, size_t patch_bytes, unsigned f
  * hnsw_slim.searchKnn(vec, k, out) itself (hnsw_slim_server.cc:69-98, hnsw_slim_server_patch.cc:133-160), /setEf
  * calls setEf (:100-115).  hs_service_query is that handler body for the GPU engine: thread-safe and blocking, it
  * puts the query into the batch that is currently collecting and returns when the batch has been searched.  A
- * dispatcher thread hands a batch to hs_search_batch as soon as the previous one has completed (while one batch
- * is on the GPU the next one fills: the batch size follows the load), when it holds max_batch queries, or — if
- * max_wait_us > 0 — once its first query has waited that long.  Batches live in page-locked mapped memory and are
- * searched in place.  A batch holds requests of ONE k (ef = max(ef_, k), slim.h:2080); a request with another k
- * goes to the next batch.  labels_out: k labels, nearest first; dists_out may be NULL.
+ * dispatcher thread submits a batch (hs_search_batch_submit, batch overlap on: small batches run side by side on
+ * the GPU) as soon as it holds a query — or, if max_wait_us > 0, once it is full or its first query has waited that
+ * long — and a completion thread wakes the callers batch by batch.  Up to 8 batches are between "collecting" and
+ * "answered"; when all are, arrivals share the next buffer that frees up, so the batch size follows the load: a
+ * lone query is answered at once, a busy server fills its batches (max_batch queries at most).  Batches live in
+ * page-locked mapped memory and are searched in place.  A batch holds requests of ONE k (ef = max(ef_, k),
+ * slim.h:2080); a request with another k goes to the next batch.  labels_out: k labels, nearest first; dists_out
+ * may be NULL.  The service owns the handle's submit queue (no hs_search_batch_submit / _wait* by others meanwhile)
+ * and switches hs_set_overlap on.
  *   set_ef   setEf for the batches launched from now on
  *   patch    hs_patch_apply between two batches: requests that have joined a batch are answered on the old
  *            index, later ones wait and see the patched one (the reference's patchFromStream is not synchronised
@@ -138,7 +142,7 @@ typedef struct {
   uint64_t batches, queries;       /* launches, and the queries they carried */
   uint64_t max_batch;              /* largest batch launched                 */
   uint64_t patches;
-  double busy_seconds;             /* time spent inside hs_search_batch      */
+  double busy_seconds;             /* time the completion thread spent waiting for batches */
 } hs_service_stats;
 int hs_service_create(hs_index *, size_t max_batch, unsigned max_wait_us, size_t k_max, hs_service **out);
 int hs_service_query(hs_service *, const float *vec, size_t k, uint32_t *labels_out, float *dists_out);
@@ -247,7 +251,8 @@ int hs_search_batch_submit(hs_index *, const float *queries, size_t nq, size_t k
 int hs_search_batch_wait(hs_index *);
 /* Blocks until the OLDEST batch that was submitted and not yet waited for is complete (batches
  * complete in submission order), so a caller can keep a fixed number of batches in flight:
- * submit, submit, { wait_oldest, consume, submit } ...  Returns at once when nothing is outstanding. */
+ * submit, submit, { wait_oldest, consume, submit } ...  Returns at once when nothing is outstanding.  The wait
+ * does not hold the handle's lock: one thread may submit while another waits (one waiting thread at a time). */
 int hs_search_batch_wait_oldest(hs_index *);
 
 /* hs_search_batch that also returns per-query counters: per_query_counts[2*i] = distances
@@ -258,7 +263,11 @@ int hs_search_batch_counts(hs_index *, const float *queries, size_t nq, size_t k
 /* Same with DEVICE buffers (d_queries nq x dim, d_labels nq x k, d_dists nq x k or
  * NULL) on CUDA stream `stream` (a cudaStream_t, 0 = legacy default stream);
  * asynchronous, no host<->device copies.  This is what the device-resident
- * benchmark number and multi-GPU sharding use. */
+ * benchmark number and multi-GPU sharding use.  Thread-safe (the enqueue is serialised per handle; the call
+ * selects the index's device).  One restriction: launches of ONE handle must be in flight on one stream at a
+ * time — for large ef / dim the per-warp visited tables live in a global scratch area of two halves that
+ * consecutive launches alternate between, which only orders correctly within a stream.  Use one handle per
+ * stream (hs_load twice) to search the same index from several streams at once. */
 int hs_search_batch_device(hs_index *, const float *d_queries, size_t nq, size_t k,
                            uint32_t *d_labels, float *d_dists, void *stream);
 

@@ -229,14 +229,14 @@ def test_hash_reset_keeps_results(small_corpus, monkeypatch):
 
 @pytest.mark.parametrize("dim,rank,metric", [(128, 14, 0), (96, 12, 0), (128, 14, 1)])
 def test_ef_129_to_256_compact_pool_and_visited_table(dim, rank, metric):
-    """ef 129..256 at 96 / 128-dim rows: register pools of 5 / 6 / 8 slots with the expanded mark in the id word
+    """ef 129..256 at 96 / 128-dim rows: register pools of 5 / 6 / 7 / 8 slots with the expanded mark in the id word
     (RegPool32C) and the compact 16-bit visited table (cv_test_and_set) — bit-exact ids, distances and per-query
     counters against the oracle, whichever home the visited set has."""
     c = get_corpus(n=30000, nq=200, dim=dim, rank=rank, metric=metric)
     orc = rh.Oracle(c.graph, c.dim, metric)
     ix = capi.Index(c.graph, c.dim, metric=metric)
     tie_queries = 0
-    for ef in (129, 160, 161, 192, 193, 256):
+    for ef in (129, 160, 161, 192, 193, 224, 225, 256):
         olab, odist, ond, onh, oties = orc.search_ties(c.queries, 10, ef, order=rh.ORDER_GPU, team=8)
         # Counters are compared on every query without an exact fp32 tie at the ef boundary (hso_search_ties: a
         # result trimmed while tying with the new worst one).  Such ties the engine reproduces through its ghost
@@ -253,7 +253,7 @@ def test_ef_129_to_256_compact_pool_and_visited_table(dim, rank, metric):
             bad = np.nonzero((cnt[:, 0] != ond) | (cnt[:, 1] != onh))[0]
             assert clean[bad].sum() == 0, (ef, mode, bad.tolist(), cnt[bad].tolist(), ond[bad].tolist(), onh[bad].tolist())
             assert len(bad) <= 1, (ef, mode, bad.tolist())
-    assert tie_queries <= 12          # the exemption is the exception: a handful of the 1200 (query, ef) pairs
+    assert tie_queries <= 16          # the exemption is the exception: a handful of the 1600 (query, ef) pairs
 
 
 def test_compact_visited_table_reset_and_overflow():
