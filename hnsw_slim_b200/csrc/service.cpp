@@ -56,6 +56,7 @@ struct Batch {
   int rc = HS_OK;
   std::string err;
   Clock::time_point t0;
+  std::condition_variable done;        // the callers of THIS batch sleep here: a completion wakes them, not everybody
 };
 
 constexpr int kDepth = 8;              // ring buffers; at most kDepth batches between "filling" and "answered"
@@ -72,8 +73,8 @@ struct hs_service {
   bool pinned = false;
 
   std::mutex mu;
-  std::condition_variable cv_join, cv_work, cv_flight, cv_done, cv_idle;
-  std::vector<Batch> b;
+  std::condition_variable cv_join, cv_work, cv_flight, cv_idle;
+  Batch b[kDepth];
   int fill = 0;
   std::deque<int> inflight;            // submitted, not yet completed — in submission order
   bool closing = false, closing_completer = false, paused = false;
@@ -92,8 +93,8 @@ struct hs_service {
   }
   // the fill point moves to a free buffer, if there is one (else arrivals wait for the next to free up)
   void advance_fill() {
-    for (int i = 1; i <= (int)b.size(); ++i) {
-      const int c = (fill + i) % (int)b.size();
+    for (int i = 1; i <= kDepth; ++i) {
+      const int c = (fill + i) % kDepth;
       if (b[c].state == State::Filling && b[c].count == 0) {
         fill = c;
         return;
@@ -110,7 +111,7 @@ struct hs_service {
     st.queries += done.count;
     st.max_batch = std::max<uint64_t>(st.max_batch, done.count);
     st.busy_seconds += seconds;
-    cv_done.notify_all();
+    done.done.notify_all();
   }
 };
 
@@ -193,9 +194,7 @@ static int service_create(hs_index *ix, hs_service_backend_fn fn, void *ctx, siz
   hs_service *s = nullptr;
   try {
     s = new hs_service;
-    s->b.resize(kDepth);
   } catch (const std::bad_alloc &) {
-    delete s;
     set_error("hs_service_create: out of host memory");
     return HS_ERR_NOMEM;
   }
@@ -212,7 +211,7 @@ static int service_create(hs_index *ix, hs_service_backend_fn fn, void *ctx, siz
     // page-locked + mapped: hs_search_batch_submit uses the buffers in place
     ok = cudaSetDevice(ix->device) == cudaSuccess;
     s->pinned = true;
-    for (size_t i = 0; i < s->b.size() && ok; ++i) {
+    for (int i = 0; i < kDepth && ok; ++i) {
       ok = cudaHostAlloc(reinterpret_cast<void **>(&s->b[i].q), qb, cudaHostAllocMapped | cudaHostAllocPortable) == cudaSuccess &&
            cudaHostAlloc(reinterpret_cast<void **>(&s->b[i].lab), rb, cudaHostAllocMapped | cudaHostAllocPortable) == cudaSuccess &&
            cudaHostAlloc(reinterpret_cast<void **>(&s->b[i].dist), rb, cudaHostAllocMapped | cudaHostAllocPortable) == cudaSuccess;
@@ -220,7 +219,7 @@ static int service_create(hs_index *ix, hs_service_backend_fn fn, void *ctx, siz
     if (!ok) set_error(std::string("hs_service_create: cudaHostAlloc: ") + cudaGetErrorString(cudaGetLastError()));
     if (ok) hs_set_overlap(ix, 1);        // consecutive small launches run side by side (see the header comment)
   } else {
-    for (size_t i = 0; i < s->b.size() && ok; ++i) {
+    for (int i = 0; i < kDepth && ok; ++i) {
       s->b[i].q = static_cast<float *>(std::malloc(qb));
       s->b[i].lab = static_cast<uint32_t *>(std::malloc(rb));
       s->b[i].dist = static_cast<float *>(std::malloc(rb));
@@ -282,7 +281,7 @@ int hs_service_query(hs_service *s, const float *vec, size_t k, uint32_t *labels
   std::memcpy(bt->q + slot * s->dim, vec, s->dim * sizeof(float));
   const unsigned long long want = bt->ticket + 1;
   if (slot == 0 || bt->count == s->max_batch) s->cv_work.notify_one();
-  s->cv_done.wait(lk, [&] { return bt->ticket >= want && bt->state == State::Draining; });
+  bt->done.wait(lk, [&] { return bt->ticket >= want && bt->state == State::Draining; });
   const int rc = bt->rc;
   if (rc == HS_OK) {
     std::memcpy(labels_out, bt->lab + slot * k, k * 4);
@@ -293,7 +292,7 @@ int hs_service_query(hs_service *s, const float *vec, size_t k, uint32_t *labels
   if (--bt->readers == 0) {             // last reader: the buffer may fill again
     bt->count = 0;
     bt->state = State::Filling;
-    if (s->b[s->fill].state != State::Filling) s->fill = (int)(bt - s->b.data());     // arrivals were waiting for a buffer
+    if (s->b[s->fill].state != State::Filling) s->fill = (int)(bt - s->b);     // arrivals were waiting for a buffer
     s->cv_join.notify_all();
     s->cv_work.notify_one();
     if (s->idle()) s->cv_idle.notify_all();

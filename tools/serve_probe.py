@@ -25,9 +25,9 @@ ap.add_argument("--n", type=int, default=200000)
 ap.add_argument("--n0", type=int, default=190000)
 ap.add_argument("--rounds", type=int, default=2)
 ap.add_argument("--dim", type=int, default=128)
-ap.add_argument("--nq", type=int, default=10000)
+ap.add_argument("--nq", type=int, default=100000)
 ap.add_argument("--ef", type=int, default=100)
-ap.add_argument("--threads", type=str, default="1,16,64,256")
+ap.add_argument("--threads", type=str, default="16,64,256,1024,4096")
 a = ap.parse_args()
 
 td = tempfile.mkdtemp(prefix="hs_serve_")
