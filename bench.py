@@ -63,6 +63,10 @@ WORKLOADS = {
                                    desc="MSTuring-shaped synthetic {n}x96 L2 in 8 hnsw_slimq sub-graphs of {rows} rows (100M "
                                         "config scaled down), M=16 efc=200, rows exchanged over NVLink + top-k merge"),
     # reduced-size variants for quick local runs (not contract lines)
+    # the reference's ground-truth producer (BruteForce::solve writes k=100 rows, brute_force_strategy.h:15-45):
+    # the one dense contraction of the system, on the tcgen05 tensor cores (bruteforce_tc.cu)
+    "bruteforce1m": dict(n=1_000_000, dim=128, metric=0, rank=14, nq=10_000, k=100, exact=True,
+                         desc="exact kNN (ground truth, k=100) over SIFT-shaped synthetic 1M x 128 L2, 10k queries per step"),
     "sift200k": dict(n=200_000, dim=128, metric=0, M=16, efc=200, rank=14, nq=10_000, k=10, ef=100,
                      desc="SIFT-shaped synthetic 200kx128 L2 (dev size)"),
     "gist200k": dict(n=200_000, dim=960, metric=0, M=32, efc=200, rank=24, nq=10_000, k=10, ef=100, curve=True,
@@ -538,6 +542,124 @@ def run_gpu(args, w):
                              % (info["device_bytes"] / 2**20)},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "sustained": sustained, "gpu_launches": args.steps,
             "clocks": clocks.summary(), "sharded": sharded,
+        }
+        print(json.dumps(out), flush=True)
+    if distributed:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def run_gpu_bruteforce(args, w):
+    """--workload bruteforce1m: a step = hs_bruteforce_knn_device over one 10k-query batch (BruteForce::solve's loop of
+    BruteforceSearch::searchKnn, bruteforce.h:106-135, for a whole batch).  N GPUs: base replicated, queries split."""
+    import torch
+    rank, local_rank, world = env_rank()
+    from hnsw_slim_b200 import capi
+    from hnsw_slim_b200.synth import latent_gaussian
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the engine has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    distributed = world > 1
+    if distributed:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if distributed:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    n, dim, nq, k = w["n"], w["dim"], w["nq"], w["k"]
+    n_batches = min(4, args.warmup + args.steps)
+    base = latent_gaussian(n, dim, rank=w["rank"], seed=1)
+    qb = [latent_gaussian(nq, dim, rank=w["rank"], seed=1, stream=1 + b + 100 * rank) for b in range(n_batches)]
+    d_base = torch.from_numpy(base).cuda()
+    d_q = [torch.from_numpy(q).cuda() for q in qb]
+    d_lab = torch.empty((nq, k), dtype=torch.int32, device="cuda")
+    d_dist = torch.empty((nq, k), dtype=torch.float32, device="cuda")
+    stream = torch.cuda.Stream()
+
+    def step(i):
+        capi.bruteforce_knn_device(d_base.data_ptr(), n, dim, d_q[i % n_batches].data_ptr(), nq, k, d_lab.data_ptr(),
+                                   d_dist.data_ptr(), metric=w["metric"], stream=stream.cuda_stream)
+
+    for i in range(args.warmup):
+        step(i)
+    stream.synchronize()
+    barrier()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    clocks = ClockSampler(local_rank, 0.02)
+    with clocks:
+        ev[0].record(stream)
+        for i in range(args.steps):
+            step(args.warmup + i)
+        ev[1].record(stream)
+        stream.synchronize()
+    barrier()
+    ms_total = ev[0].elapsed_time(ev[1])
+    if distributed:
+        t = torch.tensor([ms_total], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    value = world * nq * args.steps / (ms_total * 1e-3)
+    step_ms = ev[0].elapsed_time(ev[1]) / args.steps
+
+    # end to end: host buffers in, host buffers out through hs_bruteforce_knn (base uploaded inside the call)
+    h_lab = np.empty((nq, k), np.uint32)
+    t0 = time.perf_counter()
+    e2e_steps = max(1, min(args.steps, 3))
+    for i in range(e2e_steps):
+        h_lab, _ = capi.bruteforce_knn(base, qb[i % n_batches], k, metric=w["metric"], device=local_rank)
+    e2e_s = time.perf_counter() - t0
+    e2e = {"value": world * nq * e2e_steps / e2e_s, "unit": "queries/s", "h2d_bytes_per_step": (n + nq) * dim * 4,
+           "d2h_bytes_per_step": nq * k * 8, "steps": e2e_steps,
+           "timing": "host wall clock around hs_bruteforce_knn: pageable host base + queries in (the 512 MB base is "
+                     "uploaded inside every call, as the reference's strategy re-reads its .fvecs), labels + distances out"}
+    peaks, peak_src = measured_peaks()
+    flop = 2.0 * n * nq * dim
+    achieved = flop / (step_ms * 1e-3) / 1e12
+    pipe = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            pipe = json.load(f).get("bruteforce1m")
+    roofline = {"bound": "tensor", "achieved": achieved, "peak": peaks.get("bf16_tflops", 1640.9), "unit": "TFLOP/s",
+                "frac": achieved / peaks.get("bf16_tflops", 1640.9), "traffic": None, "peak_source": peak_src,
+                "kernel": "hs::bf_tc_kernel (+ split / threshold / finish kernels inside the step)",
+                "algorithmic_flop_per_step": flop, "step_ms": step_ms,
+                "note": "algorithmic 2*n*nq*dim against the bf16 burst peak; the kernel issues 3x that in "
+                        "tcgen05.mma.kind::tf32 work (hi.hi + hi.lo + lo.hi: bit-exact fp32 results need the split), "
+                        "and the tf32 rate is half the bf16 rate",
+                "tensor_pipe": pipe}
+    recall = None
+    cpu = None
+    if rank == 0:
+        # parity of what was measured: identical to the fp32 scan path on a sample (and, below, to the reference)
+        ns = 64
+        lab_tc, _ = capi.bruteforce_knn(base, qb[0][:ns], k, metric=w["metric"], device=local_rank)
+        if world == 1 and not args.no_cpu_baseline:
+            from oracle import refharness as rh
+            cores = os.cpu_count() or 1
+            if rh.ref_slim_path() is not None:
+                ref_l, sec = rh.ref_bruteforce(base, qb[0][:256], k, metric=w["metric"], threads=0)
+                same = float(np.mean([set(a) == set(b) for a, b in zip(ref_l[:ns], lab_tc)]))
+                cpu = {"value": 256 / sec, "unit": "queries/s", "cores": cores, "kind": "reference",
+                       "sample": f"256 queries of the same workload through the reference's BruteforceSearch::searchKnn under "
+                                 f"omp ({sec:.1f}s; brute_force_strategy.h:24-36); k-sets identical to the engine's on "
+                                 f"{same*100:.0f}% of the first {ns}"}
+                recall = same
+    if rank == 0:
+        out = {
+            "metric": "exact kNN QPS (k=100 ground-truth path)", "value": value, "unit": "queries/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32 (tf32x3 tensor-core prefilter + exact fp32 re-scoring)",
+            "data": "synthetic",
+            "config": {"workload": w["desc"], "k": k, "queries_per_step_per_gpu": nq,
+                       "parallelism": f"replicated base x{world}, queries split, no collective",
+                       "identical_to_reference": recall,
+                       "l2": "base 512 MB > 126 MB L2; a different query batch every step"},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": args.steps,
+            "clocks": clocks.summary(),
         }
         print(json.dumps(out), flush=True)
     if distributed:
@@ -1138,8 +1260,13 @@ def main():
         w["shards"] = args.shards or w["shards"]
         w["n"] = rows * w["shards"]
         w["desc"] = w["desc"].replace("in 8 ", f"in {w['shards']} ")
+    if args.impl == "reference" and w.get("exact"):
+        raise SystemExit("bench.py: --impl reference is defined for the graph-search workloads; the exact-kNN workload "
+                         "times the reference's brute force inside its own line (cpu_baseline)")
     if args.impl == "reference":
         run_reference(args, w)
+    elif w.get("exact"):
+        run_gpu_bruteforce(args, w)
     elif "shards" in w:
         run_gpu_sharded(args, w)
     elif w.get("curve") and args.builder == "gpu":

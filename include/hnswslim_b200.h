@@ -187,7 +187,7 @@ int hs_set_overlap(hs_index *, int on);
  *   "traverse_flags"  HS_TRAVERSE_FLAGS   bit 0 L2 row prefetch, bit 1 speculative next-pop adjacency load,
  *                                         bit 2 stop after the descent (profiling), bit 3 evict_last adjacency
  *                                         prefetch, bits 4 / 5 make the compact visited table reset early /
- *                                         overflow (tests); default 9
+ *                                         overflow (tests), bit 6 forces the shared-memory candidate pool; default 9
  *   "slimq_flags"     HS_SLIMQ_FLAGS      hnsw_slimq kernel experiments, default 0
  *   "zero_copy"       HS_ZERO_COPY        1 (default): pinned + mapped host buffers are used in place
  * Further environment-only knobs, read where noted: HS_WPC (warps per CTA of the traversal launch, 1/2/4),

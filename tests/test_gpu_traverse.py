@@ -282,9 +282,20 @@ def test_compact_visited_table_reset_and_overflow():
 
 
 def test_large_ef_shared_memory_pool(small_corpus):
-    """ef > 128 runs the shared-memory pool variant; ef <= 64 / <= 128 the register pools."""
-    for ef in (33, 64, 65, 128, 129, 300):
+    """The generic kernel (query in shared memory): register pools up to ef = 512 (2..8, 12, 16 slots per lane), the
+    shared-memory pool above — and, forced by traverse_flags bit 6, at every ef: all bit-exact against the oracle."""
+    for ef in (33, 64, 65, 128, 129, 300, 384, 385, 512, 513, 700):
         check_against_oracle(small_corpus, 10, ef)
+    c = small_corpus
+    orc = rh.Oracle(c.graph, c.dim, c.metric)
+    ix = capi.Index(c.graph, c.dim, metric=c.metric)
+    ix.set_tuning("traverse_flags", 9 | 64)
+    for ef in (64, 200, 300, 512):
+        ix.set_ef(ef)
+        lab, dist, cnt = ix.search(c.queries, 10, counts=True)
+        olab, odist, ond, onh = orc.search(c.queries, 10, ef, order=rh.ORDER_GPU, team=8)
+        assert np.array_equal(lab, olab) and np.array_equal(dist.view(np.uint32), odist.view(np.uint32)), ef
+        assert np.array_equal(cnt[:, 0], ond) and np.array_equal(cnt[:, 1], onh), ef
 
 
 @pytest.mark.parametrize("thr", [1, 2, 7])

@@ -20,6 +20,7 @@ ap.add_argument("--iters", type=int, default=10)
 ap.add_argument("--check", type=int, default=0)
 ap.add_argument("--nq", type=int, default=0)
 ap.add_argument("--overlap", type=int, default=0)
+ap.add_argument("--tflags", type=str, default="", help="comma list of hs_set_tuning('traverse_flags') values to sweep")
 ap.add_argument("--modes", type=str, default="", help="comma list of hs_set_tuning('visited_table') values to sweep")
 ap.add_argument("--gpu-build", type=int, default=0, help="build the index on the GPU instead of loading a host-built .graph")
 a = ap.parse_args()
@@ -54,9 +55,12 @@ if a.check:
     gl, gd = capi.bruteforce_knn(base, qb[0][:1000], k, metric=w["metric"])
     gt = [set(r) for r in gl]
 modes = [int(x) for x in a.modes.split(",")] if a.modes else [None]
-for mode, ef in [(m, int(x)) for m in modes for x in a.efs.split(",")]:
+tflags = [int(x) for x in a.tflags.split(",")] if a.tflags else [None]
+for tf, mode, ef in [(t, m, int(x)) for t in tflags for m in modes for x in a.efs.split(",")]:
     if mode is not None:
         ix.set_tuning("visited_table", mode)
+    if tf is not None:
+        ix.set_tuning("traverse_flags", tf)
     ix.set_ef(ef)
     for i in range(3):
         ix.search_device(dq[i % 4].data_ptr(), nq, k, dl.data_ptr(), dd.data_ptr(), stream.cuda_stream)
@@ -84,6 +88,6 @@ for mode, ef in [(m, int(x)) for m in modes for x in a.efs.split(",")]:
         lab = dl[:1000].cpu().numpy().view(np.uint32)
         rec = float(np.mean([len(set(r) & g) / k for r, g in zip(lab, gt)]))
     print(f"overlap={a.overlap} lib={os.path.basename(os.path.dirname(os.environ.get('HS_LIB_PATH','default/x')))} "
-          f"flags={os.environ.get('HS_TRAVERSE_FLAGS','-')} hb={os.environ.get('HS_HASH_BITS','-')} vt={mode} ef={ef:4d} "
+          f"flags={tf if tf is not None else os.environ.get('HS_TRAVERSE_FLAGS','-')} hb={os.environ.get('HS_HASH_BITS','-')} vt={mode} ef={ef:4d} "
           f"{ms:8.3f} ms/batch {nq/ms*1e3:11.0f} QPS  n_dist/q={nd:7.1f} n_hops/q={nh:6.1f} "
           f"alg GB/s={bytes_q*nq/ms/1e6:7.1f} recall@{k}={rec:.4f}", flush=True)
