@@ -7,7 +7,7 @@
 // mutuallyConnectNewElement), then (2) HNSW-Slim's pruning into the CHAL layout
 // (slim.h:867-1108 convertFromHNSW) and (3) the file format of saveIndex (slim.h:717-751).
 // Written from the algorithm descriptions; the output is loadable by the reference's own
-// HierarchicalNSWSlim::loadIndex (tests/test_builder.py checks that with oracle/_ref).
+// HierarchicalNSWSlim::loadIndex (tests/test_host.py::test_builder_writes_the_reference_format checks that with oracle/_ref).
 #include <algorithm>
 #include <atomic>
 #include <cmath>

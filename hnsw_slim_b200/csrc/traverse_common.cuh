@@ -591,7 +591,9 @@ struct RegPool {
   // slimq.h:741-745: a scored neighbour enters unless the pool is full and it is worse than
   // the worst entry, or it was expanded already (== a flagged copy of its key is in the pool:
   // an expanded entry that left the pool is worse than the worst from then on)
-  __device__ __forceinline__ unsigned admit_q(bool valid, uint64_t key) {
+  // maybe: lanes whose candidate MAY have an expanded copy in the pool (a filter without false negatives, e.g. the
+  // kernel's Bloom word); the duplicate scan is skipped for the others
+  __device__ __forceinline__ unsigned admit_q(bool valid, uint64_t key, unsigned maybe = FULL) {
     unsigned entered = 0;
     unsigned todo = __ballot_sync(FULL, valid);
     if (todo == 0) return 0;
@@ -607,11 +609,13 @@ struct RegPool {
       const int src = __ffs(todo) - 1;
       todo &= todo - 1;
       const uint64_t ck = __shfl_sync(FULL, key, src);
-      const uint64_t fk = ck | (uint64_t)FLAG;
-      bool dup = false;
+      if ((maybe >> src) & 1u) {
+        const uint64_t fk = ck | (uint64_t)FLAG;
+        bool dup = false;
 #pragma unroll
-      for (int s = 0; s < SLOTS; ++s) dup |= (k[s] == fk);
-      if (__any_sync(FULL, dup)) continue;
+        for (int s = 0; s < SLOTS; ++s) dup |= (k[s] == fk);
+        if (__any_sync(FULL, dup)) continue;
+      }
       if (size < ef) {
         if ((int)(size & 31) == lane) put(size, ck);
         ++size;
@@ -825,7 +829,7 @@ struct RegPool32 {
   // slimq.h:741-745: a scored neighbour enters unless the pool is full and it is worse than the
   // worst entry, or it was expanded already (== an expanded copy of the node is in the pool: an
   // expanded entry that left the pool is worse than the worst from then on)
-  __device__ __forceinline__ unsigned admit_q(bool valid, uint64_t key) {
+  __device__ __forceinline__ unsigned admit_q(bool valid, uint64_t key, unsigned maybe = FULL) {
     const uint32_t d = (uint32_t)(key >> 32), cid = (uint32_t)key;
     unsigned entered = 0;
     unsigned todo = __ballot_sync(FULL, valid);
@@ -840,10 +844,12 @@ struct RegPool32 {
       const int src = __ffs(todo) - 1;
       todo &= todo - 1;
       const uint32_t cd = __shfl_sync(FULL, d, src), ci = __shfl_sync(FULL, cid, src);
-      bool dup = false;
+      if ((maybe >> src) & 1u) {
+        bool dup = false;
 #pragma unroll
-      for (int s = 0; s < SLOTS; ++s) dup |= (id[s] == ci && ku[s] == 0xffffffffu && kd[s] != 0u);
-      if (__any_sync(FULL, dup)) continue;
+        for (int s = 0; s < SLOTS; ++s) dup |= (id[s] == ci && ku[s] == 0xffffffffu && kd[s] != 0u);
+        if (__any_sync(FULL, dup)) continue;
+      }
       if (size < ef) {
         if ((int)(size & 31) == lane) put(size, cd, ci);
         ++size;
@@ -1193,7 +1199,7 @@ struct SmemPool {
     if (o < 0) return kInvalid;
     return (uint32_t)__shfl_sync(FULL, (uint32_t)min_un, o);
   }
-  __device__ __forceinline__ unsigned admit_q(bool valid, uint64_t key) {
+  __device__ __forceinline__ unsigned admit_q(bool valid, uint64_t key, unsigned maybe = FULL) {
     unsigned entered = 0;
     unsigned todo = __ballot_sync(FULL, valid);
     if (todo == 0) return 0;
@@ -1208,10 +1214,12 @@ struct SmemPool {
       const int src = __ffs(todo) - 1;
       todo &= todo - 1;
       const uint64_t ck = __shfl_sync(FULL, key, src);
-      const uint64_t fk = ck | (uint64_t)FLAG;
-      bool dup = false;
-      for (uint32_t e = lane; e < size; e += 32) dup |= (pool[e] == fk);
-      if (__any_sync(FULL, dup)) continue;
+      if ((maybe >> src) & 1u) {
+        const uint64_t fk = ck | (uint64_t)FLAG;
+        bool dup = false;
+        for (uint32_t e = lane; e < size; e += 32) dup |= (pool[e] == fk);
+        if (__any_sync(FULL, dup)) continue;
+      }
       if (size < ef) {
         if ((int)(size & 31) == lane) {
           pool[size] = ck;

@@ -53,9 +53,6 @@ namespace {
 #ifndef HS_TRAVERSE_MIN_CTAS_BIG
 #define HS_TRAVERSE_MIN_CTAS_BIG 6 // same for the pools of 5..8 register slots per lane (ef 129..256)
 #endif
-#ifndef HS_TRAVERSE_MIN_CTAS_HUGE
-#define HS_TRAVERSE_MIN_CTAS_HUGE 6 // same for the 12 / 16-slot pools of the generic kernel (ef 257..512)
-#endif
 #ifndef HS_TRAVERSE_U
 #define HS_TRAVERSE_U 1            // x4 rows whose loads are in flight per warp
 #endif
@@ -72,7 +69,7 @@ template <int SLOTS> struct PoolSel {
 template <> struct PoolSel<0> { using type = SmemPool; };
 
 template <int CPL, int METRIC, int SLOTS>
-__global__ void __launch_bounds__(128, SLOTS >= 12 ? HS_TRAVERSE_MIN_CTAS_HUGE : (SLOTS >= 5 ? HS_TRAVERSE_MIN_CTAS_BIG : HS_TRAVERSE_MIN_CTAS))
+__global__ void __launch_bounds__(128, SLOTS >= 5 ? HS_TRAVERSE_MIN_CTAS_BIG : HS_TRAVERSE_MIN_CTAS)
 traverse_kernel(const __grid_constant__ TraverseParams p) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int lane = threadIdx.x & 31;
@@ -460,8 +457,6 @@ int dispatch(int cpl, int metric, int slots, F &&f) {
 #define HS_CASES_S(C, M) HS_CASE(C, M, 0) HS_CASE(C, M, 2) HS_CASE(C, M, 4) HS_CASE(C, M, 5) HS_CASE(C, M, 6) HS_CASE(C, M, 7) HS_CASE(C, M, 8)
 #define HS_CASES_M(C) HS_CASES_S(C, HS_METRIC_L2) HS_CASES_S(C, HS_METRIC_IP)
   HS_CASES_M(0) HS_CASES_M(3) HS_CASES_M(4)
-  // the generic kernel keeps its query in shared memory: registers are free for pools of 12 / 16 slots (ef <= 512)
-  HS_CASE(0, HS_METRIC_L2, 12) HS_CASE(0, HS_METRIC_L2, 16) HS_CASE(0, HS_METRIC_IP, 12) HS_CASE(0, HS_METRIC_IP, 16)
 #endif
 #undef HS_CASES_M
 #undef HS_CASES_S
@@ -503,16 +498,19 @@ int traverse_launch_c(int cpl, int metric, int slots, const TraverseParams &p, c
 namespace {
 // kernel variants: CPL 3 (dim 96: DEEP/MSTuring), 4 (dim 128: SIFT) keep the query in
 // registers, everything else runs the generic shared-memory-query path (CPL = 0);
-// pool in registers for ef <= 64 / 128 / 160 / 192 / 224 / 256 (2 / 4 / 5 / 6 / 7 / 8 slots per lane) and, in the generic
-// kernel, ef <= 384 / 512 (12 / 16 slots); in shared memory above.
+// pool in registers for ef <= 64 / 128 / 160 / 192 / 224 / 256 (2 / 4 / 5 / 6 / 7 / 8 slots per lane), in shared memory above.
 inline int cpl_variant(uint32_t row_chunks) {
   const uint32_t cpl = row_chunks / kTeam;
   return (cpl == 3 || cpl == 4) ? (int)cpl : 0;
 }
+// Register pools of 12 / 16 slots for ef 257..512 in the generic kernel (its query sits in shared memory) were
+// measured and lose to the shared-memory pool there (GIST-shaped 200k x 960: ef=400 193 k vs 236 k QPS even with a
+// 96-register budget, profiles/r02_probe_bigpool.txt): a large-dim hop is row traffic, and the pool's registers
+// are taken from the loads in flight.
 inline int slots_variant(uint32_t ef, int cplv, uint32_t flags = 0) {
+  (void)cplv;
   if (flags & 64u) return 0;         // traverse_flags bit 6: the shared-memory pool whatever ef is (A/B runs, tests)
-  if (ef > 256) return cplv == 0 ? (ef <= 384 ? 12 : (ef <= 512 ? 16 : 0)) : 0;
-  return ef <= 64 ? 2 : (ef <= 128 ? 4 : (ef <= 160 ? 5 : (ef <= 192 ? 6 : (ef <= 224 ? 7 : 8))));
+  return ef <= 64 ? 2 : (ef <= 128 ? 4 : (ef <= 160 ? 5 : (ef <= 192 ? 6 : (ef <= 224 ? 7 : (ef <= 256 ? 8 : 0)))));
 }
 inline uint32_t align_up(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
 constexpr uint32_t kSmemPerSm = 227u * 1024u;

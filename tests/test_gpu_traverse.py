@@ -282,7 +282,7 @@ def test_compact_visited_table_reset_and_overflow():
 
 
 def test_large_ef_shared_memory_pool(small_corpus):
-    """The generic kernel (query in shared memory): register pools up to ef = 512 (2..8, 12, 16 slots per lane), the
+    """The generic kernel (query in shared memory): register pools up to ef = 256 (2..8 slots per lane), the
     shared-memory pool above — and, forced by traverse_flags bit 6, at every ef: all bit-exact against the oracle."""
     for ef in (33, 64, 65, 128, 129, 300, 384, 385, 512, 513, 700):
         check_against_oracle(small_corpus, 10, ef)
