@@ -515,13 +515,14 @@ int hs::search_device(hs_index *ix, const float *d_queries, size_t nq, size_t k,
   p.flags = ix->traverse_flags;
   TraverseLaunch l{};
   int rc = HS_OK;
-  if (ix->plan_ok && ix->plan_ef == p.ef && ix->plan_nq == nq) {   // same shape as the last call: reuse its plan
+  if (ix->plan_ok && ix->plan_ef == p.ef) {   // same index, ef and knobs as the last call: reuse its plan
     l = ix->plan_l;
     p.hash_bits = ix->plan_p.hash_bits;
     p.smem_per_warp = ix->plan_p.smem_per_warp;
     p.off_hash = ix->plan_p.off_hash;
     p.off_stage = ix->plan_p.off_stage;
     p.off_query = ix->plan_p.off_query;
+    if (ix->plan_nq != nq) resize_traverse_launch(p, (int)nq, &l);      // only the grid depends on the batch size
   } else {
     rc = plan_traverse(p, ix->info.metric, ix->hash_bits_override, ix->ghash_mode, ix->sm_count, (int)nq, &l);
     if (rc != HS_OK) return rc;

@@ -67,7 +67,7 @@ struct hs_index {
   hs::TraverseQLaunch planq_l{};
   hs::TraverseQParams planq_p{};
   // completion events of the batches handed to hs_search_batch_submit and not yet waited for (FIFO)
-  static constexpr int kEventRing = 16;
+  static constexpr int kEventRing = 64;
   cudaEvent_t ev_ring[kEventRing] = {};
   unsigned long long ev_head = 0, ev_tail = 0;      // [head, tail) are outstanding
   bool zero_copy = true;                   // hs_search_batch reads/writes pinned+mapped host buffers in place

@@ -6,7 +6,7 @@
 // (patchFromStream, slim.h:2206-2388).  A GPU answers a BATCH per launch, so the handler's one call becomes:
 // copy the query into the batch that is currently filling, sleep, wake up with the answer.
 //
-// Batches live in a small ring of page-locked, mapped host buffers (hs_search_batch_submit reads the queries
+// Batches live in a ring of 32 page-locked, mapped host buffers (hs_search_batch_submit reads the queries
 // and writes the result rows in place, no staging copies).  Two threads drive the ring:
 //   dispatcher  hands the filling batch to hs_search_batch_submit as soon as it holds a query (or, with
 //               max_wait_us > 0, once it is full / its first query has waited that long) and moves the fill
@@ -59,7 +59,11 @@ struct Batch {
   std::condition_variable done;        // the callers of THIS batch sleep here: a completion wakes them, not everybody
 };
 
-constexpr int kDepth = 8;              // ring buffers; at most kDepth batches between "filling" and "answered"
+// Ring buffers: at most kDepth batches between "filling" and "answered" (below hs_index::kEventRing).  A closed loop
+// of T clients keeps T queries in flight; the more batches they may spread over, the closer a request's latency is
+// to the ~0.3 ms of its own traversal (small launches run side by side: the GPU holds 3552 query warps at once).
+constexpr int kDepth = 32;
+static_assert(kDepth < hs_index::kEventRing, "the service must not fill the handle's event ring");
 
 }  // namespace
 

@@ -601,16 +601,25 @@ int plan_traverse(TraverseParams &p, int metric, int hash_bits_override, int gha
     set_error("traverse_kernel does not fit on an SM (cudaOccupancyMaxActiveBlocksPerMultiprocessor)");
     return HS_ERR_CUDA;
   }
-  const int resident = sm_count * per_sm;
-  const int need = (nq + wpc - 1) / wpc;
-  out->grid = need < resident ? (need > 0 ? need : 1) : resident;
+  out->resident = sm_count * per_sm;
   out->ghash = ghash;
   out->cvtab = cvtab;
-  out->ghash_bytes = ghash ? ((size_t)out->grid * wpc * 4) << bits : 0;
+  resize_traverse_launch(p, nq, out);
+  return HS_OK;
+}
+
+// The only part of a launch plan that depends on the batch size: the grid (and what follows from it).  Everything
+// else — kernel variant, shared-memory layout, CTA shape, occupancy — is a function of (index, ef, knobs), which is
+// what makes a cached plan reusable for batches of any size (a server's batches differ in size every time, and the
+// occupancy queries of a full plan cost tens of microseconds).
+void resize_traverse_launch(const TraverseParams &p, int nq, TraverseLaunch *l) {
+  const int wpc = l->warps_per_cta;
+  const int need = (nq + wpc - 1) / wpc;
+  l->grid = need < l->resident ? (need > 0 ? need : 1) : l->resident;
+  l->ghash_bytes = l->ghash ? ((size_t)l->grid * wpc * 4) << p.hash_bits : 0;
   // two overlapping launches alternate between two scratch halves (hs_api.cu); a third launch can
   // only become resident next to them when a grid does not fill the GPU — no overlap then
-  out->may_overlap = !ghash || out->grid == resident;
-  return HS_OK;
+  l->may_overlap = !l->ghash || l->grid == l->resident;
 }
 
 int launch_traverse(const TraverseParams &p, int metric, const TraverseLaunch &l, cudaStream_t stream) {

@@ -41,6 +41,7 @@ struct TraverseParams {
 
 struct TraverseLaunch {
   int warps_per_cta;
+  int resident;          // CTAs the GPU holds at once with this shape (sm_count x CTAs per SM): the grid's upper bound
   int grid;
   size_t smem_bytes;
   bool cvtab;            // compact 16-bit visited table in shared memory (traverse_fp32_c.cu)
@@ -56,6 +57,8 @@ struct TraverseLaunch {
 // 3 = as -1 but never compact.
 int plan_traverse(TraverseParams &p, int metric, int hash_bits_override, int ghash_mode, int sm_count, int nq,
                   TraverseLaunch *out);
+// Adapts a plan made for one batch size to another (p must carry the plan's hash_bits).
+void resize_traverse_launch(const TraverseParams &p, int nq, TraverseLaunch *l);
 int launch_traverse(const TraverseParams &p, int metric, const TraverseLaunch &l, cudaStream_t stream);
 
 }  // namespace hs
