@@ -64,6 +64,12 @@ struct Batch {
 // to the ~0.3 ms of its own traversal (small launches run side by side: the GPU holds 3552 query warps at once).
 constexpr int kDepth = 32;
 static_assert(kDepth < hs_index::kEventRing, "the service must not fill the handle's event ring");
+// ... but a launch costs the host tens of microseconds (submit, event, completion hand-over), so a batch of one or
+// two queries is only worth launching while few batches are in flight: beyond kEagerDepth of them a batch waits
+// until it holds kEagerBatch queries (or a batch in flight completes).  Few clients thus get ring-of-8 behaviour
+// (their batches grow while the ring is busy), many clients the deep ring.
+constexpr int kEagerDepth = 8;
+constexpr size_t kEagerBatch = 8;
 
 }  // namespace
 
@@ -116,6 +122,7 @@ struct hs_service {
     st.max_batch = std::max<uint64_t>(st.max_batch, done.count);
     st.busy_seconds += seconds;
     done.done.notify_all();
+    cv_work.notify_one();               // a batch left the ring: the dispatcher may launch a small one again
   }
 };
 
@@ -132,6 +139,10 @@ void hs_service::dispatch_loop() {
       const auto deadline = cur.t0 + std::chrono::microseconds(max_wait_us);
       cv_work.wait_until(lk, deadline, [&] { return closing || paused || cur.count >= max_batch; });
     }
+    // small batches only while the ring is nearly empty (see kEagerDepth); completions and arrivals wake us
+    cv_work.wait(lk, [&] {
+      return closing || paused || (int)inflight.size() < kEagerDepth || cur.count >= std::min(kEagerBatch, max_batch);
+    });
     const int me = fill;
     cur.state = State::Running;
     cur.ticket++;
@@ -284,7 +295,7 @@ int hs_service_query(hs_service *s, const float *vec, size_t k, uint32_t *labels
   }
   std::memcpy(bt->q + slot * s->dim, vec, s->dim * sizeof(float));
   const unsigned long long want = bt->ticket + 1;
-  if (slot == 0 || bt->count == s->max_batch) s->cv_work.notify_one();
+  if (slot == 0 || bt->count == s->max_batch || bt->count == kEagerBatch) s->cv_work.notify_one();
   bt->done.wait(lk, [&] { return bt->ticket >= want && bt->state == State::Draining; });
   const int rc = bt->rc;
   if (rc == HS_OK) {

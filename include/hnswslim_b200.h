@@ -126,7 +126,8 @@ int hs_patch_apply(hs_index *, const void *patch, size_t patch_bytes, unsigned f
  * dispatcher thread submits a batch (hs_search_batch_submit, batch overlap on: small batches run side by side on
  * the GPU) as soon as it holds a query — or, if max_wait_us > 0, once it is full or its first query has waited that
  * long — and a completion thread wakes the callers batch by batch.  Up to 32 batches are between "collecting" and
- * "answered"; when all are, arrivals share the next buffer that frees up, so the batch size follows the load: a
+ * "answered" (batches of fewer than 8 queries only while fewer than 8 are); when all are, arrivals share the next
+ * buffer that frees up, so the batch size follows the load: a
  * lone query is answered at once, a busy server fills its batches (max_batch queries at most).  Batches live in
  * page-locked mapped memory and are searched in place.  A batch holds requests of ONE k (ef = max(ef_, k),
  * slim.h:2080); a request with another k goes to the next batch.  labels_out: k labels, nearest first; dists_out
