@@ -1554,9 +1554,10 @@ int hs_debug_patch(hs_host_graph *h, const void *patch, size_t patch_bytes, unsi
   return guarded("hs_debug_patch", [&]() -> int {
     HostGraph &g = h->g;
     PatchSet ps;
-    // the host image grows as needed: no capacity limit
+    // the host image grows as needed, within reason: a corrupt element count must not turn into a 100 GB resize
+    const uint64_t cap = std::min<uint64_t>((1ull << 31) - 1, g.n + (1ull << 22));
     int rc = parse_patch(static_cast<const uint8_t *>(patch), patch_bytes, g.dim, (flags & HS_PATCH_INLINE_ROWS) != 0, g.n,
-                         (1ull << 31) - 1, &ps);
+                         cap, &ps);
     if (rc != HS_OK) return rc;
     PatchRows pr;
     pr.rows = rows;

@@ -349,3 +349,46 @@ def test_gpu_patch_matches_oracle_and_reference_client(tmp_path, metric, dim, M)
     lab, _ = ix.search(q, K)
     rec_ours = float(np.mean([len(set(x) & set(y)) / K for x, y in zip(lab, gt)]))
     assert abs(rec_ours - rec_srv) <= 0.01, (rec_ours, rec_srv)
+
+
+def test_patch_parser_survives_random_corruption():
+    """Memory safety of the stream parser: 400 randomly corrupted copies of a valid stream (byte flips, truncations,
+    duplicated slices) are each either rejected with a status code or applied to a consistent image — ids in range,
+    rows padded, counts matching — and never crash the process."""
+    z, graph, streams = _golden()
+    dim = int(z["dim"])
+    rng = np.random.default_rng(12345)
+    good = np.frombuffer(streams[0], np.uint8)
+    applied = rejected = 0
+    for trial in range(400):
+        b = good.copy()
+        kind = trial % 4
+        if kind == 0:                                            # a few byte flips anywhere
+            at = rng.integers(0, b.size, size=rng.integers(1, 6))
+            b[at] = rng.integers(0, 256, size=at.size, dtype=np.uint8)
+        elif kind == 1:                                          # flips inside the header and the first records
+            at = rng.integers(0, 200, size=rng.integers(1, 4))
+            b[at] = rng.integers(0, 256, size=at.size, dtype=np.uint8)
+        elif kind == 2:                                          # truncation
+            b = b[: rng.integers(0, b.size)]
+        else:                                                    # a slice duplicated in place
+            lo = int(rng.integers(24, b.size - 64))
+            ln = int(rng.integers(1, 64))
+            b = np.concatenate([b[:lo], b[lo:lo + ln], b[lo:]])
+        hg = capi.HostGraph(graph, dim)
+        try:
+            info = hg.patch(b.tobytes(), rows=z["base"])
+        except capi.HsError as e:
+            assert e.code in (-1, -2, -4, -5), e
+            assert hg.info()["n"] == int(z["n0"])
+            rejected += 1
+            continue
+        applied += 1
+        n = hg.info()["n"]
+        assert n == info["n_after"] and n >= int(z["n0"])      # a corrupted element count is a (legal) growth of the host image
+        for i in rng.integers(0, n, size=40):
+            lvl, _, _ = hg.node(int(i))
+            for l in range(lvl + 1):
+                r = hg.row(int(i), l)
+                assert (r < n).all()
+    assert rejected > 200 and applied + rejected == 400
