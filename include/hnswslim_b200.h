@@ -104,7 +104,9 @@ int hs_load_memory(const void *graph_bytes, size_t graph_size, int kind, int met
  *   rows, row_labels               the row i with row_labels[i] == label   patchFromStream(in, new_data), slim.h:2343-2388
  * Synchronous.  The call waits for the batches submitted through this handle (hs_search_batch_submit); launches
  * the caller made on its own streams (hs_search_batch_device) must have completed — patchFromStream is not
- * synchronised with searchKnn in the reference either.  On error the index is unchanged.  hnsw_slim only. */
+ * synchronised with searchKnn in the reference either.  A stream that fails validation leaves the index
+ * unchanged; a CUDA failure in the middle of an update (HS_ERR_CUDA / HS_ERR_NOMEM) does not — free the handle
+ * then.  hnsw_slim only. */
 #define HS_PATCH_INLINE_ROWS 1u
 typedef struct {
   uint64_t n_before, n_after;        /* cur_element_count_ before / after                         */
@@ -137,7 +139,8 @@ int hs_patch_apply(hs_index *, const void *patch, size_t patch_bytes, unsigned f
  *   patch    hs_patch_apply between two batches: requests that have joined a batch are answered on the old
  *            index, later ones wait and see the patched one (the reference's patchFromStream is not synchronised
  *            with its searches at all)
- * The index is borrowed: free the service first. */
+ * The index is borrowed: free the service first, and only when no hs_service_query call is in progress (requests
+ * that have joined a batch are still answered; later ones fail). */
 typedef struct hs_service hs_service;
 typedef struct {
   uint64_t batches, queries;       /* launches, and the queries they carried */
