@@ -206,3 +206,33 @@ def test_threshold_level_against_live_reference(thr):
         else:
             assert same.mean() >= 0.995, (thr, ef, same.mean())
             assert (nd[same] == rcnt[same]).all()
+
+
+def test_tie_events_are_reported():
+    """hso_search_ties = hso_search + the per-query count of exact fp32 ties at the ef boundary (a result trimmed
+    while the new worst carries the bit-identical distance).  On the golden corpus (distinct rows) there are none;
+    on a corpus in which every row exists three times they are the rule; ids, distances and counters are those of
+    hso_search either way."""
+    import tempfile
+    z = np.load(os.path.join(GOLDEN, "slim_l2_2k.npz"))
+    q = z["queries"]
+    orc = rh.Oracle(os.path.join(GOLDEN, "slim_l2_2k.graph"), 16)
+    for ef in (10, 40, 100):
+        a = orc.search(q, 10, ef, order=rh.ORDER_GPU, team=8)
+        b = orc.search_ties(q, 10, ef, order=rh.ORDER_GPU, team=8)
+        assert all(np.array_equal(x, y) for x, y in zip(a, b[:4]))
+        assert int(b[4].sum()) == 0
+    if not rh.ref_slim_path():
+        pytest.skip("the all-ties corpus is built with the reference builder (oracle/_ref)")
+    rng = np.random.default_rng(3)
+    rows = rng.standard_normal((700, 16)).astype(np.float32)
+    base = np.repeat(rows, 3, axis=0)                            # every vector three times, bit for bit
+    queries = rng.standard_normal((60, 16)).astype(np.float32)
+    with tempfile.TemporaryDirectory() as td:
+        g = os.path.join(td, "ties.graph")
+        rh.ref_slim_build(base, g, M=8, ef_construction=60, threads=1)
+        orc = rh.Oracle(g, 16)
+        a = orc.search(queries, 10, 12, order=rh.ORDER_GPU, team=8)
+        b = orc.search_ties(queries, 10, 12, order=rh.ORDER_GPU, team=8)
+        assert all(np.array_equal(x, y) for x, y in zip(a, b[:4]))
+        assert (b[4] > 0).mean() > 0.5, b[4]
