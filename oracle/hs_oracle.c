@@ -477,6 +477,14 @@ static void heap_pop(pairfu *h, size_t n, int maxheap) {
 }
 
 /* ----------------------------------------------------------------- search -- */
+/* optional trace of the expanded nodes of ONE query (hso_debug_trace) */
+static _Thread_local uint32_t *g_trace = NULL;
+static _Thread_local size_t g_trace_cap = 0, g_trace_n = 0;
+static inline void trace_node(uint32_t id) {
+  if (g_trace && g_trace_n < g_trace_cap) g_trace[g_trace_n] = id;
+  if (g_trace) g_trace_n++;
+}
+
 typedef struct {
   pairfu *top;     /* max-heap, ef+1 */
   pairfu *cand;    /* min-heap, grows */
@@ -523,6 +531,7 @@ static void beam_layer(const hso_index *ix, const float *q, int layer, scratch *
     int cnt = hso_node_neighbors(ix, cur.id, layer, &ids);
     if (cnt == 0) continue;
     if (n_hops) (*n_hops)++;
+    trace_node(cur.id);
     for (int j = 0; j < cnt; j++) {
       uint32_t c = ids[j];
       if (s->visited[c] == s->tag) continue;
@@ -658,6 +667,255 @@ int hso_search_ties(const hso_index *ix, const float *queries, size_t nq, size_t
     free(s.visited);
   }
   return 0;
+}
+
+/* ------------------------------------------------- the ENGINE's algorithm -- */
+/* hso_search_pool: a CPU restatement, not of the reference, but of what the CUDA traversal kernel does
+ * (hnsw_slim_b200/csrc/traverse_fp32.cu + RegPool32 / RegPool32C in traverse_common.cuh) — one pool of at most ef
+ * (distance, id) entries spread over 32 columns ("lanes") of `slots` entries, an "expanded" mark per entry, the
+ * seven-entry ghost list for exact ties — with the kernel's placement and tie rules spelled out step by step:
+ *   append      while the pool has room, entry number e goes to lane e % 32, slot e / 32
+ *   worst       the largest distance word; among equal ones the LOWEST lane, then the lowest slot, is displaced
+ *   pop         the smallest distance word among unexpanded entries; lowest lane, then lowest slot
+ *   ghost       when the displaced entry is unexpanded and ANOTHER LANE's column maximum carries the same
+ *               distance word it is remembered, and expanded once the pool has no unexpanded entry left, if its
+ *               distance still equals the pool's worst one and the pool is full
+ * It exists to measure, on the CPU and at any scale, where a single-pool engine parts from the reference's two
+ * heaps (slim.h:321-457): everywhere except at exact fp32 ties at the ef boundary the two must agree to the bit,
+ * ids, distances and per-query counters (tests/test_oracle.py), and what remains at the ties — the one blind spot
+ * of the ghost rule, a tie inside ONE column — can be counted.  Register pools only (ef <= 256), threshold_level 0,
+ * no delete marks; the visited set is exact (the kernel's tables are, short of resets that only add evaluations). */
+typedef struct {
+  uint32_t kd, id;        /* ordered-uint distance (0 = empty slot), node id */
+  uint8_t expanded;
+} pslot;
+
+static inline uint32_t f2ord_u(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+static inline float ord2f_u(uint32_t u) {
+  uint32_t v = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;
+  float f;
+  memcpy(&f, &v, 4);
+  return f;
+}
+static int pool_slots_for(size_t ef) {   /* slots_variant, traverse_fp32.cu */
+  return ef <= 64 ? 2 : (ef <= 128 ? 4 : (ef <= 160 ? 5 : (ef <= 192 ? 6 : (ef <= 224 ? 7 : (ef <= 256 ? 8 : 0)))));
+}
+
+static void search_one_pool(const hso_index *ix, const float *q, size_t k, size_t ef_in, uint16_t *visited,
+                            uint16_t tag, pslot *pool, int team, uint32_t *out_labels, float *out_dists,
+                            uint32_t *n_dist, uint32_t *n_hops, uint32_t *n_ghosts) {
+  const int order = HSO_ORDER_GPU;
+  uint32_t nd = 0, nh = 0, ng = 0, nblind = 0;
+  uint32_t cur = ix->enterpoint;
+  float curdist = hso_dist(q, hso_node_vector(ix, cur), ix->dim, ix->metric, order, team);
+  nd++;
+  for (int level = ix->maxlevel; level > ix->threshold_level; level--) {     /* the descent is the reference's */
+    int changed = 1;
+    while (changed) {
+      changed = 0;
+      const uint32_t *ids;
+      int cnt = hso_node_neighbors(ix, cur, level, &ids);
+      if (cnt == 0) continue;
+      nh++;
+      for (int i = 0; i < cnt; i++) {
+        float d = hso_dist(q, hso_node_vector(ix, ids[i]), ix->dim, ix->metric, order, team);
+        nd++;
+        if (d < curdist) {
+          curdist = d;
+          cur = ids[i];
+          changed = 1;
+        }
+      }
+    }
+  }
+  const size_t ef = ef_in > k ? ef_in : k;
+  const int slots = pool_slots_for(ef);
+  const int cap = slots * 32;
+  memset(pool, 0, sizeof(pslot) * (size_t)cap);
+#define PS(lane, slot) pool[(slot) * 32 + (lane)]
+  size_t size = 1;
+  PS(0, 0).kd = f2ord_u(curdist);
+  PS(0, 0).id = cur;
+  visited[cur] = tag;
+  uint32_t gd[7], gi[7], gcnt = 0;          /* the ghost list (kGhostCap = 7) */
+
+  for (;;) {
+    /* pop_closest_unexpanded */
+    uint32_t g = 0xffffffffu;
+    for (int e = 0; e < cap; e++)
+      if (pool[e].kd && !pool[e].expanded && pool[e].kd < g) g = pool[e].kd;
+    uint32_t node = 0xffffffffu;
+    if (g != 0xffffffffu) {
+      for (int lane = 0; lane < 32 && node == 0xffffffffu; lane++)
+        for (int sl = 0; sl < slots; sl++)
+          if (PS(lane, sl).kd == g && !PS(lane, sl).expanded) {
+            PS(lane, sl).expanded = 1;
+            node = PS(lane, sl).id;
+            break;
+          }
+    } else if (gcnt) {
+      /* take_ghost */
+      uint32_t worst = 0;
+      for (int e = 0; e < cap; e++)
+        if (pool[e].kd > worst) worst = pool[e].kd;
+      int o = -1;
+      for (uint32_t j = 0; j < gcnt; j++)
+        if (size >= ef && gd[j] == worst) {
+          o = (int)j;
+          break;
+        }
+      if (o < 0) {
+        gcnt = 0;
+      } else {
+        gd[o] = 0;             /* taken */
+        node = gi[o];
+        ng++;
+      }
+    }
+    if (node == 0xffffffffu) break;
+
+    const uint32_t *ids;
+    int cnt = hso_node_neighbors(ix, node, 0, &ids);
+    if (cnt > 0) nh++;
+    if (cnt > 0) trace_node(node);
+    for (int seg = 0; seg < cnt; seg += 32) {      /* the kernel walks the row 32 ids at a time */
+      uint32_t cid[32];
+      float cdist[32];
+      int count = 0;
+      for (int j = seg; j < cnt && j < seg + 32; j++) {
+        uint32_t c = ids[j];
+        if (visited[c] == tag) continue;
+        visited[c] = tag;
+        cid[count++] = c;
+      }
+      for (int j = 0; j < count; j++)
+        cdist[j] = hso_dist(q, hso_node_vector(ix, cid[j]), ix->dim, ix->metric, order, team);
+      nd += (uint32_t)count;
+      /* admit, candidate by candidate in list order */
+      int j = 0;
+      while (j < count && size < ef) {              /* room left: appended unconditionally */
+        const size_t e = size++;
+        PS(e & 31, e >> 5).kd = f2ord_u(cdist[j]);
+        PS(e & 31, e >> 5).id = cid[j];
+        PS(e & 31, e >> 5).expanded = 0;
+        j++;
+      }
+      for (; j < count; j++) {
+        uint32_t cm[32], worst = 0;
+        for (int lane = 0; lane < 32; lane++) {
+          cm[lane] = 0;
+          for (int sl = 0; sl < slots; sl++)
+            if (PS(lane, sl).kd > cm[lane]) cm[lane] = PS(lane, sl).kd;
+          if (cm[lane] > worst) worst = cm[lane];
+        }
+        const uint32_t cd = f2ord_u(cdist[j]);
+        if (!(cd < worst)) continue;                /* the reference's strict lowerBound > dist */
+        int owner = -1, lanes_at_worst = 0;
+        for (int lane = 0; lane < 32; lane++)
+          if (cm[lane] == worst) {
+            if (owner < 0) owner = lane;
+            lanes_at_worst++;
+          }
+        int sl = 0;
+        while (PS(owner, sl).kd != worst) sl++;
+        if (lanes_at_worst > 1 && !PS(owner, sl).expanded && gcnt < 7) {     /* ghost_append */
+          gd[gcnt] = worst;
+          gi[gcnt] = PS(owner, sl).id;
+          gcnt++;
+        }
+        if (lanes_at_worst == 1 && !PS(owner, sl).expanded) {     /* the blind spot: the tie partner sits in the same column */
+          for (int s2 = sl + 1; s2 < slots; s2++)
+            if (PS(owner, s2).kd == worst) {
+              nblind++;
+              break;
+            }
+        }
+        PS(owner, sl).kd = cd;
+        PS(owner, sl).id = cid[j];
+        PS(owner, sl).expanded = 0;
+      }
+    }
+  }
+#undef PS
+  /* results: the k smallest (distance word, id) keys */
+  size_t used = 0;
+  pairfu *res = (pairfu *)malloc(sizeof(pairfu) * (size_t)cap);
+  for (int e = 0; e < cap; e++)
+    if (pool[e].kd) {
+      res[used].d = ord2f_u(pool[e].kd);
+      res[used].id = pool[e].id;
+      used++;
+    }
+  qsort(res, used, sizeof(pairfu), cmp_pair);
+  for (size_t i = 0; i < k; i++) {
+    if (i < used) {
+      out_labels[i] = (uint32_t)hso_node_label(ix, res[i].id);
+      if (out_dists) out_dists[i] = res[i].d;
+    } else {
+      out_labels[i] = 0xFFFFFFFFu;
+      if (out_dists) out_dists[i] = INFINITY;
+    }
+  }
+  free(res);
+  if (n_dist) *n_dist = nd;
+  if (n_hops) *n_hops = nh;
+  if (n_ghosts) *n_ghosts = ng | (nblind << 16);
+}
+
+int hso_search_pool(const hso_index *ix, const float *queries, size_t nq, size_t k, size_t ef, int team, int threads,
+                    uint32_t *out_labels, float *out_dists, uint32_t *n_dist, uint32_t *n_hops, uint32_t *n_ghosts) {
+  if (ix->n == 0) return 0;
+  const size_t efx = ef > k ? ef : k;
+  if (pool_slots_for(efx) == 0 || ix->threshold_level != 0 || ix->has_deleted) {
+    snprintf(g_err, sizeof g_err, "hso_search_pool: register pools only (ef <= 256), threshold_level 0, no deletes");
+    return -1;
+  }
+#ifdef _OPENMP
+  if (threads <= 0) threads = omp_get_num_procs();
+#else
+  threads = 1;
+#endif
+#pragma omp parallel num_threads(threads)
+  {
+    uint16_t *visited = (uint16_t *)calloc(ix->n, sizeof(uint16_t));
+    pslot *pool = (pslot *)malloc(sizeof(pslot) * 8 * 32);
+    uint16_t tag = 0;
+#pragma omp for schedule(dynamic)
+    for (size_t i = 0; i < nq; i++) {
+      tag++;
+      if (tag == 0) {
+        memset(visited, 0, sizeof(uint16_t) * ix->n);
+        tag++;
+      }
+      search_one_pool(ix, queries + i * ix->dim, k, ef, visited, tag, pool, team, out_labels + i * k,
+                      out_dists ? out_dists + i * k : NULL, n_dist ? n_dist + i : NULL, n_hops ? n_hops + i : NULL,
+                      n_ghosts ? n_ghosts + i : NULL);
+    }
+    free(visited);
+    free(pool);
+  }
+  return 0;
+}
+
+/* The base-layer expansion order of one query under hso_search (which = 0) or hso_search_pool (which = 1): node
+ * ids in the order they were expanded; returns how many there were (may exceed cap). */
+size_t hso_debug_trace(const hso_index *ix, const float *query, size_t k, size_t ef, int which, int team,
+                       uint32_t *out_ids, size_t cap) {
+  uint32_t lab[4096];
+  if (k > 4096) return 0;
+  g_trace = out_ids;
+  g_trace_cap = cap;
+  g_trace_n = 0;
+  if (which == 0)
+    hso_search_ties(ix, query, 1, k, ef, HSO_ORDER_GPU, team, 1, lab, NULL, NULL, NULL, NULL);
+  else
+    hso_search_pool(ix, query, 1, k, ef, team, 1, lab, NULL, NULL, NULL, NULL);
+  g_trace = NULL;
+  return g_trace_n;
 }
 
 /* ------------------------------------------------------------ brute force -- */

@@ -80,6 +80,20 @@ int hso_search_ties(const hso_index *, const float *queries, size_t nq, size_t k
                     int order, int team, int threads, uint32_t *out_labels, float *out_dists,
                     uint32_t *n_dist, uint32_t *n_hops, uint32_t *n_ties);
 
+/* The ENGINE's traversal restated on the CPU (not the reference's): one pool of <= ef entries in 32 columns with
+ * the CUDA kernel's placement, tie and ghost rules (hnsw_slim_b200/csrc/traverse_fp32.cu, traverse_common.cuh
+ * RegPool32 / ghost_append), distances in the kernel's association (HSO_ORDER_GPU).  Same outputs as hso_search
+ * plus n_ghosts (low 16 bits: ghost entries expanded per query; high 16 bits: unexpanded entries displaced while
+ * their tie partner sat in the SAME column, which the ghost rule does not see).  It must equal hso_search to the bit on every query without an
+ * exact tie at the ef boundary (hso_search_ties); what differs at the ties is the measured reach of the engine's
+ * documented blind spot.  ef <= 256, threshold_level 0, no delete marks; returns -1 otherwise. */
+int hso_search_pool(const hso_index *, const float *queries, size_t nq, size_t k, size_t ef, int team, int threads,
+                    uint32_t *out_labels, float *out_dists, uint32_t *n_dist, uint32_t *n_hops, uint32_t *n_ghosts);
+
+/* diagnostics: the base-layer expansion order of ONE query under hso_search (which = 0) / hso_search_pool (1) */
+size_t hso_debug_trace(const hso_index *, const float *query, size_t k, size_t ef, int which, int team,
+                       uint32_t *out_ids, size_t cap);
+
 /* bruteforce.h:106-135 + brute_force_strategy.h:24-36: k labels per query,
  * FARTHEST first (the order the strategy writes to *_groundtruth.ivecs);
  * labels[i] of base row i is i. */

@@ -687,6 +687,9 @@ def oracle_lib():
         L.hso_search_ties.restype = C.c_int
         L.hso_search_ties.argtypes = [C.c_void_p, _f32p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_int, C.c_int, C.c_int,
                                       _u32p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.hso_search_pool.restype = C.c_int
+        L.hso_search_pool.argtypes = [C.c_void_p, _f32p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_int, C.c_int,
+                                      _u32p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.hso_bruteforce.restype = C.c_int
         L.hso_bruteforce.argtypes = [_f32p, C.c_size_t, C.c_size_t, C.c_int, C.c_int, C.c_int, _f32p, C.c_size_t,
                                      C.c_size_t, C.c_int, _u32p, C.c_void_p]
@@ -766,6 +769,19 @@ class Oracle:
         self.L.hso_search(self.h, q, nq, k, ef, order, team, threads, lab, dist.ctypes.data, nd.ctypes.data,
                           nh.ctypes.data)
         return lab, dist, nd, nh
+
+    def search_pool(self, q, k: int, ef: int, team: int = 8, threads: int = 0):
+        """hso_search_pool: the ENGINE's single-pool algorithm restated on the CPU -> labels, dists, n_dist, n_hops,
+        n_ghosts (low 16 bits: ghosts expanded; high 16 bits: same-column tie displacements; oracle/hs_oracle.h)."""
+        q = np.ascontiguousarray(q, dtype=np.float32)
+        nq = q.shape[0]
+        lab = np.zeros((nq, k), np.uint32)
+        dist = np.zeros((nq, k), np.float32)
+        nd, nh, ng = np.zeros(nq, np.uint32), np.zeros(nq, np.uint32), np.zeros(nq, np.uint32)
+        if self.L.hso_search_pool(self.h, q, nq, k, ef, team, threads, lab, dist.ctypes.data, nd.ctypes.data,
+                                  nh.ctypes.data, ng.ctypes.data) != 0:
+            raise RuntimeError(self.L.hso_last_error().decode())
+        return lab, dist, nd, nh, ng
 
     def search_ties(self, q, k: int, ef: int, order: int = ORDER_GPU, team: int = 8, threads: int = 0):
         """search() + n_ties[nq]: exact-tie events at the ef boundary per query (hso_search_ties)."""

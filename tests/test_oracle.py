@@ -236,3 +236,55 @@ def test_tie_events_are_reported():
         b = orc.search_ties(queries, 10, 12, order=rh.ORDER_GPU, team=8)
         assert all(np.array_equal(x, y) for x, y in zip(a, b[:4]))
         assert (b[4] > 0).mean() > 0.5, b[4]
+
+
+@pytest.mark.parametrize("name,metric", [("slim_l2_2k", 0), ("slim_ip_1k", 1)])
+def test_pool_emulator_equals_the_reference_semantics(name, metric):
+    """hso_search_pool restates the ENGINE's algorithm (one pool in 32 columns, the kernel's placement, tie and
+    ghost rules); hso_search restates the REFERENCE's (two heaps).  They must agree to the bit — ids, distances,
+    evaluation and hop counters — on every query without an exact fp32 tie at the ef boundary."""
+    z = np.load(os.path.join(GOLDEN, f"{name}.npz"))
+    q = z["queries"]
+    orc = rh.Oracle(os.path.join(GOLDEN, f"{name}.graph"), 16, metric)
+    for ef in (10, 33, 64, 100, 129, 161, 200, 256):
+        lab, dist, nd, nh, nt = orc.search_ties(q, 10, ef, order=rh.ORDER_GPU, team=8)
+        pl, pd, pnd, pnh, png = orc.search_pool(q, 10, ef, team=8)
+        clean = nt == 0
+        assert clean.mean() > 0.9
+        assert np.array_equal(pl[clean], lab[clean]) and np.array_equal(pd[clean].view(np.uint32), dist[clean].view(np.uint32))
+        assert np.array_equal(pnd[clean], nd[clean]) and np.array_equal(pnh[clean], nh[clean])
+    with pytest.raises(RuntimeError):
+        orc.search_pool(q, 10, 300)                              # register pools only
+
+
+@needs_ref
+def test_pool_emulator_on_a_live_corpus():
+    """The same on a 20k x 128 corpus, plus the all-ties corpus where the two algorithms are ALLOWED to part:
+    the emulator must still return a valid answer (sorted, distinct ids) with recall equal within 0.5 pp."""
+    import tempfile
+    from hnsw_slim_b200.synth import make_dataset
+    base, q = make_dataset(20000, 300, 128, rank=14, seed=2)
+    with tempfile.TemporaryDirectory() as td:
+        g = os.path.join(td, "g.graph")
+        rh.ref_slim_build(base, g, M=16, ef_construction=100, threads=1)
+        orc = rh.Oracle(g, 128)
+        for ef in (50, 100, 200):
+            lab, dist, nd, nh, nt = orc.search_ties(q, 10, ef, order=rh.ORDER_GPU, team=8)
+            pl, pd, pnd, pnh, _ = orc.search_pool(q, 10, ef, team=8)
+            clean = nt == 0
+            assert np.array_equal(pl[clean], lab[clean]) and np.array_equal(pnd[clean], nd[clean])
+            assert np.array_equal(pnh[clean], nh[clean])
+        rng = np.random.default_rng(3)
+        rows = rng.standard_normal((700, 16)).astype(np.float32)
+        tb = np.repeat(rows, 3, axis=0)
+        tq = rng.standard_normal((60, 16)).astype(np.float32)
+        g2 = os.path.join(td, "ties.graph")
+        rh.ref_slim_build(tb, g2, M=8, ef_construction=60, threads=1)
+        o2 = rh.Oracle(g2, 16)
+        for ef in (12, 24, 40):
+            lab, dist, *_ = o2.search_ties(tq, 10, ef, order=rh.ORDER_GPU, team=8)
+            pl, pd, *_ = o2.search_pool(tq, 10, ef, team=8)
+            assert (np.diff(pd, axis=1) >= 0).all()
+            assert all(len(set(r)) == 10 for r in pl)
+            # the same distance multiset on almost every row (ties only reorder equal distances)
+            assert np.mean(np.all(pd.view(np.uint32) == dist.view(np.uint32), axis=1)) >= 0.9
