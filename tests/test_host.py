@@ -312,3 +312,17 @@ def test_reference_loads_engine_built_slimq_graph(tmp_path):
     hg = capi.HostGraph(graph, dim, kind=capi.HS_KIND_SLIMQ)
     for i in (0, 17, n - 1):
         assert np.array_equal(hg.row(i, 0), r.node(i)[3])
+
+
+def test_every_environment_knob_is_documented_in_the_header():
+    """The library reads a few tuning knobs from the environment (hs_load / plan time); each of them must be named
+    in include/hnswslim_b200.h next to hs_set_tuning."""
+    hdr = open(os.path.join(ROOT, "include", "hnswslim_b200.h")).read()
+    names = set()
+    csrc = os.path.join(ROOT, "hnsw_slim_b200", "csrc")
+    for f in os.listdir(csrc):
+        names |= set(re.findall(r'getenv\("([A-Z0-9_]+)"\)', open(os.path.join(csrc, f)).read()))
+    names |= set(re.findall(r'environ\.get\("(HS_[A-Z0-9_]+)"', open(os.path.join(ROOT, "hnsw_slim_b200", "capi.py")).read()))
+    assert len(names) >= 8
+    missing = sorted(n for n in names if n not in hdr)
+    assert not missing, f"environment knobs not documented in the header: {missing}"
