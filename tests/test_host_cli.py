@@ -198,3 +198,33 @@ def test_cli_serve_with_patches(tmp_path):
     gt, _ = capi.bruteforce_knn(base, q, 10)
     want = float(np.mean([len(set(a) & set(b)) / 10 for a, b in zip(lab, gt)]))
     assert abs(got - want) < 1e-6 and got > 0.9
+
+
+def test_host_util_reads_and_writes_vecs(tmp_path):
+    """host/util.h (ReadData / WriteData of .fvecs / .ivecs: one image per file, row headers checked) round-trips
+    files written by the Python side byte for byte, across its 8 MB slab boundary, and rejects a bad row header."""
+    host = os.path.join(os.path.dirname(hs_build.HERE), "hnsw_slim_b200", "host")
+    src = tmp_path / "t.cc"
+    src.write_text('#include "util.h"\n'
+                   'int main(int argc, char **argv) {\n'
+                   '  std::vector<float> rows; uint32_t num = 0, dim = 0;\n'
+                   '  ReadData(argv[1], rows, num, dim);\n'
+                   '  WriteData(argv[2], rows, num, dim);\n'
+                   '  return 0;\n}\n')
+    exe = str(tmp_path / "t")
+    subprocess.run(["/usr/bin/g++", "-std=c++17", "-O1", "-Wall", "-I", host, "-o", exe, str(src)], check=True)
+    rng = np.random.default_rng(0)
+    for n, d in ((1000, 33), (6000, 960), (1, 1)):
+        a = rng.standard_normal((n, d)).astype(np.float32)
+        fin, fout = str(tmp_path / f"in_{n}.fvecs"), str(tmp_path / f"out_{n}.fvecs")
+        vecs_io.write_vecs(fin, a)
+        r = subprocess.run([exe, fin, fout], capture_output=True, text=True)
+        assert r.returncode == 0 and f"num: {n}" in r.stdout and f"dim: {d}" in r.stdout
+        assert open(fin, "rb").read() == open(fout, "rb").read()
+    bad = np.fromfile(str(tmp_path / "in_1000.fvecs"), np.int32)
+    bad[5 * 34] = 32                                          # the header of row 5
+    bad.tofile(str(tmp_path / "bad.fvecs"))
+    r = subprocess.run([exe, str(tmp_path / "bad.fvecs"), str(tmp_path / "o")], capture_output=True, text=True)
+    assert r.returncode != 0 and "open file error" in r.stdout and "row 5" in r.stdout
+    r = subprocess.run([exe, str(tmp_path / "missing.fvecs"), str(tmp_path / "o")], capture_output=True, text=True)
+    assert r.returncode != 0 and "open file error" in r.stdout
